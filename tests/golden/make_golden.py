@@ -1,0 +1,235 @@
+"""Generate the golden fixtures in this directory by running the REFERENCE's own code (mounted read-only at
+/root/reference) in the build container.  The GPU box has no /root/reference, so the outputs are committed.
+
+    python tests/golden/make_golden.py
+
+Writes
+  gm_transcripts.npz      -- GroupMatching transcripts (reference class + numpy RandomState)
+  learner_<case>.npz      -- EntityMAC forward / greedy actions / one QLearner.train step per alg config
+
+The synthetic inputs come from oracle.learner_oracle.synthetic_batch (input generation only); every OUTPUT
+stored here is produced by reference classes (envs.group_matching.GroupMatching, controllers.EntityMAC,
+learners.QLearner).
+"""
+import os
+import sys
+from collections import defaultdict
+from types import SimpleNamespace
+
+import numpy as np
+import torch as th
+import yaml
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+sys.path.insert(0, HERE)
+
+import ref_shim  # noqa: E402
+
+ref_shim.install()
+
+from oracle.learner_oracle import synthetic_batch  # noqa: E402
+
+
+# ----------------------------------------------------------------------------------------------
+def make_env_transcripts():
+    GM = ref_shim.group_matching_cls()
+    rng = np.random.RandomState(2024)
+    cases = []
+    fixed = [dict(n_agents=4, n_states=6, n_groups=2, rand_trans=0.1, episode_limit=50),   # BASELINE config 1/2
+             dict(n_agents=8, n_states=6, n_groups=2, rand_trans=0.1, episode_limit=50),   # env yaml default
+             dict(n_agents=8, n_states=6, n_groups=3, rand_trans=0.1, episode_limit=50),   # overlapping/empty groups
+             dict(n_agents=4, n_states=10, n_groups=2, rand_trans=0.1, episode_limit=50),  # class defaults
+             dict(n_agents=1, n_states=1, n_groups=1, rand_trans=1.0, episode_limit=3),
+             dict(n_agents=5, n_states=3, n_groups=4, rand_trans=0.5, episode_limit=7),
+             dict(n_agents=16, n_states=5, n_groups=2, rand_trans=0.0, episode_limit=20)]
+    out = {}
+    for ci, cfg in enumerate(fixed):
+        for seed in [0, 1, 12345 + ci, 2 ** 31 + 17]:
+            env = GM(seed=seed, **cfg)
+            na = cfg["n_agents"]
+            locs, rews, flags, acts, ents, gts, resets = [], [], [], [], [], [], []
+            for ep in range(3):
+                env.reset()
+                resets.append(len(rews))
+                locs.append(env.agent_locs.argmax(1).astype(np.int32))
+                ents.append(np.stack(env.get_entities()))
+                gts.append(env.get_masks()[2])
+                done = False
+                while not done:
+                    a = rng.randint(0, 3, size=na)
+                    r, done, info = env.step(a)
+                    acts.append(a.astype(np.int64))
+                    rews.append(np.float64(r))
+                    flags.append(int(done) | (int(info["solved"]) << 1) | (int(info.get("episode_limit", False)) << 2))
+                    locs.append(env.agent_locs.argmax(1).astype(np.int32))
+                    ents.append(np.stack(env.get_entities()))
+                    gts.append(env.get_masks()[2])
+            key = "c%d_s%d" % (ci, seed)
+            out[key + "_cfg"] = np.array([cfg["n_agents"], cfg["n_states"], cfg["n_groups"], cfg["episode_limit"]], np.int64)
+            out[key + "_rt"] = np.float64(cfg["rand_trans"])
+            out[key + "_seed"] = np.int64(seed)
+            out[key + "_actions"] = np.stack(acts)
+            out[key + "_reward"] = np.array(rews, np.float64)
+            out[key + "_flags"] = np.array(flags, np.int32)
+            out[key + "_locs"] = np.stack(locs)
+            out[key + "_entities"] = np.stack(ents).astype(np.float32)
+            out[key + "_gt"] = np.stack(gts).astype(np.uint8)
+            out[key + "_resets"] = np.array(resets, np.int64)
+            cases.append(key)
+    out["cases"] = np.array(cases)
+    np.savez_compressed(os.path.join(HERE, "gm_transcripts.npz"), **out)
+    print("gm_transcripts.npz: %d cases" % len(cases))
+
+
+# ----------------------------------------------------------------------------------------------
+class _ConsoleStub:
+    def info(self, *a, **k):
+        pass
+
+
+class _LoggerStub:
+    def __init__(self):
+        self.stats = defaultdict(list)
+        self.console_logger = _ConsoleStub()
+
+    def log_stat(self, key, value, t, to_sacred=True):
+        self.stats[key].append(float(value))
+
+
+def _ref_args(alg, **over):
+    cfg_dir = os.path.join(ref_shim.REF_SRC, "config")
+    with open(os.path.join(cfg_dir, "default.yaml")) as f:
+        cfg = yaml.safe_load(f)
+    with open(os.path.join(cfg_dir, "algs", alg + ".yaml")) as f:
+        cfg.update(yaml.safe_load(f))
+    cfg.update(over)
+    return SimpleNamespace(**cfg)
+
+
+def _t2n(d):
+    return {k: v.detach().cpu().numpy().copy() for k, v in d.items()}
+
+
+def make_learner_case(name, alg, B, T, na, ne, ed, A, seed, gt=False, **over):
+    from components.episode_buffer import EpisodeBatch
+    from components.transforms import OneHot
+    from controllers import REGISTRY as mac_REGISTRY
+    from learners import REGISTRY as le_REGISTRY
+
+    args = _ref_args(alg, **over)
+    args.n_agents, args.n_actions, args.n_entities, args.entity_shape = na, A, ne, ed
+    args.entity_scheme, args.gt_mask_avail, args.device = True, gt, "cpu"
+    args.learner_log_interval = 1
+    th.manual_seed(seed)
+    scheme = {
+        "entities": {"vshape": ed, "group": "entities"},
+        "obs_mask": {"vshape": ne, "group": "entities", "dtype": th.uint8},
+        "entity_mask": {"vshape": ne, "dtype": th.uint8},
+        "actions": {"vshape": (1,), "group": "agents", "dtype": th.long},
+        "avail_actions": {"vshape": (A,), "group": "agents", "dtype": th.int},
+        "reward": {"vshape": (1,)},
+        "terminated": {"vshape": (1,), "dtype": th.uint8},
+    }
+    if gt:
+        scheme["gt_mask"] = {"vshape": ne, "group": "agents", "dtype": th.uint8}
+    groups = {"agents": na, "entities": ne}
+    preprocess = {"actions": ("actions_onehot", [OneHot(out_dim=A)])}
+    batch = EpisodeBatch(scheme, groups, B, T, preprocess=preprocess, device="cpu")
+    mac = mac_REGISTRY[args.mac](batch.scheme, groups, args)
+    logger = _LoggerStub()
+    learner = le_REGISTRY[args.learner](mac, batch.scheme, logger, args)
+    # make the target nets differ from the online nets (stronger check than the identical copies at init)
+    gen = th.Generator().manual_seed(seed + 99)
+    for p in list(learner.target_mac.parameters()) + (list(learner.target_mixer.parameters()) if learner.mixer is not None else []):
+        p.data.add_(0.05 * th.randn(p.shape, generator=gen))
+
+    syn = synthetic_batch(th.Generator().manual_seed(seed + 1), B, T, na, ne, ed, A, gt_mask=gt, pad=(ne > na) or not gt)
+    if gt:  # group matching style: nothing masked, gt_mask symmetric-ish block structure
+        syn["obs_mask"].zero_()
+        syn["entity_mask"].zero_()
+    for k, v in syn.items():
+        batch.data.transition_data[k][:] = v
+
+    out = {"meta_alg": np.array(alg), "meta_dims": np.array([B, T, na, ne, ed, A], np.int64)}
+    for k, v in vars(args).items():
+        if isinstance(v, (int, float, bool, str)) or v is None:
+            out["arg_" + k] = np.array("None" if v is None else v)
+    for k, v in syn.items():
+        out["in_" + k] = v.numpy()
+    for k, v in _t2n(mac.agent.state_dict()).items():
+        out["agent_" + k] = v
+    for k, v in _t2n(learner.target_mac.agent.state_dict()).items():
+        out["tagent_" + k] = v
+    if learner.mixer is not None:
+        for k, v in _t2n(learner.mixer.state_dict()).items():
+            out["mixer_" + k] = v
+        for k, v in _t2n(learner.target_mixer.state_dict()).items():
+            out["tmixer_" + k] = v
+
+    imagine = "imagine" in args.agent
+    rng_seed = seed + 7
+    # the partition draw of entity_{rnn,ff}_agent.py (th.rand(bs,1,1) then th.bernoulli) replicated under the same seed
+    th.manual_seed(rng_seed)
+    probs = th.rand(B, 1, 1).repeat(1, 1, ne)
+    group_a = th.bernoulli(probs).to(th.uint8).reshape(B, ne)
+    out["group_a"] = group_a.numpy()
+
+    # --- forward only: plain and imagine ------------------------------------------------------
+    with th.no_grad():
+        mac.init_hidden(B)
+        out["fwd_mac_out"] = mac.forward(batch, t=None).numpy()
+        if imagine:
+            th.manual_seed(rng_seed)
+            mac.init_hidden(B)
+            q3, (wm, im) = mac.forward(batch, t=None, imagine=True,
+                                       use_gt_factors=args.train_gt_factors,
+                                       use_rand_gt_factors=args.train_rand_gt_factors)
+            out["fwd_imagine_out"] = q3.numpy()
+            out["fwd_wmask"] = wm.numpy().astype(np.uint8)
+            out["fwd_imask"] = im.numpy().astype(np.uint8)
+        # sequential greedy acting (BasicMAC.select_actions, test_mode=True), hidden state carried over t
+        mac.init_hidden(B)
+        acts, qs = [], []
+        for t in range(T):
+            a, q = mac.select_actions(batch, t_ep=t, t_env=0, test_mode=True, ret_agent_outs=True)
+            acts.append(a.numpy())
+            qs.append(q.numpy())
+        out["greedy_actions"] = np.stack(acts, 1).astype(np.int64)
+        out["greedy_q"] = np.stack(qs, 1)
+
+    # --- one full train step --------------------------------------------------------------------
+    th.manual_seed(rng_seed)
+    learner.train(batch, t_env=10, episode_num=0)
+    for k, v in logger.stats.items():
+        out["stat_" + k] = np.float64(v[0])
+    for k, p in mac.agent.named_parameters():
+        out["grad_agent_" + k] = p.grad.numpy().copy()
+        out["new_agent_" + k] = p.detach().numpy().copy()
+    if learner.mixer is not None:
+        for k, p in learner.mixer.named_parameters():
+            out["grad_mixer_" + k] = p.grad.numpy().copy()
+            out["new_mixer_" + k] = p.detach().numpy().copy()
+    np.savez_compressed(os.path.join(HERE, "learner_%s.npz" % name), **out)
+    print("learner_%s.npz: loss=%.6f grad_norm=%.6f" % (name, out["stat_loss"], out["stat_grad_norm"]))
+
+
+SMALL = dict(attn_embed_dim=32, attn_n_heads=2, hypernet_embed=32, mixing_embed_dim=8, rnn_hidden_dim=16)
+
+if __name__ == "__main__":
+    make_env_transcripts()
+    make_learner_case("refil", "refil", B=3, T=6, na=3, ne=5, ed=6, A=4, seed=11, **SMALL)
+    make_learner_case("qmix_atten", "qmix_atten", B=3, T=5, na=3, ne=5, ed=6, A=4, seed=12, **SMALL)
+    make_learner_case("refil_gm", "refil_group_matching", B=4, T=6, na=4, ne=4, ed=12, A=3, seed=13, gt=True,
+                      attn_embed_dim=32, attn_n_heads=4, hypernet_embed=32, mixing_embed_dim=8)
+    make_learner_case("qmix_atten_gm", "qmix_atten_group_matching", B=4, T=6, na=4, ne=4, ed=12, A=3, seed=14, gt=True,
+                      attn_embed_dim=32, attn_n_heads=4, hypernet_embed=32, mixing_embed_dim=8)
+    make_learner_case("refil_vdn", "refil_vdn", B=3, T=5, na=3, ne=5, ed=6, A=4, seed=15,
+                      attn_embed_dim=32, attn_n_heads=2, rnn_hidden_dim=16)
+    make_learner_case("vdn_atten", "vdn_atten", B=3, T=5, na=3, ne=5, ed=6, A=4, seed=16,
+                      attn_embed_dim=32, attn_n_heads=2, rnn_hidden_dim=16)
+    make_learner_case("refil_abs_tanh", "refil", B=2, T=4, na=2, ne=4, ed=5, A=3, seed=17,
+                      softmax_mixing_weights=False, mixer_non_lin="tanh", **SMALL)
+    make_learner_case("refil_gm_randgt", "refil_group_matching", B=3, T=5, na=4, ne=4, ed=12, A=3, seed=18, gt=True,
+                      train_rand_gt_factors=True, attn_embed_dim=32, attn_n_heads=4, hypernet_embed=32,
+                      mixing_embed_dim=8)
