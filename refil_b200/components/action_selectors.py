@@ -1,0 +1,37 @@
+"""Action selection on device (reference: src/components/action_selectors.py:36-63).
+
+Greedy index parity: unavailable actions are -inf and the FIRST maximum wins (torch `max(dim)[1]` on CPU), computed
+by the `refil_select_actions` kernel.  Exploration draws two uniforms per (env, agent) with torch's device generator
+(u_pick < eps -> the floor(u_act * n_avail)-th available action), which is Categorical(avail) in distribution."""
+import torch
+
+from .. import ops
+from .epsilon_schedules import DecayThenFlatSchedule
+
+REGISTRY = {}
+
+
+class EpsilonGreedyActionSelector:
+    def __init__(self, args):
+        self.args = args
+        self.schedule = DecayThenFlatSchedule(args.epsilon_start, args.epsilon_finish, args.epsilon_anneal_time,
+                                              decay="linear")
+        self.epsilon = self.schedule.eval(0)
+
+    def select_action(self, agent_inputs, avail_actions, t_env, test_mode=False, est_flags=None, out=None):
+        """agent_inputs [bs, na, A] f32, avail_actions [bs, na, A] int32 -> actions [bs, na] int64."""
+        self.epsilon = 0.0 if test_mode else self.schedule.eval(t_env)
+        q = agent_inputs.contiguous()
+        avail = avail_actions.to(torch.int32).contiguous()
+        bs, na, A = q.shape
+        if out is None:
+            out = torch.zeros(bs, na, dtype=torch.int64, device=q.device)
+        u_pick = u_act = None
+        if self.epsilon > 0.0:
+            u = torch.rand(2, bs, na, device=q.device)
+            u_pick, u_act = u[0], u[1]
+        ops.select_actions(q, avail, u_pick, u_act, est_flags, self.epsilon, out, bs, na, A)
+        return out
+
+
+REGISTRY["epsilon_greedy"] = EpsilonGreedyActionSelector

@@ -1,0 +1,201 @@
+"""Double-Q TD learner with the REFIL auxiliary loss, as one explicit forward/backward schedule of sm_100a kernels.
+
+API mirror of /root/reference/src/learners/q_learner.py:10-229 (QLearner): ctor (mac, scheme, logger, args);
+train(batch, t_env, episode_num); cuda(); save_models(path); load_models(path, evaluate); _update_targets().
+Arithmetic follows q_learner.py:66-182; the schedule differs from the reference on purpose:
+  * fc1 / in_trans of the agent and of hyper_w_1 run ONCE for the three imagine copies (the reference repeats them 3x);
+  * hyper_w_final / hyper_b_1 / V are evaluated once for the plain and the imagine mix (identical inputs);
+  * losses are kept as sums; the division by sum(mask), the global-norm clip and RMSprop run in one kernel after the
+    single all-reduce of [flat grads | loss statistics] (multi-GPU: replay sharded over episodes).
+"""
+import os
+
+import torch
+import torch.distributed as dist
+
+from .. import ops
+from ..modules.nets import Mixer
+from ..modules.params import Workspace
+
+N_STATS = 8
+
+
+class QLearner:
+    def __init__(self, mac, scheme, logger, args):
+        self.args = args
+        self.mac = mac
+        self.logger = logger
+        self.device = mac.agent.store.flat.device
+        self.last_target_update_episode = 0
+        self.imagine = "imagine" in args.agent
+        self.ein = mac.agent.ein
+
+        self.mixer = None
+        if args.mixer is not None:
+            if args.mixer not in Mixer.HYPERS:
+                raise ValueError("Mixer %s not recognised (flat-state `qmix` is out of scope)." % args.mixer)
+            self.mixer = Mixer(args, self.ein, self.device, tag="mixer")
+            self.target_mixer = Mixer(args, self.ein, self.device, tag="target_mixer")
+            self.target_mixer.load_state_dict(self.mixer.state_dict())
+        self.target_mac = type(mac)(mac.scheme, mac.groups, args)
+        self.target_mac.load_state(mac)
+        self._bind_flat()
+        self.ws = Workspace(self.device)
+        self.log_stats_t = -self.args.learner_log_interval - 1
+
+    # ---- flat parameter / gradient / optimiser state -----------------------------------------------------------
+    def _bind_flat(self):
+        stores = [self.mac.agent.store] + ([self.mixer.store] if self.mixer is not None else [])
+        self.n_params = sum(s.padded_size for s in stores)
+        dev = self.device
+        self.flat = torch.zeros(self.n_params, dtype=torch.float32, device=dev)
+        self.gradbuf = torch.zeros(self.n_params + N_STATS, dtype=torch.float32, device=dev)   # [grads | loss stats]
+        self.square_avg = torch.zeros(self.n_params, dtype=torch.float32, device=dev)          # RMSprop state
+        off = 0
+        for s in stores:
+            s.rebind(self.flat[off:off + s.padded_size], self.gradbuf[off:off + s.padded_size])
+            off += s.padded_size
+        self.params = list(self.mac.parameters()) + (list(self.mixer.parameters()) if self.mixer is not None else [])
+        self.stats64 = torch.zeros(N_STATS, dtype=torch.float64, device=dev)
+        self.sumsq = torch.zeros(1, dtype=torch.float64, device=dev)
+        self.grad_norm = torch.zeros(1, dtype=torch.float32, device=dev)
+
+    def cuda(self):
+        self.mac.cuda()
+        self.target_mac.cuda()
+        if self.mixer is not None:
+            self.mixer.cuda()
+            self.target_mixer.cuda()
+        if self.mac.agent.store.flat.device != self.device:
+            self.device = self.mac.agent.store.flat.device
+            self._bind_flat()
+            self.ws = Workspace(self.device)
+
+    # ---- the training step ---------------------------------------------------------------------------------------
+    def train(self, batch, t_env, episode_num, group_bits=None):
+        args, ws = self.args, self.ws
+        B, T = batch.batch_size, batch.max_seq_length
+        na, A = args.n_agents, args.n_actions
+        N = B * T
+        actions = batch["actions"].contiguous().view(N, na)
+        avail = batch["avail_actions"].contiguous().view(N, na, A)
+        reward = batch["reward"].contiguous().view(N)
+        terminated = batch["terminated"].contiguous().view(N)
+        filled = batch["filled"].contiguous().view(N)
+
+        # online agent on all T steps, 3 mask copies when imagining (q_learner.py:79-109)
+        self.mac.init_hidden(B)
+        q_all, spec, mix, inp = self.mac.forward(batch, None, imagine=self.imagine,
+                                                 use_gt_factors=getattr(args, "train_gt_factors", False),
+                                                 use_rand_gt_factors=getattr(args, "train_rand_gt_factors", False),
+                                                 group_bits=group_bits, train=True, ret_plan=True)
+        C = spec.C
+        chosen = ops.gather_chosen(q_all, actions, ws.get("chosen", (3, N, na)), C, N * na, A)
+        # target agent + double-Q selection (q_learner.py:111-126)
+        self.target_mac.init_hidden(B)
+        q_tgt, _, _, _ = self.target_mac.forward(batch, None, ret_plan=True, inputs=inp)
+        tgt_max = ops.target_max(q_all[0], q_tgt[0], avail, ws.get("tgt_max", (N, na)), None, N * na, A, args.double_q)
+        # mixers (q_learner.py:129-154)
+        ents, la, em = inp["entities"], inp["last_action"], inp["entity_mask"]
+        qtot, qtot_im = self.mixer.forward(chosen[0], chosen[1] if self.imagine else None,
+                                           chosen[2] if self.imagine else None, ents, la, em, T,
+                                           imagine_masks=mix if self.imagine else None)
+        tgt_tot, _ = self.target_mixer.forward(tgt_max, None, None, ents, la, em, T)
+        # targets, TD errors, masked losses as sums (q_learner.py:157-172)
+        self.stats64.zero_()
+        g_plain = ws.get("g_plain", (N,))
+        g_im = ws.get("g_im", (N,)) if self.imagine else None
+        ops.td_loss(qtot, qtot_im, tgt_tot, reward, terminated, filled, g_plain, g_im, None, self.stats64, B, T,
+                    args.gamma, args.lmbda if self.imagine else 0.0)
+        # backward (q_learner.py:175-176)
+        self.gradbuf.zero_()
+        dq = self.mixer.backward(g_plain, g_im)
+        dQ = ops.scatter_dq(dq, actions, ws.get("dQ", (C * N * na, A)), C, N * na, A, T, na)
+        self.mac.agent.backward(dQ)
+        # one all-reduce of [grads | stats], then normalise + clip + RMSprop (q_learner.py:177-178)
+        ops.pack_stats(self.stats64, self.gradbuf[self.n_params:], N_STATS)
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(self.gradbuf)
+        self.sumsq.zero_()
+        ops.grad_sumsq(self.gradbuf, self.n_params, self.sumsq)
+        ops.clip_rmsprop_step(self.flat, self.gradbuf, self.square_avg, self.n_params,
+                              self.gradbuf[self.n_params:self.n_params + 1], self.sumsq, self.grad_norm,
+                              args.grad_norm_clip, args.lr, args.optim_alpha, args.optim_eps,
+                              getattr(args, "weight_decay", 0))
+
+        if (episode_num - self.last_target_update_episode) / args.target_update_interval >= 1.0:
+            self._update_targets()
+            self.last_target_update_episode = episode_num
+
+        if t_env - self.log_stats_t >= args.learner_log_interval:
+            st = self.gradbuf[self.n_params:].double().cpu()      # the only host sync of the step
+            m = float(st[0])
+            td, td_im = float(st[1]) / m, float(st[2]) / m
+            loss = (1 - args.lmbda) * td + args.lmbda * td_im if self.imagine else td
+            self.logger.log_stat("loss", loss, t_env)
+            if self.imagine:
+                self.logger.log_stat("im_loss", td_im, t_env)
+            self.logger.log_stat("grad_norm", float(self.grad_norm.item()), t_env)
+            self.logger.log_stat("td_error_abs", float(st[3]) / m, t_env)
+            self.logger.log_stat("q_taken_mean", float(st[4]) / (m * na), t_env)
+            self.logger.log_stat("target_mean", float(st[5]) / (m * na), t_env)
+            self.log_stats_t = t_env
+
+    def _update_targets(self):
+        self.target_mac.load_state(self.mac)
+        if self.mixer is not None:
+            self.target_mixer.load_state_dict(self.mixer.state_dict())
+        if self.logger is not None:
+            self.logger.console_logger.info("Updated target network")
+
+    # ---- checkpoints (file names and state_dict keys of q_learner.py:216-229) ---------------------------------------
+    def _opt_state_dict(self):
+        state, off = {}, 0
+        stores = [self.mac.agent.store] + ([self.mixer.store] if self.mixer is not None else [])
+        idx = 0
+        for s in stores:
+            o = off
+            for k, shp in s.specs.items():
+                n = 1
+                for d in shp:
+                    n *= d
+                state[idx] = {"step": 0, "square_avg": self.square_avg[o:o + n].view(shp).detach().cpu().clone()}
+                o += n
+                idx += 1
+            off += s.padded_size
+        a = self.args
+        group = {"lr": a.lr, "momentum": 0, "alpha": a.optim_alpha, "eps": a.optim_eps, "centered": False,
+                 "weight_decay": getattr(a, "weight_decay", 0), "params": list(range(idx))}
+        return {"state": state, "param_groups": [group]}
+
+    def _load_opt_state_dict(self, sd):
+        off, idx = 0, 0
+        stores = [self.mac.agent.store] + ([self.mixer.store] if self.mixer is not None else [])
+        for s in stores:
+            o = off
+            for k, shp in s.specs.items():
+                n = 1
+                for d in shp:
+                    n *= d
+                st = sd["state"].get(idx)
+                if st is not None and "square_avg" in st:
+                    self.square_avg[o:o + n].copy_(st["square_avg"].reshape(-1).to(self.device))
+                o += n
+                idx += 1
+            off += s.padded_size
+
+    def save_models(self, path):
+        self.mac.save_models(path)
+        if self.mixer is not None:
+            torch.save({k: v.detach().cpu() for k, v in self.mixer.state_dict().items()}, os.path.join(path, "mixer.th"))
+        torch.save(self._opt_state_dict(), os.path.join(path, "opt.th"))
+
+    def load_models(self, path, evaluate=False):
+        self.mac.load_models(path)
+        self.target_mac.load_models(path)      # target nets are re-loaded from the online weights (q_learner.py:224-225)
+        if not evaluate:
+            if self.mixer is not None:
+                sd = torch.load(os.path.join(path, "mixer.th"), map_location="cpu")
+                self.mixer.load_state_dict(sd)
+                self.target_mixer.load_state_dict(sd)
+            self._load_opt_state_dict(torch.load(os.path.join(path, "opt.th"), map_location="cpu"))

@@ -1,0 +1,326 @@
+"""Entity-attention networks of the learner hot path, as explicit forward / hand-written backward schedules over the
+sm_100a kernels (no autograd on the product path).
+
+Mirrors (state_dict keys included):
+  /root/reference/src/modules/layers/attention.py:6-79          EntityAttentionLayer  -> AttnTrunk (fc1 + in_trans + MHA + out_trans)
+  /root/reference/src/modules/agents/entity_rnn_agent.py:7-126  (Imagine)EntityAttentionRNNAgent -> EntityAttnAgent(rnn=True)
+  /root/reference/src/modules/agents/entity_ff_agent.py:7-135   (Imagine)EntityAttentionFFAgent  -> EntityAttnAgent(rnn=False)
+  /root/reference/src/modules/mixers/flex_qmix.py:7-57          AttentionHyperNet -> AttnHyperNet
+
+Row conventions: N = B*T rows of (b, t); entity rows [N*ne, .]; agent rows of a copy stack [C*N*na, .] ordered
+(copy, b, t, agent).  The reference's 3x `repeat` of the inputs for the imagine copies never happens: fc1 and in_trans
+run once, the attention kernel resolves the three masks against one QKV tile.
+"""
+from collections import OrderedDict
+
+import torch
+
+from .. import ops
+from .params import ParamStore, Workspace, init_linear_, init_uniform_
+
+
+class MaskSpec:
+    """Attention masks of one forward: up to 3 copies of (explicit u8 mask or None, stride per (b,t) row, mode bits),
+    plus the per-episode random group bits and the entity mask the closed-form modes need."""
+
+    def __init__(self, copies, group_bits=None, entity_mask=None):
+        self.copies = list(copies)
+        self.group_bits = group_bits
+        self.entity_mask = entity_mask
+
+    @property
+    def C(self):
+        return len(self.copies)
+
+
+class AttnTrunk:
+    """x1 = relu(fc1([ents | onehot(last action)])); QKV = in_trans(x1); masked MHA for C mask copies;
+    x2 = [relu] out_trans(.) with inactive-agent rows zeroed."""
+
+    def __init__(self, store, prefix, ws, tag, ein, d, n_heads, n_agents, n_actions):
+        self.s, self.pre, self.ws, self.tag = store, prefix, ws, tag
+        self.ein, self.d, self.H, self.na, self.A = ein, d, n_heads, n_agents, n_actions
+        # attention.py:18-19 registers sqrt(head_dim) as a buffer: keep the key so checkpoints interchange
+        store.buffers[prefix + "attn.scale_factor"] = torch.tensor(float(d // n_heads)).sqrt()
+
+    @staticmethod
+    def specs(prefix, ein, d):
+        return OrderedDict([(prefix + "fc1.weight", (d, ein)), (prefix + "fc1.bias", (d,)),
+                            (prefix + "attn.in_trans.weight", (3 * d, d)),
+                            (prefix + "attn.out_trans.weight", (d, d)), (prefix + "attn.out_trans.bias", (d,))])
+
+    def init(self, gen):
+        p, pre = self.s.p, self.pre
+        init_linear_(gen, p[pre + "fc1.weight"], p[pre + "fc1.bias"])
+        init_linear_(gen, p[pre + "attn.in_trans.weight"])
+        init_linear_(gen, p[pre + "attn.out_trans.weight"], p[pre + "attn.out_trans.bias"])
+
+    def forward(self, ents, la, masks, T, relu_out=False):
+        """ents [N, ne, ed] f32, la [N, ne] i32 or None -> x2 [C*N*na, d]"""
+        p, pre, ws, tag = self.s.p, self.pre, self.ws, self.tag
+        N, ne = ents.shape[0], ents.shape[1]
+        C, d, na = masks.C, self.d, self.na
+        x1 = ws.get(tag + ".x1", (N * ne, d))
+        ops.embed_fwd(ents, la, self.A, p[pre + "fc1.weight"], p[pre + "fc1.bias"], x1, relu=True)
+        qkv = ws.get(tag + ".qkv", (N * ne, 3 * d))
+        ops.linear_fwd(x1, p[pre + "attn.in_trans.weight"], None, qkv)
+        att = ws.get(tag + ".att", (C * N * na, d))
+        ops.masked_attn_fwd(qkv, att, masks.copies, masks.group_bits, masks.entity_mask, N, T, ne, na, d, self.H)
+        x2 = ws.get(tag + ".x2", (C * N * na, d))
+        self.row_mask = (masks.entity_mask, na, N * na) if masks.entity_mask is not None else None
+        ops.linear_fwd(att, p[pre + "attn.out_trans.weight"], p[pre + "attn.out_trans.bias"], x2, relu=relu_out,
+                       row_mask=self.row_mask)
+        self.saved = (ents, la, masks, T, relu_out, x1, qkv, att, x2, N, ne)
+        return x2
+
+    def backward(self, dx2):
+        p, g, pre, ws = self.s.p, self.s.g, self.pre, self.ws
+        ents, la, masks, T, relu_out, x1, qkv, att, x2, N, ne = self.saved
+        C, d, na = masks.C, self.d, self.na
+        relu_y = x2 if relu_out else None
+        ops.linear_bwd_weight(dx2, att, g[pre + "attn.out_trans.weight"], g[pre + "attn.out_trans.bias"],
+                              relu_y=relu_y, row_mask=self.row_mask)
+        datt = ws.get("scratch.datt", (C * N * na, d))
+        ops.linear_bwd_data(dx2, p[pre + "attn.out_trans.weight"], datt, relu_y=relu_y, row_mask=self.row_mask)
+        dqkv = ws.get("scratch.dqkv", (N * ne, 3 * d))
+        ops.masked_attn_bwd(qkv, datt, dqkv, masks.copies, masks.group_bits, masks.entity_mask, N, T, ne, na, d, self.H)
+        ops.linear_bwd_weight(dqkv, x1, g[pre + "attn.in_trans.weight"], None)
+        dx1 = ws.get("scratch.dx1", (N * ne, d))
+        ops.linear_bwd_data(dqkv, p[pre + "attn.in_trans.weight"], dx1)
+        ops.embed_bwd_weight(dx1, x1, ents, la, self.A, g[pre + "fc1.weight"], g[pre + "fc1.bias"])
+
+
+class EntityAttnAgent:
+    """Per-agent utility network (shared parameters).  rnn=True: fc1-attn-fc2-GRU-fc3 (entity_rnn_agent.py:31-64);
+    rnn=False: fc1-attn-relu-fc2 (entity_ff_agent.py:30-57)."""
+
+    def __init__(self, input_shape, args, device, ws=None, tag="agent", seed=None):
+        self.args = args
+        self.rnn = "rnn" in args.agent
+        self.ein, self.d, self.H = int(input_shape), int(args.attn_embed_dim), int(args.attn_n_heads)
+        self.na, self.A, self.r = int(args.n_agents), int(args.n_actions), int(args.rnn_hidden_dim)
+        self.one_hot_la = bool(args.entity_last_action)
+        specs = AttnTrunk.specs("", self.ein, self.d)
+        if self.rnn:
+            specs.update(OrderedDict([("fc2.weight", (self.r, self.d)), ("fc2.bias", (self.r,)),
+                                      ("rnn.weight_ih", (3 * self.r, self.r)), ("rnn.weight_hh", (3 * self.r, self.r)),
+                                      ("rnn.bias_ih", (3 * self.r,)), ("rnn.bias_hh", (3 * self.r,)),
+                                      ("fc3.weight", (self.A, self.r)), ("fc3.bias", (self.A,))]))
+        else:
+            specs.update(OrderedDict([("fc2.weight", (self.A, self.d)), ("fc2.bias", (self.A,))]))
+        self.store = ParamStore(specs, device)
+        self.ws = ws if ws is not None else Workspace(device)
+        self.tag = tag
+        self.trunk = AttnTrunk(self.store, "", self.ws, tag, self.ein, self.d, self.H, self.na, self.A)
+        gen = torch.Generator().manual_seed(int(seed) if seed is not None else torch.initial_seed() % (2 ** 31))
+        self.trunk.init(gen)
+        p = self.store.p
+        if self.rnn:
+            init_linear_(gen, p["fc2.weight"], p["fc2.bias"])
+            bound = 1.0 / (self.r ** 0.5)
+            for k in ("rnn.weight_ih", "rnn.weight_hh", "rnn.bias_ih", "rnn.bias_hh"):
+                init_uniform_(gen, p[k], bound)
+            init_linear_(gen, p["fc3.weight"], p["fc3.bias"])
+        else:
+            init_linear_(gen, p["fc2.weight"], p["fc2.bias"])
+
+    # reference nn.Module surface used by BasicMAC ---------------------------------------------------------
+    def init_hidden(self):
+        return torch.zeros(1, self.r, device=self.store.flat.device)  # entity_rnn_agent.py:27-29
+
+    def parameters(self):
+        return self.store.parameters()
+
+    def named_parameters(self):
+        return self.store.named_parameters()
+
+    def state_dict(self):
+        return self.store.state_dict()
+
+    def load_state_dict(self, sd, strict=True):
+        self.store.load_state_dict(sd, strict)
+
+    def cuda(self):
+        self.store.to("cuda")
+        self.ws.device = self.store.flat.device
+        return self
+
+    def train(self, mode=True):
+        return self
+
+    def eval(self):
+        return self
+
+    # ---------------------------------------------------------------------------------------------------------
+    def forward(self, ents, la, masks, B, T, h0=None, train=False):
+        """ents [B*T, ne, ed]; masks: MaskSpec (C copies); h0 [C*B*na, r] or None (zeros).
+        Returns q [C, B*T, na, A] and the hidden-state stack hs [C*B*T*na, r] (rnn) / x2 (ff)."""
+        p, ws, tag = self.store.p, self.ws, self.tag
+        N, C, na = B * T, masks.C, self.na
+        R = C * N * na
+        x2 = self.trunk.forward(ents, la if self.one_hot_la else None, masks, T, relu_out=not self.rnn)
+        rm = self.trunk.row_mask
+        q = ws.get(tag + ".q", (R, self.A))
+        if self.rnn:
+            x3 = ws.get(tag + ".x3", (R, self.r))
+            ops.linear_fwd(x2, p["fc2.weight"], p["fc2.bias"], x3, relu=True)
+            gi = ws.get(tag + ".gi", (R, 3 * self.r))
+            ops.linear_fwd(x3, p["rnn.weight_ih"], p["rnn.bias_ih"], gi)
+            hs = ws.get(tag + ".hs", (R, self.r))
+            gates = ws.get(tag + ".gates", (R, 4 * self.r)) if train else None
+            ops.gru_scan_fwd(gi, p["rnn.weight_hh"], p["rnn.bias_hh"], h0, hs, gates, C * B * na, T, na)
+            ops.linear_fwd(hs, p["fc3.weight"], p["fc3.bias"], q, row_mask=rm)
+            self.saved = (x2, x3, hs, gates, h0, B, T, C)
+            return q.view(C, N, na, self.A), hs
+        ops.linear_fwd(x2, p["fc2.weight"], p["fc2.bias"], q, row_mask=rm)
+        self.saved = (x2, None, None, None, None, B, T, C)
+        return q.view(C, N, na, self.A), x2
+
+    def backward(self, dq):
+        """dq [C*N*na, A] -> accumulates into the gradient views of the store."""
+        p, g, ws = self.store.p, self.store.g, self.ws
+        x2, x3, hs, gates, h0, B, T, C = self.saved
+        na, rm = self.na, self.trunk.row_mask
+        R = dq.shape[0]
+        dx2 = ws.get("scratch.dx2", (R, self.d))
+        if self.rnn:
+            ops.linear_bwd_weight(dq, hs, g["fc3.weight"], g["fc3.bias"], row_mask=rm)
+            dhs = ws.get("scratch.dhs", (R, self.r))
+            ops.linear_bwd_data(dq, p["fc3.weight"], dhs, row_mask=rm)
+            dgi = ws.get("scratch.dgi", (R, 3 * self.r))
+            dgh = ws.get("scratch.dgh", (R, 3 * self.r))
+            ops.gru_scan_bwd(dhs, gates, hs, h0, p["rnn.weight_hh"], dgi, dgh, C * B * na, T, na)
+            ops.linear_bwd_weight(dgi, x3, g["rnn.weight_ih"], g["rnn.bias_ih"])
+            ops.gru_bwd_weight_hh(dgh, hs, na, T, g["rnn.weight_hh"], g["rnn.bias_hh"])
+            dx3 = ws.get("scratch.dx3", (R, self.r))
+            ops.linear_bwd_data(dgi, p["rnn.weight_ih"], dx3)
+            ops.linear_bwd_weight(dx3, x2, g["fc2.weight"], g["fc2.bias"], relu_y=x3)
+            ops.linear_bwd_data(dx3, p["fc2.weight"], dx2, relu_y=x3)
+        else:
+            ops.linear_bwd_weight(dq, x2, g["fc2.weight"], g["fc2.bias"], row_mask=rm)
+            ops.linear_bwd_data(dq, p["fc2.weight"], dx2, row_mask=rm)
+        self.trunk.backward(dx2)
+
+
+class AttnHyperNet:
+    """fc1 - masked attention - fc2 hypernetwork (flex_qmix.py:40-50); the mode reduction (matrix / vector /
+    alt_vector / scalar, :51-57) is fused into the mixer kernel."""
+
+    def __init__(self, store, prefix, ws, tag, args, ein):
+        self.s, self.pre, self.ws, self.tag = store, prefix, ws, tag
+        self.he, self.me, self.na = int(args.hypernet_embed), int(args.mixing_embed_dim), int(args.n_agents)
+        self.trunk = AttnTrunk(store, prefix, ws, tag, ein, self.he, int(args.attn_n_heads), self.na, int(args.n_actions))
+
+    @staticmethod
+    def specs(prefix, ein, he, me):
+        s = AttnTrunk.specs(prefix, ein, he)
+        s.update(OrderedDict([(prefix + "fc2.weight", (me, he)), (prefix + "fc2.bias", (me,))]))
+        return s
+
+    def init(self, gen):
+        self.trunk.init(gen)
+        init_linear_(gen, self.s.p[self.pre + "fc2.weight"], self.s.p[self.pre + "fc2.bias"])
+
+    def forward(self, ents, la, masks, T):
+        p, pre = self.s.p, self.pre
+        x2 = self.trunk.forward(ents, la, masks, T)
+        x3 = self.ws.get(self.tag + ".x3", (x2.shape[0], self.me))
+        ops.linear_fwd(x2, p[pre + "fc2.weight"], p[pre + "fc2.bias"], x3, row_mask=self.trunk.row_mask)
+        self.x2 = x2
+        return x3
+
+    def backward(self, dx3):
+        p, g, pre = self.s.p, self.s.g, self.pre
+        rm = self.trunk.row_mask
+        ops.linear_bwd_weight(dx3, self.x2, g[pre + "fc2.weight"], g[pre + "fc2.bias"], row_mask=rm)
+        dx2 = self.ws.get("scratch.dx2h", (dx3.shape[0], self.he))
+        ops.linear_bwd_data(dx3, p[pre + "fc2.weight"], dx2, row_mask=rm)
+        self.trunk.backward(dx2)
+
+
+class Mixer:
+    """FlexQMixer / LinearFlexQMixer / VDNMixer (modules/mixers/flex_qmix.py:60-172, vdn.py:5-10) over [N] rows."""
+
+    HYPERS = {"flex_qmix": ["hyper_w_1.", "hyper_w_final.", "hyper_b_1.", "V."], "lin_flex_qmix": ["hyper_w_1.", "V."],
+              "vdn": []}
+
+    def __init__(self, args, ein, device, ws=None, tag="mixer", seed=None):
+        self.args, self.kind_name = args, args.mixer
+        self.kind = ops.MIX_KIND[args.mixer]
+        self.na, self.me = int(args.n_agents), int(getattr(args, "mixing_embed_dim", 1) or 1)
+        self.softmax_w = bool(getattr(args, "softmax_mixing_weights", True))
+        self.tanh_nl = getattr(args, "mixer_non_lin", "elu") == "tanh"
+        self.ws = ws if ws is not None else Workspace(device)
+        self.tag = tag
+        specs = OrderedDict()
+        for h in self.HYPERS[args.mixer]:
+            specs.update(AttnHyperNet.specs(h, ein, int(args.hypernet_embed), self.me))  # vdn: no hypernets
+        self.store = ParamStore(specs, device)
+        self.nets = OrderedDict((h, AttnHyperNet(self.store, h, self.ws, tag + "." + h, args, ein))
+                                for h in self.HYPERS[args.mixer])
+        gen = torch.Generator().manual_seed(int(seed) if seed is not None else torch.initial_seed() % (2 ** 31))
+        for n in self.nets.values():
+            n.init(gen)
+
+    def parameters(self):
+        return self.store.parameters()
+
+    def named_parameters(self):
+        return self.store.named_parameters()
+
+    def state_dict(self):
+        return self.store.state_dict()
+
+    def load_state_dict(self, sd, strict=True):
+        self.store.load_state_dict(sd, strict)
+
+    def cuda(self):
+        self.store.to("cuda")
+        return self
+
+    def train(self, mode=True):
+        return self
+
+    def eval(self):
+        return self
+
+    def forward(self, q, qW, qI, ents, la, entity_mask, T, imagine_masks=None):
+        """q [N, na] (+ qW, qI when imagine); ents [N, ne, ed]; entity_mask [N, ne].
+        imagine_masks: (copy_W, copy_I) MaskSpec-style copy tuples + group bits, or None.
+        Returns (q_tot [N], q_tot_im [N] or None)."""
+        ws, tag = self.ws, self.tag
+        N = ents.shape[0]
+        imagine = imagine_masks is not None
+        qtot = ws.get(tag + ".qtot", (N,))
+        qtot_im = ws.get(tag + ".qtot_im", (N,)) if imagine else None
+        outs = {}
+        if self.kind != 2:
+            default = (None, 0, ops.ATTN_DEFAULT)
+            for h, net in self.nets.items():
+                if h == "hyper_w_1." and imagine:
+                    copies, gbits = imagine_masks
+                    m = MaskSpec([default] + list(copies), gbits, entity_mask)
+                else:
+                    m = MaskSpec([default], None, entity_mask)
+                outs[h] = net.forward(ents, la, m, T)
+        w1 = outs.get("hyper_w_1.")
+        self.saved = (q, qW, qI, outs, N, imagine)
+        ops.mixer_fwd(self.kind, w1, outs.get("hyper_b_1."), outs.get("hyper_w_final."), outs.get("V."), q, qW, qI,
+                      qtot, qtot_im, N, self.na, self.me, 3 if imagine else 1, imagine, self.softmax_w, self.tanh_nl)
+        return qtot, qtot_im
+
+    def backward(self, g_plain, g_im):
+        """-> dq, dqW, dqI [N, na]; hypernet parameter gradients are accumulated."""
+        ws, tag = self.ws, self.tag
+        q, qW, qI, outs, N, imagine = self.saved
+        na = self.na
+        dq = ws.get(tag + ".dq", (3, N, na))
+        d = {h: ws.get(tag + ".d" + h, tuple(o.shape)) for h, o in outs.items()}
+        ops.mixer_bwd(self.kind, outs.get("hyper_w_1."), outs.get("hyper_b_1."), outs.get("hyper_w_final."),
+                      outs.get("V."), q, qW, qI, g_plain, g_im, d.get("hyper_w_1."), d.get("hyper_b_1."),
+                      d.get("hyper_w_final."), d.get("V."), dq[0], dq[1] if imagine else None,
+                      dq[2] if imagine else None, N, na, self.me, 3 if imagine else 1, imagine, self.softmax_w,
+                      self.tanh_nl)
+        for h, net in self.nets.items():
+            net.backward(d[h])
+        return dq

@@ -1,0 +1,193 @@
+"""Tensor-level wrappers over the C ABI (include/refil_b200.h).  PyTorch is used for device memory and streams only;
+every function here enqueues hand-written sm_100a kernels on the current CUDA stream.  No CPU fallback: a
+non-CUDA tensor raises."""
+import torch
+
+from . import _lib
+
+ATTN_PART_WITHIN, ATTN_PART_INTERACT, ATTN_ACTIVE0, ATTN_DEFAULT = 1, 2, 4, 8
+MIX_KIND = {"flex_qmix": 0, "lin_flex_qmix": 1, "vdn": 2}
+
+_launches = 0  # number of kernels-launching C-ABI calls issued (bench.py reports it as gpu_launches)
+
+
+def launch_count():
+    return _launches
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t, dtype=None):
+    """device pointer of a contiguous CUDA tensor (None -> NULL)"""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise _lib.RefilError("refil_b200 kernels need CUDA tensors (got a %s tensor); there is no CPU fallback" % t.device)
+    if not t.is_contiguous():
+        raise _lib.RefilError("tensor of shape %s is not contiguous" % (tuple(t.shape),))
+    if dtype is not None and t.dtype != dtype:
+        raise _lib.RefilError("expected dtype %s, got %s" % (dtype, t.dtype))
+    return t.data_ptr()
+
+
+def _call(name, *args):
+    global _launches
+    _launches += 1
+    _lib.call(name, *args, _stream())
+
+
+F32, U8, I32, I64, F64 = torch.float32, torch.uint8, torch.int32, torch.int64, torch.float64
+
+
+def _rm(row_mask):
+    """row mask spec (entity_mask [N, ne] u8, na, rows_per_copy) or None"""
+    if row_mask is None:
+        return None, 1, 1, 1
+    em, na, mper = row_mask
+    return _p(em, U8), na, em.shape[-1], mper
+
+
+# ---------------------------------------------------------------------------------------------------- dense
+def linear_fwd(A, W, bias, out, relu=False, row_mask=None):
+    M, K = A.shape
+    N = W.shape[0]
+    em, na, ne, mper = _rm(row_mask)
+    _call("linear_fwd", _p(A, F32), K, _p(W, F32), W.shape[1], _p(bias, F32), _p(out, F32), N, M, N, K, int(relu),
+          em, na, ne, mper)
+    return out
+
+
+def embed_fwd(entities, last_action, n_actions, W, bias, out, relu=True):
+    M = entities.numel() // entities.shape[-1]
+    ed = entities.shape[-1]
+    _call("embed_fwd", _p(entities, F32), ed, _p(last_action, I32), n_actions, _p(W, F32), _p(bias, F32), _p(out, F32),
+          M, W.shape[0], int(relu))
+    return out
+
+
+def linear_bwd_data(dC, W, dA, relu_y=None, row_mask=None):
+    M, N = dC.shape
+    K = W.shape[1]
+    em, na, ne, mper = _rm(row_mask)
+    _call("linear_bwd_data", _p(dC, F32), N, _p(relu_y, F32), N, em, na, ne, mper, _p(W, F32), K, _p(dA, F32), K, M, N, K)
+    return dA
+
+
+def linear_bwd_weight(dC, A, dW, db, relu_y=None, row_mask=None):
+    M, N = dC.shape
+    K = A.shape[1]
+    em, na, ne, mper = _rm(row_mask)
+    _call("linear_bwd_weight", _p(dC, F32), N, _p(relu_y, F32), N, em, na, ne, mper, _p(A, F32), K, _p(dW, F32), K,
+          _p(db, F32), M, N, K)
+
+
+def embed_bwd_weight(dC, relu_y, entities, last_action, n_actions, dW, db):
+    M, N = dC.shape
+    _call("embed_bwd_weight", _p(dC, F32), N, _p(relu_y, F32), N, _p(entities, F32), entities.shape[-1],
+          _p(last_action, I32), n_actions, _p(dW, F32), _p(db, F32), M, N)
+
+
+def gru_bwd_weight_hh(dGH, HS, n_agents, T, dWhh, dbhh):
+    M, r = HS.shape
+    _call("gru_bwd_weight_hh", _p(dGH, F32), _p(HS, F32), n_agents, T, _p(dWhh, F32), _p(dbhh, F32), M, r)
+
+
+def last_action_index(actions, out, n_entities):
+    B, T, na = actions.shape[0], actions.shape[1], actions.shape[2]
+    _call("last_action_index", _p(actions, I64), _p(out, I32), B, T, na, n_entities)
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------- attention
+def _copies(copies):
+    m = [None, None, None]
+    s = [0, 0, 0]
+    mode = [0, 0, 0]
+    for i, (mask, stride, md) in enumerate(copies):
+        m[i] = _p(mask, U8)
+        s[i] = int(stride)
+        mode[i] = int(md)
+    return m + s + mode
+
+
+def masked_attn_fwd(qkv, out, copies, group_bits, entity_mask, N, T, ne, nq, d, H):
+    _call("masked_attn_fwd", _p(qkv, F32), _p(out, F32), *_copies(copies), _p(group_bits, U8), _p(entity_mask, U8),
+          N, T, ne, nq, d, H, len(copies))
+    return out
+
+
+def masked_attn_bwd(qkv, dout, dqkv, copies, group_bits, entity_mask, N, T, ne, nq, d, H):
+    _call("masked_attn_bwd", _p(qkv, F32), _p(dout, F32), _p(dqkv, F32), *_copies(copies), _p(group_bits, U8),
+          _p(entity_mask, U8), N, T, ne, nq, d, H, len(copies))
+    return dqkv
+
+
+# ---------------------------------------------------------------------------------------------------- GRU
+def gru_scan_fwd(GI, Whh, bhh, h0, HS, gates, n_seq, T, na):
+    r = Whh.shape[1]
+    _call("gru_scan_fwd", _p(GI, F32), _p(Whh, F32), _p(bhh, F32), _p(h0, F32), _p(HS, F32), _p(gates, F32), n_seq, T,
+          na, r)
+    return HS
+
+
+def gru_scan_bwd(dHS, gates, HS, h0, Whh, dGI, dGH, n_seq, T, na):
+    r = Whh.shape[1]
+    _call("gru_scan_bwd", _p(dHS, F32), _p(gates, F32), _p(HS, F32), _p(h0, F32), _p(Whh, F32), _p(dGI, F32),
+          _p(dGH, F32), n_seq, T, na, r)
+
+
+# ---------------------------------------------------------------------------------------------------- mixers / TD
+def mixer_fwd(kind, W1, B1, WF, V, q, qW, qI, qtot, qtot_im, N, na, me, w1_copies, imagine, softmax_w, tanh_nl):
+    _call("mixer_fwd", kind, _p(W1, F32), _p(B1, F32), _p(WF, F32), _p(V, F32), _p(q, F32), _p(qW, F32), _p(qI, F32),
+          _p(qtot, F32), _p(qtot_im, F32), N, na, me, w1_copies, int(imagine), int(softmax_w), int(tanh_nl))
+
+
+def mixer_bwd(kind, W1, B1, WF, V, q, qW, qI, g_plain, g_im, dW1, dB1, dWF, dV, dq, dqW, dqI, N, na, me, w1_copies,
+              imagine, softmax_w, tanh_nl):
+    _call("mixer_bwd", kind, _p(W1, F32), _p(B1, F32), _p(WF, F32), _p(V, F32), _p(q, F32), _p(qW, F32), _p(qI, F32),
+          _p(g_plain, F32), _p(g_im, F32), _p(dW1, F32), _p(dB1, F32), _p(dWF, F32), _p(dV, F32), _p(dq, F32),
+          _p(dqW, F32), _p(dqI, F32), N, na, me, w1_copies, int(imagine), int(softmax_w), int(tanh_nl))
+
+
+def gather_chosen(Q, actions, chosen, copies, rows_per_copy, A):
+    _call("gather_chosen", _p(Q, F32), _p(actions, I64), _p(chosen, F32), copies, rows_per_copy, A)
+    return chosen
+
+
+def scatter_dq(dchosen, actions, dQ, copies, rows_per_copy, A, T, na):
+    _call("scatter_dq", _p(dchosen, F32), _p(actions, I64), _p(dQ, F32), copies, rows_per_copy, A, T, na)
+    return dQ
+
+
+def target_max(q_online, q_target, avail, tgt, cur_max, rows, A, double_q):
+    _call("target_max", _p(q_online, F32), _p(q_target, F32), _p(avail, I32), _p(tgt, F32), _p(cur_max, I64), rows, A,
+          int(double_q))
+    return tgt
+
+
+def td_loss(qtot, qtot_im, tgt_tot, reward, terminated, filled, g_plain, g_im, targets_out, stats, B, T, gamma, lmbda):
+    _call("td_loss", _p(qtot, F32), _p(qtot_im, F32), _p(tgt_tot, F32), _p(reward, F32), _p(terminated, U8),
+          _p(filled, I64), _p(g_plain, F32), _p(g_im, F32), _p(targets_out, F32), _p(stats, F64), B, T, float(gamma),
+          float(lmbda))
+
+
+def grad_sumsq(grads, n_params, out):
+    _call("grad_sumsq", _p(grads, F32), n_params, _p(out, F64))
+
+
+def pack_stats(stats, tail, n):
+    _call("pack_stats", _p(stats, F64), _p(tail, F32), n)
+
+
+def clip_rmsprop_step(params, grads, square_avg, n_params, mask_sum, sumsq, grad_norm_out, clip, lr, alpha, eps, wd):
+    _call("clip_rmsprop_step", _p(params, F32), _p(grads, F32), _p(square_avg, F32), n_params, _p(mask_sum, F32),
+          _p(sumsq, F64), _p(grad_norm_out, F32), float(clip), float(lr), float(alpha), float(eps), float(wd))
+
+
+# ---------------------------------------------------------------------------------------------------- acting / env
+def select_actions(q, avail, u_pick, u_act, est_flags, epsilon, actions_out, B, na, A):
+    _call("select_actions", _p(q, F32), na * A, _p(avail, I32), na * A, _p(u_pick, F32), _p(u_act, F32),
+          _p(est_flags, I32), float(epsilon), _p(actions_out, I64), na, B, na, A)
+    return actions_out

@@ -1,0 +1,253 @@
+"""GPU parity of the individual sm_100a kernels (through the C ABI) against the CPU oracle / plain torch fp32.
+Tolerance: 1e-4 relative (BASELINE.json north_star) -- in practice the fp32-FMA kernels land near 1e-6."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+def _close(a, b, rtol=1e-4, atol=1e-5, what=""):
+    a, b = a.detach().cpu().float(), b.detach().cpu().float()
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    err = (a - b).abs().max().item() if a.numel() else 0.0
+    assert torch.allclose(a, b, rtol=rtol, atol=atol), (what, err, b.abs().max().item())
+
+
+@pytest.mark.parametrize("M,N,K,relu", [(1000, 384, 128, False), (777, 64, 128, True), (513, 14, 64, False),
+                                        (96, 32, 32, True), (5, 3, 7, False), (2000, 128, 53, True)])
+def test_linear_fwd_bwd(M, N, K, relu):
+    from refil_b200 import ops
+    g = torch.Generator().manual_seed(M + N)
+    A, W, b = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) * 0.2, torch.randn(N, generator=g)
+    dC = torch.randn(M, N, generator=g)
+    Ar, Wr, br = A.clone().requires_grad_(), W.clone().requires_grad_(), b.clone().requires_grad_()
+    y = Ar @ Wr.t() + br
+    if relu:
+        y = torch.relu(y)
+    y.backward(dC)
+    Ad, Wd, bd, dCd = A.to(DEV), W.to(DEV), b.to(DEV), dC.to(DEV)
+    out = torch.empty(M, N, device=DEV)
+    ops.linear_fwd(Ad, Wd, bd, out, relu=relu)
+    _close(out, y, what="fwd")
+    dA = torch.empty(M, K, device=DEV)
+    ops.linear_bwd_data(dCd, Wd, dA, relu_y=out if relu else None)
+    _close(dA, Ar.grad, what="dA")
+    dW, db = torch.zeros(N, K, device=DEV), torch.zeros(N, device=DEV)
+    ops.linear_bwd_weight(dCd, Ad, dW, db, relu_y=out if relu else None)
+    _close(dW, Wr.grad, rtol=2e-4, atol=2e-4, what="dW")
+    _close(db, br.grad, rtol=2e-4, atol=2e-4, what="db")
+
+
+def test_linear_row_mask_and_embed():
+    from refil_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    C, N, na, ne, d, ed, A = 3, 40, 3, 5, 32, 6, 4
+    em = (torch.rand(N, ne, generator=g) < 0.3).to(torch.uint8)
+    X = torch.randn(C * N * na, d, generator=g)
+    W, b = torch.randn(16, d, generator=g) * 0.3, torch.randn(16, generator=g)
+    ref = (X @ W.t() + b).view(C, N, na, 16).masked_fill(em[:, :na].bool().view(1, N, na, 1), 0.0).view(-1, 16)
+    out = torch.empty(C * N * na, 16, device=DEV)
+    ops.linear_fwd(X.to(DEV), W.to(DEV), b.to(DEV), out, row_mask=(em.to(DEV), na, N * na))
+    _close(out, ref, what="rowmask")
+    # embed over the virtual concat [ents | onehot(la)]
+    ents = torch.rand(N, ne, ed, generator=g)
+    la = torch.randint(-1, A, (N, ne), generator=g).to(torch.int32)
+    W1, b1 = torch.randn(d, ed + A, generator=g) * 0.3, torch.randn(d, generator=g)
+    oh = torch.zeros(N, ne, A)
+    for k in range(A):
+        oh[..., k] = (la == k).float()
+    cat = torch.cat([ents, oh], -1).view(N * ne, ed + A)
+    W1r, b1r = W1.clone().requires_grad_(), b1.clone().requires_grad_()
+    y = torch.relu(cat @ W1r.t() + b1r)
+    dY = torch.randn(N * ne, d, generator=g)
+    y.backward(dY)
+    x1 = torch.empty(N * ne, d, device=DEV)
+    ops.embed_fwd(ents.to(DEV), la.to(DEV), A, W1.to(DEV), b1.to(DEV), x1)
+    _close(x1, y, what="embed")
+    dW, db = torch.zeros(d, ed + A, device=DEV), torch.zeros(d, device=DEV)
+    ops.embed_bwd_weight(dY.to(DEV), x1, ents.to(DEV), la.to(DEV), A, dW, db)
+    _close(dW, W1r.grad, rtol=2e-4, atol=2e-4, what="embed dW")
+    _close(db, b1r.grad, rtol=2e-4, atol=2e-4, what="embed db")
+
+
+@pytest.mark.parametrize("ne,na,d,H", [(5, 3, 32, 2), (4, 4, 32, 4), (24, 8, 128, 4), (32, 32, 64, 4), (1, 1, 32, 2)])
+def test_masked_attention_fwd_bwd(ne, na, d, H):
+    from oracle import learner_oracle as lo
+    from refil_b200 import ops
+    g = torch.Generator().manual_seed(ne * 100 + na)
+    B, T = 3, 4
+    N = B * T
+    x = torch.randn(N, ne, d, generator=g)
+    w_in = torch.randn(3 * d, d, generator=g) / d ** 0.5
+    em = torch.zeros(B, T, ne, dtype=torch.uint8)
+    if ne > 2:
+        em[0, :, ne - 1] = 1
+        em[1, :, na - 1] = 1
+    obs = (torch.rand(N, ne, ne, generator=g) < 0.3).to(torch.uint8)
+    obs[2] = 1                                        # a unit whose rows are fully masked -> zeros, not NaN
+    gbits = (torch.rand(B, ne, generator=g) < 0.5).to(torch.uint8)
+    m = lo.imagine_masks(gbits, em[:, 0], na)
+    rep = lambda t: t.unsqueeze(1).expand(B, T, na, ne).reshape(N, na, ne)
+    emN = em.view(N, ne)
+    dflt = (emN[:, :na].bool().unsqueeze(2) | emN.bool().unsqueeze(1)).to(torch.uint8)
+    masks = [obs[:, :na], ((obs[:, :na] + rep(m["within"])) > 0).to(torch.uint8),
+             ((obs[:, :na] + rep(m["interact"])) > 0).to(torch.uint8)]
+    masks2 = [dflt, rep(m["within_noobs"]), rep(m["interact_noobs"])]
+    post = torch.zeros(N, na, dtype=torch.uint8)
+    eye_w, zero_b = torch.eye(d), torch.zeros(d)
+    qkv = (x @ w_in.t()).detach().requires_grad_()          # leaf: the kernel's input is QKV itself
+    eye3 = torch.eye(3 * d)
+    douts = torch.randn(3, N, na, d, generator=g)
+    for name, mlist, copies in (
+            ("agent", masks, [(obs.to(DEV), ne * ne, 0), (obs.to(DEV), ne * ne, 1), (obs.to(DEV), ne * ne, 2)]),
+            ("mixer", masks2, [(None, 0, 8), (None, 0, 1 | 4), (None, 0, 2 | 4)])):
+        refs = [lo.entity_attention(qkv, eye3, eye_w, zero_b, mk, post, H) for mk in mlist]
+        out = torch.empty(3, N, na, d, device=DEV)
+        qkv_d = qkv.detach().reshape(N * ne, 3 * d).to(DEV)
+        ops.masked_attn_fwd(qkv_d, out, copies, gbits.to(DEV), emN.to(DEV), N, T, ne, na, d, H)
+        for c in range(3):
+            _close(out[c], refs[c], what="%s fwd copy %d" % (name, c))
+        assert torch.isfinite(out).all()
+        loss = sum((r * douts[c]).sum() for c, r in enumerate(refs))
+        (dqkv_ref,) = torch.autograd.grad(loss, qkv)
+        dqkv = torch.empty(N * ne, 3 * d, device=DEV)
+        ops.masked_attn_bwd(qkv_d, douts.to(DEV), dqkv, copies, gbits.to(DEV), emN.to(DEV), N, T, ne, na, d, H)
+        _close(dqkv, dqkv_ref.reshape(N * ne, 3 * d), what="%s dqkv" % name)
+
+
+@pytest.mark.parametrize("r,na,CB,T", [(16, 3, 9, 6), (64, 8, 5, 7), (32, 1, 1, 1), (128, 2, 3, 3)])
+def test_gru_scan_fwd_bwd(r, na, CB, T):
+    from oracle import learner_oracle as lo
+    from refil_b200 import ops
+    g = torch.Generator().manual_seed(r + na)
+    R = CB * T * na
+    gi = torch.randn(R, 3 * r, generator=g)
+    whh = (torch.randn(3 * r, r, generator=g) / r ** 0.5)
+    bhh = torch.randn(3 * r, generator=g) * 0.1
+    h0 = torch.randn(CB * na, r, generator=g) * 0.5
+    dhs = torch.randn(R, r, generator=g)
+    gir, whr, bhr = gi.clone().requires_grad_(), whh.clone().requires_grad_(), bhh.clone().requires_grad_()
+    gi4 = gir.view(CB, T, na, 3 * r)
+    h = h0.clone()
+    hs = []
+    wih_eye = torch.zeros(3 * r, 3 * r)          # feed gi through gru_cell: x = gi, W_ih = I, b_ih = 0
+    for t in range(T):
+        x = gi4[:, t].reshape(CB * na, 3 * r)
+        gh = h @ whr.t() + bhr
+        i_r, i_z, i_n = x.chunk(3, 1)
+        h_r, h_z, h_n = gh.chunk(3, 1)
+        rg, zg = torch.sigmoid(i_r + h_r), torch.sigmoid(i_z + h_z)
+        ng = torch.tanh(i_n + rg * h_n)
+        h = (1 - zg) * ng + zg * h
+        hs.append(h.view(CB, na, r))
+    hs_ref = torch.stack(hs, 1).reshape(R, r)
+    (hs_ref * dhs).sum().backward()
+    HS, gates = torch.empty(R, r, device=DEV), torch.empty(R, 4 * r, device=DEV)
+    ops.gru_scan_fwd(gi.to(DEV), whh.to(DEV), bhh.to(DEV), h0.to(DEV), HS, gates, CB * na, T, na)
+    _close(HS, hs_ref, what="hs")
+    dGI, dGH = torch.empty(R, 3 * r, device=DEV), torch.empty(R, 3 * r, device=DEV)
+    ops.gru_scan_bwd(dhs.to(DEV), gates, HS, h0.to(DEV), whh.to(DEV), dGI, dGH, CB * na, T, na)
+    _close(dGI, gir.grad, what="dgi")
+    # recurrent weight gradient from dGH and the shifted state stack (h0 = 0 in training; use zeros here)
+    HS0, gates0 = torch.empty(R, r, device=DEV), torch.empty(R, 4 * r, device=DEV)
+    ops.gru_scan_fwd(gi.to(DEV), whh.to(DEV), bhh.to(DEV), None, HS0, gates0, CB * na, T, na)
+    ops.gru_scan_bwd(dhs.to(DEV), gates0, HS0, None, whh.to(DEV), dGI, dGH, CB * na, T, na)
+    dW, db = torch.zeros(3 * r, r, device=DEV), torch.zeros(3 * r, device=DEV)
+    ops.gru_bwd_weight_hh(dGH, HS0, na, T, dW, db)
+    gir2, whr2, bhr2 = gi.clone().requires_grad_(), whh.clone().requires_grad_(), bhh.clone().requires_grad_()
+    h = torch.zeros(CB * na, r)
+    hs = []
+    for t in range(T):
+        h = lo.gru_cell(gir2.view(CB, T, na, 3 * r)[:, t].reshape(CB * na, 3 * r), h, torch.eye(3 * r), whr2,
+                        torch.zeros(3 * r), bhr2)
+        hs.append(h.view(CB, na, r))
+    (torch.stack(hs, 1).reshape(R, r) * dhs).sum().backward()
+    _close(dW, whr2.grad, rtol=2e-4, atol=2e-4, what="dWhh")
+    _close(db, bhr2.grad, rtol=2e-4, atol=2e-4, what="dbhh")
+
+
+@pytest.mark.parametrize("kind,imagine,softmax,tanh", [("flex_qmix", True, True, False), ("flex_qmix", False, True, False),
+                                                       ("flex_qmix", True, False, True), ("lin_flex_qmix", True, True, False),
+                                                       ("lin_flex_qmix", False, False, False), ("vdn", True, True, False)])
+def test_mixer_combine_fwd_bwd(kind, imagine, softmax, tanh):
+    import torch.nn.functional as F
+    from refil_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    N, na, me = 37, 3, 8
+    Cw = 3 if imagine else 1
+    W1 = torch.randn(Cw, N, na, me, generator=g).requires_grad_()
+    B1, WF, V = [torch.randn(N, na, me, generator=g).requires_grad_() for _ in range(3)]
+    q, qW, qI = [torch.randn(N, na, generator=g).requires_grad_() for _ in range(3)]
+    gp, gi = torch.randn(N, generator=g), torch.randn(N, generator=g)
+
+    def mixw(x, dim):
+        return torch.softmax(x, dim) if softmax else x.abs()
+
+    def flex(qs, w1raw):
+        w1 = mixw(w1raw, -1)
+        pre = torch.bmm(qs.unsqueeze(1), w1) + B1.mean(1).unsqueeze(1)
+        hid = torch.tanh(pre) if tanh else F.elu(pre)
+        wf = mixw(WF.mean(1), -1)
+        return (torch.bmm(hid, wf.unsqueeze(2)).view(N) + V.mean((1, 2)))
+
+    def lin(qs, w1raw):
+        w1 = mixw(w1raw.mean(-1), 1)
+        return (qs * w1).sum(1) + V.mean((1, 2))
+
+    if kind == "vdn":
+        y, y_im = q.sum(1), torch.cat([qW, qI], 1).sum(1)
+    else:
+        f = flex if kind == "flex_qmix" else lin
+        y = f(q, W1[0])
+        y_im = f(torch.cat([qW, qI], 1), torch.cat([W1[1], W1[2]], 1)) if imagine else None
+    loss = (y * gp).sum() + ((y_im * gi).sum() if imagine else 0.0)
+    loss.backward()
+    d = lambda t: t.detach().to(DEV).contiguous()
+    qtot, qtot_im = torch.empty(N, device=DEV), torch.empty(N, device=DEV)
+    k = ops.MIX_KIND[kind]
+    ops.mixer_fwd(k, d(W1), d(B1), d(WF), d(V), d(q), d(qW), d(qI), qtot, qtot_im if imagine else None, N, na, me, Cw,
+                  imagine, softmax, tanh)
+    _close(qtot, y, what="qtot")
+    if imagine:
+        _close(qtot_im, y_im, what="qtot_im")
+    dW1, dB1, dWF, dV = [torch.full_like(d(t), 7.0) for t in (W1, B1, WF, V)]
+    dq = torch.full((3, N, na), 7.0, device=DEV)
+    ops.mixer_bwd(k, d(W1), d(B1), d(WF), d(V), d(q), d(qW), d(qI), d(gp), d(gi) if imagine else None, dW1, dB1, dWF, dV,
+                  dq[0], dq[1] if imagine else None, dq[2] if imagine else None, N, na, me, Cw, imagine, softmax, tanh)
+    _close(dq[0], q.grad, what="dq")
+    if imagine:
+        _close(dq[1], qW.grad, what="dqW")
+        _close(dq[2], qI.grad, what="dqI")
+    if kind != "vdn":
+        _close(dW1, W1.grad, what="dW1")
+        _close(dV, V.grad, what="dV")
+    if kind == "flex_qmix":
+        _close(dB1, B1.grad, what="dB1")
+        _close(dWF, WF.grad, what="dWF")
+
+
+def test_select_actions_first_max_and_epsilon():
+    from refil_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    B, na, A = 64, 4, 6
+    q = torch.randint(0, 3, (B, na, A), generator=g).float()          # many ties -> first-max rule matters
+    avail = (torch.rand(B, na, A, generator=g) < 0.6).to(torch.int32)
+    avail[..., 1] = 1
+    mq = q.clone()
+    mq[avail == 0] = -float("inf")
+    ref = mq.max(dim=2)[1]
+    out = torch.zeros(B, na, dtype=torch.int64, device=DEV)
+    ops.select_actions(q.to(DEV), avail.to(DEV), None, None, None, 0.0, out, B, na, A)
+    assert torch.equal(out.cpu(), ref)
+    u = torch.rand(2, B, na, device=DEV)
+    ops.select_actions(q.to(DEV), avail.to(DEV), u[0].contiguous(), u[1].contiguous(), None, 1.0, out, B, na, A)
+    picked = torch.gather(avail, 2, out.cpu().unsqueeze(-1))
+    assert (picked == 1).all()                                         # exploration only picks available actions
+
+
+def test_missing_cuda_fails_loudly():
+    from refil_b200 import _lib, ops
+    with pytest.raises(_lib.RefilError):
+        ops.linear_fwd(torch.zeros(4, 4), torch.zeros(4, 4), None, torch.zeros(4, 4))

@@ -1,0 +1,111 @@
+"""GPU parity of the learner hot path against the fixtures recorded from the reference's EntityMAC + QLearner
+(tests/golden/learner_*.npz) and against the CPU oracle at a larger size.  Tolerances: 1e-4 relative on utilities
+and losses (north_star); greedy action indices bit-exact."""
+import pytest
+import torch
+
+from golden_util import learner_cases, load_learner_case
+from gpu_util import build_product
+
+pytestmark = pytest.mark.gpu
+CASES = learner_cases()
+DEV = "cuda:0"
+
+
+def _close(a, b, rtol=1e-4, atol=2e-6, what=""):
+    a, b = a.detach().cpu().float(), b.detach().cpu().float()
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    assert torch.allclose(a, b, rtol=rtol, atol=atol), (what, (a - b).abs().max().item(), b.abs().max().item())
+
+
+def _setup(name):
+    c = load_learner_case(name)
+    batch, mac, learner, logger = build_product(c.args, c.dims, c.batch, DEV)
+    mac.agent.load_state_dict(c.agent)
+    learner.target_mac.agent.load_state_dict(c.tagent)
+    if c.mixer:
+        learner.mixer.load_state_dict(c.mixer)
+        learner.target_mixer.load_state_dict(c.tmixer)
+    return c, batch, mac, learner, logger
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_forward_and_greedy_actions(name):
+    c, batch, mac, learner, _ = _setup(name)
+    B, T, na, ne, ed, A = c.dims
+    mac.init_hidden(B)
+    _close(mac.forward(batch, t=None), c.fwd["mac_out"], what="mac_out")
+    if "imagine" in c.args.agent:
+        mac.init_hidden(B)
+        q3, (wm, im) = mac.forward(batch, t=None, imagine=True, use_gt_factors=c.args.train_gt_factors,
+                                   use_rand_gt_factors=c.args.train_rand_gt_factors, group_bits=c.group_a.to(DEV))
+        _close(q3, c.fwd["imagine_out"], what="imagine_out")
+        assert torch.equal(wm.cpu(), c.fwd["wmask"]) and torch.equal(im.cpu(), c.fwd["imask"])
+    mac.init_hidden(B)
+    acts, qs = [], []
+    for t in range(T):
+        a, q = mac.select_actions(batch, t_ep=t, t_env=0, test_mode=True, ret_agent_outs=True)
+        acts.append(a.cpu())
+        qs.append(q.cpu())
+    _close(torch.stack(qs, 1), c.greedy_q, what="greedy_q")
+    assert torch.equal(torch.stack(acts, 1), c.greedy_actions)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_train_step_matches_reference(name):
+    c, batch, mac, learner, logger = _setup(name)
+    learner.train(batch, t_env=10, episode_num=0, group_bits=c.group_a.to(DEV))
+    torch.cuda.synchronize()
+    s = c.stats
+    for k in ("loss", "im_loss", "grad_norm", "td_error_abs", "q_taken_mean", "target_mean"):
+        if k in s:
+            got = logger.stats[k][0]
+            assert abs(got - s[k]) <= 1e-4 * max(1.0, abs(s[k])), (k, got, s[k])
+    for k, g in c.grad_agent.items():
+        _close(mac.agent.store.g[k], g, rtol=2e-4, atol=2e-6, what="grad agent " + k)
+    for k, g in c.grad_mixer.items():
+        _close(learner.mixer.store.g[k], g, rtol=2e-4, atol=2e-6, what="grad mixer " + k)
+    for k, p in c.new_agent.items():
+        assert float((mac.agent.store.p[k].cpu() - p).abs().max()) <= 1e-4, k
+    for k, p in c.new_mixer.items():
+        assert float((learner.mixer.store.p[k].cpu() - p).abs().max()) <= 1e-4, k
+
+
+@pytest.mark.parametrize("alg", ["refil", "qmix_atten", "refil_gm"])
+def test_train_step_matches_oracle_mid_size(alg):
+    """Same seeded inputs through the CUDA path and the CPU oracle at a size the oracle finishes in seconds."""
+    from oracle import learner_oracle as lo
+    gen = torch.Generator().manual_seed(123)
+    if alg == "refil_gm":
+        B, T, na, ne, ed, A = 6, 9, 4, 4, 12, 3
+        args = lo.default_args(agent="imagine_entity_attend_ff", mixer="lin_flex_qmix", attn_embed_dim=64,
+                               hypernet_embed=64, entity_last_action=False)
+    else:
+        B, T, na, ne, ed, A = 5, 12, 8, 24 if alg == "refil" else 16, 39, 14
+        args = lo.default_args(agent="imagine_entity_attend_rnn" if alg == "refil" else "entity_attend_rnn")
+    args.n_agents, args.n_actions, args.n_entities, args.entity_shape = na, A, ne, ed
+    args.mac, args.learner, args.agent_output_type, args.action_selector = "entity_mac", "q_learner", "q", "epsilon_greedy"
+    args.target_update_interval, args.learner_log_interval, args.gt_mask_avail = 200, 1, False
+    ein = ed + (A if args.entity_last_action else 0)
+    syn = lo.synthetic_batch(gen, B, T, na, ne, ed, A, pad=alg != "refil_gm")
+    agent_p, mixer_p = lo.init_agent_params(gen, args, ein), lo.init_mixer_params(gen, args, ein)
+    tagent_p = {k: v + 0.05 * torch.randn(v.shape, generator=gen) for k, v in agent_p.items()}
+    tmixer_p = {k: v + 0.05 * torch.randn(v.shape, generator=gen) for k, v in mixer_p.items()}
+    group_a = (torch.rand(B, ne, generator=gen) < 0.5).to(torch.uint8)
+    ref = lo.train_step(agent_p, mixer_p, tagent_p, tmixer_p, syn, args, group_a=group_a)
+    batch, mac, learner, logger = build_product(args, (B, T, na, ne, ed, A), syn, DEV)
+    mac.agent.load_state_dict(agent_p)
+    learner.target_mac.agent.load_state_dict(tagent_p)
+    learner.mixer.load_state_dict(mixer_p)
+    learner.target_mixer.load_state_dict(tmixer_p)
+    learner.train(batch, t_env=10, episode_num=0, group_bits=group_a.to(DEV))
+    torch.cuda.synchronize()
+    loss = float(ref["loss"])
+    assert abs(logger.stats["loss"][0] - loss) <= 1e-4 * max(1.0, abs(loss))
+    gn = float(ref["grad_norm"])
+    assert abs(logger.stats["grad_norm"][0] - gn) <= 1e-4 * max(1.0, gn)
+    scale = max(float(g.abs().max()) for g in ref["grads_agent"].values())
+    for k, g in ref["grads_agent"].items():
+        _close(mac.agent.store.g[k], g, rtol=2e-4, atol=2e-5 * scale, what="grad agent " + k)
+    for k, g in ref["grads_mixer"].items():
+        _close(learner.mixer.store.g[k], g, rtol=2e-4, atol=2e-5 * scale, what="grad mixer " + k)
