@@ -1,0 +1,424 @@
+#!/usr/bin/env python
+"""Benchmark of the REFIL hot path on B200 (contract: see the task's bench.py section).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload ns|cfg3|gm]
+
+One "step" = one QLearner.train pass (online + target forward, TD loss, hand-written backward, clip + RMSprop, and the
+gradient all-reduce when N > 1) over one synthetic replay batch.  Default workload = BASELINE.json's north-star shape
+(REFIL, B=128 episodes per GPU, T=60, 8 agents, 24 entities, d=128).  `value` = learner transitions/s with the batch
+resident in HBM; `e2e` = the same through the public API with the batch in pinned HOST memory (H2D copy of every input
+tensor + D2H read of the loss inside the timed region).  The Group Matching env kernel is measured in the same run and
+reported under "env".  `--impl reference` times the CPU restatement of the reference (oracle/, torch-CPU, all host
+threads) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (alg, B per GPU, T, na, ne, ed, A, overrides)
+    "ns": ("refil", 128, 60, 8, 24, 39, 14, {}),
+    "cfg3": ("qmix_atten", 64, 60, 8, 16, 39, 14, {}),
+    "gm": ("refil_group_matching", 4096, 51, 4, 4, 12, 3, {}),
+}
+
+
+def make_args(alg, na, ne, ed, A):
+    from types import SimpleNamespace
+    a = dict(gamma=0.99, lr=0.0005, optim_alpha=0.99, optim_eps=0.00001, grad_norm_clip=10, weight_decay=0,
+             double_q=True, lmbda=0.5, attn_n_heads=4, attn_embed_dim=128, hypernet_embed=128, mixing_embed_dim=32,
+             rnn_hidden_dim=64, softmax_mixing_weights=True, entity_last_action=True, mixer="flex_qmix",
+             agent="imagine_entity_attend_rnn", gt_obs_mask=False, train_gt_factors=False, train_rand_gt_factors=False,
+             test_gt_factors=False, pooling_type=None, epsilon_start=1.0, epsilon_finish=0.05,
+             epsilon_anneal_time=500000, mac="entity_mac", learner="q_learner", agent_output_type="q",
+             action_selector="epsilon_greedy", target_update_interval=200, learner_log_interval=10 ** 12,
+             gt_mask_avail=False, n_agents=na, n_actions=A, n_entities=ne, entity_shape=ed)
+    if alg == "qmix_atten":
+        a.update(agent="entity_attend_rnn")
+    elif alg == "refil_group_matching":
+        a.update(agent="imagine_entity_attend_ff", mixer="lin_flex_qmix", attn_embed_dim=64, hypernet_embed=64,
+                 entity_last_action=False)
+    return SimpleNamespace(**a)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                if len(f) >= 9:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        self.stop_flag = True
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(s[1]) for s in self.samples)
+        reasons = set()
+        for s in self.samples:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][2]), "reasons": sorted(reasons),
+                "samples": len(self.samples)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d["hbm_gbs"], d["bf16_tflops"], d.get("bf16_tflops_sustained", d["bf16_tflops"]), "measured"
+    return 6650.0, 1590.0, 1400.0, "fallback"
+
+
+# --------------------------------------------------------------------------------------------------------------------
+def cpu_reference_rate(alg, T, na, ne, ed, A, budget_s=15.0, sample_B=4, seed=0):
+    """Reference algorithm on the host cores: torch-CPU restatement in oracle/ (kind "port"), bounded sample."""
+    import torch
+    from oracle import learner_oracle as lo
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    args = make_args(alg, na, ne, ed, A)
+    gen = torch.Generator().manual_seed(seed)
+    ein = ed + (A if args.entity_last_action else 0)
+    syn = lo.synthetic_batch(gen, sample_B, T, na, ne, ed, A, pad=ne > na)
+    ap, mp = lo.init_agent_params(gen, args, ein), lo.init_mixer_params(gen, args, ein)
+    group_a = (torch.rand(sample_B, ne, generator=gen) < 0.5).to(torch.uint8)
+    lo.train_step(ap, mp, ap, mp, syn, args, group_a=group_a)          # warm-up
+    times = []
+    t_end = time.perf_counter() + budget_s
+    while len(times) < 3 or (time.perf_counter() < t_end and len(times) < 50):
+        t0 = time.perf_counter()
+        lo.train_step(ap, mp, ap, mp, syn, args, group_a=group_a)
+        times.append(time.perf_counter() - t0)
+    best = sorted(times)[len(times) // 2]
+    return {"value": sample_B * (T - 1) / best, "unit": "transitions/s", "cores": cores, "kind": "port",
+            "sample": "%d timed QLearner.train steps (median) of the torch-CPU oracle on B=%d episodes of the same "
+                      "(T=%d, agents=%d, entities=%d) workload, %d torch threads" % (len(times), sample_B, T, na, ne, cores),
+            "ms_per_step": best * 1e3}
+
+
+def cpu_env_rate(na, budget_s=5.0):
+    from oracle.gm_env_oracle import GroupMatchingOracle
+    env = GroupMatchingOracle(n_agents=na, n_states=6, n_groups=2, rand_trans=0.1, episode_limit=50, seed=0)
+    env.reset()
+    n = 200000
+    t0 = time.perf_counter()
+    done = env.bench_loop(n)
+    dt = time.perf_counter() - t0
+    return {"value": done / dt, "unit": "env-steps/s", "cores": 1, "kind": "port",
+            "sample": "%d steps of the C oracle (step + entities + masks), 1 thread" % done}
+
+
+# --------------------------------------------------------------------------------------------------------------------
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    alg, B, T, na, ne, ed, A, _ = WORKLOADS[a.workload]
+    sample_B = 4 if a.workload != "gm" else 64
+    import torch
+    from oracle import learner_oracle as lo
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    args = make_args(alg, na, ne, ed, A)
+    gen = torch.Generator().manual_seed(0)
+    ein = ed + (A if args.entity_last_action else 0)
+    syn = lo.synthetic_batch(gen, sample_B, T, na, ne, ed, A, pad=ne > na)
+    ap, mp = lo.init_agent_params(gen, args, ein), lo.init_mixer_params(gen, args, ein)
+    group_a = (torch.rand(sample_B, ne, generator=gen) < 0.5).to(torch.uint8)
+    for _ in range(max(1, min(a.warmup, 2))):
+        lo.train_step(ap, mp, ap, mp, syn, args, group_a=group_a)
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        lo.train_step(ap, mp, ap, mp, syn, args, group_a=group_a)
+    dt = (time.perf_counter() - t0) / a.steps
+    v = sample_B * (T - 1) / dt
+    sample = ("each step = one torch-CPU QLearner.train restatement (oracle/learner_oracle.py) on B=%d episodes of the "
+              "(T=%d, agents=%d, entities=%d, d=128) workload, %d threads" % (sample_B, T, na, ne, cores))
+    print(json.dumps({
+        "impl": "reference", "metric": "learner transitions/sec", "value": v, "unit": "transitions/s",
+        "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a.workload, sample_B, T, na, ne), "sample_B": sample_B},
+        "cpu_baseline": {"value": v, "unit": "transitions/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "transitions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_name(w, B, T, na, ne):
+    alg = WORKLOADS[w][0]
+    return "%s learner step, synthetic replay (B=%d per GPU, T=%d, agents=%d, entities=%d, d=%d)" % (
+        alg, B, T, na, ne, 64 if w == "gm" else 128)
+
+
+# --------------------------------------------------------------------------------------------------------------------
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    from refil_b200 import ops
+    from refil_b200.components.episode_buffer import EpisodeBatch
+    from refil_b200.controllers import REGISTRY as mac_REGISTRY
+    from refil_b200.envs.group_matching import GroupMatchingBatch
+    from refil_b200.learners import REGISTRY as le_REGISTRY
+    from refil_b200.utils.synthetic import entity_scheme, synthetic_replay
+
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = "cuda:%d" % local
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+    alg, B, T, na, ne, ed, A, _ = WORKLOADS[a.workload]
+    if a.batch:
+        B = a.batch
+    args = make_args(alg, na, ne, ed, A)
+    args.device = dev
+
+    class Log:
+        class console_logger:
+            @staticmethod
+            def info(*x, **k):
+                pass
+
+        def log_stat(self, *x, **k):
+            pass
+
+    scheme, groups, preprocess = entity_scheme(na, ne, ed, A, gt_mask=(a.workload == "gm"))
+    syn = synthetic_replay(B, T, na, ne, ed, A, seed=1000 + rank, gt_mask=(a.workload == "gm"), pad=ne > na)
+    args.gt_mask_avail = a.workload == "gm"
+    batch = EpisodeBatch(scheme, groups, B, T, preprocess=preprocess, device=dev)
+    host = {k: v.pin_memory() for k, v in syn.items()}
+    for k, v in host.items():
+        batch.data.transition_data[k].copy_(v)
+    torch.manual_seed(0)                       # identical initial weights on every rank
+    mac = mac_REGISTRY[args.mac](batch.scheme, groups, args)
+    learner = le_REGISTRY[args.learner](mac, batch.scheme, Log(), args)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    ep = [0]
+
+    def step_resident(i):
+        ep[0] += 1
+        learner.train(batch, t_env=ep[0], episode_num=ep[0])
+
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+
+    def step_e2e(i):
+        for k, v in host.items():
+            batch.data.transition_data[k].copy_(v, non_blocking=True)
+        ep[0] += 1
+        learner.train(batch, t_env=ep[0], episode_num=ep[0])
+        learner.gradbuf[learner.n_params:].cpu()          # D2H read of the step's loss statistics (syncs)
+
+    for i in range(max(a.warmup, 3)):
+        step_resident(i)
+    clocks = ClockSampler(local)
+    clocks.start()
+    l0 = ops.launch_count()
+    ms = timed(step_resident, a.steps)
+    launches = ops.launch_count() - l0
+    clk = clocks.summary()
+    for i in range(2):
+        step_e2e(i)
+    ms_e2e = timed(step_e2e, a.steps)
+    trans = world * B * (T - 1)
+    value = trans * a.steps / (ms * 1e-3)
+    e2e = trans * a.steps / (ms_e2e * 1e-3)
+
+    # ---- per-kernel breakdown (instrumented repeat of the step, events around every launch) -------------------
+    ops.set_timing(True)
+    step_resident(0)
+    step_resident(1)
+    tsum = ops.timing_summary()
+    ops.set_timing(False)
+    kern = {k: {"launches": v[0] // 2, "ms_per_step": v[1] / 2} for k, v in tsum.items()}
+    hbm, tf_burst, tf_sus, src = peaks()
+    d = args.attn_embed_dim
+    N = B * T
+    C_agent = 3 if "imagine" in args.agent else 1
+    n_hyper = {"flex_qmix": 4, "lin_flex_qmix": 2, "vdn": 0}[args.mixer]
+    w1c = 3 if (C_agent == 3 and n_hyper) else 1
+    # attention units (one (b,t) x one mask copy) of the forward launches: online agent, target agent, online + target mixers
+    fwd_units = N * (C_agent + 1) + (N * (w1c + n_hyper - 1) + N * n_hyper if n_hyper else 0)
+    unit_bytes = 4 * d * (2 * ne + 2 * na) + na * ne
+    att = kern.get("masked_attn_fwd")
+    roof_att = None
+    if att:
+        ach = fwd_units * unit_bytes / (att["ms_per_step"] * 1e-3) / 1e9
+        roof_att = {"kernel": "attn_fwd_kernel (K2 masked MHA)", "bound": "hbm", "achieved": ach, "peak": hbm,
+                    "unit": "GB/s", "frac": ach / hbm, "traffic": None, "units_per_step": fwd_units,
+                    "bytes_per_unit": unit_bytes, "peak_source": src,
+                    "timing": "per-launch CUDA events on an instrumented repeat of the step"}
+    dom = max(kern.items(), key=lambda kv: kv[1]["ms_per_step"])
+    gemm_names = ("linear_fwd", "linear_bwd_data", "linear_bwd_weight", "embed_fwd", "embed_bwd_weight",
+                  "gru_bwd_weight_hh")
+    gemm_ms = sum(kern[k]["ms_per_step"] for k in gemm_names if k in kern)
+    flops = step_flops(args, B, T, na, ne, ed, A)
+    ach_tf = flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms else 0.0
+    roofline = {"kernel": "sgemm_kernel (all dense layers: %s)" % dom[0], "bound": "tensor", "achieved": ach_tf,
+                "peak": tf_sus, "unit": "TFLOP/s", "frac": ach_tf / tf_sus, "traffic": None, "peak_source": src,
+                "note": "fp32 FFMA GEMMs today (exact-fp32 parity); peak quoted is the measured bf16 tensor figure",
+                "gemm_ms_per_step": gemm_ms, "gemm_flop_per_step": flops}
+
+    out = {
+        "metric": "learner transitions/sec", "value": value, "unit": "transitions/s", "n_gpus": world, "steps": a.steps,
+        "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a.workload, B, T, na, ne), "global_batch_episodes": world * B,
+                   "parallelism": "dp%d (episodes sharded, one all-reduce of grads+stats)" % world,
+                   "l2": "working set per step (%.1f GB of activations) exceeds the 126 MB L2" % (learner_bytes(learner, mac) / 1e9)},
+        "e2e": {"value": e2e, "unit": "transitions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 32,
+                "ms_per_step": ms_e2e / a.steps},
+        "gpu_launches": launches, "clocks": clk, "roofline": roofline, "roofline_attention": roof_att,
+        "kernels_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in sorted(kern.items(), key=lambda kv: -kv[1]["ms_per_step"])},
+    }
+    # ---- env kernel in the same run ---------------------------------------------------------------------------
+    if rank == 0 or world > 1:
+        out["env"] = bench_env(dev, world, rank, a, hbm, src)
+    if rank == 0 and world == 1 and not a.no_cpu:
+        out["cpu_baseline"] = cpu_reference_rate(alg, T, na, ne, ed, A, sample_B=4 if a.workload != "gm" else 64)
+        out["env"]["cpu_baseline"] = cpu_env_rate(8)
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def learner_bytes(learner, mac):
+    n = learner.ws.nbytes() + mac.agent.ws.nbytes() + learner.target_mac.agent.ws.nbytes()
+    if learner.mixer is not None:
+        n += learner.mixer.ws.nbytes() + learner.target_mixer.ws.nbytes()
+    return n
+
+
+def step_flops(args, B, T, na, ne, ed, A):
+    """Dense-layer FLOPs actually executed per train step (de-duplicated schedule: fc1/in_trans once per net)."""
+    N = B * T
+    d, he, me, r = args.attn_embed_dim, args.hypernet_embed, args.mixing_embed_dim, args.rnn_hidden_dim
+    ein = ed + (A if args.entity_last_action else 0)
+    rnn = "rnn" in args.agent
+    C = 3 if "imagine" in args.agent else 1
+
+    def trunk(dm, copies):
+        return 2 * ne * ein * dm + 2 * ne * dm * 3 * dm + copies * 2 * na * dm * dm
+
+    def head(copies):
+        if rnn:
+            return copies * (2 * na * d * r + 2 * na * r * 3 * r + 2 * na * r * A)
+        return copies * 2 * na * d * A
+    agent_f = trunk(d, C) + head(C)
+    tgt_f = trunk(d, 1) + head(1)
+    n_h = {"flex_qmix": 4, "lin_flex_qmix": 2, "vdn": 0}[args.mixer]
+    mix_f = tgt_mix_f = 0
+    if n_h:
+        w1_copies = 3 if C == 3 else 1
+        mix_f = trunk(he, w1_copies) + w1_copies * 2 * na * he * me + (n_h - 1) * (trunk(he, 1) + 2 * na * he * me)
+        tgt_mix_f = n_h * (trunk(he, 1) + 2 * na * he * me)
+    return N * (3 * (agent_f + mix_f) + tgt_f + tgt_mix_f)       # fwd + 2x for backward on the online nets
+
+
+def bench_env(dev, world, rank, a, hbm, src):
+    import torch
+    import torch.distributed as dist
+    from refil_b200.envs.group_matching import GroupMatchingBatch
+    na, ns, ng, lim = 8, 6, 2, 50
+    E = 32768 // max(world, 1) if world > 1 else 32768
+    T = lim + 1
+    env = GroupMatchingBatch(E, n_agents=na, n_states=ns, n_groups=ng, rand_trans=0.1, episode_limit=lim, seed=0,
+                             device=dev, first_env_index=rank * E)
+    ed = env.get_entity_size()
+    b = dict(entities=torch.zeros(E, T, na, ed, device=dev), gt_mask=torch.zeros(E, T, na, na, dtype=torch.uint8, device=dev),
+             obs_mask=torch.zeros(E, T, na, na, dtype=torch.uint8, device=dev),
+             entity_mask=torch.zeros(E, T, na, dtype=torch.uint8, device=dev),
+             avail_actions=torch.zeros(E, T, na, 3, dtype=torch.int32, device=dev),
+             actions=torch.randint(0, 3, (E, T, na, 1), device=dev), reward=torch.zeros(E, T, 1, device=dev),
+             terminated=torch.zeros(E, T, 1, dtype=torch.uint8, device=dev),
+             filled=torch.zeros(E, T, 1, dtype=torch.int64, device=dev))
+
+    def rollout():
+        env.reset(b)
+        for ts in range(lim):
+            env.step(b, ts)
+
+    for _ in range(3):
+        rollout()
+    env.step_counter.zero_()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 5
+    e0.record()
+    for _ in range(reps):
+        rollout()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    steps = env.step_counter.clone().double()
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(steps)
+    rate = float(steps.item()) / (float(ms.item()) * 1e-3)
+    bytes_per_step = 16 * na + 22 + 4 * na * ed + 25.6 * na
+    ach = rate * bytes_per_step / 1e9
+    return {"metric": "GroupMatching env-steps/sec", "value": rate, "unit": "env-steps/s", "n_envs": E * world,
+            "n_agents": na, "ms_per_rollout": float(ms.item()) / reps, "env_steps_per_rollout": float(steps.item()) / reps,
+            "config": "group_matching 8 agents, 6 states, 2 groups, rand_trans 0.1, limit 50; random action tape; "
+                      "reset + 50 step launches per rollout, rollout tensors written in place",
+            "roofline": {"kernel": "gm_step_kernel (K0)", "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s",
+                         "frac": ach / hbm, "traffic": None, "bytes_per_env_step": bytes_per_step, "peak_source": src}}
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="ns", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="episodes per GPU (default: the workload's)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    a = ap.parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

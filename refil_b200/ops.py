@@ -32,10 +32,35 @@ def _p(t, dtype=None):
     return t.data_ptr()
 
 
+_timing = None  # when enabled: {kernel name: [cuda event pairs]}
+
+
+def set_timing(enabled):
+    """Per-entry-point CUDA-event timing (bench.py's per-kernel breakdown; never on during the timed region)."""
+    global _timing
+    _timing = {} if enabled else None
+
+
+def timing_summary():
+    """-> {name: (launches, total_ms)}; synchronises."""
+    torch.cuda.synchronize()
+    out = {}
+    for name, evs in (_timing or {}).items():
+        out[name] = (len(evs), sum(a.elapsed_time(b) for a, b in evs))
+    return out
+
+
 def _call(name, *args):
     global _launches
     _launches += 1
+    if _timing is None:
+        _lib.call(name, *args, _stream())
+        return
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
     _lib.call(name, *args, _stream())
+    b.record()
+    _timing.setdefault(name, []).append((a, b))
 
 
 F32, U8, I32, I64, F64 = torch.float32, torch.uint8, torch.int32, torch.int64, torch.float64

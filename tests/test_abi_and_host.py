@@ -1,0 +1,124 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/refil_b200.h declares (no compute calls),
+the product path refuses to run without CUDA, and the host-side containers behave like the reference's."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from refil_b200 import _lib, build
+    build.build()
+    return _lib
+
+
+def test_library_exports_every_declared_symbol(lib):
+    protos = lib.parse_header()
+    assert len(protos) >= 27
+    so = ctypes.CDLL(lib.SO_PATH)
+    for name in protos:
+        assert hasattr(so, name), name
+    out = subprocess.run(["nm", "-D", "--defined-only", lib.SO_PATH], capture_output=True, text=True).stdout
+    exported = {l.split()[-1] for l in out.splitlines() if " T " in l and l.split()[-1].startswith("refil_")}
+    assert exported == set(protos), exported ^ set(protos)
+    L = lib.load()
+    assert L.refil_abi_version() == 1
+    assert L.refil_last_error() is not None
+
+
+def test_sass_is_sm100a(lib):
+    out = subprocess.run(["cuobjdump", "-lelf", lib.SO_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out, out[:200]
+
+
+def test_no_cpu_fallback():
+    from refil_b200 import _lib, ops
+    with pytest.raises(_lib.RefilError):
+        ops.linear_fwd(torch.zeros(2, 2), torch.zeros(2, 2), None, torch.zeros(2, 2))
+    from refil_b200.envs.group_matching import GroupMatchingBatch
+    with pytest.raises(_lib.RefilError):
+        GroupMatchingBatch(4, device="cpu")
+
+
+def test_product_path_never_imports_oracle():
+    bad = []
+    for d, _, files in os.walk(os.path.join(ROOT, "refil_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(d, f)).read()
+                if "import oracle" in src or "from oracle" in src:
+                    bad.append(f)
+    assert not bad, bad
+
+
+def test_epsilon_schedule_matches_reference_formula():
+    from refil_b200.components.epsilon_schedules import DecayThenFlatSchedule
+    s = DecayThenFlatSchedule(1.0, 0.05, 500000, decay="linear")
+    assert s.eval(0) == 1.0 and s.eval(10 ** 9) == 0.05 and abs(s.eval(250000) - 0.525) < 1e-12
+    e = DecayThenFlatSchedule(1.0, 0.05, 1000, decay="exp")
+    assert abs(e.eval(1000) - 0.05) < 1e-12 and e.eval(0) == 1.0
+
+
+def _scheme():
+    from refil_b200.components.transforms import OneHot
+    scheme = {"entities": {"vshape": 3, "group": "entities"}, "actions": {"vshape": (1,), "group": "agents", "dtype": torch.long},
+              "reward": {"vshape": (1,)}, "terminated": {"vshape": (1,), "dtype": torch.uint8}}
+    return scheme, {"agents": 2, "entities": 4}, {"actions": ("actions_onehot", [OneHot(out_dim=5)])}
+
+
+def test_episode_batch_update_slice_and_preprocess():
+    from refil_b200.components.episode_buffer import EpisodeBatch
+    scheme, groups, pre = _scheme()
+    b = EpisodeBatch(scheme, groups, 3, 4, preprocess=pre, device="cpu")
+    assert b["entities"].shape == (3, 4, 4, 3) and b["actions_onehot"].shape == (3, 4, 2, 5) and b["filled"].dtype == torch.long
+    b.update({"actions": [[1, 4], [0, 2], [3, 3]]}, ts=1)
+    assert int(b["filled"][:, 1].sum()) == 3 and int(b["filled"].sum()) == 3
+    assert torch.equal(b["actions_onehot"][1, 1].argmax(-1), torch.tensor([0, 2]))
+    b.update({"reward": [(0.5,)], "terminated": [(True,)]}, bs=[2], ts=2, mark_filled=False)
+    assert float(b["reward"][2, 2, 0]) == 0.5 and int(b["terminated"][2, 2, 0]) == 1 and int(b["filled"][2, 2, 0]) == 0
+    s = b[1:3, :2]
+    assert s.batch_size == 2 and s.max_seq_length == 2 and s["actions"].shape == (2, 2, 2, 1)
+    g = b[[0, 2]]
+    assert g.batch_size == 2 and torch.equal(g["actions"][1], b["actions"][2])
+    only = b[("reward", "terminated")]
+    assert set(only.data.transition_data) == {"reward", "terminated"}
+    assert int(b.max_t_filled()) == 1
+    with pytest.raises(ValueError):
+        b.update({"reward": np.zeros((3, 4, 2))})
+
+
+def test_replay_buffer_ring_and_sampling():
+    from refil_b200.components.episode_buffer import EpisodeBatch, ReplayBuffer
+    scheme, groups, pre = _scheme()
+    rb = ReplayBuffer(scheme, groups, 5, 4, preprocess=pre, device="cpu")
+    assert not rb.can_sample(1)
+    for i in range(4):
+        ep = EpisodeBatch(scheme, groups, 2, 4, preprocess=pre, device="cpu")
+        ep.update({"reward": torch.full((2, 4, 1), float(i))})
+        rb.insert_episode_batch(ep)
+    assert rb.episodes_in_buffer == 5 and rb.buffer_index == 3           # 8 inserts into a ring of 5
+    assert [float(rb["reward"][k, 0, 0]) for k in range(5)] == [2.0, 3.0, 3.0, 1.0, 2.0]
+    np.random.seed(0)
+    s = rb.sample(3)
+    assert s.batch_size == 3 and s["reward"].shape == (3, 4, 1)
+    assert rb.sample(5).batch_size == 5
+
+
+def test_param_store_views_and_state_dict():
+    from collections import OrderedDict
+    from refil_b200.modules.params import ParamStore
+    a = ParamStore(OrderedDict([("w", (3, 5)), ("b", (3,))]), "cpu")
+    a.p["w"].fill_(2.0)
+    flat, grad = torch.zeros(40), torch.zeros(40)
+    a.rebind(flat[8:8 + a.padded_size], grad[8:8 + a.padded_size])
+    assert float(flat[8:23].sum()) == 30.0 and a.p["w"].data_ptr() == flat[8:].data_ptr()
+    a.load_state_dict({"w": torch.ones(3, 5), "b": torch.arange(3.0)})
+    assert float(flat[23:26].sum()) == 3.0
+    with pytest.raises(KeyError):
+        a.load_state_dict({"w": torch.ones(3, 5)})
