@@ -99,6 +99,17 @@ int refil_gru_bwd_weight_hh(const float* dGH, const float* HS, int n_agents, int
 int refil_last_action_index(const long long* actions, int32_t* la, int B, int T, int n_agents, int n_entities,
                             cudaStream_t stream);
 
+/* ---- the same dense layers on the tcgen05 tensor cores (3xTF32 split, fp32 accumulate in TMEM; fp32-grade accuracy):
+ *      C[M,N] = [rowmask_c][relu]( g(A)[M,K] B[N,K]^T + bias ),  B[j,i] = B[j*b_stride_n + i*b_stride_k],
+ *      g = relu'(relu_y) and/or row mask on A (backward-data use).  refil_tc_gemm_supported() != 0 iff the shape
+ *      can run here (K % 32 == 0, N % 16 == 0, ...); otherwise use refil_linear_fwd / refil_linear_bwd_data. */
+int refil_tc_gemm_supported(int M, int N, int K);
+int refil_tc_gemm_tn(const float* A, long long lda, const float* relu_y, long long ldy,
+                     const uint8_t* a_row_entity_mask, int a_na, int a_ne, int a_rows_per_copy, const float* B,
+                     long long b_stride_n, long long b_stride_k, const float* bias, int relu,
+                     const uint8_t* c_row_entity_mask, int c_na, int c_ne, int c_rows_per_copy, float* C,
+                     long long ldc, int M, int N, int K, cudaStream_t stream);
+
 /* ---- masked multi-head attention over entities: modules/layers/attention.py:43-64 with the mask algebra of
  *      agents/entity_rnn_agent.py:79-124 resolved on the fly.  QKV [N, ne, 3d]; OUT / dOUT [C, N, nq, d]. */
 int refil_masked_attn_fwd(const float* qkv, float* out, const uint8_t* mask0, const uint8_t* mask1,

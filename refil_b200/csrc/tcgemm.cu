@@ -1,0 +1,386 @@
+// Dense layers on the 5th-generation tensor cores with fp32-grade accuracy: 3xTF32 split GEMM on tcgen05.mma.
+//
+//   C[M, N] = epi( g(A)[M, K] * B[N, K]^T )        ("TN": both operands K-major)
+//     forward  : A = activations, B = nn.Linear weight [out, in], epi = +bias, relu, inactive-agent row mask
+//     bwd-data : A = upstream gradient with fused relu' / row mask (g), B = W^T given by strides (elements of B are
+//                read as B[j*sbj + i*sbi], so no transposed copy of the weight is ever made)
+//   (nn.Linear of /root/reference/src/modules/layers/attention.py:21-22, agents/entity_rnn_agent.py:12,23-25,
+//    mixers/flex_qmix.py:29,39 and their autograd.)
+//
+// Why 3xTF32: the parity bar is 1e-4 relative on fp32 utilities / TD loss and bit-exact greedy indices; one TF32 (or
+// bf16) pass has ~2^-11 relative input error and does not hold it.  Each fp32 operand x is
+// split into hi = x & 0xffffe000 (exactly representable in TF32) and lo = x - hi (exact in fp32; <= 2^-11 |x|), and
+//   A*B ~= A_lo*B_hi + A_hi*B_lo + A_hi*B_hi   accumulated in fp32 in tensor memory,
+// which leaves ~2^-21 relative error per product -- fp32 grade.
+//
+// Structure (one persistent CTA per SM, 416 threads, warp-specialised):
+//   warps 0-3   epilogue: tcgen05.ld the 128 x BN fp32 accumulator out of TMEM (lane = row), bias / relu / row mask, store
+//   warp  4     TMEM allocation + single-thread tcgen05.mma issue (kind::tf32, M=128, N=BN, K=8 per instruction)
+//   warps 5-8, 9-12  two A-producer groups taking alternate K chunks (two chunks of global loads in flight per SM):
+//               coalesced 128-bit loads, all issued before the first use -> hi/lo split -> 128B-swizzled K-major tiles
+//   The weight tile (BN x K, hi and lo) is split ONCE per CTA and stays resident in shared memory: every CTA keeps one
+//   n-tile and walks the m-tiles.  smem = B_hi/B_lo [K/32][BN][32] + ring of S stages {A_hi, A_lo [128][32]} fp32 with
+//   mbarrier full/empty pairs; TMEM holds two accumulators so the epilogue of tile i overlaps the main loop of tile i+1.
+#include "common.cuh"
+
+#define TC_BM 128
+#define TC_BK 32
+#define TC_THREADS 416
+#define TC_MAX_STAGES 4
+
+struct TcArgs {
+    const float* A; long long lda;
+    const float* relu_y; long long ldy;      // optional: A element is zeroed where relu_y <= 0
+    const uint8_t* a_rowmask; int a_na, a_ne, a_mper;   // optional: A row zeroed (stack of [C, N, na] rows)
+    const float* B; long long sbj, sbi;      // B[j, i] = B[j*sbj + i*sbi], j < N (output col), i < K (reduction)
+    float* C; long long ldc;
+    const float* bias; int relu;
+    const uint8_t* c_rowmask; int c_na, c_ne, c_mper;
+    int M, N, K, BN, n_tiles, m_tiles, stages;
+    uint32_t idesc;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t addr = smem_u32(bar), done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row atoms 1024 bytes apart (cute::UMMA::SmemDescriptor)
+__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3fff);        // start address, 16-byte units
+    d |= (uint64_t)1 << 16;                        // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;              // stride byte offset: next 8-row group
+    d |= (uint64_t)1 << 46;                        // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
+    return d;
+}
+
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+
+__device__ __forceinline__ bool tc_row_masked(const uint8_t* em, int na, int ne, int mper, long long r) {
+    if (!em) return false;
+    int idx = (int)(r % mper);
+    int n = idx / na, a = idx - n * na;
+    return em[(size_t)n * ne + a] != 0;
+}
+
+// split 4 fp32 values and store them at the swizzled position of (row, 16-byte chunk) in the hi / lo tiles
+__device__ __forceinline__ void tc_store_split(float* hi_tile, float* lo_tile, int row, int chunk, float4 v) {
+    const int off = row * 32 + ((chunk ^ (row & 7)) << 2);
+    float4 h, l;
+    h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+    h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+    h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+    h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+    l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+    *reinterpret_cast<float4*>(hi_tile + off) = h;
+    *reinterpret_cast<float4*>(lo_tile + off) = l;
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_tn_kernel(TcArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // 1024-byte aligned base (dynamic smem is only guaranteed 16-byte aligned)
+    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int BN = a.BN;
+    const int S = a.stages, KC = a.K / TC_BK;
+    const uint32_t a_bytes = TC_BM * 128, b_bytes = (uint32_t)BN * 128;
+    const uint32_t stage_bytes = 2 * a_bytes;
+    uint8_t* smem_b = smem;                                   // [KC][hi | lo][BN][128 B]
+    uint8_t* smem_a = smem + (size_t)KC * 2 * b_bytes;        // [S][hi | lo][128][128 B]
+    __shared__ uint64_t full_bar[TC_MAX_STAGES], empty_bar[TC_MAX_STAGES], tmem_full[2], tmem_empty[2];
+    __shared__ uint32_t tmem_base_s;
+    __shared__ __align__(16) float epi_stage[4 * 32 * 36];   // per-warp 32 x 32 transpose buffer (row stride 36)
+    __shared__ __align__(16) float epi_bias[256];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nt = blockIdx.x % a.n_tiles;                    // this CTA's n-tile (fixed), m-tiles strided
+    const int mt0 = blockIdx.x / a.n_tiles, mt_step = gridDim.x / a.n_tiles;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; s++) { mbar_init(&full_bar[s], 128); mbar_init(&empty_bar[s], 1); }
+        for (int b = 0; b < 2; b++) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    // resident weight tile: split once per CTA
+    {
+        const int k4 = a.K >> 2;
+        for (int f = threadIdx.x; f < BN * k4; f += TC_THREADS) {
+            const int r = f / k4, kq = f - r * k4;           // row of the tile, 16-byte chunk along K
+            const int kc = kq >> 3, c = kq & 7;
+            const long long j = (long long)nt * BN + r;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (j < a.N) {
+                const float* p = a.B + j * a.sbj + (long long)(kq * 4) * a.sbi;
+                if (a.sbi == 1) v = __ldg(reinterpret_cast<const float4*>(p));
+                else { v.x = __ldg(p); v.y = __ldg(p + a.sbi); v.z = __ldg(p + 2 * a.sbi); v.w = __ldg(p + 3 * a.sbi); }
+            }
+            float* hi = reinterpret_cast<float*>(smem_b + (size_t)kc * 2 * b_bytes);
+            tc_store_split(hi, hi + BN * 32, r, c, v);
+        }
+        for (int c = threadIdx.x; c < BN; c += TC_THREADS) epi_bias[c] = a.bias ? __ldg(a.bias + (long long)nt * BN + c) : 0.f;
+        fence_async_smem();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp < 4) {
+        // ===================== epilogue =====================
+        // TMEM (lane = row) -> registers -> bias / relu / row mask -> per-warp smem transpose buffer -> full 128-byte
+        // row segments to global (4 rows x 128 B per store instruction instead of 32 rows x 16 B)
+        float* stg = epi_stage + warp * (32 * 36);
+        int it = 0;
+        for (int mt = mt0; mt < a.m_tiles; mt += mt_step, it++) {
+            const int buf = it & 1;
+            mbar_wait(&tmem_full[buf], (it >> 1) & 1);
+            tc_fence_after();
+            const long long row0 = (long long)mt * TC_BM + warp * 32;
+            const long long myrow = row0 + lane;
+            const bool masked = myrow < a.M && tc_row_masked(a.c_rowmask, a.c_na, a.c_ne, a.c_mper, myrow);
+            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * BN);
+            float* cbase = a.C + row0 * a.ldc + (long long)nt * BN;
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                const int width = min(32, BN - c0);            // BN is a multiple of 16
+                uint32_t r[32];
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                    : "r"(taddr + (uint32_t)c0));
+                if (width == 32) {
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                        : "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                        : "r"(taddr + (uint32_t)(c0 + 16)));
+                }
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    if (4 * q < width) {
+                        const float4 b4 = *reinterpret_cast<const float4*>(epi_bias + c0 + 4 * q);
+                        float4 v;
+                        v.x = __uint_as_float(r[4 * q + 0]) + b4.x;
+                        v.y = __uint_as_float(r[4 * q + 1]) + b4.y;
+                        v.z = __uint_as_float(r[4 * q + 2]) + b4.z;
+                        v.w = __uint_as_float(r[4 * q + 3]) + b4.w;
+                        if (a.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                        if (masked) v = make_float4(0.f, 0.f, 0.f, 0.f);
+                        *reinterpret_cast<float4*>(stg + lane * 36 + 4 * q) = v;
+                    }
+                }
+                __syncwarp();
+                const int cpr = width >> 2;                    // 16-byte chunks per row: 8 or 4
+                const int rpi = 32 / cpr;                      // rows per store instruction: 4 or 8
+                const int rl = lane / cpr, ch = lane - rl * cpr;
+                for (int rb = 0; rb < 32; rb += rpi) {
+                    const int rr = rb + rl;
+                    if (row0 + rr < a.M) {
+                        const float4 v = *reinterpret_cast<const float4*>(stg + rr * 36 + 4 * ch);
+                        *reinterpret_cast<float4*>(cbase + (long long)rr * a.ldc + c0 + 4 * ch) = v;
+                    }
+                }
+                __syncwarp();
+            }
+            tc_fence_before();
+            mbar_arrive(&tmem_empty[buf]);
+        }
+    } else if (warp == 4) {
+        // ===================== MMA issuer =====================
+        int it = 0, stage = 0;
+        uint32_t phase = 0;
+        for (int mt = mt0; mt < a.m_tiles; mt += mt_step, it++) {
+            const int buf = it & 1;
+            mbar_wait(&tmem_empty[buf], ((it >> 1) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
+            for (int kc = 0; kc < KC; kc++) {
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t sa = smem_u32(smem_a + (size_t)stage * stage_bytes);
+                    const uint32_t sb = smem_u32(smem_b + (size_t)kc * 2 * b_bytes);
+                    const uint64_t a_hi = tc_smem_desc(sa), a_lo = tc_smem_desc(sa + a_bytes);
+                    const uint64_t b_hi = tc_smem_desc(sb), b_lo = tc_smem_desc(sb + b_bytes);
+#pragma unroll
+                    for (int ks = 0; ks < TC_BK / 8; ks++) {
+                        const uint64_t adv = (uint64_t)(ks * 2);       // +32 bytes inside the 128B swizzle row
+                        tc_mma(tmem_d, a_lo + adv, b_hi + adv, a.idesc, (kc | ks) != 0);
+                        tc_mma(tmem_d, a_hi + adv, b_lo + adv, a.idesc, 1);
+                        tc_mma(tmem_d, a_hi + adv, b_hi + adv, a.idesc, 1);
+                    }
+                    tc_commit(&empty_bar[stage]);                  // frees the smem stage when these MMAs retire
+                    if (kc == KC - 1) tc_commit(&tmem_full[buf]);  // accumulator complete -> epilogue
+                }
+                __syncwarp();
+                if (++stage == S) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else {
+        // ===================== A producers: group 0 = warps 5-8 (even chunks), group 1 = warps 9-12 (odd chunks) ====
+        // thread -> fixed 16-byte chunk c of rows r0 + 16 i (i < 8): one base pointer per tile, constant smem offsets
+        const int grp = warp < 9 ? 0 : 1;
+        const int pt = threadIdx.x - (grp ? 288 : 160);     // 0..127 within the group
+        const int r0 = pt >> 3, c = pt & 7;
+        const int soff = r0 * 32 + ((c ^ (r0 & 7)) << 2);   // float offset of (r0, c); row r0 + 16 i adds 512 i
+        const long long rstep = 16 * a.lda, ystep = 16 * a.ldy;
+        int stage = 0, chunk_ctr = 0;
+        uint32_t phase = 0;
+        for (int mt = mt0; mt < a.m_tiles; mt += mt_step) {
+            const long long rowb = (long long)mt * TC_BM + r0;
+            const float* pa = a.A + rowb * a.lda + c * 4;
+            const float* py = a.relu_y ? a.relu_y + rowb * a.ldy + c * 4 : nullptr;
+            uint32_t valid = 0;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const long long row = rowb + 16 * i;
+                if (row < a.M && !tc_row_masked(a.a_rowmask, a.a_na, a.a_ne, a.a_mper, row)) valid |= 1u << i;
+            }
+            for (int kc = 0; kc < KC; kc++, chunk_ctr++) {
+                if ((chunk_ctr & 1) == grp) {
+                    const int k0 = kc * TC_BK;
+                    float4 va[8];
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        va[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (valid & (1u << i)) va[i] = __ldg(reinterpret_cast<const float4*>(pa + i * rstep + k0));
+                    }
+                    if (py) {
+#pragma unroll
+                        for (int i = 0; i < 8; i++) {
+                            if (valid & (1u << i)) {
+                                const float4 y = __ldg(reinterpret_cast<const float4*>(py + i * ystep + k0));
+                                if (!(y.x > 0.f)) va[i].x = 0.f;
+                                if (!(y.y > 0.f)) va[i].y = 0.f;
+                                if (!(y.z > 0.f)) va[i].z = 0.f;
+                                if (!(y.w > 0.f)) va[i].w = 0.f;
+                            }
+                        }
+                    }
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    float* ahi = reinterpret_cast<float*>(smem_a + (size_t)stage * stage_bytes) + soff;
+                    float* alo = ahi + TC_BM * 32;
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        float4 h, l;
+                        h.x = __uint_as_float(__float_as_uint(va[i].x) & 0xffffe000u);
+                        h.y = __uint_as_float(__float_as_uint(va[i].y) & 0xffffe000u);
+                        h.z = __uint_as_float(__float_as_uint(va[i].z) & 0xffffe000u);
+                        h.w = __uint_as_float(__float_as_uint(va[i].w) & 0xffffe000u);
+                        l.x = va[i].x - h.x; l.y = va[i].y - h.y; l.z = va[i].z - h.z; l.w = va[i].w - h.w;
+                        *reinterpret_cast<float4*>(ahi + i * 512) = h;
+                        *reinterpret_cast<float4*>(alo + i * 512) = l;
+                    }
+                    fence_async_smem();           // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+                    mbar_arrive(&full_bar[stage]);
+                }
+                if (++stage == S) { stage = 0; phase ^= 1; }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+    }
+}
+
+// n-tile width: multiple of 16 dividing N, <= 256, with the resident split weight (2 * BN * K fp32) within budget
+static int tc_pick_bn(int N, int K) {
+    const int budget = 128 * 1024;
+    int best = 0;
+    for (int bn = 16; bn <= 256 && bn <= N; bn += 16)
+        if (N % bn == 0 && (long long)2 * bn * K * 4 <= budget) best = bn;
+    return best;
+}
+
+// Can this problem run on the tensor-core path?  (else the caller uses the fp32 FFMA kernel)
+extern "C" int refil_tc_gemm_supported(int M, int N, int K) {
+    if (M < 1 || K < TC_BK || K % TC_BK != 0 || N < 16 || N % 16 != 0) return 0;
+    return tc_pick_bn(N, K) > 0;
+}
+
+extern "C" int refil_tc_gemm_tn(const float* A, long long lda, const float* relu_y, long long ldy,
+                                const uint8_t* a_row_entity_mask, int a_na, int a_ne, int a_rows_per_copy,
+                                const float* B, long long b_stride_n, long long b_stride_k, const float* bias,
+                                int relu, const uint8_t* c_row_entity_mask, int c_na, int c_ne, int c_rows_per_copy,
+                                float* C, long long ldc, int M, int N, int K, cudaStream_t stream) {
+    REFIL_CHECK_ARG(A && B && C, "tc_gemm_tn: null pointer");
+    REFIL_CHECK_ARG(refil_tc_gemm_supported(M, N, K), "tc_gemm_tn: unsupported shape M=%d N=%d K=%d", M, N, K);
+    REFIL_CHECK_ARG((lda % 4) == 0 && (ldc % 4) == 0 && ((uintptr_t)A % 16) == 0 && ((uintptr_t)C % 16) == 0,
+                    "tc_gemm_tn: A / C must be 16-byte aligned with leading dimensions divisible by 4");
+    REFIL_CHECK_ARG(!relu_y || ((ldy % 4) == 0 && ((uintptr_t)relu_y % 16) == 0), "tc_gemm_tn: relu_y alignment");
+    REFIL_CHECK_ARG(b_stride_k != 1 || ((b_stride_n % 4) == 0 && ((uintptr_t)B % 16) == 0), "tc_gemm_tn: B alignment");
+    TcArgs a{};
+    a.A = A; a.lda = lda; a.relu_y = relu_y; a.ldy = ldy;
+    a.a_rowmask = a_row_entity_mask; a.a_na = a_na > 0 ? a_na : 1; a.a_ne = a_ne; a.a_mper = a_rows_per_copy > 0 ? a_rows_per_copy : 1;
+    a.B = B; a.sbj = b_stride_n; a.sbi = b_stride_k;
+    a.C = C; a.ldc = ldc; a.bias = bias; a.relu = relu;
+    a.c_rowmask = c_row_entity_mask; a.c_na = c_na > 0 ? c_na : 1; a.c_ne = c_ne; a.c_mper = c_rows_per_copy > 0 ? c_rows_per_copy : 1;
+    a.M = M; a.N = N; a.K = K;
+    const int BN = tc_pick_bn(N, K);
+    a.BN = BN;
+    a.n_tiles = N / BN;
+    a.m_tiles = refil_cdiv(M, TC_BM);
+    const size_t b_res = (size_t)2 * BN * K * 4, stage_bytes = 2 * (size_t)TC_BM * 128;
+    int stages = (int)((200 * 1024 - b_res) / stage_bytes);
+    if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+    REFIL_CHECK_ARG(stages >= 2, "tc_gemm_tn: shared memory budget (N=%d K=%d)", N, K);
+    a.stages = stages;
+    // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=tf32, both K-major, N>>3, M>>4
+    a.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    const size_t smem = b_res + stages * stage_bytes + 1024;
+    static size_t attr_smem = 0;
+    if (smem > attr_smem) {
+        cudaError_t e = cudaFuncSetAttribute(tc_gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) {
+            refil_set_error("tc_gemm_tn: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
+            return REFIL_ERR_CUDA;
+        }
+        attr_smem = smem;
+    }
+    const int sms = refil_num_sms();
+    int per_n = sms / a.n_tiles;                 // CTAs per n-tile
+    if (per_n < 1) per_n = 1;
+    if (per_n > a.m_tiles) per_n = a.m_tiles;
+    const int grid = per_n * a.n_tiles;
+    tc_gemm_tn_kernel<<<grid, TC_THREADS, smem, stream>>>(a);
+    REFIL_CHECK_LAUNCH("tc_gemm_tn");
+    return REFIL_OK;
+}

@@ -75,9 +75,28 @@ def _rm(row_mask):
 
 
 # ---------------------------------------------------------------------------------------------------- dense
+USE_TENSOR_CORES = True     # tcgen05 3xTF32 path for eligible shapes; False = fp32 FFMA kernel everywhere
+TC_MIN_ROWS = 256
+
+
+def _tc_ok(M, N, K):
+    return USE_TENSOR_CORES and M >= TC_MIN_ROWS and _lib.load().refil_tc_gemm_supported(M, N, K) != 0
+
+
+def tc_gemm_tn(A, B, sbn, sbk, out, N, K, bias=None, relu=False, relu_y=None, a_row_mask=None, c_row_mask=None):
+    M = A.shape[0]
+    aem, ana, ane, amper = _rm(a_row_mask)
+    cem, cna, cne, cmper = _rm(c_row_mask)
+    _call("tc_gemm_tn", _p(A, F32), A.shape[1], _p(relu_y, F32), A.shape[1], aem, ana, ane, amper, _p(B, F32), sbn, sbk,
+          _p(bias, F32), int(relu), cem, cna, cne, cmper, _p(out, F32), out.shape[1], M, N, K)
+    return out
+
+
 def linear_fwd(A, W, bias, out, relu=False, row_mask=None):
     M, K = A.shape
     N = W.shape[0]
+    if _tc_ok(M, N, K):
+        return tc_gemm_tn(A, W, K, 1, out, N, K, bias=bias, relu=relu, c_row_mask=row_mask)
     em, na, ne, mper = _rm(row_mask)
     _call("linear_fwd", _p(A, F32), K, _p(W, F32), W.shape[1], _p(bias, F32), _p(out, F32), N, M, N, K, int(relu),
           em, na, ne, mper)
@@ -95,6 +114,8 @@ def embed_fwd(entities, last_action, n_actions, W, bias, out, relu=True):
 def linear_bwd_data(dC, W, dA, relu_y=None, row_mask=None):
     M, N = dC.shape
     K = W.shape[1]
+    if _tc_ok(M, K, N):      # dA[M,K] = g(dC)[M,N] W[N,K]: "B"[j=k, i=n] = W[n*K + k]
+        return tc_gemm_tn(dC, W, 1, K, dA, K, N, relu_y=relu_y, a_row_mask=row_mask)
     em, na, ne, mper = _rm(row_mask)
     _call("linear_bwd_data", _p(dC, F32), N, _p(relu_y, F32), N, em, na, ne, mper, _p(W, F32), K, _p(dA, F32), K, M, N, K)
     return dA

@@ -28,15 +28,19 @@ def test_linear_fwd_bwd(M, N, K, relu):
         y = torch.relu(y)
     y.backward(dC)
     Ad, Wd, bd, dCd = A.to(DEV), W.to(DEV), b.to(DEV), dC.to(DEV)
+    # absolute tolerance relative to the magnitude of the accumulated products (fp32 FFMA ~1e-6, 3xTF32 ~4e-6 of it)
+    s_fwd = float((A.abs() @ W.abs().t()).max())
+    s_da = float((dC.abs() @ W.abs()).max())
+    s_dw = float((dC.abs().t() @ A.abs()).max())
     out = torch.empty(M, N, device=DEV)
     ops.linear_fwd(Ad, Wd, bd, out, relu=relu)
-    _close(out, y, what="fwd")
+    _close(out, y, atol=5e-6 * s_fwd, what="fwd")
     dA = torch.empty(M, K, device=DEV)
     ops.linear_bwd_data(dCd, Wd, dA, relu_y=out if relu else None)
-    _close(dA, Ar.grad, what="dA")
+    _close(dA, Ar.grad, atol=5e-6 * s_da, what="dA")
     dW, db = torch.zeros(N, K, device=DEV), torch.zeros(N, device=DEV)
     ops.linear_bwd_weight(dCd, Ad, dW, db, relu_y=out if relu else None)
-    _close(dW, Wr.grad, rtol=2e-4, atol=2e-4, what="dW")
+    _close(dW, Wr.grad, rtol=2e-4, atol=5e-6 * s_dw, what="dW")
     _close(db, br.grad, rtol=2e-4, atol=2e-4, what="db")
 
 
@@ -251,3 +255,48 @@ def test_missing_cuda_fails_loudly():
     from refil_b200 import _lib, ops
     with pytest.raises(_lib.RefilError):
         ops.linear_fwd(torch.zeros(4, 4), torch.zeros(4, 4), None, torch.zeros(4, 4))
+
+
+@pytest.mark.parametrize("M,N,K", [(1000, 384, 128), (300, 64, 64), (4096, 192, 64), (129, 128, 128), (20000, 32, 128),
+                                   (513, 256, 32), (2048, 16, 64)])
+def test_tc_gemm_3xtf32_forward(M, N, K):
+    """tcgen05 3xTF32 GEMM vs float64: fp32-grade accuracy (a single TF32 pass would be ~1e-3)."""
+    from refil_b200 import _lib, ops
+    assert _lib.load().refil_tc_gemm_supported(M, N, K)
+    g = torch.Generator().manual_seed(M + N + K)
+    A, W, b = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) * 0.3, torch.randn(N, generator=g)
+    C, na, ne = 1, 4, 6
+    em = None
+    if M % na == 0:
+        em = (torch.rand(M // na, ne, generator=g) < 0.3).to(torch.uint8)
+    ref = A.double() @ W.double().t() + b.double()
+    ref = torch.relu(ref)
+    if em is not None:
+        ref = ref.view(M // na, na, N).masked_fill(em[:, :na].bool().unsqueeze(-1), 0.0).view(M, N)
+    out = torch.full((M, N), float("nan"), device=DEV)
+    ops.tc_gemm_tn(A.to(DEV), W.to(DEV), K, 1, out, N, K, bias=b.to(DEV), relu=True,
+                   c_row_mask=(em.to(DEV), na, M) if em is not None else None)
+    torch.cuda.synchronize()
+    err = (out.cpu().double() - ref).abs().max().item()
+    scale = (A.abs().double() @ W.abs().double().t()).max().item()
+    assert err <= 4e-6 * scale, (err, scale)
+
+
+@pytest.mark.parametrize("M,N,K", [(1000, 384, 128), (777 * 4, 64, 128), (2048, 128, 128), (600, 192, 64)])
+def test_tc_gemm_3xtf32_backward_data(M, N, K):
+    """dA = (dC * relu'(y) * rowmask) W through the strided-B form, vs float64."""
+    from refil_b200 import ops
+    g = torch.Generator().manual_seed(M + N)
+    dC, W = torch.randn(M, N, generator=g), torch.randn(N, K, generator=g) * 0.3
+    y = torch.randn(M, N, generator=g)
+    na, ne = 4, 5
+    em = (torch.rand(M // na, ne, generator=g) < 0.3).to(torch.uint8)
+    gmat = dC.double() * (y > 0).double()
+    gmat = gmat.view(M // na, na, N).masked_fill(em[:, :na].bool().unsqueeze(-1), 0.0).view(M, N)
+    ref = gmat @ W.double()
+    dA = torch.full((M, K), float("nan"), device=DEV)
+    ops.linear_bwd_data(dC.to(DEV), W.to(DEV), dA, relu_y=y.to(DEV), row_mask=(em.to(DEV), na, M))
+    torch.cuda.synchronize()
+    err = (dA.cpu().double() - ref).abs().max().item()
+    scale = (gmat.abs() @ W.abs().double()).max().item()
+    assert err <= 4e-6 * scale, (err, scale)
