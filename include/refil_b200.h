@@ -110,6 +110,13 @@ int refil_tc_gemm_tn(const float* A, long long lda, const float* relu_y, long lo
                      const uint8_t* c_row_entity_mask, int c_na, int c_ne, int c_rows_per_copy, float* C,
                      long long ldc, int M, int N, int K, cudaStream_t stream);
 
+/* weight gradient on the tensor cores: dW[P,Q] += g(X)[M,P]^T Y[M,Q]; db[P] += colsum g(X) (db may be null) */
+int refil_tc_wgrad_supported(int M, int P, int Q);
+int refil_tc_gemm_wgrad(const float* X, long long ldx, const float* relu_y, long long ldy,
+                        const uint8_t* x_row_entity_mask, int na, int ne, int rows_per_copy, const float* Y,
+                        long long ldyy, float* dW, long long lddw, float* db, int M, int P, int Q,
+                        cudaStream_t stream);
+
 /* ---- masked multi-head attention over entities: modules/layers/attention.py:43-64 with the mask algebra of
  *      agents/entity_rnn_agent.py:79-124 resolved on the fly.  QKV [N, ne, 3d]; OUT / dOUT [C, N, nq, d]. */
 int refil_masked_attn_fwd(const float* qkv, float* out, const uint8_t* mask0, const uint8_t* mask1,

@@ -384,3 +384,272 @@ extern "C" int refil_tc_gemm_tn(const float* A, long long lda, const float* relu
     REFIL_CHECK_LAUNCH("tc_gemm_tn");
     return REFIL_OK;
 }
+
+// =====================================================================================================================
+// Weight gradient on the tensor cores:  dW[P, Q] += g(X)[M, P]^T Y[M, Q],  db[P] += colsum g(X)
+//   (autograd of the same nn.Linear layers; X = upstream gradient with fused relu' / row mask, Y = layer input)
+// The reduction runs over the ROWS of both row-major operands, i.e. both are "MN-major" for the tensor core: a chunk of
+// 32 rows is staged as-is in the only MN-major layout tf32 supports (cute::UMMA::Layout_MN_SW128_32B_Atom, descriptor layout
+// type SWIZZLE_128B_BASE32B): atoms of 4 rows x 128 bytes, 32-byte groups XOR-swizzled with the row index, and tcgen05.mma
+// transposes on the fly (instruction descriptor a_major = b_major = MN).  Each CTA owns one 128-wide
+// p-tile and a contiguous range of row chunks, accumulates its partial [128 x BQ] tile in TMEM and adds it to dW with
+// vector atomics.  The bias gradient is the extra column Q: the Y tile carries one more 32-wide atom whose first
+// column is the constant 1 (written once), so db costs no extra pass over X.
+// =====================================================================================================================
+struct TcWArgs {
+    const float* X; long long ldx;
+    const float* relu_y; long long ldy;
+    const uint8_t* x_rowmask; int na, ne, mper;
+    const float* Y; long long ldyy;
+    float* dW; long long lddw;
+    float* db;
+    int M, P, Q, BQ, p_tiles, splits, stages, chunks_per_split;
+    uint32_t idesc;
+};
+
+// MN-major tf32: atoms of 4 k-rows x 128 B (512 B); LBO = stride between atoms along MN, SBO = between atoms along K
+__device__ __forceinline__ uint64_t tc_smem_desc_mn(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3fff);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)1 << 61;                        // SWIZZLE_128B_BASE32B
+    return d;
+}
+
+// float offset of (row r < 32, 16-byte chunk c16) inside a [32 rows][n_atoms * 32 floats] MN-major tile
+__device__ __forceinline__ int tc_mn_off(int r, int c16, int n_atoms) {
+    const int ka = r >> 2, kr = r & 3, at = c16 >> 3, c8 = c16 & 7;
+    return (ka * n_atoms + at) * 128 + kr * 32 + ((((c8 >> 1) ^ kr) << 3) | ((c8 & 1) << 2));
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_wgrad_kernel(TcWArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int BQ = a.BQ, S = a.stages;
+    const int xa = 4, ya = BQ / 32;                         // MN atoms of the X tile (128 wide) and the Y tile
+    const uint32_t x_bytes = 32 * 128 * 4, y_bytes = 32 * (uint32_t)BQ * 4;
+    const uint32_t stage_bytes = 2 * x_bytes + 2 * y_bytes; // X_hi | X_lo | Y_hi | Y_lo
+    __shared__ uint64_t full_bar[TC_MAX_STAGES], empty_bar[TC_MAX_STAGES], acc_bar;
+    __shared__ uint32_t tmem_base_s;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ptile = blockIdx.x % a.p_tiles, split = blockIdx.x / a.p_tiles;
+    const int chunks_total = (a.M + 31) / 32;
+    const int c_begin = split * a.chunks_per_split, c_end = min(chunks_total, c_begin + a.chunks_per_split);
+    const int n_chunks = max(0, c_end - c_begin);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; s++) { mbar_init(&full_bar[s], 128); mbar_init(&empty_bar[s], 1); }
+        mbar_init(&acc_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(256u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    // constant "ones" atom of every stage's Y tile (hi: column Q = 1, rest 0; lo: 0), written once
+    for (int s = 0; s < S; s++) {
+        float* yhi = reinterpret_cast<float*>(smem + (size_t)s * stage_bytes + 2 * x_bytes);
+        float* ylo = reinterpret_cast<float*>(smem + (size_t)s * stage_bytes + 2 * x_bytes + y_bytes);
+        for (int f = threadIdx.x; f < 32 * 32; f += TC_THREADS) {         // 32 rows x 32 floats of the last MN atom
+            const int r = f >> 5, e = f & 31;
+            const int off = tc_mn_off(r, (ya - 1) * 8 + (e >> 2), ya) + (e & 3);
+            yhi[off] = (e == 0) ? 1.f : 0.f;
+            ylo[off] = 0.f;
+        }
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp < 4) {
+        // ===================== epilogue: TMEM partial tile -> vector atomics into dW / db =====================
+        if (n_chunks > 0) {
+            mbar_wait(&acc_bar, 0);
+            tc_fence_after();
+            const int p = ptile * 128 + warp * 32 + lane;
+            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+            for (int c0 = 0; c0 < a.Q + 16; c0 += 16) {
+                uint32_t r[16];
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                    : "r"(taddr + (uint32_t)c0));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (p < a.P) {
+                    if (c0 < a.Q) {
+                        float* dst = a.dW + (long long)p * a.lddw + c0;
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            float4 v = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
+                                                   __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+                            atomicAdd(reinterpret_cast<float4*>(dst + 4 * q), v);
+                        }
+                    } else if (a.db) {
+                        atomicAdd(a.db + p, __uint_as_float(r[0]));       // column Q: sum over rows of g(X)[:, p]
+                    }
+                }
+            }
+        }
+    } else if (warp == 4) {
+        // ===================== MMA issuer =====================
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int ch = 0; ch < n_chunks; ch++) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t sx = smem_u32(smem + (size_t)stage * stage_bytes);
+                const uint32_t sy = sx + 2 * x_bytes;
+#pragma unroll
+                for (int ks = 0; ks < 4; ks++) {                          // 4 MMAs of K = 8 rows = 2 k-atoms each
+                    const uint64_t x_hi = tc_smem_desc_mn(sx + ks * xa * 1024, 512, xa * 512);
+                    const uint64_t x_lo = tc_smem_desc_mn(sx + x_bytes + ks * xa * 1024, 512, xa * 512);
+                    const uint64_t y_hi = tc_smem_desc_mn(sy + ks * ya * 1024, 512, ya * 512);
+                    const uint64_t y_lo = tc_smem_desc_mn(sy + y_bytes + ks * ya * 1024, 512, ya * 512);
+                    tc_mma(tmem_base, x_lo, y_hi, a.idesc, (ch | ks) != 0);
+                    tc_mma(tmem_base, x_hi, y_lo, a.idesc, 1);
+                    tc_mma(tmem_base, x_hi, y_hi, a.idesc, 1);
+                }
+                tc_commit(&empty_bar[stage]);
+                if (ch == n_chunks - 1) tc_commit(&acc_bar);
+            }
+            __syncwarp();
+            if (++stage == S) { stage = 0; phase ^= 1; }
+        }
+    } else {
+        // ===================== producers (two groups, alternate chunks): straight 128-byte row-segment copies ====
+        const int grp = warp < 9 ? 0 : 1;
+        const int pt = threadIdx.x - (grp ? 288 : 160);
+        // X tile: 32 rows x 32 chunks(16 B); thread -> fixed chunk cx of rows (pt >> 5) + 4 i
+        const int cx = pt & 31, rx0 = pt >> 5;
+        const int pcol = ptile * 128 + cx * 4;
+        const bool x_in = pcol < a.P;                     // P is a multiple of 4 (checked on the host)
+        // Y tile: 32 rows x cpr chunks; thread -> fixed chunk cy of rows (pt / cpr) + (128 / cpr) i
+        const int cpr = a.Q >> 2, ry0 = pt / cpr, cy = pt - ry0 * cpr, ry_step = 128 / cpr, ny = (32 * cpr) >> 7;
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int ch = 0; ch < n_chunks; ch++) {
+            if ((ch & 1) == grp) {
+                const long long m0 = (long long)(c_begin + ch) * 32;
+                float4 vx[8], vy[16];
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const long long row = m0 + rx0 + 4 * i;
+                    vx[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (x_in && row < a.M && !tc_row_masked(a.x_rowmask, a.na, a.ne, a.mper, row)) {
+                        vx[i] = __ldg(reinterpret_cast<const float4*>(a.X + row * a.ldx + pcol));
+                        if (a.relu_y) {
+                            const float4 y = __ldg(reinterpret_cast<const float4*>(a.relu_y + row * a.ldy + pcol));
+                            if (!(y.x > 0.f)) vx[i].x = 0.f;
+                            if (!(y.y > 0.f)) vx[i].y = 0.f;
+                            if (!(y.z > 0.f)) vx[i].z = 0.f;
+                            if (!(y.w > 0.f)) vx[i].w = 0.f;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    vy[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (i < ny) {
+                        const long long row = m0 + ry0 + ry_step * i;
+                        if (row < a.M) vy[i] = __ldg(reinterpret_cast<const float4*>(a.Y + row * a.ldyy + cy * 4));
+                    }
+                }
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                float* xhi = reinterpret_cast<float*>(smem + (size_t)stage * stage_bytes);
+                float* xlo = xhi + 32 * 128;
+                float* yhi = xhi + 2 * 32 * 128;
+                float* ylo = yhi + 32 * BQ;
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const int off = tc_mn_off(rx0 + 4 * i, cx, xa);
+                    float4 h, l;
+                    h.x = __uint_as_float(__float_as_uint(vx[i].x) & 0xffffe000u);
+                    h.y = __uint_as_float(__float_as_uint(vx[i].y) & 0xffffe000u);
+                    h.z = __uint_as_float(__float_as_uint(vx[i].z) & 0xffffe000u);
+                    h.w = __uint_as_float(__float_as_uint(vx[i].w) & 0xffffe000u);
+                    l.x = vx[i].x - h.x; l.y = vx[i].y - h.y; l.z = vx[i].z - h.z; l.w = vx[i].w - h.w;
+                    *reinterpret_cast<float4*>(xhi + off) = h;
+                    *reinterpret_cast<float4*>(xlo + off) = l;
+                }
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    if (i < ny) {
+                        const int off = tc_mn_off(ry0 + ry_step * i, cy, ya);
+                        float4 h, l;
+                        h.x = __uint_as_float(__float_as_uint(vy[i].x) & 0xffffe000u);
+                        h.y = __uint_as_float(__float_as_uint(vy[i].y) & 0xffffe000u);
+                        h.z = __uint_as_float(__float_as_uint(vy[i].z) & 0xffffe000u);
+                        h.w = __uint_as_float(__float_as_uint(vy[i].w) & 0xffffe000u);
+                        l.x = vy[i].x - h.x; l.y = vy[i].y - h.y; l.z = vy[i].z - h.z; l.w = vy[i].w - h.w;
+                        *reinterpret_cast<float4*>(yhi + off) = h;
+                        *reinterpret_cast<float4*>(ylo + off) = l;
+                    }
+                }
+                fence_async_smem();
+                mbar_arrive(&full_bar[stage]);
+            }
+            if (++stage == S) { stage = 0; phase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u));
+    }
+}
+
+extern "C" int refil_tc_wgrad_supported(int M, int P, int Q) {
+    if (M < 32 || P < 4 || P % 4 != 0) return 0;
+    return (Q == 32 || Q == 64 || Q == 128) ? 1 : 0;
+}
+
+extern "C" int refil_tc_gemm_wgrad(const float* X, long long ldx, const float* relu_y, long long ldy,
+                                   const uint8_t* x_row_entity_mask, int na, int ne, int rows_per_copy,
+                                   const float* Y, long long ldyy, float* dW, long long lddw, float* db, int M, int P,
+                                   int Q, cudaStream_t stream) {
+    REFIL_CHECK_ARG(X && Y && dW, "tc_gemm_wgrad: null pointer");
+    REFIL_CHECK_ARG(refil_tc_wgrad_supported(M, P, Q), "tc_gemm_wgrad: unsupported shape M=%d P=%d Q=%d", M, P, Q);
+    REFIL_CHECK_ARG((ldx % 4) == 0 && (ldyy % 4) == 0 && (lddw % 4) == 0 && ((uintptr_t)X % 16) == 0 &&
+                    ((uintptr_t)Y % 16) == 0 && ((uintptr_t)dW % 16) == 0, "tc_gemm_wgrad: alignment");
+    REFIL_CHECK_ARG(!relu_y || ((ldy % 4) == 0 && ((uintptr_t)relu_y % 16) == 0), "tc_gemm_wgrad: relu_y alignment");
+    TcWArgs a{};
+    a.X = X; a.ldx = ldx; a.relu_y = relu_y; a.ldy = ldy;
+    a.x_rowmask = x_row_entity_mask; a.na = na > 0 ? na : 1; a.ne = ne; a.mper = rows_per_copy > 0 ? rows_per_copy : 1;
+    a.Y = Y; a.ldyy = ldyy; a.dW = dW; a.lddw = lddw; a.db = db;
+    a.M = M; a.P = P; a.Q = Q;
+    a.BQ = Q + 32;
+    a.p_tiles = refil_cdiv(P, 128);
+    const int chunks_total = refil_cdiv(M, 32);
+    int splits = refil_num_sms() / a.p_tiles;
+    if (splits < 1) splits = 1;
+    if (splits > chunks_total) splits = chunks_total;
+    a.chunks_per_split = refil_cdiv(chunks_total, splits);
+    a.splits = refil_cdiv(chunks_total, a.chunks_per_split);
+    const size_t stage_bytes = 2 * (size_t)32 * 128 * 4 + 2 * (size_t)32 * a.BQ * 4;
+    int stages = (int)((200 * 1024) / stage_bytes);
+    if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+    a.stages = stages;
+    // D=f32, A=B=tf32, A and B MN-major (bits 15, 16), N = BQ, M = 128
+    a.idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(a.BQ >> 3) << 17) |
+              ((uint32_t)(128 >> 4) << 24);
+    const size_t smem = stages * stage_bytes + 1024;
+    static size_t attr_smem = 0;
+    if (smem > attr_smem) {
+        cudaError_t e = cudaFuncSetAttribute(tc_gemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) {
+            refil_set_error("tc_gemm_wgrad: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
+            return REFIL_ERR_CUDA;
+        }
+        attr_smem = smem;
+    }
+    tc_gemm_wgrad_kernel<<<a.p_tiles * a.splits, TC_THREADS, smem, stream>>>(a);
+    REFIL_CHECK_LAUNCH("tc_gemm_wgrad");
+    return REFIL_OK;
+}

@@ -125,6 +125,10 @@ def linear_bwd_weight(dC, A, dW, db, relu_y=None, row_mask=None):
     M, N = dC.shape
     K = A.shape[1]
     em, na, ne, mper = _rm(row_mask)
+    if USE_TENSOR_CORES and M >= TC_MIN_ROWS and _lib.load().refil_tc_wgrad_supported(M, N, K) != 0:
+        _call("tc_gemm_wgrad", _p(dC, F32), N, _p(relu_y, F32), N, em, na, ne, mper, _p(A, F32), K, _p(dW, F32), K,
+              _p(db, F32), M, N, K)
+        return
     _call("linear_bwd_weight", _p(dC, F32), N, _p(relu_y, F32), N, em, na, ne, mper, _p(A, F32), K, _p(dW, F32), K,
           _p(db, F32), M, N, K)
 

@@ -300,3 +300,27 @@ def test_tc_gemm_3xtf32_backward_data(M, N, K):
     err = (dA.cpu().double() - ref).abs().max().item()
     scale = (gmat.abs() @ W.abs().double()).max().item()
     assert err <= 4e-6 * scale, (err, scale)
+
+
+@pytest.mark.parametrize("M,P,Q", [(5000, 384, 128), (777 * 4, 64, 128), (4096, 128, 128), (600, 192, 64), (40000, 32, 128),
+                                   (1000, 128, 32), (333 * 4, 20, 64)])
+def test_tc_wgrad_3xtf32(M, P, Q):
+    """dW = (dC * relu'(y) * rowmask)^T A and db = colsum, on tcgen05 with MN-major operands, vs float64."""
+    from refil_b200 import _lib, ops
+    assert _lib.load().refil_tc_wgrad_supported(M, P, Q)
+    g = torch.Generator().manual_seed(M + P)
+    dC, A = torch.randn(M, P, generator=g), torch.randn(M, Q, generator=g)
+    y = torch.randn(M, P, generator=g)
+    na, ne = 4, 5
+    em = (torch.rand(M // na, ne, generator=g) < 0.3).to(torch.uint8)
+    gmat = dC.double() * (y > 0).double()
+    gmat = gmat.view(M // na, na, P).masked_fill(em[:, :na].bool().unsqueeze(-1), 0.0).view(M, P)
+    ref_w, ref_b = gmat.t() @ A.double(), gmat.sum(0)
+    dW, db = torch.ones(P, Q, device=DEV), torch.ones(P, device=DEV)          # accumulates into existing values
+    ops.linear_bwd_weight(dC.to(DEV), A.to(DEV), dW, db, relu_y=y.to(DEV), row_mask=(em.to(DEV), na, M))
+    torch.cuda.synchronize()
+    scale = (gmat.abs().t() @ A.abs().double()).max().item()
+    err = (dW.cpu().double() - 1.0 - ref_w).abs().max().item()
+    assert err <= 4e-6 * scale, ("dW", err, scale)
+    errb = (db.cpu().double() - 1.0 - ref_b).abs().max().item()
+    assert errb <= 4e-6 * gmat.abs().sum(0).max().item(), ("db", errb)
