@@ -96,6 +96,9 @@ int refil_embed_bwd_weight(const float* dC, int lddc, const float* relu_y, int l
                            cudaStream_t stream);
 int refil_gru_bwd_weight_hh(const float* dGH, const float* HS, int n_agents, int T, float* dWhh, float* dbhh, int M,
                             int r, cudaStream_t stream);
+/* padded network input [rows, padded_width] = [entities | onehot(last action) | 0] shared by fc1 of every network */
+int refil_pack_inputs(const float* entities, int ed, const int32_t* last_action, int n_actions, float* out,
+                      long long rows, int padded_width, cudaStream_t stream);
 int refil_last_action_index(const long long* actions, int32_t* la, int B, int T, int n_agents, int n_entities,
                             cudaStream_t stream);
 

@@ -49,6 +49,12 @@ class EntityMAC(BasicMAC):
         inp["entity_mask"] = batch["entity_mask"][:, t].contiguous().view(bs * ts, ne)
         if getattr(args, "gt_mask_avail", False):
             inp["gt_mask"] = batch["gt_mask"][:, t].contiguous().view(bs * ts, args.n_agents, ne)
+        inp["xin"] = None
+        if ops.USE_TENSOR_CORES and bs * ts * ne >= ops.TC_MIN_ROWS:
+            # [entities | onehot(last action) | 0] padded to a multiple of 32 columns, shared by fc1 of every network
+            kp = (self.agent.ein + 31) // 32 * 32
+            xin = torch.empty(bs * ts * ne, kp, dtype=torch.float32, device=ents.device)
+            inp["xin"] = ops.pack_inputs(inp["entities"], la, args.n_actions, xin)
         return inp
 
     def draw_groups(self, bs, ne, device):
@@ -118,7 +124,8 @@ class EntityMAC(BasicMAC):
             if h0.shape[0] == bs * na and C > 1:
                 h0 = h0.repeat(C, 1)
             h0 = h0.contiguous()
-        q, hs = self.agent.forward(inp["entities"], inp["last_action"], spec, bs, ts, h0=h0, train=train)
+        q, hs = self.agent.forward(inp["entities"], inp["last_action"], spec, bs, ts, h0=h0, train=train,
+                                   xin=inp.get("xin"))
         if self.agent.rnn:
             # entity_rnn_agent.py:64 returns the whole stack; only the last step is ever carried forward
             self.hidden_states = hs.view(C * bs, ts, na, self.agent.r)[:, -1].clone()

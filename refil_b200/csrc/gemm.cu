@@ -156,3 +156,28 @@ extern "C" int refil_last_action_index(const long long* actions, int32_t* la, in
     REFIL_CHECK_LAUNCH("last_action_index");
     return REFIL_OK;
 }
+
+// Materialise the padded network input once per step: out[r, :] = [entities[r, :ed] | onehot(last_action[r], A) | 0...]
+// (row width Kp = multiple of 32) so that fc1 of all ten networks (agent, 4 hypernets, and their targets) runs as a plain
+// K-major tensor-core GEMM over the same buffer (controllers/entity_controller.py:14-27, learners/q_learner.py:52-60).
+__global__ void pack_inputs_kernel(const float* __restrict__ ents, const int32_t* __restrict__ la, float* __restrict__ out,
+                                   long long R, int ed, int A, int Kp) {
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= R * Kp) return;
+    long long r = idx / Kp;
+    int c = (int)(idx - r * Kp);
+    float v = 0.f;
+    if (c < ed) v = __ldg(ents + r * ed + c);
+    else if (la && c < ed + A) v = (la[r] == c - ed) ? 1.f : 0.f;
+    out[idx] = v;
+}
+
+extern "C" int refil_pack_inputs(const float* entities, int ed, const int32_t* last_action, int n_actions, float* out,
+                                 long long rows, int padded_width, cudaStream_t stream) {
+    REFIL_CHECK_ARG(entities && out && rows > 0 && ed > 0, "pack_inputs: bad arguments");
+    REFIL_CHECK_ARG(padded_width >= ed + (last_action ? n_actions : 0), "pack_inputs: padded width %d too small", padded_width);
+    long long n = rows * padded_width;
+    pack_inputs_kernel<<<refil_cdiv(n, 256), 256, 0, stream>>>(entities, last_action, out, rows, ed, n_actions, padded_width);
+    REFIL_CHECK_LAUNCH("pack_inputs");
+    return REFIL_OK;
+}

@@ -525,70 +525,84 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_wgrad_kernel(TcWArgs a)
         // ===================== producers (two groups, alternate chunks): straight 128-byte row-segment copies ====
         const int grp = warp < 9 ? 0 : 1;
         const int pt = threadIdx.x - (grp ? 288 : 160);
-        // X tile: 32 rows x 32 chunks(16 B); thread -> fixed chunk cx of rows (pt >> 5) + 4 i
+        // X tile: 32 rows x 32 chunks(16 B); thread -> fixed chunk cx of rows rx0 + 4 i  (rx0 < 4, i < 8)
         const int cx = pt & 31, rx0 = pt >> 5;
         const int pcol = ptile * 128 + cx * 4;
         const bool x_in = pcol < a.P;                     // P is a multiple of 4 (checked on the host)
-        // Y tile: 32 rows x cpr chunks; thread -> fixed chunk cy of rows (pt / cpr) + (128 / cpr) i
+        const int offx0 = tc_mn_off(rx0, cx, xa), offx_step = xa * 128;            // row + 4 -> next k-atom
+        // Y tile: 32 rows x cpr chunks; thread -> fixed chunk cy of rows ry0 + ry_step i  (ry_step = 128 / cpr in {4,8,16})
         const int cpr = a.Q >> 2, ry0 = pt / cpr, cy = pt - ry0 * cpr, ry_step = 128 / cpr, ny = (32 * cpr) >> 7;
+        const int offy0 = tc_mn_off(ry0, cy, ya), offy_step = (ry_step >> 2) * ya * 128;
+        const float* px = a.X + pcol;
+        const float* pr = a.relu_y ? a.relu_y + pcol : nullptr;
+        const float* py = a.Y + cy * 4;
         int stage = 0;
         uint32_t phase = 0;
         for (int ch = 0; ch < n_chunks; ch++) {
             if ((ch & 1) == grp) {
                 const long long m0 = (long long)(c_begin + ch) * 32;
-                float4 vx[8], vy[16];
+                uint32_t valid = 0;
 #pragma unroll
                 for (int i = 0; i < 8; i++) {
                     const long long row = m0 + rx0 + 4 * i;
+                    if (x_in && row < a.M && !tc_row_masked(a.x_rowmask, a.na, a.ne, a.mper, row)) valid |= 1u << i;
+                }
+                // every global load of the chunk is issued before the first use
+                float4 vx[8], vr[8], vy[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
                     vx[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (x_in && row < a.M && !tc_row_masked(a.x_rowmask, a.na, a.ne, a.mper, row)) {
-                        vx[i] = __ldg(reinterpret_cast<const float4*>(a.X + row * a.ldx + pcol));
-                        if (a.relu_y) {
-                            const float4 y = __ldg(reinterpret_cast<const float4*>(a.relu_y + row * a.ldy + pcol));
-                            if (!(y.x > 0.f)) vx[i].x = 0.f;
-                            if (!(y.y > 0.f)) vx[i].y = 0.f;
-                            if (!(y.z > 0.f)) vx[i].z = 0.f;
-                            if (!(y.w > 0.f)) vx[i].w = 0.f;
-                        }
+                    if (valid & (1u << i)) vx[i] = __ldg(reinterpret_cast<const float4*>(px + (m0 + rx0 + 4 * i) * a.ldx));
+                }
+                if (pr) {
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        vr[i] = make_float4(1.f, 1.f, 1.f, 1.f);
+                        if (valid & (1u << i)) vr[i] = __ldg(reinterpret_cast<const float4*>(pr + (m0 + rx0 + 4 * i) * a.ldy));
                     }
                 }
 #pragma unroll
-                for (int i = 0; i < 16; i++) {
+                for (int i = 0; i < 8; i++) {
                     vy[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (i < ny) {
-                        const long long row = m0 + ry0 + ry_step * i;
-                        if (row < a.M) vy[i] = __ldg(reinterpret_cast<const float4*>(a.Y + row * a.ldyy + cy * 4));
+                    const long long row = m0 + ry0 + ry_step * i;
+                    if (i < ny && row < a.M) vy[i] = __ldg(reinterpret_cast<const float4*>(py + row * a.ldyy));
+                }
+                if (pr) {
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        if (!(vr[i].x > 0.f)) vx[i].x = 0.f;
+                        if (!(vr[i].y > 0.f)) vx[i].y = 0.f;
+                        if (!(vr[i].z > 0.f)) vx[i].z = 0.f;
+                        if (!(vr[i].w > 0.f)) vx[i].w = 0.f;
                     }
                 }
                 mbar_wait(&empty_bar[stage], phase ^ 1);
-                float* xhi = reinterpret_cast<float*>(smem + (size_t)stage * stage_bytes);
+                float* xhi = reinterpret_cast<float*>(smem + (size_t)stage * stage_bytes) + offx0;
                 float* xlo = xhi + 32 * 128;
-                float* yhi = xhi + 2 * 32 * 128;
+                float* yhi = reinterpret_cast<float*>(smem + (size_t)stage * stage_bytes) + 2 * 32 * 128 + offy0;
                 float* ylo = yhi + 32 * BQ;
 #pragma unroll
                 for (int i = 0; i < 8; i++) {
-                    const int off = tc_mn_off(rx0 + 4 * i, cx, xa);
                     float4 h, l;
                     h.x = __uint_as_float(__float_as_uint(vx[i].x) & 0xffffe000u);
                     h.y = __uint_as_float(__float_as_uint(vx[i].y) & 0xffffe000u);
                     h.z = __uint_as_float(__float_as_uint(vx[i].z) & 0xffffe000u);
                     h.w = __uint_as_float(__float_as_uint(vx[i].w) & 0xffffe000u);
                     l.x = vx[i].x - h.x; l.y = vx[i].y - h.y; l.z = vx[i].z - h.z; l.w = vx[i].w - h.w;
-                    *reinterpret_cast<float4*>(xhi + off) = h;
-                    *reinterpret_cast<float4*>(xlo + off) = l;
+                    *reinterpret_cast<float4*>(xhi + i * offx_step) = h;
+                    *reinterpret_cast<float4*>(xlo + i * offx_step) = l;
                 }
 #pragma unroll
-                for (int i = 0; i < 16; i++) {
+                for (int i = 0; i < 8; i++) {
                     if (i < ny) {
-                        const int off = tc_mn_off(ry0 + ry_step * i, cy, ya);
                         float4 h, l;
                         h.x = __uint_as_float(__float_as_uint(vy[i].x) & 0xffffe000u);
                         h.y = __uint_as_float(__float_as_uint(vy[i].y) & 0xffffe000u);
                         h.z = __uint_as_float(__float_as_uint(vy[i].z) & 0xffffe000u);
                         h.w = __uint_as_float(__float_as_uint(vy[i].w) & 0xffffe000u);
                         l.x = vy[i].x - h.x; l.y = vy[i].y - h.y; l.z = vy[i].z - h.z; l.w = vy[i].w - h.w;
-                        *reinterpret_cast<float4*>(yhi + off) = h;
-                        *reinterpret_cast<float4*>(ylo + off) = l;
+                        *reinterpret_cast<float4*>(yhi + i * offy_step) = h;
+                        *reinterpret_cast<float4*>(ylo + i * offy_step) = l;
                     }
                 }
                 fence_async_smem();

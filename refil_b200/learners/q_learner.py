@@ -99,8 +99,8 @@ class QLearner:
         ents, la, em = inp["entities"], inp["last_action"], inp["entity_mask"]
         qtot, qtot_im = self.mixer.forward(chosen[0], chosen[1] if self.imagine else None,
                                            chosen[2] if self.imagine else None, ents, la, em, T,
-                                           imagine_masks=mix if self.imagine else None)
-        tgt_tot, _ = self.target_mixer.forward(tgt_max, None, None, ents, la, em, T)
+                                           imagine_masks=mix if self.imagine else None, xin=inp.get("xin"))
+        tgt_tot, _ = self.target_mixer.forward(tgt_max, None, None, ents, la, em, T, xin=inp.get("xin"))
         # targets, TD errors, masked losses as sums (q_learner.py:157-172)
         self.stats64.zero_()
         g_plain = ws.get("g_plain", (N,))

@@ -55,13 +55,19 @@ class AttnTrunk:
         init_linear_(gen, p[pre + "attn.in_trans.weight"])
         init_linear_(gen, p[pre + "attn.out_trans.weight"], p[pre + "attn.out_trans.bias"])
 
-    def forward(self, ents, la, masks, T, relu_out=False):
-        """ents [N, ne, ed] f32, la [N, ne] i32 or None -> x2 [C*N*na, d]"""
+    def forward(self, ents, la, masks, T, relu_out=False, xin=None):
+        """ents [N, ne, ed] f32, la [N, ne] i32 or None -> x2 [C*N*na, d].
+        xin: optional packed input [N*ne, Kp] (ops.pack_inputs) -> fc1 runs on the tensor cores with a zero-padded weight."""
         p, pre, ws, tag = self.s.p, self.pre, self.ws, self.tag
         N, ne = ents.shape[0], ents.shape[1]
         C, d, na = masks.C, self.d, self.na
         x1 = ws.get(tag + ".x1", (N * ne, d))
-        ops.embed_fwd(ents, la, self.A, p[pre + "fc1.weight"], p[pre + "fc1.bias"], x1, relu=True)
+        if xin is not None:
+            w1p = ws.get(tag + ".w1p", (d, xin.shape[1]), zero=True)
+            w1p[:, :self.ein].copy_(p[pre + "fc1.weight"])
+            ops.linear_fwd(xin, w1p, p[pre + "fc1.bias"], x1, relu=True)
+        else:
+            ops.embed_fwd(ents, la, self.A, p[pre + "fc1.weight"], p[pre + "fc1.bias"], x1, relu=True)
         qkv = ws.get(tag + ".qkv", (N * ne, 3 * d))
         ops.linear_fwd(x1, p[pre + "attn.in_trans.weight"], None, qkv)
         att = ws.get(tag + ".att", (C * N * na, d))
@@ -70,12 +76,12 @@ class AttnTrunk:
         self.row_mask = (masks.entity_mask, na, N * na) if masks.entity_mask is not None else None
         ops.linear_fwd(att, p[pre + "attn.out_trans.weight"], p[pre + "attn.out_trans.bias"], x2, relu=relu_out,
                        row_mask=self.row_mask)
-        self.saved = (ents, la, masks, T, relu_out, x1, qkv, att, x2, N, ne)
+        self.saved = (ents, la, masks, T, relu_out, x1, qkv, att, x2, N, ne, xin)
         return x2
 
     def backward(self, dx2):
         p, g, pre, ws = self.s.p, self.s.g, self.pre, self.ws
-        ents, la, masks, T, relu_out, x1, qkv, att, x2, N, ne = self.saved
+        ents, la, masks, T, relu_out, x1, qkv, att, x2, N, ne, xin = self.saved
         C, d, na = masks.C, self.d, self.na
         relu_y = x2 if relu_out else None
         ops.linear_bwd_weight(dx2, att, g[pre + "attn.out_trans.weight"], g[pre + "attn.out_trans.bias"],
@@ -87,7 +93,12 @@ class AttnTrunk:
         ops.linear_bwd_weight(dqkv, x1, g[pre + "attn.in_trans.weight"], None)
         dx1 = ws.get("scratch.dx1", (N * ne, d))
         ops.linear_bwd_data(dqkv, p[pre + "attn.in_trans.weight"], dx1)
-        ops.embed_bwd_weight(dx1, x1, ents, la, self.A, g[pre + "fc1.weight"], g[pre + "fc1.bias"])
+        if xin is not None:
+            dw1p = ws.get("scratch.dw1p", (d, xin.shape[1]), zero=True)
+            ops.linear_bwd_weight(dx1, xin, dw1p, g[pre + "fc1.bias"], relu_y=x1)
+            g[pre + "fc1.weight"].add_(dw1p[:, :self.ein])
+        else:
+            ops.embed_bwd_weight(dx1, x1, ents, la, self.A, g[pre + "fc1.weight"], g[pre + "fc1.bias"])
 
 
 class EntityAttnAgent:
@@ -152,13 +163,13 @@ class EntityAttnAgent:
         return self
 
     # ---------------------------------------------------------------------------------------------------------
-    def forward(self, ents, la, masks, B, T, h0=None, train=False):
+    def forward(self, ents, la, masks, B, T, h0=None, train=False, xin=None):
         """ents [B*T, ne, ed]; masks: MaskSpec (C copies); h0 [C*B*na, r] or None (zeros).
         Returns q [C, B*T, na, A] and the hidden-state stack hs [C*B*T*na, r] (rnn) / x2 (ff)."""
         p, ws, tag = self.store.p, self.ws, self.tag
         N, C, na = B * T, masks.C, self.na
         R = C * N * na
-        x2 = self.trunk.forward(ents, la if self.one_hot_la else None, masks, T, relu_out=not self.rnn)
+        x2 = self.trunk.forward(ents, la if self.one_hot_la else None, masks, T, relu_out=not self.rnn, xin=xin)
         rm = self.trunk.row_mask
         q = ws.get(tag + ".q", (R, self.A))
         if self.rnn:
@@ -221,9 +232,9 @@ class AttnHyperNet:
         self.trunk.init(gen)
         init_linear_(gen, self.s.p[self.pre + "fc2.weight"], self.s.p[self.pre + "fc2.bias"])
 
-    def forward(self, ents, la, masks, T):
+    def forward(self, ents, la, masks, T, xin=None):
         p, pre = self.s.p, self.pre
-        x2 = self.trunk.forward(ents, la, masks, T)
+        x2 = self.trunk.forward(ents, la, masks, T, xin=xin)
         x3 = self.ws.get(self.tag + ".x3", (x2.shape[0], self.me))
         ops.linear_fwd(x2, p[pre + "fc2.weight"], p[pre + "fc2.bias"], x3, row_mask=self.trunk.row_mask)
         self.x2 = x2
@@ -284,7 +295,7 @@ class Mixer:
     def eval(self):
         return self
 
-    def forward(self, q, qW, qI, ents, la, entity_mask, T, imagine_masks=None):
+    def forward(self, q, qW, qI, ents, la, entity_mask, T, imagine_masks=None, xin=None):
         """q [N, na] (+ qW, qI when imagine); ents [N, ne, ed]; entity_mask [N, ne].
         imagine_masks: (copy_W, copy_I) MaskSpec-style copy tuples + group bits, or None.
         Returns (q_tot [N], q_tot_im [N] or None)."""
@@ -302,7 +313,7 @@ class Mixer:
                     m = MaskSpec([default] + list(copies), gbits, entity_mask)
                 else:
                     m = MaskSpec([default], None, entity_mask)
-                outs[h] = net.forward(ents, la, m, T)
+                outs[h] = net.forward(ents, la, m, T, xin=xin)
         w1 = outs.get("hyper_w_1.")
         self.saved = (q, qW, qI, outs, N, imagine)
         ops.mixer_fwd(self.kind, w1, outs.get("hyper_b_1."), outs.get("hyper_w_final."), outs.get("V."), q, qW, qI,

@@ -144,6 +144,13 @@ def gru_bwd_weight_hh(dGH, HS, n_agents, T, dWhh, dbhh):
     _call("gru_bwd_weight_hh", _p(dGH, F32), _p(HS, F32), n_agents, T, _p(dWhh, F32), _p(dbhh, F32), M, r)
 
 
+def pack_inputs(entities, last_action, n_actions, out):
+    rows = entities.numel() // entities.shape[-1]
+    _call("pack_inputs", _p(entities, F32), entities.shape[-1], _p(last_action, I32), n_actions, _p(out, F32), rows,
+          out.shape[-1])
+    return out
+
+
 def last_action_index(actions, out, n_entities):
     B, T, na = actions.shape[0], actions.shape[1], actions.shape[2]
     _call("last_action_index", _p(actions, I64), _p(out, I32), B, T, na, n_entities)

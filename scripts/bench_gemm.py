@@ -38,3 +38,19 @@ for name, M, N, K in shapes:
     print("%-14s M=%6d N=%3d K=%3d | fwd simt %.3f ms (%.1f TF)  tc %.3f ms (%.1f TF, %.0f GB/s) | bwd-data simt %.3f  tc %.3f ms (%.1f TF)" % (
         name, M, N, K, res[("fwd", False)], fl / res[("fwd", False)] / 1e9, res[("fwd", True)], fl / res[("fwd", True)] / 1e9,
         byts / res[("fwd", True)] / 1e6, res[("bwd", False)], res[("bwd", True)], fl / res[("bwd", True)] / 1e9))
+
+print("--- weight gradient dW[P,Q] = dC[M,P]^T A[M,Q] (+db) ---")
+for name, M, P, Q in [("in_trans", 184320, 384, 128), ("out_trans C=3", 184320, 128, 128), ("fc1 (packed)", 184320, 128, 64),
+                      ("gi", 184320, 192, 64), ("fc2 hyper", 61440, 32, 128)]:
+    if only and only not in name:
+        continue
+    dC, A, y = torch.randn(M, P, device=DEV), torch.randn(M, Q, device=DEV), torch.randn(M, P, device=DEV)
+    dW, db = torch.zeros(P, Q, device=DEV), torch.zeros(P, device=DEV)
+    res = {}
+    for tc in (False, True):
+        ops.USE_TENSOR_CORES = tc
+        res[tc] = timeit(lambda: ops.linear_bwd_weight(dC, A, dW, db))
+        res[(tc, "relu")] = timeit(lambda: ops.linear_bwd_weight(dC, A, dW, db, relu_y=y))
+    byts = 4.0 * (M * P + M * Q)
+    print("%-14s M=%6d P=%3d Q=%3d | simt %.3f ms  tc %.3f ms (%.0f GB/s) | with relu': simt %.3f  tc %.3f ms" % (
+        name, M, P, Q, res[False], res[True], byts / res[True] / 1e6, res[(False, "relu")], res[(True, "relu")]))
