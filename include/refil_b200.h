@@ -142,8 +142,8 @@ int refil_gru_scan_bwd(const float* dHS, const float* gates, const float* HS, co
 
 /* ---- mixers: mixers/flex_qmix.py:79-121 (flex), :136-172 (lin_flex), vdn.py:9-10 ------------------------------ */
 int refil_mixer_fwd(int kind, const float* W1, const float* B1, const float* WF, const float* V, const float* q,
-                    const float* qW, const float* qI, float* qtot, float* qtot_im, int N, int n_agents,
-                    int mixing_embed, int w1_copies, int imagine, int softmax_weights, int tanh_nonlin,
+                    const float* qW, const float* qI, float* qtot, float* qtot_im, float* ingroup_out, int N,
+                    int n_agents, int mixing_embed, int w1_copies, int imagine, int softmax_weights, int tanh_nonlin,
                     cudaStream_t stream);
 int refil_mixer_bwd(int kind, const float* W1, const float* B1, const float* WF, const float* V, const float* q,
                     const float* qW, const float* qI, const float* g_plain, const float* g_im, float* dW1, float* dB1,

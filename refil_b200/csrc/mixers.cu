@@ -24,6 +24,7 @@ struct MixArgs {
     const float *W1, *B1, *WF, *V;
     const float *q, *qW, *qI;
     float *qtot, *qtot_im;
+    float* ingroup;   // optional [N]: sum of the first na imagine mixing weights (flex_qmix.py:167-171, logging only)
     // backward
     const float *g_plain, *g_im;  // dL/dq_tot, dL/dq_tot_im  [N]
     float *dW1, *dB1, *dWF, *dV;  // same shapes as the inputs
@@ -213,6 +214,10 @@ __global__ void __launch_bounds__(128) lin_mix_kernel(MixArgs a, int backward) {
         if (!backward) {
             const float y = warp_sum(qv * w) + v;
             if (lane == 0) (comb ? a.qtot_im : a.qtot)[n] = y;
+            if (comb && a.ingroup) {
+                const float ing = warp_sum(lane < na ? w : 0.f);
+                if (lane == 0) a.ingroup[n] = ing;
+            }
         } else {
             const float g = comb ? a.g_im[n] : a.g_plain[n];
             dv += g;
@@ -284,16 +289,18 @@ static int mix_check(const char* name, int kind, const MixArgs& a) {
 }
 
 extern "C" int refil_mixer_fwd(int kind, const float* W1, const float* B1, const float* WF, const float* V,
-                               const float* q, const float* qW, const float* qI, float* qtot, float* qtot_im, int N,
-                               int n_agents, int mixing_embed, int w1_copies, int imagine, int softmax_weights,
-                               int tanh_nonlin, cudaStream_t stream) {
+                               const float* q, const float* qW, const float* qI, float* qtot, float* qtot_im,
+                               float* ingroup_out, int N, int n_agents, int mixing_embed, int w1_copies, int imagine,
+                               int softmax_weights, int tanh_nonlin, cudaStream_t stream) {
     MixArgs a{};
     a.W1 = W1; a.B1 = B1; a.WF = WF; a.V = V; a.q = q; a.qW = qW; a.qI = qI; a.qtot = qtot; a.qtot_im = qtot_im;
+    a.ingroup = ingroup_out;
     a.N = N; a.na = n_agents; a.me = mixing_embed; a.Cw = w1_copies; a.imagine = imagine;
     a.softmax_w = softmax_weights; a.tanh_nl = tanh_nonlin;
     int rc = mix_check("mixer_fwd", kind, a);
     if (rc) return rc;
     REFIL_CHECK_ARG(qtot && (!imagine || qtot_im), "mixer_fwd: output is null");
+    REFIL_CHECK_ARG(!ingroup_out || (kind == MIX_LIN && imagine), "mixer_fwd: ingroup_out needs the linear mixer in imagine mode");
     if (kind == MIX_FLEX) flex_mix_fwd_kernel<<<refil_cdiv(N, 4), 128, 0, stream>>>(a);
     else if (kind == MIX_LIN) lin_mix_kernel<<<refil_cdiv(N, 4), 128, 0, stream>>>(a, 0);
     else vdn_mix_kernel<<<refil_cdiv(N, 128), 128, 0, stream>>>(a, 0);

@@ -83,6 +83,17 @@ class QLearner:
         terminated = batch["terminated"].contiguous().view(N)
         filled = batch["filled"].contiguous().view(N)
 
+        will_log = t_env - self.log_stats_t >= args.learner_log_interval
+        gt_ingroup = None
+        log_gt = will_log and self.imagine and getattr(args, "test_gt_factors", False) and args.mixer == "lin_flex_qmix"
+        if log_gt:
+            # logging-only pass with the ground-truth factorisation (q_learner.py:98-105,138-147), same weights, no grads
+            self.mac.init_hidden(B)
+            q_gt, _, mix_gt, inp_gt = self.mac.forward(batch, None, imagine=True, use_gt_factors=True, ret_plan=True)
+            ch_gt = ops.gather_chosen(q_gt, actions, ws.get("chosen_gt", (3, N, na)), 3, N * na, A)
+            self.mixer.forward(ch_gt[0], ch_gt[1], ch_gt[2], inp_gt["entities"], inp_gt["last_action"],
+                               inp_gt["entity_mask"], T, imagine_masks=mix_gt, xin=inp_gt.get("xin"), ret_ingroup=True)
+            gt_ingroup = self.mixer.ingroup.view(B, T)[:, :-1].mean()
         # online agent on all T steps, 3 mask copies when imagining (q_learner.py:79-109)
         self.mac.init_hidden(B)
         q_all, spec, mix, inp = self.mac.forward(batch, None, imagine=self.imagine,
@@ -99,7 +110,9 @@ class QLearner:
         ents, la, em = inp["entities"], inp["last_action"], inp["entity_mask"]
         qtot, qtot_im = self.mixer.forward(chosen[0], chosen[1] if self.imagine else None,
                                            chosen[2] if self.imagine else None, ents, la, em, T,
-                                           imagine_masks=mix if self.imagine else None, xin=inp.get("xin"))
+                                           imagine_masks=mix if self.imagine else None, xin=inp.get("xin"),
+                                           ret_ingroup=log_gt)
+        ingroup = self.mixer.ingroup.view(B, T)[:, :-1].mean() if log_gt else None
         tgt_tot, _ = self.target_mixer.forward(tgt_max, None, None, ents, la, em, T, xin=inp.get("xin"))
         # targets, TD errors, masked losses as sums (q_learner.py:157-172)
         self.stats64.zero_()
@@ -127,7 +140,7 @@ class QLearner:
             self._update_targets()
             self.last_target_update_episode = episode_num
 
-        if t_env - self.log_stats_t >= args.learner_log_interval:
+        if will_log:
             st = self.gradbuf[self.n_params:].double().cpu()      # the only host sync of the step
             m = float(st[0])
             td, td_im = float(st[1]) / m, float(st[2]) / m
@@ -135,6 +148,9 @@ class QLearner:
             self.logger.log_stat("loss", loss, t_env)
             if self.imagine:
                 self.logger.log_stat("im_loss", td_im, t_env)
+            if log_gt:
+                self.logger.log_stat("ingroup_prop", float(ingroup.item()), t_env)
+                self.logger.log_stat("gt_ingroup_prop", float(gt_ingroup.item()), t_env)
             self.logger.log_stat("grad_norm", float(self.grad_norm.item()), t_env)
             self.logger.log_stat("td_error_abs", float(st[3]) / m, t_env)
             self.logger.log_stat("q_taken_mean", float(st[4]) / (m * na), t_env)

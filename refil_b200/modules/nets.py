@@ -295,7 +295,7 @@ class Mixer:
     def eval(self):
         return self
 
-    def forward(self, q, qW, qI, ents, la, entity_mask, T, imagine_masks=None, xin=None):
+    def forward(self, q, qW, qI, ents, la, entity_mask, T, imagine_masks=None, xin=None, ret_ingroup=False):
         """q [N, na] (+ qW, qI when imagine); ents [N, ne, ed]; entity_mask [N, ne].
         imagine_masks: (copy_W, copy_I) MaskSpec-style copy tuples + group bits, or None.
         Returns (q_tot [N], q_tot_im [N] or None)."""
@@ -316,8 +316,10 @@ class Mixer:
                 outs[h] = net.forward(ents, la, m, T, xin=xin)
         w1 = outs.get("hyper_w_1.")
         self.saved = (q, qW, qI, outs, N, imagine)
+        self.ingroup = ws.get(tag + ".ingroup", (N,)) if (ret_ingroup and imagine and self.kind == 1) else None
         ops.mixer_fwd(self.kind, w1, outs.get("hyper_b_1."), outs.get("hyper_w_final."), outs.get("V."), q, qW, qI,
-                      qtot, qtot_im, N, self.na, self.me, 3 if imagine else 1, imagine, self.softmax_w, self.tanh_nl)
+                      qtot, qtot_im, N, self.na, self.me, 3 if imagine else 1, imagine, self.softmax_w, self.tanh_nl,
+                      ingroup=self.ingroup)
         return qtot, qtot_im
 
     def backward(self, g_plain, g_im):

@@ -196,9 +196,11 @@ def gru_scan_bwd(dHS, gates, HS, h0, Whh, dGI, dGH, n_seq, T, na):
 
 
 # ---------------------------------------------------------------------------------------------------- mixers / TD
-def mixer_fwd(kind, W1, B1, WF, V, q, qW, qI, qtot, qtot_im, N, na, me, w1_copies, imagine, softmax_w, tanh_nl):
+def mixer_fwd(kind, W1, B1, WF, V, q, qW, qI, qtot, qtot_im, N, na, me, w1_copies, imagine, softmax_w, tanh_nl,
+              ingroup=None):
     _call("mixer_fwd", kind, _p(W1, F32), _p(B1, F32), _p(WF, F32), _p(V, F32), _p(q, F32), _p(qW, F32), _p(qI, F32),
-          _p(qtot, F32), _p(qtot_im, F32), N, na, me, w1_copies, int(imagine), int(softmax_w), int(tanh_nl))
+          _p(qtot, F32), _p(qtot_im, F32), _p(ingroup, F32), N, na, me, w1_copies, int(imagine), int(softmax_w),
+          int(tanh_nl))
 
 
 def mixer_bwd(kind, W1, B1, WF, V, q, qW, qI, g_plain, g_im, dW1, dB1, dWF, dV, dq, dqW, dqI, N, na, me, w1_copies,
