@@ -189,7 +189,10 @@ def run_ours(a):
     torch.cuda.set_device(local)
     dev = "cuda:%d" % local
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device(dev))
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the single JSON line
+        from refil_b200 import parallel
+        parallel.init_distributed(backend="nccl", device=dev)
     alg, B, T, na, ne, ed, A, _ = WORKLOADS[a.workload]
     if a.batch:
         B = a.batch

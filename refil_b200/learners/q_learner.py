@@ -11,9 +11,7 @@ Arithmetic follows q_learner.py:66-182; the schedule differs from the reference 
 import os
 
 import torch
-import torch.distributed as dist
-
-from .. import ops
+from .. import ops, parallel
 from ..modules.nets import Mixer
 from ..modules.params import Workspace
 
@@ -127,8 +125,7 @@ class QLearner:
         self.mac.agent.backward(dQ)
         # one all-reduce of [grads | stats], then normalise + clip + RMSprop (q_learner.py:177-178)
         ops.pack_stats(self.stats64, self.gradbuf[self.n_params:], N_STATS)
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(self.gradbuf)
+        parallel.all_reduce_sum_(self.gradbuf)
         self.sumsq.zero_()
         ops.grad_sumsq(self.gradbuf, self.n_params, self.sumsq)
         ops.clip_rmsprop_step(self.flat, self.gradbuf, self.square_avg, self.n_params,
