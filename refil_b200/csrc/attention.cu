@@ -20,10 +20,12 @@
 //   part I (mode&3 == 2): masked iff    i, j are in the same random group and both present at t = 0
 // A row whose entities are all masked yields zeros (attention.py:58-60).
 //
-// Work decomposition: one CTA per (b, t); warp w owns head h = w (+ k*nwarps).  Phase A maps lanes to
-// entities j (logits, warp-shuffle softmax), phase B maps lanes to the head feature k (weighted sum of V).
-// The QKV tile (ne x 3d floats) is staged once in shared memory with rows padded by 4 floats so the
-// 128-bit row reads of phase A are conflict-free.
+// Work decomposition: every WARP is an independent persistent worker that walks (b, t) units.  The K|V rows of a unit
+// (ne x 2d floats) are staged in the warp's shared-memory tile by TMA bulk copies (cp.async.bulk + mbarrier); Q rows are
+// read straight from global into registers.  Lane = (agent i, head h): each thread owns one attention row, so logits,
+// the masked softmax and the weighted sum over V never leave its registers (no shuffles, no shared-memory round trips);
+// the masks are resolved once per row with warp ballots (lane = entity j).  Threads of different heads read K/V chunks
+// in a head-rotated order so that the four distinct broadcast addresses of a warp load hit different banks.
 #include "common.cuh"
 
 #define ATT_THREADS 128
@@ -58,17 +60,9 @@ __device__ __forceinline__ bool att_masked(const AttnArgs& a, int c, int n, int 
     return m;
 }
 
-// stage the [ne, 3d] tile of unit n into smem rows of stride ld (floats)
-__device__ __forceinline__ void att_load_tile(float* tile, const float* __restrict__ src, int ne, int w, int ld) {
-    const int n4 = w >> 2;
-    for (int f = threadIdx.x; f < ne * n4; f += ATT_THREADS) {
-        int r = f / n4, c4 = f - r * n4;
-        float4 v = __ldg(reinterpret_cast<const float4*>(src + (size_t)r * w) + c4);
-        *reinterpret_cast<float4*>(tile + r * ld + c4 * 4) = v;
-    }
-}
 
-// ---- TMA (bulk async copy) staging of one (b, t) unit: ne row copies of 3d floats into padded smem rows ----------
+#define ATT_MAX_WARPS 8
+
 __device__ __forceinline__ uint32_t att_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void att_mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(att_smem_u32(bar)), "r"(count));
@@ -85,10 +79,12 @@ __device__ __forceinline__ void att_mbar_wait(uint64_t* bar, uint32_t parity) {
             : "memory");
     } while (!done);
 }
-// called by one full warp: lane 0 arms the barrier with the byte count, lanes < rows issue one row copy each
-__device__ __forceinline__ void att_tma_load_rows(float* tile, const float* src, int rows, int w, int ld, uint64_t* bar,
-                                                  int lane) {
+// one full warp: lane 0 arms the barrier with the byte count, lanes < rows issue one bulk row copy each (TMA, 1-D)
+__device__ __forceinline__ void att_tma_load_rows(float* tile, const float* src, long long src_stride, int rows, int w,
+                                                  int ld, uint64_t* bar, int lane) {
     const uint32_t bytes = (uint32_t)w * 4u;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic accesses of the tile are ordered first
+    __syncwarp();
     if (lane == 0) {
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(att_smem_u32(bar)), "r"(bytes * (uint32_t)rows)
                      : "memory");
@@ -97,78 +93,54 @@ __device__ __forceinline__ void att_tma_load_rows(float* tile, const float* src,
     if (lane < rows) {
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                          att_smem_u32(tile + lane * ld)),
-                     "l"(src + (size_t)lane * w), "r"(bytes), "r"(att_smem_u32(bar))
+                     "l"(src + (size_t)lane * src_stride), "r"(bytes), "r"(att_smem_u32(bar))
                      : "memory");
     }
 }
 
-// mask bits of lane j for every query row i and copy c (bit i set = masked); the masks do not depend on the head
-__device__ __forceinline__ void att_mask_bits(const AttnArgs& a, int n, int lane, int g_j, int ina_j, int em_j,
-                                              uint32_t mb[ATT_MAX_COPIES]) {
+// mask words of attention row i (one per copy, bit j set = entity j masked or padding), built with ballots: lane = entity
+__device__ __forceinline__ void att_row_masks(const AttnArgs& a, int n, int lane, int ib, int ipp, int il, int g_j,
+                                              int ina_j, int em_j, uint32_t mb[ATT_MAX_COPIES]) {
 #pragma unroll
-    for (int c = 0; c < ATT_MAX_COPIES; c++) mb[c] = 0;
-    for (int i = 0; i < a.nq; i++) {
+    for (int c = 0; c < ATT_MAX_COPIES; c++) mb[c] = 0xffffffffu;
+    for (int r = 0; r < ipp; r++) {
+        const int i = ib + r;
+        if (i >= a.nq) break;
         const int g_i = __shfl_sync(0xffffffffu, g_j, i), ina_i = __shfl_sync(0xffffffffu, ina_j, i),
                   em_i = __shfl_sync(0xffffffffu, em_j, i);
 #pragma unroll
         for (int c = 0; c < ATT_MAX_COPIES; c++) {
             if (c < a.C) {
-                bool m = lane >= a.ne || att_masked(a, c, n, i, lane, g_i, g_j, ina_i, ina_j, em_i, em_j);
-                mb[c] |= (m ? 1u : 0u) << i;
+                const bool m = lane >= a.ne || att_masked(a, c, n, i, lane, g_i, g_j, ina_i, ina_j, em_i, em_j);
+                const uint32_t word = __ballot_sync(0xffffffffu, m);
+                if (il == r) mb[c] = word;
             }
         }
     }
 }
 
-// softmax of 8 query rows at once: lane = (row i = lane >> 2, quarter s = lane & 3), 8 logits per lane; rows whose
-// entities are all masked produce zeros (attention.py:58-60)
-__device__ __forceinline__ void att_softmax8(float* sl, int lane) {
-    float* row = sl + (lane >> 2) * 36 + (lane & 3) * 8;
-    float4 v0 = *reinterpret_cast<const float4*>(row), v1 = *reinterpret_cast<const float4*>(row + 4);
-    float m = fmaxf(fmaxf(fmaxf(v0.x, v0.y), fmaxf(v0.z, v0.w)), fmaxf(fmaxf(v1.x, v1.y), fmaxf(v1.z, v1.w)));
-    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
-    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
-    const float mm = (m == -INFINITY) ? 0.f : m;          // exp(-inf - 0) = 0 for masked entries
-    v0.x = __expf(v0.x - mm); v0.y = __expf(v0.y - mm); v0.z = __expf(v0.z - mm); v0.w = __expf(v0.w - mm);
-    v1.x = __expf(v1.x - mm); v1.y = __expf(v1.y - mm); v1.z = __expf(v1.z - mm); v1.w = __expf(v1.w - mm);
-    float sum = ((v0.x + v0.y) + (v0.z + v0.w)) + ((v1.x + v1.y) + (v1.z + v1.w));
-    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-    const float r = sum > 0.f ? 1.f / sum : 0.f;
-    v0.x *= r; v0.y *= r; v0.z *= r; v0.w *= r; v1.x *= r; v1.y *= r; v1.z *= r; v1.w *= r;
-    *reinterpret_cast<float4*>(row) = v0;
-    *reinterpret_cast<float4*>(row + 4) = v1;
-}
-
-// Persistent CTAs walk the (b, t) units; the QKV tile of the next unit is in flight (TMA bulk copies + mbarrier) while
-// the current one is processed.  Per head: phase A lanes = entities (Q.K dot products, 8 query rows per pass),
-// phase S lanes = (row, quarter) softmax of the 8 rows at once, phase B lanes = head features (weights x V).
-template <int HD>
-__global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(AttnArgs a) {
+template <int HD, int NEB>
+__global__ void __launch_bounds__(32 * ATT_MAX_WARPS) attn_fwd_kernel(AttnArgs a, int tile_floats, int warp_floats) {
     extern __shared__ __align__(16) float smem[];
-    const int d = a.d, ne = a.ne, nq = a.nq, ld = 3 * d + 4;
-    float* tiles = smem;                              // [2][ne][ld]
-    float* slog = tiles + 2 * ne * ld;                // [nwarps][8][36]
-    __shared__ uint64_t full_bar[2];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = ATT_THREADS / 32;
-    if (threadIdx.x == 0) {
-        att_mbar_init(&full_bar[0], 1);
-        att_mbar_init(&full_bar[1], 1);
+    constexpr int NCH = HD / 4;
+    const int d = a.d, ne = a.ne, nq = a.nq, H = a.H, ldk = 2 * d + 4;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
+    float* kv = smem + (size_t)warp * warp_floats;                       // [NEB][ldk]: K | V rows of the current unit
+    float* lgs = kv + tile_floats + lane;                                // [NEB][32]: my row of logits, lgs[j * 32]
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + (size_t)wpc * warp_floats) + warp;
+    if (lane == 0) {
+        att_mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    __syncthreads();
-    if (warp == 0 && (int)blockIdx.x < a.N)
-        att_tma_load_rows(tiles, a.qkv + (size_t)blockIdx.x * ne * 3 * d, ne, 3 * d, ld, &full_bar[0], lane);
+    for (int f = ne * ldk + lane; f < NEB * ldk; f += 32) kv[f] = 0.f;   // padding rows stay zero
+    __syncwarp();
+    const int ipp = 32 / H, h = lane % H, il = lane / H;
     const float inv_scale = 1.f / sqrtf((float)HD);
-    float* sl = slog + warp * (8 * 36);
-    int it = 0;
-    for (int n = blockIdx.x; n < a.N; n += gridDim.x, it++) {
-        const int st = it & 1;
-        const int n_next = n + gridDim.x;
-        if (warp == 0 && n_next < a.N)               // stage st^1 was released by the __syncthreads of the last unit
-            att_tma_load_rows(tiles + (st ^ 1) * ne * ld, a.qkv + (size_t)n_next * ne * 3 * d, ne, 3 * d, ld,
-                              &full_bar[st ^ 1], lane);
-        const int b = n / a.T;
+    const long long gw = (long long)blockIdx.x * wpc + warp, GW = (long long)gridDim.x * wpc;
+    uint32_t parity = 0;
+    for (long long n = gw; n < a.N; n += GW) {
+        att_tma_load_rows(kv, a.qkv + ((size_t)n * ne) * 3 * d + d, 3 * d, ne, 2 * d, ldk, bar, lane);
+        const int b = (int)(n / a.T);
         int g_j = 0, ina_j = 0, em_j = 0;
         if (lane < ne) {
             if (a.group_bits) g_j = a.group_bits[(size_t)b * ne + lane];
@@ -177,192 +149,284 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(AttnArgs a) {
                 em_j = a.entity_mask[(size_t)n * ne + lane];
             }
         }
-        uint32_t mb[ATT_MAX_COPIES];
-        att_mask_bits(a, n, lane, g_j, ina_j, em_j, mb);
-        att_mbar_wait(&full_bar[st], (it >> 1) & 1);
-        const float* tile = tiles + st * ne * ld;
-        for (int h = warp; h < a.H; h += nwarps) {
-            float kr[HD];
-            if (lane < ne) {
+        bool waited = false;
+        for (int ib = 0; ib < nq; ib += ipp) {
+            const int i = ib + il;
+            const bool active = i < nq;
+            uint32_t mb[ATT_MAX_COPIES];
+            att_row_masks(a, (int)n, lane, ib, ipp, il, g_j, ina_j, em_j, mb);
+            // my Q row, chunks in head-rotated order
+            float q[HD];
+            const float* qsrc = a.qkv + ((size_t)n * ne + (active ? i : 0)) * 3 * d + h * HD;
 #pragma unroll
-                for (int k = 0; k < HD; k += 4) {
-                    float4 v = *reinterpret_cast<const float4*>(tile + lane * ld + d + h * HD + k);
-                    kr[k] = v.x; kr[k + 1] = v.y; kr[k + 2] = v.z; kr[k + 3] = v.w;
-                }
-            } else {
-#pragma unroll
-                for (int k = 0; k < HD; k++) kr[k] = 0.f;
+            for (int kc = 0; kc < NCH; kc++) {
+                const float4 v = active ? __ldg(reinterpret_cast<const float4*>(qsrc + 4 * ((kc + h) & (NCH - 1))))
+                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+                q[4 * kc] = v.x; q[4 * kc + 1] = v.y; q[4 * kc + 2] = v.z; q[4 * kc + 3] = v.w;
             }
-            float vc[ATT_MAX_NE];
+            if (!waited) { att_mbar_wait(bar, parity); parity ^= 1; waited = true; }
+            const float* kbase = kv + h * HD;
+            float mx[ATT_MAX_COPIES] = {-INFINITY, -INFINITY, -INFINITY};
+#pragma unroll 4
+            for (int j = 0; j < NEB; j++) {
+                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-            for (int j = 0; j < ATT_MAX_NE; j++) vc[j] = (j < ne && lane < HD) ? tile[j * ld + 2 * d + h * HD + lane] : 0.f;
-            for (int ib = 0; ib < nq; ib += 8) {
-                float lg[8];
-#pragma unroll
-                for (int ii = 0; ii < 8; ii++) {
-                    float dot = 0.f;
-                    if (ib + ii < nq) {
-                        const float* qrow = tile + (ib + ii) * ld + h * HD;
-#pragma unroll
-                        for (int k = 0; k < HD; k += 4) {
-                            float4 q = *reinterpret_cast<const float4*>(qrow + k);
-                            dot = fmaf(q.x, kr[k], dot);
-                            dot = fmaf(q.y, kr[k + 1], dot);
-                            dot = fmaf(q.z, kr[k + 2], dot);
-                            dot = fmaf(q.w, kr[k + 3], dot);
-                        }
-                    }
-                    lg[ii] = dot * inv_scale;
+                for (int kc = 0; kc < NCH; kc++) {
+                    const float4 k4 = *reinterpret_cast<const float4*>(kbase + j * ldk + 4 * ((kc + h) & (NCH - 1)));
+                    s0 = fmaf(q[4 * kc], k4.x, s0);
+                    s1 = fmaf(q[4 * kc + 1], k4.y, s1);
+                    s2 = fmaf(q[4 * kc + 2], k4.z, s2);
+                    s3 = fmaf(q[4 * kc + 3], k4.w, s3);
                 }
-                for (int c = 0; c < a.C; c++) {
-                    const uint32_t bits = mb[c] >> ib;
+                const float lg = ((s0 + s1) + (s2 + s3)) * inv_scale;
+                lgs[j * 32] = lg;
 #pragma unroll
-                    for (int ii = 0; ii < 8; ii++) sl[ii * 36 + lane] = ((bits >> ii) & 1u) ? -INFINITY : lg[ii];
-                    __syncwarp();
-                    att_softmax8(sl, lane);
-                    __syncwarp();
-                    if (lane < HD) {
+                for (int c = 0; c < ATT_MAX_COPIES; c++)
+                    if (!((mb[c] >> j) & 1u)) mx[c] = fmaxf(mx[c], lg);
+            }
 #pragma unroll
-                        for (int ii = 0; ii < 8; ii++) {
-                            if (ib + ii < nq) {
-                                float acc = 0.f;
+            for (int c = 0; c < ATT_MAX_COPIES; c++) {
+                if (c < a.C) {
+                    const uint32_t bits = mb[c];
+                    const float m = mx[c];
+                    float acc[HD];
 #pragma unroll
-                                for (int j4 = 0; j4 < ATT_MAX_NE / 4; j4++) {
-                                    if (4 * j4 < ne) {
-                                        const float4 w4 = *reinterpret_cast<const float4*>(sl + ii * 36 + 4 * j4);
-                                        acc = fmaf(w4.x, vc[4 * j4], acc);
-                                        acc = fmaf(w4.y, vc[4 * j4 + 1], acc);
-                                        acc = fmaf(w4.z, vc[4 * j4 + 2], acc);
-                                        acc = fmaf(w4.w, vc[4 * j4 + 3], acc);
-                                    }
-                                }
-                                a.out[(((size_t)c * a.N + n) * nq + ib + ii) * d + h * HD + lane] = acc;
-                            }
+                    for (int k = 0; k < HD; k++) acc[k] = 0.f;
+                    float ssum = 0.f;
+#pragma unroll 4
+                    for (int j = 0; j < NEB; j++) {
+                        const float e = ((bits >> j) & 1u) ? 0.f : __expf(lgs[j * 32] - m);
+                        ssum += e;
+#pragma unroll
+                        for (int kc = 0; kc < NCH; kc++) {
+                            const float4 v4 = *reinterpret_cast<const float4*>(kbase + j * ldk + d + 4 * ((kc + h) & (NCH - 1)));
+                            acc[4 * kc] = fmaf(e, v4.x, acc[4 * kc]);
+                            acc[4 * kc + 1] = fmaf(e, v4.y, acc[4 * kc + 1]);
+                            acc[4 * kc + 2] = fmaf(e, v4.z, acc[4 * kc + 2]);
+                            acc[4 * kc + 3] = fmaf(e, v4.w, acc[4 * kc + 3]);
                         }
                     }
-                    __syncwarp();
+                    const float r = ssum > 0.f ? 1.f / ssum : 0.f;    // all-masked row -> zeros (attention.py:58-60)
+                    if (active) {
+                        float* dst = a.out + (((size_t)c * a.N + n) * nq + i) * d + h * HD;
+#pragma unroll
+                        for (int kc = 0; kc < NCH; kc++)
+                            *reinterpret_cast<float4*>(dst + 4 * ((kc + h) & (NCH - 1))) =
+                                make_float4(acc[4 * kc] * r, acc[4 * kc + 1] * r, acc[4 * kc + 2] * r, acc[4 * kc + 3] * r);
+                    }
                 }
             }
         }
-        __syncthreads();      // every warp is done with stage st before it is refilled two units later
+        __syncwarp();          // every lane is done with the tile before the next unit's copies land in it
     }
 }
 
-// Backward: dQKV[n] = d/dQKV sum_c <dOUT[c, n], attn_c(QKV[n])>, accumulated over the copies in registers / smem.
-template <int HD>
-__global__ void __launch_bounds__(ATT_THREADS) attn_bwd_kernel(AttnArgs a) {
+// Backward: dQKV[n] = d/dQKV sum_c <dOUT[c, n], attn_c(QKV[n])>.
+//   phase 1, lane = (agent i, head h): recompute the row softmax, dw_j = <dO_i, V_j>, dlogit_j = w_j (dw_j - sum_j' w_j' dw_j')
+//            / sqrt(hd); dQ_i accumulates in registers over the copies; w and dlogit go to the warp's smem scratch;
+//   phase 2, lane = (entity j, head h): dK_j = sum_{c,i} dlogit_ij Q_i, dV_j = sum_{c,i} w_ij dO_i (Q / dO rows come
+//            back through L1), written over the K|V tile, which is then streamed out as the K|V columns of dQKV.
+template <int HD, int NEB>
+__global__ void __launch_bounds__(32 * ATT_MAX_WARPS) attn_bwd_kernel(AttnArgs a, int tile_floats, int warp_floats) {
     extern __shared__ __align__(16) float smem[];
-    const int d = a.d, ne = a.ne, nq = a.nq, ld = 3 * d + 4, ldo = d + 4;
-    float* tile = smem;                         // [ne][ld]   QKV, overwritten in place by dQKV
-    float* sdo = tile + ne * ld;                // [C][nq][ldo]
-    float* sw = sdo + a.C * nq * ldo;           // [nwarps][32]
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = ATT_THREADS / 32;
-    const int n = blockIdx.x;
-    att_load_tile(tile, a.qkv + (size_t)n * ne * 3 * d, ne, 3 * d, ld);
-    for (int c = 0; c < a.C; c++)
-        att_load_tile(sdo + c * nq * ldo, a.dout + ((size_t)c * a.N + n) * nq * d, nq, d, ldo);
-    const int b = n / a.T;
-    int g_j = 0, ina_j = 0, em_j = 0;
-    if (lane < ne) {
-        if (a.group_bits) g_j = a.group_bits[(size_t)b * ne + lane];
-        if (a.entity_mask) {
-            ina_j = a.entity_mask[((size_t)b * a.T) * ne + lane];
-            em_j = a.entity_mask[(size_t)n * ne + lane];
-        }
+    constexpr int NCH = HD / 4;
+    const int d = a.d, ne = a.ne, nq = a.nq, H = a.H, ldk = 2 * d + 4;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
+    const int ipp = 32 / H, h = lane % H, il = lane / H;
+    const int nqp = (nq + ipp - 1) / ipp * ipp;                          // agent rows padded to whole passes
+    float* kv = smem + (size_t)warp * warp_floats;                       // [NEB][ldk]
+    const int sstr = H * nqp;                                            // scratch stride between entities j
+    float* sw = kv + tile_floats;                                        // [C][NEB][H][nqp]  softmax weights
+    float* sdl = sw + a.C * NEB * sstr;                                  // [C][NEB][H][nqp]  dw, then dlogits
+    float* lgs = sdl + a.C * NEB * sstr + lane;                          // [NEB][32]         my row of logits
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + (size_t)wpc * warp_floats) + warp;
+    if (lane == 0) {
+        att_mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    __syncthreads();
-    const float scale = sqrtf((float)HD), inv_scale = 1.f / scale;
-    float* myw = sw + warp * 32;
-    for (int h = warp; h < a.H; h += nwarps) {
-        float kr[HD], vr[HD], dk[HD], dv[HD];
-#pragma unroll
-        for (int k = 0; k < HD; k++) { kr[k] = 0.f; vr[k] = 0.f; dk[k] = 0.f; dv[k] = 0.f; }
+    __syncwarp();
+    const float inv_scale = 1.f / sqrtf((float)HD);
+    const long long gw = (long long)blockIdx.x * wpc + warp, GW = (long long)gridDim.x * wpc;
+    uint32_t parity = 0;
+    for (long long n = gw; n < a.N; n += GW) {
+        for (int f = ne * ldk + lane; f < NEB * ldk; f += 32) kv[f] = 0.f;   // padding rows (the tile is reused for dK|dV)
+        att_tma_load_rows(kv, a.qkv + ((size_t)n * ne) * 3 * d + d, 3 * d, ne, 2 * d, ldk, bar, lane);
+        const int b = (int)(n / a.T);
+        int g_j = 0, ina_j = 0, em_j = 0;
         if (lane < ne) {
-#pragma unroll
-            for (int k = 0; k < HD; k += 4) {
-                float4 v = *reinterpret_cast<const float4*>(tile + lane * ld + d + h * HD + k);
-                kr[k] = v.x; kr[k + 1] = v.y; kr[k + 2] = v.z; kr[k + 3] = v.w;
-                float4 u = *reinterpret_cast<const float4*>(tile + lane * ld + 2 * d + h * HD + k);
-                vr[k] = u.x; vr[k + 1] = u.y; vr[k + 2] = u.z; vr[k + 3] = u.w;
+            if (a.group_bits) g_j = a.group_bits[(size_t)b * ne + lane];
+            if (a.entity_mask) {
+                ina_j = a.entity_mask[((size_t)b * a.T) * ne + lane];
+                em_j = a.entity_mask[(size_t)n * ne + lane];
             }
         }
-        for (int i = 0; i < nq; i++) {
-            float qr[HD];
-            float dot = 0.f;
-#pragma unroll
-            for (int k = 0; k < HD; k += 4) {
-                float4 q = *reinterpret_cast<const float4*>(tile + i * ld + h * HD + k);
-                qr[k] = q.x; qr[k + 1] = q.y; qr[k + 2] = q.z; qr[k + 3] = q.w;
-                dot = fmaf(q.x, kr[k], dot);
-                dot = fmaf(q.y, kr[k + 1], dot);
-                dot = fmaf(q.z, kr[k + 2], dot);
-                dot = fmaf(q.w, kr[k + 3], dot);
+        // dQ of the non-query rows is zero
+        {
+            const int d4 = d >> 2;
+            for (int f = lane; f < (ne - nq) * d4; f += 32) {
+                const int r = nq + f / d4, c4 = f % d4;
+                *reinterpret_cast<float4*>(a.dqkv + ((size_t)n * ne + r) * 3 * d + 4 * c4) = make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            const float logit0 = dot / scale;
-            const int g_i = __shfl_sync(0xffffffffu, g_j, i), ina_i = __shfl_sync(0xffffffffu, ina_j, i),
-                      em_i = __shfl_sync(0xffffffffu, em_j, i);
-            float dq = 0.f;  // lane k: dQ[i, h*HD + k] summed over the copies
+        }
+        bool waited = false;
+        for (int ib = 0; ib < nq; ib += ipp) {
+            const int i = ib + il;                                       // < nqp
+            const bool active = i < nq;
+            uint32_t mb[ATT_MAX_COPIES];
+            att_row_masks(a, (int)n, lane, ib, ipp, il, g_j, ina_j, em_j, mb);
+            float q[HD];
+            const float* qsrc = a.qkv + ((size_t)n * ne + (active ? i : 0)) * 3 * d + h * HD;
+#pragma unroll
+            for (int kc = 0; kc < NCH; kc++) {
+                const float4 v = active ? __ldg(reinterpret_cast<const float4*>(qsrc + 4 * ((kc + h) & (NCH - 1))))
+                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+                q[4 * kc] = v.x; q[4 * kc + 1] = v.y; q[4 * kc + 2] = v.z; q[4 * kc + 3] = v.w;
+            }
+            if (!waited) { att_mbar_wait(bar, parity); parity ^= 1; waited = true; }
+            const float* kbase = kv + h * HD;
+            float mx[ATT_MAX_COPIES] = {-INFINITY, -INFINITY, -INFINITY};
+#pragma unroll 4
+            for (int j = 0; j < NEB; j++) {
+                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+                for (int kc = 0; kc < NCH; kc++) {
+                    const float4 k4 = *reinterpret_cast<const float4*>(kbase + j * ldk + 4 * ((kc + h) & (NCH - 1)));
+                    s0 = fmaf(q[4 * kc], k4.x, s0);
+                    s1 = fmaf(q[4 * kc + 1], k4.y, s1);
+                    s2 = fmaf(q[4 * kc + 2], k4.z, s2);
+                    s3 = fmaf(q[4 * kc + 3], k4.w, s3);
+                }
+                const float lg = ((s0 + s1) + (s2 + s3)) * inv_scale;
+                lgs[j * 32] = lg;
+#pragma unroll
+                for (int c = 0; c < ATT_MAX_COPIES; c++)
+                    if (!((mb[c] >> j) & 1u)) mx[c] = fmaxf(mx[c], lg);
+            }
+            float dq[HD];
+#pragma unroll
+            for (int k = 0; k < HD; k++) dq[k] = 0.f;
+#pragma unroll
+            for (int c = 0; c < ATT_MAX_COPIES; c++) {
+                if (c < a.C) {
+                    const uint32_t bits = mb[c];
+                    const float m = mx[c];
+                    float go[HD];                                      // my dO row of this copy, rotated like q
+                    const float* gsrc = a.dout + (((size_t)c * a.N + n) * nq + (active ? i : 0)) * d + h * HD;
+#pragma unroll
+                    for (int kc = 0; kc < NCH; kc++) {
+                        const float4 v = active ? __ldg(reinterpret_cast<const float4*>(gsrc + 4 * ((kc + h) & (NCH - 1))))
+                                                : make_float4(0.f, 0.f, 0.f, 0.f);
+                        go[4 * kc] = v.x; go[4 * kc + 1] = v.y; go[4 * kc + 2] = v.z; go[4 * kc + 3] = v.w;
+                    }
+                    float* swr = sw + ((size_t)c * NEB * H + h) * nqp + i;   // [j * sstr]
+                    float* sdr = sdl + ((size_t)c * NEB * H + h) * nqp + i;
+                    float ssum = 0.f;
+#pragma unroll 4
+                    for (int j = 0; j < NEB; j++) {
+                        const float e = ((bits >> j) & 1u) ? 0.f : __expf(lgs[j * 32] - m);
+                        ssum += e;
+                        swr[j * sstr] = e;
+                    }
+                    const float r = ssum > 0.f ? 1.f / ssum : 0.f;
+                    float t = 0.f;
+#pragma unroll 4
+                    for (int j = 0; j < NEB; j++) {
+                        const float w = swr[j * sstr] * r;
+                        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+                        for (int kc = 0; kc < NCH; kc++) {
+                            const float4 v4 = *reinterpret_cast<const float4*>(kbase + j * ldk + d + 4 * ((kc + h) & (NCH - 1)));
+                            s0 = fmaf(go[4 * kc], v4.x, s0);
+                            s1 = fmaf(go[4 * kc + 1], v4.y, s1);
+                            s2 = fmaf(go[4 * kc + 2], v4.z, s2);
+                            s3 = fmaf(go[4 * kc + 3], v4.w, s3);
+                        }
+                        const float dw = (s0 + s1) + (s2 + s3);
+                        swr[j * sstr] = w;
+                        sdr[j * sstr] = dw;
+                        t = fmaf(w, dw, t);
+                    }
+#pragma unroll 4
+                    for (int j = 0; j < NEB; j++) {
+                        const float dl = swr[j * sstr] * (sdr[j * sstr] - t) * inv_scale;
+                        sdr[j * sstr] = dl;
+#pragma unroll
+                        for (int kc = 0; kc < NCH; kc++) {
+                            const float4 k4 = *reinterpret_cast<const float4*>(kbase + j * ldk + 4 * ((kc + h) & (NCH - 1)));
+                            dq[4 * kc] = fmaf(dl, k4.x, dq[4 * kc]);
+                            dq[4 * kc + 1] = fmaf(dl, k4.y, dq[4 * kc + 1]);
+                            dq[4 * kc + 2] = fmaf(dl, k4.z, dq[4 * kc + 2]);
+                            dq[4 * kc + 3] = fmaf(dl, k4.w, dq[4 * kc + 3]);
+                        }
+                    }
+                }
+            }
+            if (active) {
+                float* dst = a.dqkv + ((size_t)n * ne + i) * 3 * d + h * HD;
+#pragma unroll
+                for (int kc = 0; kc < NCH; kc++)
+                    *reinterpret_cast<float4*>(dst + 4 * ((kc + h) & (NCH - 1))) =
+                        make_float4(dq[4 * kc], dq[4 * kc + 1], dq[4 * kc + 2], dq[4 * kc + 3]);
+            }
+        }
+        __syncwarp();          // scratch complete; nobody reads K / V any more
+        // ---- phase 2: lane = 4 features (head h2, chunk kc) of every entity row -----------------------------
+        // dK_j = sum_{c,i} dlogit_ij Q_i, dV_j = sum_{c,i} w_ij dO_i: the lane keeps its slice of the Q_i / dO_i rows of
+        // 8 agents in registers (coalesced global loads), sweeps the entities j with the scratch values broadcast from
+        // shared memory, and accumulates into the K|V tile (dead as K|V by now), which becomes dK|dV.
+        if (lane < (d >> 2)) {
+            const int h2 = lane / NCH, kc2 = lane - h2 * NCH;
+            bool first = true;
             for (int c = 0; c < a.C; c++) {
-                float logit = -INFINITY;
-                if (lane < ne && !att_masked(a, c, n, i, lane, g_i, g_j, ina_i, ina_j, em_i, em_j)) logit = logit0;
-                const float m = warp_max(logit);
-                const float p = (logit == -INFINITY) ? 0.f : expf(logit - m);
-                const float s = warp_sum(p);
-                const float w = (s > 0.f) ? p / s : 0.f;
-                const float* dor = sdo + (c * nq + i) * ldo + h * HD;
-                float dw = 0.f;
+                for (int i0 = 0; i0 < nq; i0 += 8) {
+                    float4 qs[8], gs[8];
 #pragma unroll
-                for (int k = 0; k < HD; k += 4) {
-                    float4 g = *reinterpret_cast<const float4*>(dor + k);
-                    dw = fmaf(g.x, vr[k], dw);
-                    dw = fmaf(g.y, vr[k + 1], dw);
-                    dw = fmaf(g.z, vr[k + 2], dw);
-                    dw = fmaf(g.w, vr[k + 3], dw);
-                    dv[k] = fmaf(w, g.x, dv[k]);
-                    dv[k + 1] = fmaf(w, g.y, dv[k + 1]);
-                    dv[k + 2] = fmaf(w, g.z, dv[k + 2]);
-                    dv[k + 3] = fmaf(w, g.w, dv[k + 3]);
-                }
-                const float tsum = warp_sum(w * dw);
-                const float dl = w * (dw - tsum) * inv_scale;
+                    for (int ii = 0; ii < 8; ii++) {
+                        const bool ok = i0 + ii < nq;
+                        qs[ii] = ok ? __ldg(reinterpret_cast<const float4*>(a.qkv + ((size_t)n * ne + i0 + ii) * 3 * d) + lane)
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+                        gs[ii] = ok ? __ldg(reinterpret_cast<const float4*>(a.dout + (((size_t)c * a.N + n) * nq + i0 + ii) * d) + lane)
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    const float* swb = sw + ((size_t)c * NEB * H + h2) * nqp + i0;
+                    const float* sdb = sdl + ((size_t)c * NEB * H + h2) * nqp + i0;
+#pragma unroll 2
+                    for (int j = 0; j < NEB; j++) {
+                        float4 dk = make_float4(0.f, 0.f, 0.f, 0.f), dv = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                for (int k = 0; k < HD; k++) dk[k] = fmaf(dl, qr[k], dk[k]);
-                myw[lane] = dl;
-                __syncwarp();
-                if (lane < HD) {
-                    for (int j = 0; j < ne; j++) dq = fmaf(myw[j], tile[j * ld + d + h * HD + lane], dq);
+                        for (int ii = 0; ii < 8; ii++) {
+                            const float dl = sdb[j * sstr + ii], wv = swb[j * sstr + ii];
+                            dk.x = fmaf(dl, qs[ii].x, dk.x); dk.y = fmaf(dl, qs[ii].y, dk.y);
+                            dk.z = fmaf(dl, qs[ii].z, dk.z); dk.w = fmaf(dl, qs[ii].w, dk.w);
+                            dv.x = fmaf(wv, gs[ii].x, dv.x); dv.y = fmaf(wv, gs[ii].y, dv.y);
+                            dv.z = fmaf(wv, gs[ii].z, dv.z); dv.w = fmaf(wv, gs[ii].w, dv.w);
+                        }
+                        float4* kd = reinterpret_cast<float4*>(kv + j * ldk + h2 * HD + 4 * kc2);
+                        float4* vd = reinterpret_cast<float4*>(kv + j * ldk + d + h2 * HD + 4 * kc2);
+                        if (!first) {
+                            const float4 k0 = *kd, v0 = *vd;
+                            dk.x += k0.x; dk.y += k0.y; dk.z += k0.z; dk.w += k0.w;
+                            dv.x += v0.x; dv.y += v0.y; dv.z += v0.z; dv.w += v0.w;
+                        }
+                        *kd = dk;
+                        *vd = dv;
+                    }
+                    first = false;
                 }
-                __syncwarp();
             }
-            // Q_i of this head is dead for this warp from here on: overwrite with dQ_i
-            if (lane < HD) tile[i * ld + h * HD + lane] = dq;
-            __syncwarp();
         }
-        // K/V of this head are dead for this warp: overwrite rows with dK / dV, zero the unused Q rows
         __syncwarp();
-        if (lane < ne) {
-#pragma unroll
-            for (int k = 0; k < HD; k += 4) {
-                *reinterpret_cast<float4*>(tile + lane * ld + d + h * HD + k) = make_float4(dk[k], dk[k + 1], dk[k + 2], dk[k + 3]);
-                *reinterpret_cast<float4*>(tile + lane * ld + 2 * d + h * HD + k) = make_float4(dv[k], dv[k + 1], dv[k + 2], dv[k + 3]);
-            }
-            if (lane >= nq) {
-#pragma unroll
-                for (int k = 0; k < HD; k += 4)
-                    *reinterpret_cast<float4*>(tile + lane * ld + h * HD + k) = make_float4(0.f, 0.f, 0.f, 0.f);
+        // stream the dK | dV tile out as columns d..3d of dQKV (coalesced 128-bit stores)
+        {
+            const int d2 = (2 * d) >> 2;
+            float* dst = a.dqkv + ((size_t)n * ne) * 3 * d + d;
+            for (int f = lane; f < ne * d2; f += 32) {
+                const int rr = f / d2, c4 = f - rr * d2;
+                const float4 v = *reinterpret_cast<const float4*>(kv + rr * ldk + 4 * c4);
+                *reinterpret_cast<float4*>(dst + (size_t)rr * 3 * d + 4 * c4) = v;
             }
         }
-    }
-    __syncthreads();
-    // coalesced write-back of the dQKV tile
-    {
-        const int w = 3 * d, n4 = w >> 2;
-        float* dst = a.dqkv + (size_t)n * ne * w;
-        for (int f = threadIdx.x; f < ne * n4; f += ATT_THREADS) {
-            int r = f / n4, c4 = f - r * n4;
-            float4 v = *reinterpret_cast<const float4*>(tile + r * ld + c4 * 4);
-            *(reinterpret_cast<float4*>(dst + (size_t)r * w) + c4) = v;
-        }
+        __syncwarp();
     }
 }
 
@@ -377,6 +441,8 @@ static int attn_fill(AttnArgs& a, const float* qkv, const uint8_t* m0, const uin
     REFIL_CHECK_ARG(H >= 1 && d % H == 0 && d % 4 == 0, "masked_attn: embed %d / heads %d", d, H);
     const int hd = d / H;
     REFIL_CHECK_ARG(hd == 8 || hd == 16 || hd == 32, "masked_attn: head dim %d not in {8,16,32}", hd);
+    REFIL_CHECK_ARG(H <= 32 && (32 % H) == 0, "masked_attn: n_heads %d must divide 32", H);
+    REFIL_CHECK_ARG(((uintptr_t)qkv % 16) == 0, "masked_attn: QKV must be 16-byte aligned");
     int modes[3] = {mode0, mode1, mode2};
     for (int c = 0; c < C; c++) {
         REFIL_CHECK_ARG((modes[c] & ~15) == 0 && (modes[c] & 3) != 3, "masked_attn: bad mode %d", modes[c]);
@@ -392,8 +458,9 @@ static int attn_fill(AttnArgs& a, const float* qkv, const uint8_t* m0, const uin
     return REFIL_OK;
 }
 
-template <class K>
-static int attn_launch(K kernel, const AttnArgs& a, size_t smem, int grid, cudaStream_t stream, const char* name) {
+template <class K, class... Extra>
+static int attn_launch(K kernel, const AttnArgs& a, size_t smem, int grid, int warps, cudaStream_t stream,
+                       const char* name, Extra... extra) {
     if (smem > 227 * 1024) {
         refil_set_error("%s: tile needs %zu bytes of shared memory (> 227 KB)", name, smem);
         return REFIL_ERR_UNSUPPORTED;
@@ -405,8 +472,42 @@ static int attn_launch(K kernel, const AttnArgs& a, size_t smem, int grid, cudaS
             return REFIL_ERR_CUDA;
         }
     }
-    kernel<<<grid, ATT_THREADS, smem, stream>>>(a);
+    kernel<<<grid, 32 * warps, smem, stream>>>(a, extra...);
     REFIL_CHECK_LAUNCH(name);
+    return REFIL_OK;
+}
+
+// dispatch on (head dim, padded entity count)
+#define ATT_DISPATCH(KERNEL, hd, neb, ...)                                                          \
+    switch ((hd) * 100 + (neb)) {                                                                   \
+        case 808: return attn_launch(KERNEL<8, 8>, __VA_ARGS__);                                    \
+        case 816: return attn_launch(KERNEL<8, 16>, __VA_ARGS__);                                   \
+        case 824: return attn_launch(KERNEL<8, 24>, __VA_ARGS__);                                   \
+        case 832: return attn_launch(KERNEL<8, 32>, __VA_ARGS__);                                   \
+        case 1608: return attn_launch(KERNEL<16, 8>, __VA_ARGS__);                                  \
+        case 1616: return attn_launch(KERNEL<16, 16>, __VA_ARGS__);                                 \
+        case 1624: return attn_launch(KERNEL<16, 24>, __VA_ARGS__);                                 \
+        case 1632: return attn_launch(KERNEL<16, 32>, __VA_ARGS__);                                 \
+        case 3208: return attn_launch(KERNEL<32, 8>, __VA_ARGS__);                                  \
+        case 3216: return attn_launch(KERNEL<32, 16>, __VA_ARGS__);                                 \
+        case 3224: return attn_launch(KERNEL<32, 24>, __VA_ARGS__);                                 \
+        default: return attn_launch(KERNEL<32, 32>, __VA_ARGS__);                                   \
+    }
+
+static int attn_geometry(const char* name, int N, int warp_floats, int* warps, int* grid, size_t* smem) {
+    const size_t per_warp = (size_t)warp_floats * sizeof(float);
+    int w = (int)((220 * 1024) / (per_warp + 8));
+    if (w > ATT_MAX_WARPS) w = ATT_MAX_WARPS;
+    if (w < 1) {
+        refil_set_error("%s: one unit needs %zu bytes of shared memory (> 220 KB)", name, per_warp);
+        return REFIL_ERR_UNSUPPORTED;
+    }
+    *warps = w;
+    *smem = (size_t)w * per_warp + (size_t)w * 8 + 16;
+    int g = refil_num_sms();
+    const int need = refil_cdiv(N, w);
+    if (g > need) g = need;
+    *grid = g;
     return REFIL_OK;
 }
 
@@ -422,18 +523,14 @@ extern "C" int refil_masked_attn_fwd(const float* qkv, float* out, const uint8_t
     if (rc) return rc;
     REFIL_CHECK_ARG(out != nullptr, "masked_attn_fwd: out is null");
     a.out = out;
-    REFIL_CHECK_ARG(((3 * embed_dim * 4) % 16) == 0 && ((uintptr_t)qkv % 16) == 0, "masked_attn_fwd: QKV rows must be 16-byte aligned");
-    size_t smem = ((size_t)2 * n_entities * (3 * embed_dim + 4) + (ATT_THREADS / 32) * 8 * 36) * sizeof(float);
-    int per_sm = (int)((220 * 1024) / (smem + 1024));
-    if (per_sm < 1) per_sm = 1;
-    if (per_sm > 4) per_sm = 4;
-    int grid = per_sm * refil_num_sms();
-    if (grid > N) grid = N;
-    switch (embed_dim / n_heads) {
-        case 8: return attn_launch(attn_fwd_kernel<8>, a, smem, grid, stream, "masked_attn_fwd");
-        case 16: return attn_launch(attn_fwd_kernel<16>, a, smem, grid, stream, "masked_attn_fwd");
-        default: return attn_launch(attn_fwd_kernel<32>, a, smem, grid, stream, "masked_attn_fwd");
-    }
+    const int hd = embed_dim / n_heads, neb = (n_entities + 7) / 8 * 8;
+    const int tile_floats = neb * (2 * embed_dim + 4);
+    const int warp_floats = tile_floats + neb * 32;
+    int warps, grid;
+    size_t smem;
+    rc = attn_geometry("masked_attn_fwd", N, warp_floats, &warps, &grid, &smem);
+    if (rc) return rc;
+    ATT_DISPATCH(attn_fwd_kernel, hd, neb, a, smem, grid, warps, stream, "masked_attn_fwd", tile_floats, warp_floats)
 }
 
 extern "C" int refil_masked_attn_bwd(const float* qkv, const float* dout, float* dqkv, const uint8_t* mask0,
@@ -447,13 +544,16 @@ extern "C" int refil_masked_attn_bwd(const float* qkv, const float* dout, float*
                        group_bits, entity_mask, N, T, n_entities, n_queries, embed_dim, n_heads, n_copies);
     if (rc) return rc;
     REFIL_CHECK_ARG(dout && dqkv, "masked_attn_bwd: dout / dqkv is null");
+    REFIL_CHECK_ARG(((uintptr_t)dout % 16) == 0 && ((uintptr_t)dqkv % 16) == 0, "masked_attn_bwd: alignment");
     a.dout = dout;
     a.dqkv = dqkv;
-    size_t smem = ((size_t)n_entities * (3 * embed_dim + 4) + (size_t)n_copies * n_queries * (embed_dim + 4) +
-                   (ATT_THREADS / 32) * 32) * sizeof(float);
-    switch (embed_dim / n_heads) {
-        case 8: return attn_launch(attn_bwd_kernel<8>, a, smem, N, stream, "masked_attn_bwd");
-        case 16: return attn_launch(attn_bwd_kernel<16>, a, smem, N, stream, "masked_attn_bwd");
-        default: return attn_launch(attn_bwd_kernel<32>, a, smem, N, stream, "masked_attn_bwd");
-    }
+    const int hd = embed_dim / n_heads, neb = (n_entities + 7) / 8 * 8;
+    const int tile_floats = neb * (2 * embed_dim + 4);
+    const int ipp = 32 / n_heads, nqp = (n_queries + ipp - 1) / ipp * ipp;
+    const int warp_floats = tile_floats + 2 * n_copies * neb * n_heads * nqp + neb * 32;
+    int warps, grid;
+    size_t smem;
+    rc = attn_geometry("masked_attn_bwd", N, warp_floats, &warps, &grid, &smem);
+    if (rc) return rc;
+    ATT_DISPATCH(attn_bwd_kernel, hd, neb, a, smem, grid, warps, stream, "masked_attn_bwd", tile_floats, warp_floats)
 }
