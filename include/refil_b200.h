@@ -113,12 +113,14 @@ int refil_tc_gemm_tn(const float* A, long long lda, const float* relu_y, long lo
                      const uint8_t* c_row_entity_mask, int c_na, int c_ne, int c_rows_per_copy, float* C,
                      long long ldc, int M, int N, int K, cudaStream_t stream);
 
-/* weight gradient on the tensor cores: dW[P,Q] += g(X)[M,P]^T Y[M,Q]; db[P] += colsum g(X) (db may be null) */
+/* weight gradient on the tensor cores: dW[P,Q] += g(X)[M,P]^T Y[M,Q]; db[P] += colsum g(X) (db may be null).
+ * y_shift_rows > 0: Y row m is read from row m - y_shift_rows and is zero where (m / y_shift_rows) % y_period == 0
+ * (the h_{t-1} view of the GRU state stack for dW_hh: shift = n_agents, period = T) */
 int refil_tc_wgrad_supported(int M, int P, int Q);
 int refil_tc_gemm_wgrad(const float* X, long long ldx, const float* relu_y, long long ldy,
                         const uint8_t* x_row_entity_mask, int na, int ne, int rows_per_copy, const float* Y,
-                        long long ldyy, float* dW, long long lddw, float* db, int M, int P, int Q,
-                        cudaStream_t stream);
+                        long long ldyy, int y_shift_rows, int y_period, float* dW, long long lddw, float* db, int M,
+                        int P, int Q, cudaStream_t stream);
 
 /* ---- masked multi-head attention over entities: modules/layers/attention.py:43-64 with the mask algebra of
  *      agents/entity_rnn_agent.py:79-124 resolved on the fly.  QKV [N, ne, 3d]; OUT / dOUT [C, N, nq, d]. */

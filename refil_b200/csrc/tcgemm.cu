@@ -401,6 +401,7 @@ struct TcWArgs {
     const float* relu_y; long long ldy;
     const uint8_t* x_rowmask; int na, ne, mper;
     const float* Y; long long ldyy;
+    int y_shift, y_period;               // Y row m reads row m - y_shift, zero where (m / y_shift) % y_period == 0 (GRU h_{t-1})
     float* dW; long long lddw;
     float* db;
     int M, P, Q, BQ, p_tiles, splits, stages, chunks_per_split;
@@ -565,7 +566,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_wgrad_kernel(TcWArgs a)
                 for (int i = 0; i < 8; i++) {
                     vy[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                     const long long row = m0 + ry0 + ry_step * i;
-                    if (i < ny && row < a.M) vy[i] = __ldg(reinterpret_cast<const float4*>(py + row * a.ldyy));
+                    if (i < ny && row < a.M) {
+                        if (a.y_shift == 0) vy[i] = __ldg(reinterpret_cast<const float4*>(py + row * a.ldyy));
+                        else if ((((unsigned)row) / (unsigned)a.y_shift) % (unsigned)a.y_period != 0u)
+                            vy[i] = __ldg(reinterpret_cast<const float4*>(py + (row - a.y_shift) * a.ldyy));
+                    }
                 }
                 if (pr) {
 #pragma unroll
@@ -626,8 +631,8 @@ extern "C" int refil_tc_wgrad_supported(int M, int P, int Q) {
 
 extern "C" int refil_tc_gemm_wgrad(const float* X, long long ldx, const float* relu_y, long long ldy,
                                    const uint8_t* x_row_entity_mask, int na, int ne, int rows_per_copy,
-                                   const float* Y, long long ldyy, float* dW, long long lddw, float* db, int M, int P,
-                                   int Q, cudaStream_t stream) {
+                                   const float* Y, long long ldyy, int y_shift_rows, int y_period, float* dW,
+                                   long long lddw, float* db, int M, int P, int Q, cudaStream_t stream) {
     REFIL_CHECK_ARG(X && Y && dW, "tc_gemm_wgrad: null pointer");
     REFIL_CHECK_ARG(refil_tc_wgrad_supported(M, P, Q), "tc_gemm_wgrad: unsupported shape M=%d P=%d Q=%d", M, P, Q);
     REFIL_CHECK_ARG((ldx % 4) == 0 && (ldyy % 4) == 0 && (lddw % 4) == 0 && ((uintptr_t)X % 16) == 0 &&
@@ -637,6 +642,7 @@ extern "C" int refil_tc_gemm_wgrad(const float* X, long long ldx, const float* r
     a.X = X; a.ldx = ldx; a.relu_y = relu_y; a.ldy = ldy;
     a.x_rowmask = x_row_entity_mask; a.na = na > 0 ? na : 1; a.ne = ne; a.mper = rows_per_copy > 0 ? rows_per_copy : 1;
     a.Y = Y; a.ldyy = ldyy; a.dW = dW; a.lddw = lddw; a.db = db;
+    a.y_shift = y_shift_rows > 0 ? y_shift_rows : 0; a.y_period = y_period > 0 ? y_period : 1;
     a.M = M; a.P = P; a.Q = Q;
     a.BQ = Q + 32;
     a.p_tiles = refil_cdiv(P, 128);

@@ -121,7 +121,8 @@ class QLearner:
         # backward (q_learner.py:175-176)
         self.gradbuf.zero_()
         dq = self.mixer.backward(g_plain, g_im)
-        dQ = ops.scatter_dq(dq, actions, ws.get("dQ", (C * N * na, A)), C, N * na, A, T, na)
+        Ap = self.mac.agent.dq_width()        # one-hot scatter of d(chosen) into (padded) action columns
+        dQ = ops.scatter_dq(dq, actions, ws.get("dQ", (C * N * na, Ap)), C, N * na, Ap, T, na)
         self.mac.agent.backward(dQ)
         # one all-reduce of [grads | stats], then normalise + clip + RMSprop (q_learner.py:177-178)
         ops.pack_stats(self.stats64, self.gradbuf[self.n_params:], N_STATS)

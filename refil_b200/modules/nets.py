@@ -187,17 +187,36 @@ class EntityAttnAgent:
         self.saved = (x2, None, None, None, None, B, T, C)
         return q.view(C, N, na, self.A), x2
 
+    def dq_width(self):
+        """Row width of the dQ buffer the learner scatters into: padded to 32 columns on the tensor-core path so that
+        the fc3 / fc2 backward GEMMs have an aligned K (the padding columns are zero)."""
+        return 32 if (ops.USE_TENSOR_CORES and self.A <= 32) else self.A
+
     def backward(self, dq):
-        """dq [C*N*na, A] -> accumulates into the gradient views of the store."""
+        """dq [C*N*na, dq_width()] -> accumulates into the gradient views of the store."""
         p, g, ws = self.store.p, self.store.g, self.ws
         x2, x3, hs, gates, h0, B, T, C = self.saved
         na, rm = self.na, self.trunk.row_mask
-        R = dq.shape[0]
+        R, Ap = dq.shape
         dx2 = ws.get("scratch.dx2", (R, self.d))
+        wl, key = ("fc3.weight", "fc3.bias") if self.rnn else ("fc2.weight", "fc2.bias")
+        inp = hs if self.rnn else x2
+        width = self.r if self.rnn else self.d
+        dhead = ws.get("scratch.dhs", (R, self.r)) if self.rnn else dx2
+        if Ap != self.A:      # padded head: zero-padded copy of the output weight, gradient through a padded temp
+            wp = ws.get(self.tag + ".wheadp", (Ap, width), zero=True)
+            wp[:self.A].copy_(p[wl])
+            dwp = ws.get("scratch.dwheadp", (Ap, width), zero=True)
+            dbp = ws.get("scratch.dbheadp", (Ap,), zero=True)
+            ops.linear_bwd_weight(dq, inp, dwp, dbp, row_mask=rm)
+            g[wl].add_(dwp[:self.A])
+            g[key].add_(dbp[:self.A])
+            ops.linear_bwd_data(dq, wp, dhead, row_mask=rm)
+        else:
+            ops.linear_bwd_weight(dq, inp, g[wl], g[key], row_mask=rm)
+            ops.linear_bwd_data(dq, p[wl], dhead, row_mask=rm)
         if self.rnn:
-            ops.linear_bwd_weight(dq, hs, g["fc3.weight"], g["fc3.bias"], row_mask=rm)
-            dhs = ws.get("scratch.dhs", (R, self.r))
-            ops.linear_bwd_data(dq, p["fc3.weight"], dhs, row_mask=rm)
+            dhs = dhead
             dgi = ws.get("scratch.dgi", (R, 3 * self.r))
             dgh = ws.get("scratch.dgh", (R, 3 * self.r))
             ops.gru_scan_bwd(dhs, gates, hs, h0, p["rnn.weight_hh"], dgi, dgh, C * B * na, T, na)
@@ -207,9 +226,6 @@ class EntityAttnAgent:
             ops.linear_bwd_data(dgi, p["rnn.weight_ih"], dx3)
             ops.linear_bwd_weight(dx3, x2, g["fc2.weight"], g["fc2.bias"], relu_y=x3)
             ops.linear_bwd_data(dx3, p["fc2.weight"], dx2, relu_y=x3)
-        else:
-            ops.linear_bwd_weight(dq, x2, g["fc2.weight"], g["fc2.bias"], row_mask=rm)
-            ops.linear_bwd_data(dq, p["fc2.weight"], dx2, row_mask=rm)
         self.trunk.backward(dx2)
 
 

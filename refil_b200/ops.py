@@ -126,7 +126,7 @@ def linear_bwd_weight(dC, A, dW, db, relu_y=None, row_mask=None):
     K = A.shape[1]
     em, na, ne, mper = _rm(row_mask)
     if USE_TENSOR_CORES and M >= TC_MIN_ROWS and _lib.load().refil_tc_wgrad_supported(M, N, K) != 0:
-        _call("tc_gemm_wgrad", _p(dC, F32), N, _p(relu_y, F32), N, em, na, ne, mper, _p(A, F32), K, _p(dW, F32), K,
+        _call("tc_gemm_wgrad", _p(dC, F32), N, _p(relu_y, F32), N, em, na, ne, mper, _p(A, F32), K, 0, 1, _p(dW, F32), K,
               _p(db, F32), M, N, K)
         return
     _call("linear_bwd_weight", _p(dC, F32), N, _p(relu_y, F32), N, em, na, ne, mper, _p(A, F32), K, _p(dW, F32), K,
@@ -141,6 +141,10 @@ def embed_bwd_weight(dC, relu_y, entities, last_action, n_actions, dW, db):
 
 def gru_bwd_weight_hh(dGH, HS, n_agents, T, dWhh, dbhh):
     M, r = HS.shape
+    if USE_TENSOR_CORES and M >= TC_MIN_ROWS and _lib.load().refil_tc_wgrad_supported(M, 3 * r, r) != 0:
+        _call("tc_gemm_wgrad", _p(dGH, F32), 3 * r, None, 3 * r, None, 1, 1, 1, _p(HS, F32), r, n_agents, T,
+              _p(dWhh, F32), r, _p(dbhh, F32), M, 3 * r, r)
+        return
     _call("gru_bwd_weight_hh", _p(dGH, F32), _p(HS, F32), n_agents, T, _p(dWhh, F32), _p(dbhh, F32), M, r)
 
 
