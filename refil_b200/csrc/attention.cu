@@ -26,6 +26,10 @@
 // the masked softmax and the weighted sum over V never leave its registers (no shuffles, no shared-memory round trips);
 // the masks are resolved once per row with warp ballots (lane = entity j).  Threads of different heads read K/V chunks
 // in a head-rotated order so that the four distinct broadcast addresses of a warp load hit different banks.
+#include <cuda.h>   // CUtensorMap (the encode function is fetched through cudaGetDriverEntryPoint, libcuda is not linked)
+
+#include <string.h>
+
 #include "common.cuh"
 
 #define ATT_THREADS 128
@@ -98,20 +102,60 @@ __device__ __forceinline__ void att_tma_load_rows(float* tile, const float* src,
     }
 }
 
-// mask words of attention row i (one per copy, bit j set = entity j masked or padding), built with ballots: lane = entity
+// one TMA tensor copy of the whole K|V tile of unit n: box (2d, ne, 1) of the [N][ne][3d] tensor at column d
+__device__ __forceinline__ void att_tma_load_tile(float* tile, const CUtensorMap* tmap, int d, int ne, long long n,
+                                                  uint64_t* bar, int lane) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) {
+        const uint32_t bytes = (uint32_t)(ne * 2 * d) * 4u;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(att_smem_u32(bar)), "r"(bytes) : "memory");
+        asm volatile(
+            "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+            ::"r"(att_smem_u32(tile)), "l"(tmap), "r"(d), "r"(0), "r"((int)n), "r"(att_smem_u32(bar))
+            : "memory");
+    }
+}
+
+// mask words of attention row i (one per copy, bit j set = entity j masked or padding), built with ballots: lane = entity.
+// The explicit-mask bytes of all rows of the pass are fetched first (independent loads, one latency), then combined with
+// the closed-form terms; copies that share one explicit tensor (plain / within / interact over obs_mask) load it once.
 __device__ __forceinline__ void att_row_masks(const AttnArgs& a, int n, int lane, int ib, int ipp, int il, int g_j,
                                               int ina_j, int em_j, uint32_t mb[ATT_MAX_COPIES]) {
+    uint32_t ex[ATT_MAX_COPIES];          // bit r: explicit mask of (row ib + r, entity = lane)
 #pragma unroll
-    for (int c = 0; c < ATT_MAX_COPIES; c++) mb[c] = 0xffffffffu;
+    for (int c = 0; c < ATT_MAX_COPIES; c++) {
+        mb[c] = 0xffffffffu;
+        ex[c] = 0;
+        if (c < a.C && a.mask[c] && lane < a.ne) {
+            if (c > 0 && a.mask[c] == a.mask[0] && a.mask_stride_n[c] == a.mask_stride_n[0]) {
+                ex[c] = ex[0];
+            } else {
+                const uint8_t* mp = a.mask[c] + (size_t)n * a.mask_stride_n[c] + (size_t)ib * a.ne + lane;
+                for (int r0 = 0; r0 < ipp; r0 += 8) {
+                    uint8_t v[8];
+#pragma unroll
+                    for (int r = 0; r < 8; r++) v[r] = (r0 + r < ipp && ib + r0 + r < a.nq) ? mp[(size_t)(r0 + r) * a.ne] : 0;
+#pragma unroll
+                    for (int r = 0; r < 8; r++) ex[c] |= (v[r] ? 1u : 0u) << (r0 + r);
+                }
+            }
+        }
+    }
     for (int r = 0; r < ipp; r++) {
         const int i = ib + r;
         if (i >= a.nq) break;
         const int g_i = __shfl_sync(0xffffffffu, g_j, i), ina_i = __shfl_sync(0xffffffffu, ina_j, i),
                   em_i = __shfl_sync(0xffffffffu, em_j, i);
+        const bool same = (g_i == g_j) && !ina_i && !ina_j;
 #pragma unroll
         for (int c = 0; c < ATT_MAX_COPIES; c++) {
             if (c < a.C) {
-                const bool m = lane >= a.ne || att_masked(a, c, n, i, lane, g_i, g_j, ina_i, ina_j, em_i, em_j);
+                const int mode = a.mode[c], part = mode & 3;
+                bool m = lane >= a.ne || ((ex[c] >> r) & 1u);
+                if (part) m = m || (part == 1 ? !same : same);
+                if (mode & 4) m = m || ina_i || ina_j;
+                if (mode & 8) m = m || em_i || em_j;
                 const uint32_t word = __ballot_sync(0xffffffffu, m);
                 if (il == r) mb[c] = word;
             }
@@ -120,10 +164,11 @@ __device__ __forceinline__ void att_row_masks(const AttnArgs& a, int n, int lane
 }
 
 template <int HD, int NEB>
-__global__ void __launch_bounds__(32 * ATT_MAX_WARPS) attn_fwd_kernel(AttnArgs a, int tile_floats, int warp_floats) {
-    extern __shared__ __align__(16) float smem[];
+__global__ void __launch_bounds__(32 * ATT_MAX_WARPS) attn_fwd_kernel(AttnArgs a, int tile_floats, int warp_floats, const __grid_constant__ CUtensorMap tmap, int use_tmap) {
+    extern __shared__ __align__(128) float smem_raw_[];
+    float* smem = reinterpret_cast<float*>(((uintptr_t)smem_raw_ + 127) & ~(uintptr_t)127);
     constexpr int NCH = HD / 4;
-    const int d = a.d, ne = a.ne, nq = a.nq, H = a.H, ldk = 2 * d + 4;
+    const int d = a.d, ne = a.ne, nq = a.nq, H = a.H, ldk = 2 * d;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
     float* kv = smem + (size_t)warp * warp_floats;                       // [NEB][ldk]: K | V rows of the current unit
     float* lgs = kv + tile_floats + lane;                                // [NEB][32]: my row of logits, lgs[j * 32]
@@ -139,7 +184,8 @@ __global__ void __launch_bounds__(32 * ATT_MAX_WARPS) attn_fwd_kernel(AttnArgs a
     const long long gw = (long long)blockIdx.x * wpc + warp, GW = (long long)gridDim.x * wpc;
     uint32_t parity = 0;
     for (long long n = gw; n < a.N; n += GW) {
-        att_tma_load_rows(kv, a.qkv + ((size_t)n * ne) * 3 * d + d, 3 * d, ne, 2 * d, ldk, bar, lane);
+        if (use_tmap) att_tma_load_tile(kv, &tmap, d, ne, n, bar, lane);
+        else att_tma_load_rows(kv, a.qkv + ((size_t)n * ne) * 3 * d + d, 3 * d, ne, 2 * d, ldk, bar, lane);
         const int b = (int)(n / a.T);
         int g_j = 0, ina_j = 0, em_j = 0;
         if (lane < ne) {
@@ -227,10 +273,11 @@ __global__ void __launch_bounds__(32 * ATT_MAX_WARPS) attn_fwd_kernel(AttnArgs a
 //   phase 2, lane = (entity j, head h): dK_j = sum_{c,i} dlogit_ij Q_i, dV_j = sum_{c,i} w_ij dO_i (Q / dO rows come
 //            back through L1), written over the K|V tile, which is then streamed out as the K|V columns of dQKV.
 template <int HD, int NEB>
-__global__ void __launch_bounds__(32 * ATT_MAX_WARPS) attn_bwd_kernel(AttnArgs a, int tile_floats, int warp_floats) {
-    extern __shared__ __align__(16) float smem[];
+__global__ void __launch_bounds__(32 * ATT_MAX_WARPS) attn_bwd_kernel(AttnArgs a, int tile_floats, int warp_floats, const __grid_constant__ CUtensorMap tmap, int use_tmap) {
+    extern __shared__ __align__(128) float smem_raw_[];
+    float* smem = reinterpret_cast<float*>(((uintptr_t)smem_raw_ + 127) & ~(uintptr_t)127);
     constexpr int NCH = HD / 4;
-    const int d = a.d, ne = a.ne, nq = a.nq, H = a.H, ldk = 2 * d + 4;
+    const int d = a.d, ne = a.ne, nq = a.nq, H = a.H, ldk = 2 * d;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
     const int ipp = 32 / H, h = lane % H, il = lane / H;
     const int nqp = (nq + ipp - 1) / ipp * ipp;                          // agent rows padded to whole passes
@@ -250,7 +297,8 @@ __global__ void __launch_bounds__(32 * ATT_MAX_WARPS) attn_bwd_kernel(AttnArgs a
     uint32_t parity = 0;
     for (long long n = gw; n < a.N; n += GW) {
         for (int f = ne * ldk + lane; f < NEB * ldk; f += 32) kv[f] = 0.f;   // padding rows (the tile is reused for dK|dV)
-        att_tma_load_rows(kv, a.qkv + ((size_t)n * ne) * 3 * d + d, 3 * d, ne, 2 * d, ldk, bar, lane);
+        if (use_tmap) att_tma_load_tile(kv, &tmap, d, ne, n, bar, lane);
+        else att_tma_load_rows(kv, a.qkv + ((size_t)n * ne) * 3 * d + d, 3 * d, ne, 2 * d, ldk, bar, lane);
         const int b = (int)(n / a.T);
         int g_j = 0, ina_j = 0, em_j = 0;
         if (lane < ne) {
@@ -494,6 +542,34 @@ static int attn_launch(K kernel, const AttnArgs& a, size_t smem, int grid, int w
         default: return attn_launch(KERNEL<32, 32>, __VA_ARGS__);                                   \
     }
 
+// CUtensorMap of QKV viewed as [N][ne][3d] fp32 with a (2d, ne, 1) box: one TMA instruction stages a unit's K|V tile
+typedef CUresult (*att_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int attn_make_tmap(CUtensorMap* tm, const float* qkv, int N, int ne, int d) {
+    static att_encode_fn enc = nullptr;
+    static bool tried = false;
+    memset(tm, 0, sizeof(*tm));
+    if (2 * d > 256 || ne > 256) return 0;                    // box limits: fall back to per-row bulk copies
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            enc = (att_encode_fn)p;
+    }
+    if (!enc) return 0;
+    const cuuint64_t dims[3] = {(cuuint64_t)3 * d, (cuuint64_t)ne, (cuuint64_t)N};
+    const cuuint64_t strides[2] = {(cuuint64_t)3 * d * 4, (cuuint64_t)ne * 3 * d * 4};
+    const cuuint32_t box[3] = {(cuuint32_t)2 * d, (cuuint32_t)ne, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)qkv, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 1 : 0;
+}
+
 static int attn_geometry(const char* name, int N, int warp_floats, int* warps, int* grid, size_t* smem) {
     const size_t per_warp = (size_t)warp_floats * sizeof(float);
     int w = (int)((220 * 1024) / (per_warp + 8));
@@ -503,7 +579,7 @@ static int attn_geometry(const char* name, int N, int warp_floats, int* warps, i
         return REFIL_ERR_UNSUPPORTED;
     }
     *warps = w;
-    *smem = (size_t)w * per_warp + (size_t)w * 8 + 16;
+    *smem = (size_t)w * per_warp + (size_t)w * 8 + 16 + 128;
     int g = refil_num_sms();
     const int need = refil_cdiv(N, w);
     if (g > need) g = need;
@@ -524,13 +600,15 @@ extern "C" int refil_masked_attn_fwd(const float* qkv, float* out, const uint8_t
     REFIL_CHECK_ARG(out != nullptr, "masked_attn_fwd: out is null");
     a.out = out;
     const int hd = embed_dim / n_heads, neb = (n_entities + 7) / 8 * 8;
-    const int tile_floats = neb * (2 * embed_dim + 4);
-    const int warp_floats = tile_floats + neb * 32;
+    const int tile_floats = neb * 2 * embed_dim;
+    const int warp_floats = tile_floats + neb * 32;           // multiples of 32 floats: every warp tile is 128-byte aligned
+    CUtensorMap tmap;
+    const int use_tmap = attn_make_tmap(&tmap, qkv, N, n_entities, embed_dim);
     int warps, grid;
     size_t smem;
     rc = attn_geometry("masked_attn_fwd", N, warp_floats, &warps, &grid, &smem);
     if (rc) return rc;
-    ATT_DISPATCH(attn_fwd_kernel, hd, neb, a, smem, grid, warps, stream, "masked_attn_fwd", tile_floats, warp_floats)
+    ATT_DISPATCH(attn_fwd_kernel, hd, neb, a, smem, grid, warps, stream, "masked_attn_fwd", tile_floats, warp_floats, tmap, use_tmap)
 }
 
 extern "C" int refil_masked_attn_bwd(const float* qkv, const float* dout, float* dqkv, const uint8_t* mask0,
@@ -548,12 +626,14 @@ extern "C" int refil_masked_attn_bwd(const float* qkv, const float* dout, float*
     a.dout = dout;
     a.dqkv = dqkv;
     const int hd = embed_dim / n_heads, neb = (n_entities + 7) / 8 * 8;
-    const int tile_floats = neb * (2 * embed_dim + 4);
+    const int tile_floats = neb * 2 * embed_dim;
     const int ipp = 32 / n_heads, nqp = (n_queries + ipp - 1) / ipp * ipp;
-    const int warp_floats = tile_floats + 2 * n_copies * neb * n_heads * nqp + neb * 32;
+    const int warp_floats = (tile_floats + 2 * n_copies * neb * n_heads * nqp + neb * 32 + 31) / 32 * 32;
+    CUtensorMap tmap;
+    const int use_tmap = attn_make_tmap(&tmap, qkv, N, n_entities, embed_dim);
     int warps, grid;
     size_t smem;
     rc = attn_geometry("masked_attn_bwd", N, warp_floats, &warps, &grid, &smem);
     if (rc) return rc;
-    ATT_DISPATCH(attn_bwd_kernel, hd, neb, a, smem, grid, warps, stream, "masked_attn_bwd", tile_floats, warp_floats)
+    ATT_DISPATCH(attn_bwd_kernel, hd, neb, a, smem, grid, warps, stream, "masked_attn_bwd", tile_floats, warp_floats, tmap, use_tmap)
 }

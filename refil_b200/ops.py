@@ -39,14 +39,26 @@ def set_timing(enabled):
     """Per-entry-point CUDA-event timing (bench.py's per-kernel breakdown; never on during the timed region)."""
     global _timing
     _timing = {} if enabled else None
+    _work.clear()
+
+
+_work = {}    # when timing: {kernel name: [algorithmic flops, algorithmic bytes]} accumulated per call
+
+
+def _account(name, flops, nbytes):
+    if _timing is not None:
+        w = _work.setdefault(name, [0.0, 0.0])
+        w[0] += flops
+        w[1] += nbytes
 
 
 def timing_summary():
-    """-> {name: (launches, total_ms)}; synchronises."""
+    """-> {name: (launches, total_ms, algorithmic flops, algorithmic bytes)}; synchronises."""
     torch.cuda.synchronize()
     out = {}
     for name, evs in (_timing or {}).items():
-        out[name] = (len(evs), sum(a.elapsed_time(b) for a, b in evs))
+        w = _work.get(name, [0.0, 0.0])
+        out[name] = (len(evs), sum(a.elapsed_time(b) for a, b in evs), w[0], w[1])
     return out
 
 
@@ -87,6 +99,7 @@ def tc_gemm_tn(A, B, sbn, sbk, out, N, K, bias=None, relu=False, relu_y=None, a_
     M = A.shape[0]
     aem, ana, ane, amper = _rm(a_row_mask)
     cem, cna, cne, cmper = _rm(c_row_mask)
+    _account("tc_gemm_tn", 2.0 * M * N * K, 4.0 * (M * K * (2 if relu_y is not None else 1) + M * N + N * K))
     _call("tc_gemm_tn", _p(A, F32), A.shape[1], _p(relu_y, F32), A.shape[1], aem, ana, ane, amper, _p(B, F32), sbn, sbk,
           _p(bias, F32), int(relu), cem, cna, cne, cmper, _p(out, F32), out.shape[1], M, N, K)
     return out
@@ -126,6 +139,7 @@ def linear_bwd_weight(dC, A, dW, db, relu_y=None, row_mask=None):
     K = A.shape[1]
     em, na, ne, mper = _rm(row_mask)
     if USE_TENSOR_CORES and M >= TC_MIN_ROWS and _lib.load().refil_tc_wgrad_supported(M, N, K) != 0:
+        _account("tc_gemm_wgrad", 2.0 * M * N * K, 4.0 * (M * N * (2 if relu_y is not None else 1) + M * K + N * K))
         _call("tc_gemm_wgrad", _p(dC, F32), N, _p(relu_y, F32), N, em, na, ne, mper, _p(A, F32), K, 0, 1, _p(dW, F32), K,
               _p(db, F32), M, N, K)
         return
@@ -174,12 +188,16 @@ def _copies(copies):
 
 
 def masked_attn_fwd(qkv, out, copies, group_bits, entity_mask, N, T, ne, nq, d, H):
+    # algorithmic bytes per (b, t, copy) unit = 4d(2ne + 2nq) + nq*ne, flops = 4*nq*ne*d
+    _account("masked_attn_fwd", 4.0 * nq * ne * d * N * len(copies), (4.0 * d * (2 * ne + 2 * nq) + nq * ne) * N * len(copies))
     _call("masked_attn_fwd", _p(qkv, F32), _p(out, F32), *_copies(copies), _p(group_bits, U8), _p(entity_mask, U8),
           N, T, ne, nq, d, H, len(copies))
     return out
 
 
 def masked_attn_bwd(qkv, dout, dqkv, copies, group_bits, entity_mask, N, T, ne, nq, d, H):
+    _account("masked_attn_bwd", 10.0 * nq * ne * d * N * len(copies),
+             (4.0 * d * (2 * ne + 2 * nq) * 2 + nq * ne) * N * len(copies))
     _call("masked_attn_bwd", _p(qkv, F32), _p(dout, F32), _p(dqkv, F32), *_copies(copies), _p(group_bits, U8),
           _p(entity_mask, U8), N, T, ne, nq, d, H, len(copies))
     return dqkv
