@@ -16,7 +16,6 @@ import json
 import os
 import subprocess
 import sys
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -48,40 +47,57 @@ def make_args(alg, na, ne, ed, A):
     return SimpleNamespace(**a)
 
 
-class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe).  ONE long-lived
+    `nvidia-smi -lms` child started before the timed region (no fork / driver query from this process while it is timed)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
-        super().__init__(daemon=True)
-        self.index, self.samples, self.stop_flag = index, [], False
+    def __init__(self, index, enabled=True):
+        self.index, self.proc, self.enabled = index, None, enabled
 
-    def run(self):
-        while not self.stop_flag:
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                f = [x.strip() for x in out.strip().split(",")]
-                if len(f) >= 9:
-                    self.samples.append(f)
-            except Exception:
-                pass
-            time.sleep(0.1)
+    def start(self):
+        if not self.enabled:
+            return
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
 
     def summary(self):
-        self.stop_flag = True
-        if not self.samples:
+        if not self.enabled:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["sampled on rank 0 only"]}
+        samples = []
+        if self.proc is not None:
+            try:
+                self.proc.terminate()
+                out, _ = self.proc.communicate(timeout=5)
+            except Exception:
+                out = ""
+            for line in out.strip().splitlines():
+                f = [x.strip() for x in line.split(",")]
+                if len(f) >= 9:
+                    samples.append(f)
+        if not samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        sm = sorted(float(s[1]) for s in self.samples)
+        def num(x):
+            try:
+                return float(x)
+            except ValueError:
+                return 0.0
+        pmax = max(num(s[3]) for s in samples)
+        load = [s for s in samples if num(s[3]) >= 0.6 * pmax] or samples      # samples taken under load
+        sm = sorted(num(s[1]) for s in load)
         reasons = set()
-        for s in self.samples:
+        for s in load:
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][2]), "reasons": sorted(reasons),
-                "samples": len(self.samples)}
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(samples[0][2]), "reasons": sorted(reasons),
+                "samples": len(samples), "samples_under_load": len(load), "power_w_max": pmax}
 
 
 def peaks():
@@ -254,15 +270,15 @@ def run_ours(a):
 
     for i in range(max(a.warmup, 3)):
         step_resident(i)
-    clocks = ClockSampler(local)
+    clocks = ClockSampler(local, enabled=(rank == 0))
     clocks.start()
     l0 = ops.launch_count()
     ms = timed(step_resident, a.steps)
     launches = ops.launch_count() - l0
-    clk = clocks.summary()
     for i in range(2):
         step_e2e(i)
     ms_e2e = timed(step_e2e, a.steps)
+    clk = clocks.summary()           # sampled across both timed regions (resident + e2e)
     trans = world * B * (T - 1)
     value = trans * a.steps / (ms * 1e-3)
     e2e = trans * a.steps / (ms_e2e * 1e-3)
@@ -272,6 +288,7 @@ def run_ours(a):
     step_resident(0)
     step_resident(1)
     tsum = ops.timing_summary()
+    shapes = ops.shape_timing_summary()
     ops.set_timing(False)
     kern = {k: {"launches": v[0] // 2, "ms_per_step": v[1] / 2, "flop_per_step": v[2] / 2, "bytes_per_step": v[3] / 2}
             for k, v in tsum.items()}
@@ -311,6 +328,8 @@ def run_ours(a):
         "roofline_wgrad": hbm_roof("tc_gemm_wgrad", "tc_gemm_wgrad_kernel (weight gradients, MN-major tcgen05)"),
         "roofline_attention_bwd": hbm_roof("masked_attn_bwd", "attn_bwd_kernel"), "dominant_kernel": dom[0],
         "kernels_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in sorted(kern.items(), key=lambda kv: -kv[1]["ms_per_step"])},
+        # dense-layer kernels by shape [M x N x K]: (launches per step, us per launch)
+        "dense_shapes_us": {k: [v[0] // 2, round(1e3 * v[1] / max(v[0], 1), 1)] for k, v in sorted(shapes.items(), key=lambda kv: -kv[1][1])},
     }
     # ---- env kernel in the same run ---------------------------------------------------------------------------
     if rank == 0 or world > 1:

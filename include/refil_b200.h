@@ -105,8 +105,11 @@ int refil_last_action_index(const long long* actions, int32_t* la, int B, int T,
 /* ---- the same dense layers on the tcgen05 tensor cores (3xTF32 split, fp32 accumulate in TMEM; fp32-grade accuracy):
  *      C[M,N] = [rowmask_c][relu]( g(A)[M,K] B[N,K]^T + bias ),  B[j,i] = B[j*b_stride_n + i*b_stride_k],
  *      g = relu'(relu_y) and/or row mask on A (backward-data use).  refil_tc_gemm_supported() != 0 iff the shape
- *      can run here (K % 32 == 0, N % 16 == 0, ...); otherwise use refil_linear_fwd / refil_linear_bwd_data. */
+ *      can run here (K % 32 == 0, N % 32 == 0, ...); otherwise use refil_linear_fwd / refil_linear_bwd_data.
+ *      refil_tc_gemm_k_slices() > 1: the reduction is too long for a resident weight tile and is cut into k-slices whose
+ *      partial tiles are reduce-added into a zeroed C -- only for a linear epilogue (no bias / relu / output row mask). */
 int refil_tc_gemm_supported(int M, int N, int K);
+int refil_tc_gemm_k_slices(int N, int K);
 int refil_tc_gemm_tn(const float* A, long long lda, const float* relu_y, long long ldy,
                      const uint8_t* a_row_entity_mask, int a_na, int a_ne, int a_rows_per_copy, const float* B,
                      long long b_stride_n, long long b_stride_k, const float* bias, int relu,

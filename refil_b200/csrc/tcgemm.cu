@@ -13,30 +13,46 @@
 //   A*B ~= A_lo*B_hi + A_hi*B_lo + A_hi*B_hi   accumulated in fp32 in tensor memory,
 // which leaves ~2^-21 relative error per product -- fp32 grade.
 //
-// Structure (one persistent CTA per SM, 416 threads, warp-specialised):
-//   warps 0-3   epilogue: tcgen05.ld the 128 x BN fp32 accumulator out of TMEM (lane = row), bias / relu / row mask, store
-//   warp  4     TMEM allocation + single-thread tcgen05.mma issue (kind::tf32, M=128, N=BN, K=8 per instruction)
-//   warps 5-8, 9-12  two A-producer groups taking alternate K chunks (two chunks of global loads in flight per SM):
-//               coalesced 128-bit loads, all issued before the first use -> hi/lo split -> 128B-swizzled K-major tiles
-//   The weight tile (BN x K, hi and lo) is split ONCE per CTA and stays resident in shared memory: every CTA keeps one
-//   n-tile and walks the m-tiles.  smem = B_hi/B_lo [K/32][BN][32] + ring of S stages {A_hi, A_lo [128][32]} fp32 with
-//   mbarrier full/empty pairs; TMEM holds two accumulators so the epilogue of tile i overlaps the main loop of tile i+1.
+// Structure (one persistent CTA per SM, 17 warps, warp-specialised; the role index is made warp-uniform with a shuffle
+// so that the MMA warp's descriptors live in uniform registers -- no per-instruction R2UR waterfall):
+//   warps 0-7   epilogue: warp w owns TMEM lane quadrant w & 3 (rows) and every other 32-column slab (w >> 2):
+//               tcgen05.ld 32 x 32 fp32 (lane = row) -> bias / relu / row mask -> 128B-swizzled 4 KB staging tile ->
+//               ONE TMA tensor store (cp.async.bulk.tensor, or cp.reduce...add for split-K partials) per slab
+//   warp  8     TMEM allocation + tcgen05.mma issue by one elected lane (kind::tf32, M=128, N=BN, K=8 per instruction)
+//   warps 9-12, 13-16  two A-producer groups taking alternate K chunks, each with the NEXT chunk's global loads already
+//               in flight in registers (4 chunks = 64 KB of loads in flight per SM): coalesced 128-bit loads ->
+//               hi/lo split -> 128B-swizzled K-major tiles
+//   The weight tile (BN x KS, hi and lo) is split ONCE per CTA and stays resident in shared memory: every CTA keeps one
+//   (n-tile, k-slice) and walks the m-tiles.  A reduction too long for a resident tile (bwd-data of in_trans, K = 3d)
+//   is cut into k-slices whose partial tiles are summed in L2 by the TMA reduce-add store into a zeroed C.
+//   smem = B_hi/B_lo [KS/32][BN][32] + ring of S stages {A_hi, A_lo [128][32]} + 8 staging tiles; mbarrier full/empty
+//   pairs; TMEM holds two accumulators so the epilogue of tile i overlaps the main loop of tile i+1.
+#include <cuda.h>   // CUtensorMap (encode function fetched through cudaGetDriverEntryPoint; libcuda is not linked)
+
+#include <string.h>
+
 #include "common.cuh"
 
 #define TC_BM 128
 #define TC_BK 32
-#define TC_THREADS 416
+#define TC_EPI_WARPS 8
+#define TC_MMA_WARP 8
+#define TC_PROD_WARP0 9
+#define TC_THREADS (32 * 17)
+#define TC_STG_BYTES 4096
 #define TC_MAX_STAGES 4
+#define TCW_THREADS 416
 
 struct TcArgs {
     const float* A; long long lda;
     const float* relu_y; long long ldy;      // optional: A element is zeroed where relu_y <= 0
     const uint8_t* a_rowmask; int a_na, a_ne, a_mper;   // optional: A row zeroed (stack of [C, N, na] rows)
     const float* B; long long sbj, sbi;      // B[j, i] = B[j*sbj + i*sbi], j < N (output col), i < K (reduction)
-    float* C; long long ldc;
     const float* bias; int relu;
     const uint8_t* c_rowmask; int c_na, c_ne, c_mper;
-    int M, N, K, BN, n_tiles, m_tiles, stages;
+    int M, N, K;                             // K = whole reduction length
+    int KS, k_slices;                        // reduction length of one k-slice (multiple of 32), K / KS
+    int BN, n_tiles, m_tiles, stages;
     uint32_t idesc;
 };
 
@@ -67,8 +83,19 @@ __device__ __forceinline__ void tc_commit(uint64_t* bar) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// one lane of a converged warp
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
 
-// K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row atoms 1024 bytes apart (cute::UMMA::SmemDescriptor)
+// K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row atoms 1024 bytes apart (cute::UMMA::SmemDescriptor);
+// the start-address field (16-byte units) is the low 14 bits, so tiles are addressed by adding (bytes >> 4)
 __device__ __forceinline__ uint64_t tc_smem_desc(uint32_t saddr) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr >> 4) & 0x3fff);        // start address, 16-byte units
@@ -108,43 +135,94 @@ __device__ __forceinline__ void tc_store_split(float* hi_tile, float* lo_tile, i
     *reinterpret_cast<float4*>(lo_tile + off) = l;
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_tn_kernel(TcArgs a) {
+// TMA tensor stores of one 32 x 32 fp32 staging tile (128B-swizzled) at (column, row) of C; bulk-group completion
+__device__ __forceinline__ void tc_tma_store(const CUtensorMap* tmap, int col, int row, uint32_t saddr) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                 ::"l"(tmap), "r"(col), "r"(row), "r"(saddr) : "memory");
+}
+__device__ __forceinline__ void tc_tma_reduce_add(const CUtensorMap* tmap, int col, int row, uint32_t saddr) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2}], [%3];"
+                 ::"l"(tmap), "r"(col), "r"(row), "r"(saddr) : "memory");
+}
+__device__ __forceinline__ void tc_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tc_bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tc_bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// the 8 float4 of one A chunk a producer thread owns: 16-byte chunk c of rows r0 + 16 i of m-tile mt, k-chunk kc
+__device__ __forceinline__ void tc_load_a(const TcArgs& a, int mt, int kcol, int r0, int c, float4 (&va)[8]) {
+    const long long rowb = (long long)mt * TC_BM + r0;
+    const float* pa = a.A + rowb * a.lda + kcol + c * 4;
+    const long long rstep = 16 * a.lda;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const long long row = rowb + 16 * i;
+        va[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row < a.M && !tc_row_masked(a.a_rowmask, a.a_na, a.a_ne, a.a_mper, row))
+            va[i] = __ldg(reinterpret_cast<const float4*>(pa + i * rstep));
+    }
+}
+// relu' mask of the same elements: zero where the forward output was <= 0
+__device__ __forceinline__ void tc_mask_relu(const TcArgs& a, int mt, int kcol, int r0, int c, float4 (&va)[8]) {
+    const long long rowb = (long long)mt * TC_BM + r0;
+    const float* py = a.relu_y + rowb * a.ldy + kcol + c * 4;
+    const long long ystep = 16 * a.ldy;
+    float4 vy[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        vy[i] = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (rowb + 16 * i < a.M) vy[i] = __ldg(reinterpret_cast<const float4*>(py + i * ystep));
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        if (!(vy[i].x > 0.f)) va[i].x = 0.f;
+        if (!(vy[i].y > 0.f)) va[i].y = 0.f;
+        if (!(vy[i].z > 0.f)) va[i].z = 0.f;
+        if (!(vy[i].w > 0.f)) va[i].w = 0.f;
+    }
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_tn_kernel(TcArgs a, const __grid_constant__ CUtensorMap tmap_c) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024-byte aligned base (dynamic smem is only guaranteed 16-byte aligned)
     uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int BN = a.BN;
-    const int S = a.stages, KC = a.K / TC_BK;
+    const int S = a.stages, KC = a.KS / TC_BK;
     const uint32_t a_bytes = TC_BM * 128, b_bytes = (uint32_t)BN * 128;
     const uint32_t stage_bytes = 2 * a_bytes;
     uint8_t* smem_b = smem;                                   // [KC][hi | lo][BN][128 B]
     uint8_t* smem_a = smem + (size_t)KC * 2 * b_bytes;        // [S][hi | lo][128][128 B]
+    uint8_t* smem_stg = smem_a + (size_t)S * stage_bytes;     // [8 epilogue warps][32 rows][128 B], 128B-swizzled
     __shared__ uint64_t full_bar[TC_MAX_STAGES], empty_bar[TC_MAX_STAGES], tmem_full[2], tmem_empty[2];
     __shared__ uint32_t tmem_base_s;
-    __shared__ __align__(16) float epi_stage[4 * 32 * 36];   // per-warp 32 x 32 transpose buffer (row stride 36)
     __shared__ __align__(16) float epi_bias[256];
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nt = blockIdx.x % a.n_tiles;                    // this CTA's n-tile (fixed), m-tiles strided
-    const int mt0 = blockIdx.x / a.n_tiles, mt_step = gridDim.x / a.n_tiles;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform role index
+    const int lane = threadIdx.x & 31;
+    // this CTA's (n-tile, k-slice) is fixed; its m-tiles are strided over the CTAs of the same group
+    const int groups = a.n_tiles * a.k_slices;
+    const int gid = blockIdx.x % groups;
+    const int nt = gid % a.n_tiles, k_off = (gid / a.n_tiles) * a.KS;
+    const int mt0 = blockIdx.x / groups, mt_step = gridDim.x / groups;
+    const int my_tiles = mt0 < a.m_tiles ? (a.m_tiles - mt0 + mt_step - 1) / mt_step : 0;
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; s++) { mbar_init(&full_bar[s], 128); mbar_init(&empty_bar[s], 1); }
-        for (int b = 0; b < 2; b++) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 128); }
+        for (int b = 0; b < 2; b++) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 32 * TC_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 4) {
+    if (warp == TC_MMA_WARP) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512u));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
     // resident weight tile: split once per CTA
     {
-        const int k4 = a.K >> 2;
+        const int k4 = a.KS >> 2;
         for (int f = threadIdx.x; f < BN * k4; f += TC_THREADS) {
             const int r = f / k4, kq = f - r * k4;           // row of the tile, 16-byte chunk along K
             const int kc = kq >> 3, c = kq & 7;
             const long long j = (long long)nt * BN + r;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (j < a.N) {
-                const float* p = a.B + j * a.sbj + (long long)(kq * 4) * a.sbi;
+                const float* p = a.B + j * a.sbj + (long long)(k_off + kq * 4) * a.sbi;
                 if (a.sbi == 1) v = __ldg(reinterpret_cast<const float4*>(p));
                 else { v.x = __ldg(p); v.y = __ldg(p + a.sbi); v.z = __ldg(p + 2 * a.sbi); v.w = __ldg(p + 3 * a.sbi); }
             }
@@ -159,90 +237,86 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_tn_kernel(TcArgs a) {
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
 
-    if (warp < 4) {
+    if (warp < TC_EPI_WARPS) {
         // ===================== epilogue =====================
-        // TMEM (lane = row) -> registers -> bias / relu / row mask -> per-warp smem transpose buffer -> full 128-byte
-        // row segments to global (4 rows x 128 B per store instruction instead of 32 rows x 16 B)
-        float* stg = epi_stage + warp * (32 * 36);
-        int it = 0;
-        for (int mt = mt0; mt < a.m_tiles; mt += mt_step, it++) {
+        // TMEM (lane = row) -> registers -> bias / relu / row mask -> swizzled staging tile -> one TMA store per slab
+        const int quad = warp & 3, half = warp >> 2;
+        float* stg = reinterpret_cast<float*>(smem_stg + (size_t)warp * TC_STG_BYTES);
+        const uint32_t stg_addr = smem_u32(stg);
+        float* my_stg = stg + lane * 32;
+        const int sw = lane & 7;
+        for (int it = 0; it < my_tiles; it++) {
+            const int mt = mt0 + it * mt_step;
             const int buf = it & 1;
             mbar_wait(&tmem_full[buf], (it >> 1) & 1);
             tc_fence_after();
-            const long long row0 = (long long)mt * TC_BM + warp * 32;
-            const long long myrow = row0 + lane;
+            const int row0 = mt * TC_BM + quad * 32;
+            const long long myrow = (long long)row0 + lane;
             const bool masked = myrow < a.M && tc_row_masked(a.c_rowmask, a.c_na, a.c_ne, a.c_mper, myrow);
-            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * BN);
-            float* cbase = a.C + row0 * a.ldc + (long long)nt * BN;
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                const int width = min(32, BN - c0);            // BN is a multiple of 16
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * BN);
+            for (int c0 = half * 32; c0 < BN; c0 += 64) {
                 uint32_t r[32];
                 asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+                    "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                      "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                      "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                     : "r"(taddr + (uint32_t)c0));
-                if (width == 32) {
-                    asm volatile(
-                        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                        : "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-                          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                        : "r"(taddr + (uint32_t)(c0 + 16)));
-                }
+                if (lane == 0) tc_bulk_wait_read();        // the previous store of this warp has read the staging tile
+                __syncwarp();
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
                 for (int q = 0; q < 8; q++) {
-                    if (4 * q < width) {
-                        const float4 b4 = *reinterpret_cast<const float4*>(epi_bias + c0 + 4 * q);
-                        float4 v;
-                        v.x = __uint_as_float(r[4 * q + 0]) + b4.x;
-                        v.y = __uint_as_float(r[4 * q + 1]) + b4.y;
-                        v.z = __uint_as_float(r[4 * q + 2]) + b4.z;
-                        v.w = __uint_as_float(r[4 * q + 3]) + b4.w;
-                        if (a.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-                        if (masked) v = make_float4(0.f, 0.f, 0.f, 0.f);
-                        *reinterpret_cast<float4*>(stg + lane * 36 + 4 * q) = v;
-                    }
+                    const float4 b4 = *reinterpret_cast<const float4*>(epi_bias + c0 + 4 * q);
+                    float4 v;
+                    v.x = __uint_as_float(r[4 * q + 0]) + b4.x;
+                    v.y = __uint_as_float(r[4 * q + 1]) + b4.y;
+                    v.z = __uint_as_float(r[4 * q + 2]) + b4.z;
+                    v.w = __uint_as_float(r[4 * q + 3]) + b4.w;
+                    if (a.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                    if (masked) v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    *reinterpret_cast<float4*>(my_stg + ((q ^ sw) << 2)) = v;
                 }
+                fence_async_smem();                        // staging writes -> visible to the TMA (async proxy)
                 __syncwarp();
-                const int cpr = width >> 2;                    // 16-byte chunks per row: 8 or 4
-                const int rpi = 32 / cpr;                      // rows per store instruction: 4 or 8
-                const int rl = lane / cpr, ch = lane - rl * cpr;
-                for (int rb = 0; rb < 32; rb += rpi) {
-                    const int rr = rb + rl;
-                    if (row0 + rr < a.M) {
-                        const float4 v = *reinterpret_cast<const float4*>(stg + rr * 36 + 4 * ch);
-                        *reinterpret_cast<float4*>(cbase + (long long)rr * a.ldc + c0 + 4 * ch) = v;
-                    }
+                if (lane == 0 && row0 < a.M) {
+                    if (a.k_slices > 1) tc_tma_reduce_add(&tmap_c, nt * BN + c0, row0, stg_addr);
+                    else tc_tma_store(&tmap_c, nt * BN + c0, row0, stg_addr);
+                    tc_bulk_commit();
                 }
-                __syncwarp();
             }
             tc_fence_before();
             mbar_arrive(&tmem_empty[buf]);
         }
-    } else if (warp == 4) {
+        if (lane == 0) tc_bulk_wait_all();
+    } else if (warp == TC_MMA_WARP) {
         // ===================== MMA issuer =====================
-        int it = 0, stage = 0;
+        // every operand below is warp-uniform (uniform registers); one elected lane issues
+        const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+        const uint64_t desc_a0 = tc_smem_desc(smem_u32(smem_a)), desc_b0 = tc_smem_desc(smem_u32(smem_b));
+        const uint64_t a_lo_off = (uint64_t)(a_bytes >> 4), b_lo_off = (uint64_t)(b_bytes >> 4);
+        const uint32_t idesc = a.idesc;
+        int stage = 0;
         uint32_t phase = 0;
-        for (int mt = mt0; mt < a.m_tiles; mt += mt_step, it++) {
+        for (int it = 0; it < my_tiles; it++) {
             const int buf = it & 1;
             mbar_wait(&tmem_empty[buf], ((it >> 1) & 1) ^ 1);
             tc_fence_after();
-            const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
+            const uint32_t tmem_d = tmem_u + (uint32_t)(buf * BN);
             for (int kc = 0; kc < KC; kc++) {
                 mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
-                if (lane == 0) {
-                    const uint32_t sa = smem_u32(smem_a + (size_t)stage * stage_bytes);
-                    const uint32_t sb = smem_u32(smem_b + (size_t)kc * 2 * b_bytes);
-                    const uint64_t a_hi = tc_smem_desc(sa), a_lo = tc_smem_desc(sa + a_bytes);
-                    const uint64_t b_hi = tc_smem_desc(sb), b_lo = tc_smem_desc(sb + b_bytes);
+                const uint64_t a_hi = desc_a0 + (uint64_t)((uint32_t)stage * (stage_bytes >> 4));
+                const uint64_t b_hi = desc_b0 + (uint64_t)((uint32_t)kc * ((2 * b_bytes) >> 4));
+                if (elect_one()) {
 #pragma unroll
                     for (int ks = 0; ks < TC_BK / 8; ks++) {
                         const uint64_t adv = (uint64_t)(ks * 2);       // +32 bytes inside the 128B swizzle row
-                        tc_mma(tmem_d, a_lo + adv, b_hi + adv, a.idesc, (kc | ks) != 0);
-                        tc_mma(tmem_d, a_hi + adv, b_lo + adv, a.idesc, 1);
-                        tc_mma(tmem_d, a_hi + adv, b_hi + adv, a.idesc, 1);
+                        tc_mma(tmem_d, a_hi + a_lo_off + adv, b_hi + adv, idesc, (kc | ks) != 0);
+                        tc_mma(tmem_d, a_hi + adv, b_hi + b_lo_off + adv, idesc, 1);
+                        tc_mma(tmem_d, a_hi + adv, b_hi + adv, idesc, 1);
                     }
                     tc_commit(&empty_bar[stage]);                  // frees the smem stage when these MMAs retire
                     if (kc == KC - 1) tc_commit(&tmem_full[buf]);  // accumulator complete -> epilogue
@@ -252,88 +326,120 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_tn_kernel(TcArgs a) {
             }
         }
     } else {
-        // ===================== A producers: group 0 = warps 5-8 (even chunks), group 1 = warps 9-12 (odd chunks) ====
-        // thread -> fixed 16-byte chunk c of rows r0 + 16 i (i < 8): one base pointer per tile, constant smem offsets
-        const int grp = warp < 9 ? 0 : 1;
-        const int pt = threadIdx.x - (grp ? 288 : 160);     // 0..127 within the group
+        // ===================== A producers: group 0 = warps 9-12 (even chunks), group 1 = warps 13-16 (odd chunks) ====
+        // thread -> fixed 16-byte chunk c of rows r0 + 16 i (i < 8); chunk cc of the CTA = (m-tile cc / KC, k-chunk cc % KC)
+        const int grp = (warp - TC_PROD_WARP0) >> 2;
+        const int pt = (int)threadIdx.x - (TC_PROD_WARP0 * 32 + grp * 128);     // 0..127 within the group
         const int r0 = pt >> 3, c = pt & 7;
         const int soff = r0 * 32 + ((c ^ (r0 & 7)) << 2);   // float offset of (r0, c); row r0 + 16 i adds 512 i
-        const long long rstep = 16 * a.lda, ystep = 16 * a.ldy;
-        int stage = 0, chunk_ctr = 0;
-        uint32_t phase = 0;
-        for (int mt = mt0; mt < a.m_tiles; mt += mt_step) {
-            const long long rowb = (long long)mt * TC_BM + r0;
-            const float* pa = a.A + rowb * a.lda + c * 4;
-            const float* py = a.relu_y ? a.relu_y + rowb * a.ldy + c * 4 : nullptr;
-            uint32_t valid = 0;
+        const int total = my_tiles * KC;
+        const bool has_y = a.relu_y != nullptr;
+        float4 va[8], vn[8];
+        int cc = grp;
+        if (cc < total && !has_y) tc_load_a(a, mt0 + (cc / KC) * mt_step, k_off + (cc % KC) * TC_BK, r0, c, va);
+        for (; cc < total; cc += 2) {
+            const int stage = cc % S;
+            const uint32_t phase = (uint32_t)(cc / S) & 1u;
+            if (has_y) {
+                const int mt = mt0 + (cc / KC) * mt_step, kcol = k_off + (cc % KC) * TC_BK;
+                tc_load_a(a, mt, kcol, r0, c, va);
+                tc_mask_relu(a, mt, kcol, r0, c, va);
+            } else if (cc + 2 < total) {
+                const int cn = cc + 2;                     // this group's next chunk: loads in flight while this one is stored
+                tc_load_a(a, mt0 + (cn / KC) * mt_step, k_off + (cn % KC) * TC_BK, r0, c, vn);
+            }
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            float* ahi = reinterpret_cast<float*>(smem_a + (size_t)stage * stage_bytes) + soff;
+            float* alo = ahi + TC_BM * 32;
 #pragma unroll
             for (int i = 0; i < 8; i++) {
-                const long long row = rowb + 16 * i;
-                if (row < a.M && !tc_row_masked(a.a_rowmask, a.a_na, a.a_ne, a.a_mper, row)) valid |= 1u << i;
+                float4 h, l;
+                h.x = __uint_as_float(__float_as_uint(va[i].x) & 0xffffe000u);
+                h.y = __uint_as_float(__float_as_uint(va[i].y) & 0xffffe000u);
+                h.z = __uint_as_float(__float_as_uint(va[i].z) & 0xffffe000u);
+                h.w = __uint_as_float(__float_as_uint(va[i].w) & 0xffffe000u);
+                l.x = va[i].x - h.x; l.y = va[i].y - h.y; l.z = va[i].z - h.z; l.w = va[i].w - h.w;
+                *reinterpret_cast<float4*>(ahi + i * 512) = h;
+                *reinterpret_cast<float4*>(alo + i * 512) = l;
             }
-            for (int kc = 0; kc < KC; kc++, chunk_ctr++) {
-                if ((chunk_ctr & 1) == grp) {
-                    const int k0 = kc * TC_BK;
-                    float4 va[8];
+            fence_async_smem();           // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+            mbar_arrive(&full_bar[stage]);
+            if (!has_y) {
 #pragma unroll
-                    for (int i = 0; i < 8; i++) {
-                        va[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (valid & (1u << i)) va[i] = __ldg(reinterpret_cast<const float4*>(pa + i * rstep + k0));
-                    }
-                    if (py) {
-#pragma unroll
-                        for (int i = 0; i < 8; i++) {
-                            if (valid & (1u << i)) {
-                                const float4 y = __ldg(reinterpret_cast<const float4*>(py + i * ystep + k0));
-                                if (!(y.x > 0.f)) va[i].x = 0.f;
-                                if (!(y.y > 0.f)) va[i].y = 0.f;
-                                if (!(y.z > 0.f)) va[i].z = 0.f;
-                                if (!(y.w > 0.f)) va[i].w = 0.f;
-                            }
-                        }
-                    }
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
-                    float* ahi = reinterpret_cast<float*>(smem_a + (size_t)stage * stage_bytes) + soff;
-                    float* alo = ahi + TC_BM * 32;
-#pragma unroll
-                    for (int i = 0; i < 8; i++) {
-                        float4 h, l;
-                        h.x = __uint_as_float(__float_as_uint(va[i].x) & 0xffffe000u);
-                        h.y = __uint_as_float(__float_as_uint(va[i].y) & 0xffffe000u);
-                        h.z = __uint_as_float(__float_as_uint(va[i].z) & 0xffffe000u);
-                        h.w = __uint_as_float(__float_as_uint(va[i].w) & 0xffffe000u);
-                        l.x = va[i].x - h.x; l.y = va[i].y - h.y; l.z = va[i].z - h.z; l.w = va[i].w - h.w;
-                        *reinterpret_cast<float4*>(ahi + i * 512) = h;
-                        *reinterpret_cast<float4*>(alo + i * 512) = l;
-                    }
-                    fence_async_smem();           // generic-proxy smem writes -> visible to the tensor-core (async) proxy
-                    mbar_arrive(&full_bar[stage]);
-                }
-                if (++stage == S) { stage = 0; phase ^= 1; }
+                for (int i = 0; i < 8; i++) va[i] = vn[i];
             }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) {
+    if (warp == TC_MMA_WARP) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
     }
 }
 
-// n-tile width: multiple of 16 dividing N, <= 256, with the resident split weight (2 * BN * K fp32) within budget
-static int tc_pick_bn(int N, int K) {
-    const int budget = 128 * 1024;
+// CUtensorMap of C viewed as [M][N] fp32 (row stride ldc) with a (32 columns, 32 rows) box, 128B swizzle
+typedef CUresult (*tc_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int tc_make_tmap_c(CUtensorMap* tm, const float* C, long long ldc, int M, int N) {
+    static tc_encode_fn enc = nullptr;
+    static bool tried = false;
+    memset(tm, 0, sizeof(*tm));
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            enc = (tc_encode_fn)p;
+    }
+    if (!enc) return 0;
+    const cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)M};
+    const cuuint64_t strides[1] = {(cuuint64_t)ldc * 4};
+    const cuuint32_t box[2] = {32, 32};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)C, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 1 : 0;
+}
+
+// resident split weight tile (2 * BN * KS fp32) must leave room for >= 2 A stages and the staging tiles
+#define TC_B_BUDGET (128 * 1024)
+
+// k-slices: 1 if a 32-wide n-tile of the whole reduction fits the budget comfortably, else the smallest divisor of K
+// whose slice (a multiple of 32) lets a min(N, 128)-wide tile stay resident
+static int tc_pick_slices(int N, int K) {
+    const int bn = N < 128 ? N : 128;
+    for (int s = 1; s <= 8; s++) {
+        if (K % s) continue;
+        const int ks = K / s;
+        if (ks % TC_BK) continue;
+        if ((long long)2 * bn * ks * 4 <= TC_B_BUDGET) return s;
+    }
+    return 0;
+}
+
+// n-tile width: multiple of 32 dividing N, <= 256, with the resident split weight within budget
+static int tc_pick_bn(int N, int KS) {
     int best = 0;
-    for (int bn = 16; bn <= 256 && bn <= N; bn += 16)
-        if (N % bn == 0 && (long long)2 * bn * K * 4 <= budget) best = bn;
+    for (int bn = 32; bn <= 256 && bn <= N; bn += 32)
+        if (N % bn == 0 && (long long)2 * bn * KS * 4 <= TC_B_BUDGET) best = bn;
     return best;
 }
 
 // Can this problem run on the tensor-core path?  (else the caller uses the fp32 FFMA kernel)
 extern "C" int refil_tc_gemm_supported(int M, int N, int K) {
-    if (M < 1 || K < TC_BK || K % TC_BK != 0 || N < 16 || N % 16 != 0) return 0;
-    return tc_pick_bn(N, K) > 0;
+    if (M < 1 || K < TC_BK || K % TC_BK != 0 || N < 32 || N % 32 != 0) return 0;
+    const int s = tc_pick_slices(N, K);
+    if (s < 1) return 0;
+    return tc_pick_bn(N, K / s) > 0;
+}
+
+extern "C" int refil_tc_gemm_k_slices(int N, int K) {
+    if (K < TC_BK || K % TC_BK != 0 || N < 32 || N % 32 != 0) return 0;
+    return tc_pick_slices(N, K);
 }
 
 extern "C" int refil_tc_gemm_tn(const float* A, long long lda, const float* relu_y, long long ldy,
@@ -351,21 +457,32 @@ extern "C" int refil_tc_gemm_tn(const float* A, long long lda, const float* relu
     a.A = A; a.lda = lda; a.relu_y = relu_y; a.ldy = ldy;
     a.a_rowmask = a_row_entity_mask; a.a_na = a_na > 0 ? a_na : 1; a.a_ne = a_ne; a.a_mper = a_rows_per_copy > 0 ? a_rows_per_copy : 1;
     a.B = B; a.sbj = b_stride_n; a.sbi = b_stride_k;
-    a.C = C; a.ldc = ldc; a.bias = bias; a.relu = relu;
+    a.bias = bias; a.relu = relu;
     a.c_rowmask = c_row_entity_mask; a.c_na = c_na > 0 ? c_na : 1; a.c_ne = c_ne; a.c_mper = c_rows_per_copy > 0 ? c_rows_per_copy : 1;
     a.M = M; a.N = N; a.K = K;
-    const int BN = tc_pick_bn(N, K);
+    a.k_slices = tc_pick_slices(N, K);
+    a.KS = K / a.k_slices;
+    REFIL_CHECK_ARG(a.k_slices == 1 || (!bias && !relu && !c_row_entity_mask),
+                    "tc_gemm_tn: a sliced reduction (K=%d) cannot carry a non-linear epilogue", K);
+    const int BN = tc_pick_bn(N, a.KS);
     a.BN = BN;
     a.n_tiles = N / BN;
     a.m_tiles = refil_cdiv(M, TC_BM);
-    const size_t b_res = (size_t)2 * BN * K * 4, stage_bytes = 2 * (size_t)TC_BM * 128;
-    int stages = (int)((200 * 1024 - b_res) / stage_bytes);
+    const size_t b_res = (size_t)2 * BN * a.KS * 4, stage_bytes = 2 * (size_t)TC_BM * 128;
+    const size_t stg_bytes = (size_t)TC_EPI_WARPS * TC_STG_BYTES;
+    const size_t budget = 227 * 1024 - 1024 /* alignment slack */ - 2048 /* static: barriers, bias */;
+    int stages = (int)((budget - b_res - stg_bytes) / stage_bytes);
     if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
     REFIL_CHECK_ARG(stages >= 2, "tc_gemm_tn: shared memory budget (N=%d K=%d)", N, K);
     a.stages = stages;
     // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=tf32, both K-major, N>>3, M>>4
     a.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-    const size_t smem = b_res + stages * stage_bytes + 1024;
+    CUtensorMap tmap;
+    if (!tc_make_tmap_c(&tmap, C, ldc, M, N)) {
+        refil_set_error("tc_gemm_tn: cuTensorMapEncodeTiled failed (C=%p ldc=%lld M=%d N=%d)", (const void*)C, ldc, M, N);
+        return REFIL_ERR_CUDA;
+    }
+    const size_t smem = b_res + stages * stage_bytes + stg_bytes + 1024;
     static size_t attr_smem = 0;
     if (smem > attr_smem) {
         cudaError_t e = cudaFuncSetAttribute(tc_gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -375,12 +492,20 @@ extern "C" int refil_tc_gemm_tn(const float* A, long long lda, const float* relu
         }
         attr_smem = smem;
     }
+    if (a.k_slices > 1) {             // partial tiles are reduce-added into C
+        cudaError_t e = cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)N * 4, (size_t)M, stream);
+        if (e != cudaSuccess) {
+            refil_set_error("tc_gemm_tn: cudaMemset2DAsync: %s", cudaGetErrorString(e));
+            return REFIL_ERR_CUDA;
+        }
+    }
     const int sms = refil_num_sms();
-    int per_n = sms / a.n_tiles;                 // CTAs per n-tile
-    if (per_n < 1) per_n = 1;
-    if (per_n > a.m_tiles) per_n = a.m_tiles;
-    const int grid = per_n * a.n_tiles;
-    tc_gemm_tn_kernel<<<grid, TC_THREADS, smem, stream>>>(a);
+    const int groups = a.n_tiles * a.k_slices;
+    int per_g = sms / groups;                    // CTAs per (n-tile, k-slice)
+    if (per_g < 1) per_g = 1;
+    if (per_g > a.m_tiles) per_g = a.m_tiles;
+    const int grid = per_g * groups;
+    tc_gemm_tn_kernel<<<grid, TC_THREADS, smem, stream>>>(a, tmap);
     REFIL_CHECK_LAUNCH("tc_gemm_tn");
     return REFIL_OK;
 }
@@ -425,7 +550,7 @@ __device__ __forceinline__ int tc_mn_off(int r, int c16, int n_atoms) {
     return (ka * n_atoms + at) * 128 + kr * 32 + ((((c8 >> 1) ^ kr) << 3) | ((c8 & 1) << 2));
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_wgrad_kernel(TcWArgs a) {
+__global__ void __launch_bounds__(TCW_THREADS, 1) tc_gemm_wgrad_kernel(TcWArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int BQ = a.BQ, S = a.stages;
@@ -434,7 +559,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_wgrad_kernel(TcWArgs a)
     const uint32_t stage_bytes = 2 * x_bytes + 2 * y_bytes; // X_hi | X_lo | Y_hi | Y_lo
     __shared__ uint64_t full_bar[TC_MAX_STAGES], empty_bar[TC_MAX_STAGES], acc_bar;
     __shared__ uint32_t tmem_base_s;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform role index
+    const int lane = threadIdx.x & 31;
     const int ptile = blockIdx.x % a.p_tiles, split = blockIdx.x / a.p_tiles;
     const int chunks_total = (a.M + 31) / 32;
     const int c_begin = split * a.chunks_per_split, c_end = min(chunks_total, c_begin + a.chunks_per_split);
@@ -453,7 +579,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_wgrad_kernel(TcWArgs a)
     for (int s = 0; s < S; s++) {
         float* yhi = reinterpret_cast<float*>(smem + (size_t)s * stage_bytes + 2 * x_bytes);
         float* ylo = reinterpret_cast<float*>(smem + (size_t)s * stage_bytes + 2 * x_bytes + y_bytes);
-        for (int f = threadIdx.x; f < 32 * 32; f += TC_THREADS) {         // 32 rows x 32 floats of the last MN atom
+        for (int f = threadIdx.x; f < 32 * 32; f += TCW_THREADS) {         // 32 rows x 32 floats of the last MN atom
             const int r = f >> 5, e = f & 31;
             const int off = tc_mn_off(r, (ya - 1) * 8 + (e >> 2), ya) + (e & 3);
             yhi[off] = (e == 0) ? 1.f : 0.f;
@@ -498,23 +624,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_wgrad_kernel(TcWArgs a)
         }
     } else if (warp == 4) {
         // ===================== MMA issuer =====================
+        // warp-uniform descriptors (uniform registers); one elected lane issues
+        const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+        const uint32_t smem0 = smem_u32(smem);
+        const uint32_t idesc = a.idesc;
+        const uint64_t x_step = (uint64_t)((xa * 1024) >> 4), y_step = (uint64_t)((ya * 1024) >> 4);
+        const uint64_t x_lo_off = (uint64_t)(x_bytes >> 4), y_lo_off = (uint64_t)(y_bytes >> 4);
         int stage = 0;
         uint32_t phase = 0;
         for (int ch = 0; ch < n_chunks; ch++) {
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
-            if (lane == 0) {
-                const uint32_t sx = smem_u32(smem + (size_t)stage * stage_bytes);
-                const uint32_t sy = sx + 2 * x_bytes;
+            const uint32_t sx = smem0 + (uint32_t)stage * stage_bytes;
+            const uint64_t x_hi = tc_smem_desc_mn(sx, 512, xa * 512);
+            const uint64_t y_hi = tc_smem_desc_mn(sx + 2 * x_bytes, 512, ya * 512);
+            if (elect_one()) {
 #pragma unroll
                 for (int ks = 0; ks < 4; ks++) {                          // 4 MMAs of K = 8 rows = 2 k-atoms each
-                    const uint64_t x_hi = tc_smem_desc_mn(sx + ks * xa * 1024, 512, xa * 512);
-                    const uint64_t x_lo = tc_smem_desc_mn(sx + x_bytes + ks * xa * 1024, 512, xa * 512);
-                    const uint64_t y_hi = tc_smem_desc_mn(sy + ks * ya * 1024, 512, ya * 512);
-                    const uint64_t y_lo = tc_smem_desc_mn(sy + y_bytes + ks * ya * 1024, 512, ya * 512);
-                    tc_mma(tmem_base, x_lo, y_hi, a.idesc, (ch | ks) != 0);
-                    tc_mma(tmem_base, x_hi, y_lo, a.idesc, 1);
-                    tc_mma(tmem_base, x_hi, y_hi, a.idesc, 1);
+                    const uint64_t xo = (uint64_t)ks * x_step, yo = (uint64_t)ks * y_step;
+                    tc_mma(tmem_u, x_hi + x_lo_off + xo, y_hi + yo, idesc, (ch | ks) != 0);
+                    tc_mma(tmem_u, x_hi + xo, y_hi + y_lo_off + yo, idesc, 1);
+                    tc_mma(tmem_u, x_hi + xo, y_hi + yo, idesc, 1);
                 }
                 tc_commit(&empty_bar[stage]);
                 if (ch == n_chunks - 1) tc_commit(&acc_bar);
@@ -669,7 +799,7 @@ extern "C" int refil_tc_gemm_wgrad(const float* X, long long ldx, const float* r
         }
         attr_smem = smem;
     }
-    tc_gemm_wgrad_kernel<<<a.p_tiles * a.splits, TC_THREADS, smem, stream>>>(a);
+    tc_gemm_wgrad_kernel<<<a.p_tiles * a.splits, TCW_THREADS, smem, stream>>>(a);
     REFIL_CHECK_LAUNCH("tc_gemm_wgrad");
     return REFIL_OK;
 }

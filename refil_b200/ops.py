@@ -40,6 +40,16 @@ def set_timing(enabled):
     global _timing
     _timing = {} if enabled else None
     _work.clear()
+    _shape_timing.clear()
+
+
+_shape_timing = {}    # when timing: {"name[MxNxK]": [cuda event pairs]} for the dense-layer kernels
+
+
+def shape_timing_summary():
+    """-> {"name[MxNxK]": (launches, total_ms)}; synchronises."""
+    torch.cuda.synchronize()
+    return {k: (len(v), sum(a.elapsed_time(b) for a, b in v)) for k, v in _shape_timing.items()}
 
 
 _work = {}    # when timing: {kernel name: [algorithmic flops, algorithmic bytes]} accumulated per call
@@ -62,7 +72,7 @@ def timing_summary():
     return out
 
 
-def _call(name, *args):
+def _call(name, *args, shape=None):
     global _launches
     _launches += 1
     if _timing is None:
@@ -73,6 +83,8 @@ def _call(name, *args):
     _lib.call(name, *args, _stream())
     b.record()
     _timing.setdefault(name, []).append((a, b))
+    if shape is not None:
+        _shape_timing.setdefault("%s[%s]" % (name, "x".join(str(int(x)) for x in shape)), []).append((a, b))
 
 
 F32, U8, I32, I64, F64 = torch.float32, torch.uint8, torch.int32, torch.int64, torch.float64
@@ -101,14 +113,14 @@ def tc_gemm_tn(A, B, sbn, sbk, out, N, K, bias=None, relu=False, relu_y=None, a_
     cem, cna, cne, cmper = _rm(c_row_mask)
     _account("tc_gemm_tn", 2.0 * M * N * K, 4.0 * (M * K * (2 if relu_y is not None else 1) + M * N + N * K))
     _call("tc_gemm_tn", _p(A, F32), A.shape[1], _p(relu_y, F32), A.shape[1], aem, ana, ane, amper, _p(B, F32), sbn, sbk,
-          _p(bias, F32), int(relu), cem, cna, cne, cmper, _p(out, F32), out.shape[1], M, N, K)
+          _p(bias, F32), int(relu), cem, cna, cne, cmper, _p(out, F32), out.shape[1], M, N, K, shape=(M, N, K))
     return out
 
 
 def linear_fwd(A, W, bias, out, relu=False, row_mask=None):
     M, K = A.shape
     N = W.shape[0]
-    if _tc_ok(M, N, K):
+    if _tc_ok(M, N, K) and (_lib.load().refil_tc_gemm_k_slices(N, K) == 1 or (bias is None and not relu and row_mask is None)):
         return tc_gemm_tn(A, W, K, 1, out, N, K, bias=bias, relu=relu, c_row_mask=row_mask)
     em, na, ne, mper = _rm(row_mask)
     _call("linear_fwd", _p(A, F32), K, _p(W, F32), W.shape[1], _p(bias, F32), _p(out, F32), N, M, N, K, int(relu),
@@ -141,7 +153,7 @@ def linear_bwd_weight(dC, A, dW, db, relu_y=None, row_mask=None):
     if USE_TENSOR_CORES and M >= TC_MIN_ROWS and _lib.load().refil_tc_wgrad_supported(M, N, K) != 0:
         _account("tc_gemm_wgrad", 2.0 * M * N * K, 4.0 * (M * N * (2 if relu_y is not None else 1) + M * K + N * K))
         _call("tc_gemm_wgrad", _p(dC, F32), N, _p(relu_y, F32), N, em, na, ne, mper, _p(A, F32), K, 0, 1, _p(dW, F32), K,
-              _p(db, F32), M, N, K)
+              _p(db, F32), M, N, K, shape=(M, N, K))
         return
     _call("linear_bwd_weight", _p(dC, F32), N, _p(relu_y, F32), N, em, na, ne, mper, _p(A, F32), K, _p(dW, F32), K,
           _p(db, F32), M, N, K)

@@ -258,7 +258,7 @@ def test_missing_cuda_fails_loudly():
 
 
 @pytest.mark.parametrize("M,N,K", [(1000, 384, 128), (300, 64, 64), (4096, 192, 64), (129, 128, 128), (20000, 32, 128),
-                                   (513, 256, 32), (2048, 16, 64)])
+                                   (513, 256, 32), (2048, 32, 64)])
 def test_tc_gemm_3xtf32_forward(M, N, K):
     """tcgen05 3xTF32 GEMM vs float64: fp32-grade accuracy (a single TF32 pass would be ~1e-3)."""
     from refil_b200 import _lib, ops
