@@ -181,6 +181,29 @@ __device__ __forceinline__ void tc_mask_relu(const TcArgs& a, int mt, int kcol, 
     }
 }
 
+// split the 8 float4 of chunk cc into the hi / lo tiles of its pipeline stage and hand the stage to the MMA warp
+__device__ __forceinline__ void tc_store_chunk(const float4 (&va)[8], uint8_t* smem_a, uint32_t stage_bytes, int soff, int cc,
+                                               int S, uint64_t* full_bar, uint64_t* empty_bar) {
+    const int stage = cc % S;
+    const uint32_t phase = (uint32_t)(cc / S) & 1u;
+    mbar_wait(&empty_bar[stage], phase ^ 1);
+    float* ahi = reinterpret_cast<float*>(smem_a + (size_t)stage * stage_bytes) + soff;
+    float* alo = ahi + TC_BM * 32;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        float4 h, l;
+        h.x = __uint_as_float(__float_as_uint(va[i].x) & 0xffffe000u);
+        h.y = __uint_as_float(__float_as_uint(va[i].y) & 0xffffe000u);
+        h.z = __uint_as_float(__float_as_uint(va[i].z) & 0xffffe000u);
+        h.w = __uint_as_float(__float_as_uint(va[i].w) & 0xffffe000u);
+        l.x = va[i].x - h.x; l.y = va[i].y - h.y; l.z = va[i].z - h.z; l.w = va[i].w - h.w;
+        *reinterpret_cast<float4*>(ahi + i * 512) = h;
+        *reinterpret_cast<float4*>(alo + i * 512) = l;
+    }
+    fence_async_smem();           // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+    mbar_arrive(&full_bar[stage]);
+}
+
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_tn_kernel(TcArgs a, const __grid_constant__ CUtensorMap tmap_c) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024-byte aligned base (dynamic smem is only guaranteed 16-byte aligned)
@@ -334,39 +357,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_tn_kernel(TcArgs a, con
         const int soff = r0 * 32 + ((c ^ (r0 & 7)) << 2);   // float offset of (r0, c); row r0 + 16 i adds 512 i
         const int total = my_tiles * KC;
         const bool has_y = a.relu_y != nullptr;
-        float4 va[8], vn[8];
+        // ping-pong register buffers: while chunk cc is split and stored, the loads of this group's next chunk (cc + 2)
+        // are already in flight -> 4 chunks (64 KB) of global loads in flight per SM
+        float4 va[8], vb[8];
         int cc = grp;
-        if (cc < total && !has_y) tc_load_a(a, mt0 + (cc / KC) * mt_step, k_off + (cc % KC) * TC_BK, r0, c, va);
-        for (; cc < total; cc += 2) {
-            const int stage = cc % S;
-            const uint32_t phase = (uint32_t)(cc / S) & 1u;
-            if (has_y) {
+        if (has_y) {
+            for (; cc < total; cc += 2) {
                 const int mt = mt0 + (cc / KC) * mt_step, kcol = k_off + (cc % KC) * TC_BK;
                 tc_load_a(a, mt, kcol, r0, c, va);
                 tc_mask_relu(a, mt, kcol, r0, c, va);
-            } else if (cc + 2 < total) {
-                const int cn = cc + 2;                     // this group's next chunk: loads in flight while this one is stored
-                tc_load_a(a, mt0 + (cn / KC) * mt_step, k_off + (cn % KC) * TC_BK, r0, c, vn);
+                tc_store_chunk(va, smem_a, stage_bytes, soff, cc, S, full_bar, empty_bar);
             }
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            float* ahi = reinterpret_cast<float*>(smem_a + (size_t)stage * stage_bytes) + soff;
-            float* alo = ahi + TC_BM * 32;
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                float4 h, l;
-                h.x = __uint_as_float(__float_as_uint(va[i].x) & 0xffffe000u);
-                h.y = __uint_as_float(__float_as_uint(va[i].y) & 0xffffe000u);
-                h.z = __uint_as_float(__float_as_uint(va[i].z) & 0xffffe000u);
-                h.w = __uint_as_float(__float_as_uint(va[i].w) & 0xffffe000u);
-                l.x = va[i].x - h.x; l.y = va[i].y - h.y; l.z = va[i].z - h.z; l.w = va[i].w - h.w;
-                *reinterpret_cast<float4*>(ahi + i * 512) = h;
-                *reinterpret_cast<float4*>(alo + i * 512) = l;
-            }
-            fence_async_smem();           // generic-proxy smem writes -> visible to the tensor-core (async) proxy
-            mbar_arrive(&full_bar[stage]);
-            if (!has_y) {
-#pragma unroll
-                for (int i = 0; i < 8; i++) va[i] = vn[i];
+        } else if (cc < total) {
+            tc_load_a(a, mt0 + (cc / KC) * mt_step, k_off + (cc % KC) * TC_BK, r0, c, va);
+            for (;;) {
+                int cn = cc + 2;
+                if (cn < total) tc_load_a(a, mt0 + (cn / KC) * mt_step, k_off + (cn % KC) * TC_BK, r0, c, vb);
+                tc_store_chunk(va, smem_a, stage_bytes, soff, cc, S, full_bar, empty_bar);
+                cc = cn;
+                if (cc >= total) break;
+                cn = cc + 2;
+                if (cn < total) tc_load_a(a, mt0 + (cn / KC) * mt_step, k_off + (cn % KC) * TC_BK, r0, c, va);
+                tc_store_chunk(vb, smem_a, stage_bytes, soff, cc, S, full_bar, empty_bar);
+                cc = cn;
+                if (cc >= total) break;
             }
         }
     }
