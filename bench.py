@@ -205,8 +205,8 @@ def run_ours(a):
     torch.cuda.set_device(local)
     dev = "cuda:%d" % local
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the single JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+            os.environ.pop("NCCL_DEBUG")               # those levels print the NCCL banner on stdout: keep it to the JSON line
         from refil_b200 import parallel
         parallel.init_distributed(backend="nccl", device=dev)
     alg, B, T, na, ne, ed, A, _ = WORKLOADS[a.workload]
@@ -250,6 +250,8 @@ def run_ours(a):
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
+            if os.environ.get("REFIL_BENCH_DEBUG"):
+                print("rank %d: %.3f ms for %d steps" % (rank, float(ms.item()), steps), file=sys.stderr)
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
