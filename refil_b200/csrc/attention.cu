@@ -117,58 +117,103 @@ __device__ __forceinline__ void att_tma_load_tile(float* tile, const CUtensorMap
     }
 }
 
-// mask words of attention row i (one per copy, bit j set = entity j masked or padding), built with ballots: lane = entity.
-// The explicit-mask bytes of all rows of the pass are fetched first (independent loads, one latency), then combined with
-// the closed-form terms; copies that share one explicit tensor (plain / within / interact over obs_mask) load it once.
-__device__ __forceinline__ void att_row_masks(const AttnArgs& a, int n, int lane, int ib, int ipp, int il, int g_j,
-                                              int ina_j, int em_j, uint32_t mb[ATT_MAX_COPIES]) {
-    uint32_t ex[ATT_MAX_COPIES];          // bit r: explicit mask of (row ib + r, entity = lane)
+// Mask resolution, split in two so that the global bytes of the NEXT unit can be requested a whole unit of compute ahead:
+//   att_meta_load    : lane = entity j requests its group bit, t=0 / current inactive flags and the explicit-mask bytes of
+//                      the 8 query rows of the pass (copies that share copy 0's tensor load nothing);
+//   att_meta_resolve : warp ballots turn them into entity SETS (inactive at t=0, masked now, active members of group 0 / 1,
+//                      one word per explicit row); every lane then assembles the mask word of ITS query row for each copy
+//                      with plain bit algebra:  W (mode&3 == 1): everything outside my group, I (== 2): my group,
+//                      ACTIVE0 (4) / DEFAULT (8): the inactive sets, all-ones if my own row is inactive; bit j set = masked.
+struct AttMeta {
+    uint8_t v[ATT_MAX_COPIES][8];
+    int g, ina, em;
+};
+
+__device__ __forceinline__ bool att_owns_mask(const AttnArgs& a, int c) {
+    return c < a.C && a.mask[c] != nullptr &&
+           !(c > 0 && a.mask[c] == a.mask[0] && a.mask_stride_n[c] == a.mask_stride_n[0]);
+}
+
+__device__ __forceinline__ void att_meta_load(const AttnArgs& a, long long n, int lane, int ib, AttMeta& m) {
+    m.g = 0; m.ina = 0; m.em = 0;
 #pragma unroll
-    for (int c = 0; c < ATT_MAX_COPIES; c++) {
-        mb[c] = 0xffffffffu;
-        ex[c] = 0;
-        if (c < a.C && a.mask[c] && lane < a.ne) {
-            if (c > 0 && a.mask[c] == a.mask[0] && a.mask_stride_n[c] == a.mask_stride_n[0]) {
-                ex[c] = ex[0];
-            } else {
-                const uint8_t* mp = a.mask[c] + (size_t)n * a.mask_stride_n[c] + (size_t)ib * a.ne + lane;
-                for (int r0 = 0; r0 < ipp; r0 += 8) {
-                    uint8_t v[8];
+    for (int c = 0; c < ATT_MAX_COPIES; c++)
 #pragma unroll
-                    for (int r = 0; r < 8; r++) v[r] = (r0 + r < ipp && ib + r0 + r < a.nq) ? mp[(size_t)(r0 + r) * a.ne] : 0;
-#pragma unroll
-                    for (int r = 0; r < 8; r++) ex[c] |= (v[r] ? 1u : 0u) << (r0 + r);
-                }
-            }
+        for (int r = 0; r < 8; r++) m.v[c][r] = 0;
+    if (lane < a.ne) {
+        const long long b = n / a.T;
+        if (a.group_bits) m.g = a.group_bits[(size_t)b * a.ne + lane];
+        if (a.entity_mask) {
+            m.ina = a.entity_mask[((size_t)b * a.T) * a.ne + lane];
+            m.em = a.entity_mask[(size_t)n * a.ne + lane];
         }
-    }
-    for (int r = 0; r < ipp; r++) {
-        const int i = ib + r;
-        if (i >= a.nq) break;
-        const int g_i = __shfl_sync(0xffffffffu, g_j, i), ina_i = __shfl_sync(0xffffffffu, ina_j, i),
-                  em_i = __shfl_sync(0xffffffffu, em_j, i);
-        const bool same = (g_i == g_j) && !ina_i && !ina_j;
 #pragma unroll
         for (int c = 0; c < ATT_MAX_COPIES; c++) {
-            if (c < a.C) {
-                const int mode = a.mode[c], part = mode & 3;
-                bool m = lane >= a.ne || ((ex[c] >> r) & 1u);
-                if (part) m = m || (part == 1 ? !same : same);
-                if (mode & 4) m = m || ina_i || ina_j;
-                if (mode & 8) m = m || em_i || em_j;
-                const uint32_t word = __ballot_sync(0xffffffffu, m);
-                if (il == r) mb[c] = word;
+            if (att_owns_mask(a, c)) {
+                const uint8_t* mp = a.mask[c] + (size_t)n * a.mask_stride_n[c] + (size_t)ib * a.ne + lane;
+#pragma unroll
+                for (int r = 0; r < 8; r++)
+                    if (ib + r < a.nq) m.v[c][r] = mp[(size_t)r * a.ne];
             }
         }
     }
 }
 
-template <int HD, int NEB>
-__global__ void __launch_bounds__(32 * ATT_MAX_WARPS) attn_fwd_kernel(AttnArgs a, int tile_floats, int warp_floats, const __grid_constant__ CUtensorMap tmap, int use_tmap) {
+__device__ __forceinline__ void att_meta_resolve(const AttnArgs& a, long long n, int lane, int ib, int ipp, int il,
+                                                 const AttMeta& m, uint32_t mb[ATT_MAX_COPIES]) {
+    const bool in_range = lane < a.ne;
+    const uint32_t PAD = ~__ballot_sync(0xffffffffu, in_range);
+    const uint32_t INA = __ballot_sync(0xffffffffu, m.ina != 0), EM = __ballot_sync(0xffffffffu, m.em != 0);
+    const uint32_t G1 = __ballot_sync(0xffffffffu, in_range && m.g != 0 && m.ina == 0);
+    const uint32_t G0 = __ballot_sync(0xffffffffu, in_range && m.g == 0 && m.ina == 0);
+    const int i = ib + il;                                        // my query row (< 32)
+    const bool ina_i = (INA >> i) & 1u, em_i = (EM >> i) & 1u;
+    const uint32_t same = ((G1 >> i) & 1u) ? G1 : (((G0 >> i) & 1u) ? G0 : 0u);   // active entities of my row's group
+    uint32_t exw[ATT_MAX_COPIES];                                 // explicit mask word of my row
+#pragma unroll
+    for (int c = 0; c < ATT_MAX_COPIES; c++) {
+        exw[c] = 0;
+        if (att_owns_mask(a, c)) {
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+                if (r < ipp) {                                    // warp-uniform
+                    const uint32_t w = __ballot_sync(0xffffffffu, m.v[c][r] != 0);
+                    if (il == r) exw[c] = w;
+                }
+            }
+            for (int r = 8; r < ipp; r++) {                       // heads <= 2: more than 8 rows per pass (rare)
+                const bool bit = in_range && ib + r < a.nq &&
+                                 a.mask[c][(size_t)n * a.mask_stride_n[c] + (size_t)(ib + r) * a.ne + lane] != 0;
+                const uint32_t w = __ballot_sync(0xffffffffu, bit);
+                if (il == r) exw[c] = w;
+            }
+        } else if (c > 0 && c < a.C && a.mask[c] != nullptr) {
+            exw[c] = exw[0];
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < ATT_MAX_COPIES; c++) {
+        uint32_t word = 0xffffffffu;
+        if (c < a.C && i < a.nq) {
+            const int mode = a.mode[c], part = mode & 3;
+            word = PAD | exw[c];
+            if (part == 1) word |= ~same;
+            if (part == 2) word |= same;
+            if (mode & 4) word |= INA | (ina_i ? 0xffffffffu : 0u);
+            if (mode & 8) word |= EM | (em_i ? 0xffffffffu : 0u);
+        }
+        mb[c] = word;
+    }
+}
+
+template <int HD, int H>
+__global__ void __launch_bounds__(32 * ATT_MAX_WARPS) attn_fwd_kernel(AttnArgs a, int NEB, int tile_floats, int warp_floats, const __grid_constant__ CUtensorMap tmap, int use_tmap) {
     extern __shared__ __align__(128) float smem_raw_[];
-    float* smem = reinterpret_cast<float*>(((uintptr_t)smem_raw_ + 127) & ~(uintptr_t)127);
-    constexpr int NCH = HD / 4;
-    const int d = a.d, ne = a.ne, nq = a.nq, H = a.H, ldk = 2 * d;
+    // 128-byte aligned base, derived by pointer arithmetic on the __shared__ symbol so that every access below is
+    // provably shared memory (LDS / STS, not generic LD / ST)
+    float* smem = smem_raw_ + (((128u - (att_smem_u32(smem_raw_) & 127u)) & 127u) >> 2);
+    constexpr int NCH = HD / 4, d = HD * H, ldk = 2 * d;   // compile-time row strides: tile offsets become immediates
+    const int ne = a.ne, nq = a.nq;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
     float* kv = smem + (size_t)warp * warp_floats;                       // [NEB][ldk]: K | V rows of the current unit
     float* lgs = kv + tile_floats + lane;                                // [NEB][32]: my row of logits, lgs[j * 32]
@@ -179,46 +224,69 @@ __global__ void __launch_bounds__(32 * ATT_MAX_WARPS) attn_fwd_kernel(AttnArgs a
     }
     for (int f = ne * ldk + lane; f < NEB * ldk; f += 32) kv[f] = 0.f;   // padding rows stay zero
     __syncwarp();
-    const int ipp = 32 / H, h = lane % H, il = lane / H;
+    constexpr int ipp = 32 / H;
+    const int h = lane % H, il = lane / H;
+    int rot[NCH];                                        // float offset of my kc-th chunk inside a row (head-rotated)
+#pragma unroll
+    for (int kc = 0; kc < NCH; kc++) rot[kc] = h * HD + 4 * ((kc + h) & (NCH - 1));
     const float inv_scale = 1.f / sqrtf((float)HD);
     const long long gw = (long long)blockIdx.x * wpc + warp, GW = (long long)gridDim.x * wpc;
     uint32_t parity = 0;
+    // the Q row and the mask bytes of the NEXT unit are requested before the current one is computed
+    auto load_q = [&](long long n, int i, float4 (&dst)[NCH]) {
+        const float* qsrc = a.qkv + ((size_t)n * ne + i) * 3 * d;
+#pragma unroll
+        for (int kc = 0; kc < NCH; kc++) dst[kc] = __ldg(reinterpret_cast<const float4*>(qsrc + rot[kc]));
+    };
+    AttMeta mn;
+    float4 qn[NCH];
+    if (gw < a.N) {
+        att_meta_load(a, gw, lane, 0, mn);
+        load_q(gw, il < nq ? il : 0, qn);
+    }
     for (long long n = gw; n < a.N; n += GW) {
         if (use_tmap) att_tma_load_tile(kv, &tmap, d, ne, n, bar, lane);
         else att_tma_load_rows(kv, a.qkv + ((size_t)n * ne) * 3 * d + d, 3 * d, ne, 2 * d, ldk, bar, lane);
-        const int b = (int)(n / a.T);
-        int g_j = 0, ina_j = 0, em_j = 0;
-        if (lane < ne) {
-            if (a.group_bits) g_j = a.group_bits[(size_t)b * ne + lane];
-            if (a.entity_mask) {
-                ina_j = a.entity_mask[((size_t)b * a.T) * ne + lane];
-                em_j = a.entity_mask[(size_t)n * ne + lane];
-            }
+        const AttMeta mc = mn;
+        float4 qc[NCH];
+#pragma unroll
+        for (int kc = 0; kc < NCH; kc++) qc[kc] = qn[kc];
+        if (n + GW < a.N) {
+            att_meta_load(a, n + GW, lane, 0, mn);
+            load_q(n + GW, il < nq ? il : 0, qn);
         }
         bool waited = false;
         for (int ib = 0; ib < nq; ib += ipp) {
             const int i = ib + il;
             const bool active = i < nq;
             uint32_t mb[ATT_MAX_COPIES];
-            att_row_masks(a, (int)n, lane, ib, ipp, il, g_j, ina_j, em_j, mb);
-            // my Q row, chunks in head-rotated order
             float q[HD];
-            const float* qsrc = a.qkv + ((size_t)n * ne + (active ? i : 0)) * 3 * d + h * HD;
+            if (ib == 0) {
+                att_meta_resolve(a, n, lane, 0, ipp, il, mc, mb);
 #pragma unroll
-            for (int kc = 0; kc < NCH; kc++) {
-                const float4 v = active ? __ldg(reinterpret_cast<const float4*>(qsrc + 4 * ((kc + h) & (NCH - 1))))
-                                        : make_float4(0.f, 0.f, 0.f, 0.f);
-                q[4 * kc] = v.x; q[4 * kc + 1] = v.y; q[4 * kc + 2] = v.z; q[4 * kc + 3] = v.w;
+                for (int kc = 0; kc < NCH; kc++) {
+                    q[4 * kc] = qc[kc].x; q[4 * kc + 1] = qc[kc].y; q[4 * kc + 2] = qc[kc].z; q[4 * kc + 3] = qc[kc].w;
+                }
+            } else {                                               // further passes (nq > 32 / heads): loaded in place
+                AttMeta mt;
+                att_meta_load(a, n, lane, ib, mt);
+                float4 qt[NCH];
+                load_q(n, active ? i : 0, qt);
+                att_meta_resolve(a, n, lane, ib, ipp, il, mt, mb);
+#pragma unroll
+                for (int kc = 0; kc < NCH; kc++) {
+                    q[4 * kc] = qt[kc].x; q[4 * kc + 1] = qt[kc].y; q[4 * kc + 2] = qt[kc].z; q[4 * kc + 3] = qt[kc].w;
+                }
             }
             if (!waited) { att_mbar_wait(bar, parity); parity ^= 1; waited = true; }
-            const float* kbase = kv + h * HD;
+            const float* kbase = kv;
             float mx[ATT_MAX_COPIES] = {-INFINITY, -INFINITY, -INFINITY};
 #pragma unroll 4
             for (int j = 0; j < NEB; j++) {
                 float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
                 for (int kc = 0; kc < NCH; kc++) {
-                    const float4 k4 = *reinterpret_cast<const float4*>(kbase + j * ldk + 4 * ((kc + h) & (NCH - 1)));
+                    const float4 k4 = *reinterpret_cast<const float4*>(kbase + j * ldk + rot[kc]);
                     s0 = fmaf(q[4 * kc], k4.x, s0);
                     s1 = fmaf(q[4 * kc + 1], k4.y, s1);
                     s2 = fmaf(q[4 * kc + 2], k4.z, s2);
@@ -245,7 +313,7 @@ __global__ void __launch_bounds__(32 * ATT_MAX_WARPS) attn_fwd_kernel(AttnArgs a
                         ssum += e;
 #pragma unroll
                         for (int kc = 0; kc < NCH; kc++) {
-                            const float4 v4 = *reinterpret_cast<const float4*>(kbase + j * ldk + d + 4 * ((kc + h) & (NCH - 1)));
+                            const float4 v4 = *reinterpret_cast<const float4*>(kbase + j * ldk + d + rot[kc]);
                             acc[4 * kc] = fmaf(e, v4.x, acc[4 * kc]);
                             acc[4 * kc + 1] = fmaf(e, v4.y, acc[4 * kc + 1]);
                             acc[4 * kc + 2] = fmaf(e, v4.z, acc[4 * kc + 2]);
@@ -254,10 +322,10 @@ __global__ void __launch_bounds__(32 * ATT_MAX_WARPS) attn_fwd_kernel(AttnArgs a
                     }
                     const float r = ssum > 0.f ? 1.f / ssum : 0.f;    // all-masked row -> zeros (attention.py:58-60)
                     if (active) {
-                        float* dst = a.out + (((size_t)c * a.N + n) * nq + i) * d + h * HD;
+                        float* dst = a.out + (((size_t)c * a.N + n) * nq + i) * d;
 #pragma unroll
                         for (int kc = 0; kc < NCH; kc++)
-                            *reinterpret_cast<float4*>(dst + 4 * ((kc + h) & (NCH - 1))) =
+                            *reinterpret_cast<float4*>(dst + rot[kc]) =
                                 make_float4(acc[4 * kc] * r, acc[4 * kc + 1] * r, acc[4 * kc + 2] * r, acc[4 * kc + 3] * r);
                     }
                 }
@@ -272,14 +340,20 @@ __global__ void __launch_bounds__(32 * ATT_MAX_WARPS) attn_fwd_kernel(AttnArgs a
 //            / sqrt(hd); dQ_i accumulates in registers over the copies; w and dlogit go to the warp's smem scratch;
 //   phase 2, lane = (entity j, head h): dK_j = sum_{c,i} dlogit_ij Q_i, dV_j = sum_{c,i} w_ij dO_i (Q / dO rows come
 //            back through L1), written over the K|V tile, which is then streamed out as the K|V columns of dQKV.
-template <int HD, int NEB>
-__global__ void __launch_bounds__(32 * ATT_MAX_WARPS) attn_bwd_kernel(AttnArgs a, int tile_floats, int warp_floats, const __grid_constant__ CUtensorMap tmap, int use_tmap) {
+template <int HD, int H>
+__global__ void __launch_bounds__(32 * ATT_MAX_WARPS) attn_bwd_kernel(AttnArgs a, int NEB, int tile_floats, int warp_floats, const __grid_constant__ CUtensorMap tmap, int use_tmap) {
     extern __shared__ __align__(128) float smem_raw_[];
-    float* smem = reinterpret_cast<float*>(((uintptr_t)smem_raw_ + 127) & ~(uintptr_t)127);
-    constexpr int NCH = HD / 4;
-    const int d = a.d, ne = a.ne, nq = a.nq, H = a.H, ldk = 2 * d;
+    // 128-byte aligned base, derived by pointer arithmetic on the __shared__ symbol so that every access below is
+    // provably shared memory (LDS / STS, not generic LD / ST)
+    float* smem = smem_raw_ + (((128u - (att_smem_u32(smem_raw_) & 127u)) & 127u) >> 2);
+    constexpr int NCH = HD / 4, d = HD * H, ldk = 2 * d;   // compile-time row strides: tile offsets become immediates
+    const int ne = a.ne, nq = a.nq;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
-    const int ipp = 32 / H, h = lane % H, il = lane / H;
+    constexpr int ipp = 32 / H;
+    const int h = lane % H, il = lane / H;
+    int rot[NCH];                                        // float offset of my kc-th chunk inside a row (head-rotated)
+#pragma unroll
+    for (int kc = 0; kc < NCH; kc++) rot[kc] = h * HD + 4 * ((kc + h) & (NCH - 1));
     const int nqp = (nq + ipp - 1) / ipp * ipp;                          // agent rows padded to whole passes
     float* kv = smem + (size_t)warp * warp_floats;                       // [NEB][ldk]
     const int sstr = H * nqp;                                            // scratch stride between entities j
@@ -295,18 +369,29 @@ __global__ void __launch_bounds__(32 * ATT_MAX_WARPS) attn_bwd_kernel(AttnArgs a
     const float inv_scale = 1.f / sqrtf((float)HD);
     const long long gw = (long long)blockIdx.x * wpc + warp, GW = (long long)gridDim.x * wpc;
     uint32_t parity = 0;
+    // the Q row and the mask bytes of the NEXT unit are requested before the current one is computed
+    auto load_q = [&](long long n, int i, float4 (&dst)[NCH]) {
+        const float* qsrc = a.qkv + ((size_t)n * ne + i) * 3 * d;
+#pragma unroll
+        for (int kc = 0; kc < NCH; kc++) dst[kc] = __ldg(reinterpret_cast<const float4*>(qsrc + rot[kc]));
+    };
+    AttMeta mn;
+    float4 qn[NCH];
+    if (gw < a.N) {
+        att_meta_load(a, gw, lane, 0, mn);
+        load_q(gw, il < nq ? il : 0, qn);
+    }
     for (long long n = gw; n < a.N; n += GW) {
         for (int f = ne * ldk + lane; f < NEB * ldk; f += 32) kv[f] = 0.f;   // padding rows (the tile is reused for dK|dV)
         if (use_tmap) att_tma_load_tile(kv, &tmap, d, ne, n, bar, lane);
         else att_tma_load_rows(kv, a.qkv + ((size_t)n * ne) * 3 * d + d, 3 * d, ne, 2 * d, ldk, bar, lane);
-        const int b = (int)(n / a.T);
-        int g_j = 0, ina_j = 0, em_j = 0;
-        if (lane < ne) {
-            if (a.group_bits) g_j = a.group_bits[(size_t)b * ne + lane];
-            if (a.entity_mask) {
-                ina_j = a.entity_mask[((size_t)b * a.T) * ne + lane];
-                em_j = a.entity_mask[(size_t)n * ne + lane];
-            }
+        const AttMeta mc = mn;
+        float4 qc[NCH];
+#pragma unroll
+        for (int kc = 0; kc < NCH; kc++) qc[kc] = qn[kc];
+        if (n + GW < a.N) {
+            att_meta_load(a, n + GW, lane, 0, mn);
+            load_q(n + GW, il < nq ? il : 0, qn);
         }
         // dQ of the non-query rows is zero
         {
@@ -321,24 +406,37 @@ __global__ void __launch_bounds__(32 * ATT_MAX_WARPS) attn_bwd_kernel(AttnArgs a
             const int i = ib + il;                                       // < nqp
             const bool active = i < nq;
             uint32_t mb[ATT_MAX_COPIES];
-            att_row_masks(a, (int)n, lane, ib, ipp, il, g_j, ina_j, em_j, mb);
             float q[HD];
-            const float* qsrc = a.qkv + ((size_t)n * ne + (active ? i : 0)) * 3 * d + h * HD;
+            if (ib == 0) {
+                att_meta_resolve(a, n, lane, 0, ipp, il, mc, mb);
 #pragma unroll
-            for (int kc = 0; kc < NCH; kc++) {
-                const float4 v = active ? __ldg(reinterpret_cast<const float4*>(qsrc + 4 * ((kc + h) & (NCH - 1))))
-                                        : make_float4(0.f, 0.f, 0.f, 0.f);
-                q[4 * kc] = v.x; q[4 * kc + 1] = v.y; q[4 * kc + 2] = v.z; q[4 * kc + 3] = v.w;
+                for (int kc = 0; kc < NCH; kc++) {
+                    q[4 * kc] = qc[kc].x; q[4 * kc + 1] = qc[kc].y; q[4 * kc + 2] = qc[kc].z; q[4 * kc + 3] = qc[kc].w;
+                }
+            } else {                                               // further passes (nq > 32 / heads): loaded in place
+                AttMeta mt;
+                att_meta_load(a, n, lane, ib, mt);
+                float4 qt[NCH];
+                load_q(n, active ? i : 0, qt);
+                att_meta_resolve(a, n, lane, ib, ipp, il, mt, mb);
+#pragma unroll
+                for (int kc = 0; kc < NCH; kc++) {
+                    q[4 * kc] = qt[kc].x; q[4 * kc + 1] = qt[kc].y; q[4 * kc + 2] = qt[kc].z; q[4 * kc + 3] = qt[kc].w;
+                }
+            }
+            if (!active) {
+#pragma unroll
+                for (int k = 0; k < HD; k++) q[k] = 0.f;
             }
             if (!waited) { att_mbar_wait(bar, parity); parity ^= 1; waited = true; }
-            const float* kbase = kv + h * HD;
+            const float* kbase = kv;
             float mx[ATT_MAX_COPIES] = {-INFINITY, -INFINITY, -INFINITY};
 #pragma unroll 4
             for (int j = 0; j < NEB; j++) {
                 float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
                 for (int kc = 0; kc < NCH; kc++) {
-                    const float4 k4 = *reinterpret_cast<const float4*>(kbase + j * ldk + 4 * ((kc + h) & (NCH - 1)));
+                    const float4 k4 = *reinterpret_cast<const float4*>(kbase + j * ldk + rot[kc]);
                     s0 = fmaf(q[4 * kc], k4.x, s0);
                     s1 = fmaf(q[4 * kc + 1], k4.y, s1);
                     s2 = fmaf(q[4 * kc + 2], k4.z, s2);
@@ -359,10 +457,10 @@ __global__ void __launch_bounds__(32 * ATT_MAX_WARPS) attn_bwd_kernel(AttnArgs a
                     const uint32_t bits = mb[c];
                     const float m = mx[c];
                     float go[HD];                                      // my dO row of this copy, rotated like q
-                    const float* gsrc = a.dout + (((size_t)c * a.N + n) * nq + (active ? i : 0)) * d + h * HD;
+                    const float* gsrc = a.dout + (((size_t)c * a.N + n) * nq + (active ? i : 0)) * d;
 #pragma unroll
                     for (int kc = 0; kc < NCH; kc++) {
-                        const float4 v = active ? __ldg(reinterpret_cast<const float4*>(gsrc + 4 * ((kc + h) & (NCH - 1))))
+                        const float4 v = active ? __ldg(reinterpret_cast<const float4*>(gsrc + rot[kc]))
                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
                         go[4 * kc] = v.x; go[4 * kc + 1] = v.y; go[4 * kc + 2] = v.z; go[4 * kc + 3] = v.w;
                     }
@@ -383,7 +481,7 @@ __global__ void __launch_bounds__(32 * ATT_MAX_WARPS) attn_bwd_kernel(AttnArgs a
                         float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
                         for (int kc = 0; kc < NCH; kc++) {
-                            const float4 v4 = *reinterpret_cast<const float4*>(kbase + j * ldk + d + 4 * ((kc + h) & (NCH - 1)));
+                            const float4 v4 = *reinterpret_cast<const float4*>(kbase + j * ldk + d + rot[kc]);
                             s0 = fmaf(go[4 * kc], v4.x, s0);
                             s1 = fmaf(go[4 * kc + 1], v4.y, s1);
                             s2 = fmaf(go[4 * kc + 2], v4.z, s2);
@@ -400,7 +498,7 @@ __global__ void __launch_bounds__(32 * ATT_MAX_WARPS) attn_bwd_kernel(AttnArgs a
                         sdr[j * sstr] = dl;
 #pragma unroll
                         for (int kc = 0; kc < NCH; kc++) {
-                            const float4 k4 = *reinterpret_cast<const float4*>(kbase + j * ldk + 4 * ((kc + h) & (NCH - 1)));
+                            const float4 k4 = *reinterpret_cast<const float4*>(kbase + j * ldk + rot[kc]);
                             dq[4 * kc] = fmaf(dl, k4.x, dq[4 * kc]);
                             dq[4 * kc + 1] = fmaf(dl, k4.y, dq[4 * kc + 1]);
                             dq[4 * kc + 2] = fmaf(dl, k4.z, dq[4 * kc + 2]);
@@ -410,10 +508,10 @@ __global__ void __launch_bounds__(32 * ATT_MAX_WARPS) attn_bwd_kernel(AttnArgs a
                 }
             }
             if (active) {
-                float* dst = a.dqkv + ((size_t)n * ne + i) * 3 * d + h * HD;
+                float* dst = a.dqkv + ((size_t)n * ne + i) * 3 * d;
 #pragma unroll
                 for (int kc = 0; kc < NCH; kc++)
-                    *reinterpret_cast<float4*>(dst + 4 * ((kc + h) & (NCH - 1))) =
+                    *reinterpret_cast<float4*>(dst + rot[kc]) =
                         make_float4(dq[4 * kc], dq[4 * kc + 1], dq[4 * kc + 2], dq[4 * kc + 3]);
             }
         }
@@ -525,21 +623,24 @@ static int attn_launch(K kernel, const AttnArgs& a, size_t smem, int grid, int w
     return REFIL_OK;
 }
 
-// dispatch on (head dim, padded entity count)
-#define ATT_DISPATCH(KERNEL, hd, neb, ...)                                                          \
-    switch ((hd) * 100 + (neb)) {                                                                   \
-        case 808: return attn_launch(KERNEL<8, 8>, __VA_ARGS__);                                    \
-        case 816: return attn_launch(KERNEL<8, 16>, __VA_ARGS__);                                   \
-        case 824: return attn_launch(KERNEL<8, 24>, __VA_ARGS__);                                   \
-        case 832: return attn_launch(KERNEL<8, 32>, __VA_ARGS__);                                   \
-        case 1608: return attn_launch(KERNEL<16, 8>, __VA_ARGS__);                                  \
-        case 1616: return attn_launch(KERNEL<16, 16>, __VA_ARGS__);                                 \
-        case 1624: return attn_launch(KERNEL<16, 24>, __VA_ARGS__);                                 \
-        case 1632: return attn_launch(KERNEL<16, 32>, __VA_ARGS__);                                 \
-        case 3208: return attn_launch(KERNEL<32, 8>, __VA_ARGS__);                                  \
-        case 3216: return attn_launch(KERNEL<32, 16>, __VA_ARGS__);                                 \
-        case 3224: return attn_launch(KERNEL<32, 24>, __VA_ARGS__);                                 \
-        default: return attn_launch(KERNEL<32, 32>, __VA_ARGS__);                                   \
+// dispatch on (head dim, heads): both are template parameters so that every tile offset is an immediate
+#define ATT_DISPATCH(KERNEL, name, hd, heads, ...)                                                            \
+    switch ((hd) * 100 + (heads)) {                                                                           \
+        case 801: return attn_launch(KERNEL<8, 1>, __VA_ARGS__);                                              \
+        case 802: return attn_launch(KERNEL<8, 2>, __VA_ARGS__);                                              \
+        case 804: return attn_launch(KERNEL<8, 4>, __VA_ARGS__);                                              \
+        case 808: return attn_launch(KERNEL<8, 8>, __VA_ARGS__);                                              \
+        case 1601: return attn_launch(KERNEL<16, 1>, __VA_ARGS__);                                            \
+        case 1602: return attn_launch(KERNEL<16, 2>, __VA_ARGS__);                                            \
+        case 1604: return attn_launch(KERNEL<16, 4>, __VA_ARGS__);                                            \
+        case 1608: return attn_launch(KERNEL<16, 8>, __VA_ARGS__);                                            \
+        case 3201: return attn_launch(KERNEL<32, 1>, __VA_ARGS__);                                            \
+        case 3202: return attn_launch(KERNEL<32, 2>, __VA_ARGS__);                                            \
+        case 3204: return attn_launch(KERNEL<32, 4>, __VA_ARGS__);                                            \
+        case 3208: return attn_launch(KERNEL<32, 8>, __VA_ARGS__);                                            \
+        default:                                                                                              \
+            refil_set_error("%s: (head dim %d, heads %d) not instantiated (heads in {1,2,4,8})", name, hd, heads); \
+            return REFIL_ERR_UNSUPPORTED;                                                                     \
     }
 
 // CUtensorMap of QKV viewed as [N][ne][3d] fp32 with a (2d, ne, 1) box: one TMA instruction stages a unit's K|V tile
@@ -547,11 +648,9 @@ typedef CUresult (*att_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static int attn_make_tmap(CUtensorMap* tm, const float* qkv, int N, int ne, int d) {
+static att_encode_fn attn_encoder() {
     static att_encode_fn enc = nullptr;
     static bool tried = false;
-    memset(tm, 0, sizeof(*tm));
-    if (2 * d > 256 || ne > 256) return 0;                    // box limits: fall back to per-row bulk copies
     if (!tried) {
         tried = true;
         void* p = nullptr;
@@ -560,14 +659,27 @@ static int attn_make_tmap(CUtensorMap* tm, const float* qkv, int N, int ne, int 
             q == cudaDriverEntryPointSuccess)
             enc = (att_encode_fn)p;
     }
+    return enc;
+}
+
+// QKV viewed as [N][ne][3d] fp32 with a (box_cols, box_rows, 1) box
+static int attn_make_tmap_box(CUtensorMap* tm, const float* qkv, int N, int ne, int d, int box_cols, int box_rows) {
+    memset(tm, 0, sizeof(*tm));
+    if (box_cols > 256 || box_rows > 256) return 0;
+    att_encode_fn enc = attn_encoder();
     if (!enc) return 0;
     const cuuint64_t dims[3] = {(cuuint64_t)3 * d, (cuuint64_t)ne, (cuuint64_t)N};
     const cuuint64_t strides[2] = {(cuuint64_t)3 * d * 4, (cuuint64_t)ne * 3 * d * 4};
-    const cuuint32_t box[3] = {(cuuint32_t)2 * d, (cuuint32_t)ne, 1};
+    const cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)qkv, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 1 : 0;
+}
+
+// the whole K|V tile of a unit in one box (backward kernel); 0 = fall back to per-row bulk copies
+static int attn_make_tmap(CUtensorMap* tm, const float* qkv, int N, int ne, int d) {
+    return attn_make_tmap_box(tm, qkv, N, ne, d, 2 * d, ne);
 }
 
 static int attn_geometry(const char* name, int N, int warp_floats, int* warps, int* grid, size_t* smem) {
@@ -608,7 +720,7 @@ extern "C" int refil_masked_attn_fwd(const float* qkv, float* out, const uint8_t
     size_t smem;
     rc = attn_geometry("masked_attn_fwd", N, warp_floats, &warps, &grid, &smem);
     if (rc) return rc;
-    ATT_DISPATCH(attn_fwd_kernel, hd, neb, a, smem, grid, warps, stream, "masked_attn_fwd", tile_floats, warp_floats, tmap, use_tmap)
+    ATT_DISPATCH(attn_fwd_kernel, "masked_attn_fwd", hd, n_heads, a, smem, grid, warps, stream, "masked_attn_fwd", neb, tile_floats, warp_floats, tmap, use_tmap)
 }
 
 extern "C" int refil_masked_attn_bwd(const float* qkv, const float* dout, float* dqkv, const uint8_t* mask0,
@@ -635,5 +747,5 @@ extern "C" int refil_masked_attn_bwd(const float* qkv, const float* dout, float*
     size_t smem;
     rc = attn_geometry("masked_attn_bwd", N, warp_floats, &warps, &grid, &smem);
     if (rc) return rc;
-    ATT_DISPATCH(attn_bwd_kernel, hd, neb, a, smem, grid, warps, stream, "masked_attn_bwd", tile_floats, warp_floats, tmap, use_tmap)
+    ATT_DISPATCH(attn_bwd_kernel, "masked_attn_bwd", hd, n_heads, a, smem, grid, warps, stream, "masked_attn_bwd", neb, tile_floats, warp_floats, tmap, use_tmap)
 }
