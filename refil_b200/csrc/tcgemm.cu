@@ -589,8 +589,8 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) tc_gemm_wgrad_kernel(TcWArgs a
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(256u));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
-    // constant "ones" atom of every stage's Y tile (hi: column Q = 1, rest 0; lo: 0), written once
-    for (int s = 0; s < S; s++) {
+    // constant "ones" atom of every stage's Y tile (hi: column Q = 1, rest 0; lo: 0), written once (bias gradient only)
+    for (int s = 0; s < S && BQ > a.Q; s++) {
         float* yhi = reinterpret_cast<float*>(smem + (size_t)s * stage_bytes + 2 * x_bytes);
         float* ylo = reinterpret_cast<float*>(smem + (size_t)s * stage_bytes + 2 * x_bytes + y_bytes);
         for (int f = threadIdx.x; f < 32 * 32; f += TCW_THREADS) {         // 32 rows x 32 floats of the last MN atom
@@ -613,7 +613,7 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) tc_gemm_wgrad_kernel(TcWArgs a
             tc_fence_after();
             const int p = ptile * 128 + warp * 32 + lane;
             const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
-            for (int c0 = 0; c0 < a.Q + 16; c0 += 16) {
+            for (int c0 = 0; c0 < a.Q + (BQ > a.Q ? 16 : 0); c0 += 16) {
                 uint32_t r[16];
                 asm volatile(
                     "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -788,7 +788,7 @@ extern "C" int refil_tc_gemm_wgrad(const float* X, long long ldx, const float* r
     a.Y = Y; a.ldyy = ldyy; a.dW = dW; a.lddw = lddw; a.db = db;
     a.y_shift = y_shift_rows > 0 ? y_shift_rows : 0; a.y_period = y_period > 0 ? y_period : 1;
     a.M = M; a.P = P; a.Q = Q;
-    a.BQ = Q + 32;
+    a.BQ = db ? Q + 32 : Q;              // the bias gradient rides as one extra 32-wide atom whose first column is 1
     a.p_tiles = refil_cdiv(P, 128);
     const int chunks_total = refil_cdiv(M, 32);
     int splits = refil_num_sms() / a.p_tiles;

@@ -324,3 +324,18 @@ def test_tc_wgrad_3xtf32(M, P, Q):
     assert err <= 4e-6 * scale, ("dW", err, scale)
     errb = (db.cpu().double() - 1.0 - ref_b).abs().max().item()
     assert errb <= 4e-6 * gmat.abs().sum(0).max().item(), ("db", errb)
+
+
+@pytest.mark.parametrize("M,P,Q", [(5000, 384, 128), (3000, 64, 32)])
+def test_tc_wgrad_without_bias_gradient(M, P, Q):
+    """db = None (in_trans has no bias): the Y tile carries no ones-atom, N = Q exactly."""
+    from refil_b200 import ops
+    g = torch.Generator().manual_seed(M + Q)
+    dC, A = torch.randn(M, P, generator=g), torch.randn(M, Q, generator=g)
+    ref_w = dC.double().t() @ A.double()
+    dW = torch.zeros(P, Q, device=DEV)
+    ops.linear_bwd_weight(dC.to(DEV), A.to(DEV), dW, None)
+    torch.cuda.synchronize()
+    scale = (dC.abs().double().t() @ A.abs().double()).max().item()
+    err = (dW.cpu().double() - ref_w).abs().max().item()
+    assert err <= 4e-6 * scale, (err, scale)
