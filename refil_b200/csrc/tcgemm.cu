@@ -29,6 +29,7 @@
 //   pairs; TMEM holds two accumulators so the epilogue of tile i overlaps the main loop of tile i+1.
 #include <cuda.h>   // CUtensorMap (encode function fetched through cudaGetDriverEntryPoint; libcuda is not linked)
 
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -181,6 +182,67 @@ __device__ __forceinline__ void tc_mask_relu(const TcArgs& a, int mt, int kcol, 
     }
 }
 
+// Epilogue role (warps 0-7; warp w owns TMEM lane quadrant w & 3 and every other 32-column slab, w >> 2):
+// TMEM (lane = row) -> registers -> bias / relu / row mask -> swizzled staging tile -> one TMA store per slab
+__device__ __forceinline__ void tc_epilogue(const TcArgs& a, const CUtensorMap* tmap_c, int warp, int lane, int nt, int mt0,
+                                            int mt_step, int my_tiles, uint32_t tmem_base, uint8_t* smem_stg,
+                                            const float* epi_bias, uint64_t* tmem_full, uint64_t* tmem_empty) {
+    const int BN = a.BN;
+    {
+        const int quad = warp & 3, half = warp >> 2;
+        float* stg = reinterpret_cast<float*>(smem_stg + (size_t)warp * TC_STG_BYTES);
+        const uint32_t stg_addr = smem_u32(stg);
+        float* my_stg = stg + lane * 32;
+        const int sw = lane & 7;
+        for (int it = 0; it < my_tiles; it++) {
+            const int mt = mt0 + it * mt_step;
+            const int buf = it & 1;
+            mbar_wait(&tmem_full[buf], (it >> 1) & 1);
+            tc_fence_after();
+            const int row0 = mt * TC_BM + quad * 32;
+            const long long myrow = (long long)row0 + lane;
+            const bool masked = myrow < a.M && tc_row_masked(a.c_rowmask, a.c_na, a.c_ne, a.c_mper, myrow);
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * BN);
+            for (int c0 = half * 32; c0 < BN; c0 += 64) {
+                uint32_t r[32];
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+                    "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                      "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                      "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                    : "r"(taddr + (uint32_t)c0));
+                if (lane == 0) tc_bulk_wait_read();        // the previous store of this warp has read the staging tile
+                __syncwarp();
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    const float4 b4 = *reinterpret_cast<const float4*>(epi_bias + c0 + 4 * q);
+                    float4 v;
+                    v.x = __uint_as_float(r[4 * q + 0]) + b4.x;
+                    v.y = __uint_as_float(r[4 * q + 1]) + b4.y;
+                    v.z = __uint_as_float(r[4 * q + 2]) + b4.z;
+                    v.w = __uint_as_float(r[4 * q + 3]) + b4.w;
+                    if (a.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                    if (masked) v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    *reinterpret_cast<float4*>(my_stg + ((q ^ sw) << 2)) = v;
+                }
+                fence_async_smem();                        // staging writes -> visible to the TMA (async proxy)
+                __syncwarp();
+                if (lane == 0 && row0 < a.M) {
+                    if (a.k_slices > 1) tc_tma_reduce_add(tmap_c, nt * BN + c0, row0, stg_addr);
+                    else tc_tma_store(tmap_c, nt * BN + c0, row0, stg_addr);
+                    tc_bulk_commit();
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&tmem_empty[buf]);
+        }
+        if (lane == 0) tc_bulk_wait_all();
+    }
+}
+
 // split the 8 float4 of chunk cc into the hi / lo tiles of its pipeline stage and hand the stage to the MMA warp
 __device__ __forceinline__ void tc_store_chunk(const float4 (&va)[8], uint8_t* smem_a, uint32_t stage_bytes, int soff, int cc,
                                                int S, uint64_t* full_bar, uint64_t* empty_bar) {
@@ -262,58 +324,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_tn_kernel(TcArgs a, con
 
     if (warp < TC_EPI_WARPS) {
         // ===================== epilogue =====================
-        // TMEM (lane = row) -> registers -> bias / relu / row mask -> swizzled staging tile -> one TMA store per slab
-        const int quad = warp & 3, half = warp >> 2;
-        float* stg = reinterpret_cast<float*>(smem_stg + (size_t)warp * TC_STG_BYTES);
-        const uint32_t stg_addr = smem_u32(stg);
-        float* my_stg = stg + lane * 32;
-        const int sw = lane & 7;
-        for (int it = 0; it < my_tiles; it++) {
-            const int mt = mt0 + it * mt_step;
-            const int buf = it & 1;
-            mbar_wait(&tmem_full[buf], (it >> 1) & 1);
-            tc_fence_after();
-            const int row0 = mt * TC_BM + quad * 32;
-            const long long myrow = (long long)row0 + lane;
-            const bool masked = myrow < a.M && tc_row_masked(a.c_rowmask, a.c_na, a.c_ne, a.c_mper, myrow);
-            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * BN);
-            for (int c0 = half * 32; c0 < BN; c0 += 64) {
-                uint32_t r[32];
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
-                    "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-                      "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-                      "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                    : "r"(taddr + (uint32_t)c0));
-                if (lane == 0) tc_bulk_wait_read();        // the previous store of this warp has read the staging tile
-                __syncwarp();
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-                for (int q = 0; q < 8; q++) {
-                    const float4 b4 = *reinterpret_cast<const float4*>(epi_bias + c0 + 4 * q);
-                    float4 v;
-                    v.x = __uint_as_float(r[4 * q + 0]) + b4.x;
-                    v.y = __uint_as_float(r[4 * q + 1]) + b4.y;
-                    v.z = __uint_as_float(r[4 * q + 2]) + b4.z;
-                    v.w = __uint_as_float(r[4 * q + 3]) + b4.w;
-                    if (a.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-                    if (masked) v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    *reinterpret_cast<float4*>(my_stg + ((q ^ sw) << 2)) = v;
-                }
-                fence_async_smem();                        // staging writes -> visible to the TMA (async proxy)
-                __syncwarp();
-                if (lane == 0 && row0 < a.M) {
-                    if (a.k_slices > 1) tc_tma_reduce_add(&tmap_c, nt * BN + c0, row0, stg_addr);
-                    else tc_tma_store(&tmap_c, nt * BN + c0, row0, stg_addr);
-                    tc_bulk_commit();
-                }
-            }
-            tc_fence_before();
-            mbar_arrive(&tmem_empty[buf]);
-        }
-        if (lane == 0) tc_bulk_wait_all();
+        tc_epilogue(a, &tmap_c, warp, lane, nt, mt0, mt_step, my_tiles, tmem_base, smem_stg, epi_bias, tmem_full, tmem_empty);
     } else if (warp == TC_MMA_WARP) {
         // ===================== MMA issuer =====================
         // every operand below is warp-uniform (uniform registers); one elected lane issues
@@ -392,15 +403,230 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_tn_kernel(TcArgs a, con
     }
 }
 
+// =====================================================================================================================
+// TS variant: the A operand of tcgen05.mma lives in TENSOR MEMORY (lane = row, column = k), only B is read from smem.
+// In the SS kernel above the tensor pipe and the shared-memory port are both saturated by the operand reads (A 4 KB + B 4 KB
+// per 64-cycle MMA = 128 B/clk) while the producers also have to write the split tiles there.  Here
+//   warp 9      one lane streams RAW fp32 A chunks [128 x 32] into a 4-deep smem ring with TMA tensor loads (128B swizzle,
+//               out-of-range rows zero-filled by the hardware) -- no registers are held while a load is in flight;
+//   warps 10-13 converters, thread = row of the tile: 8 conflict-free LDS.128 of its swizzled row -> row mask / relu' ->
+//               hi/lo split -> two tcgen05.st (32 columns each) into a 4-deep ring of TMEM columns;
+//   warp 8      issues tcgen05.mma kind::tf32 with [tmem] A and the resident smem weight tile as B;
+//   warps 0-7   the same TMA-store epilogue.
+// Shared-memory traffic per 128 x 32 chunk drops from 144 KB to 80 KB, the A stages leave shared memory entirely
+// (TMEM: 2 x BN accumulator columns + 4 x 64 operand columns), and 64 KB of loads are in flight per SM at no register cost.
+// =====================================================================================================================
+#define TS_MMA_WARP 8
+#define TS_TMA_WARP 9
+#define TS_CONV_WARP0 10
+#define TS_THREADS (32 * 14)
+#define TS_RAW_STAGES 4
+#define TS_A_STAGES 4
+#define TS_A_COL0 256                     // operand ring: TMEM columns [256, 512), 64 per stage (hi | lo)
+
+__device__ __forceinline__ void tc_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+
+__device__ __forceinline__ void tc_tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
+        "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+          "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+          "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+
+__global__ void __launch_bounds__(TS_THREADS, 1) tc_gemm_ts_kernel(TcArgs a, const __grid_constant__ CUtensorMap tmap_c,
+                                                                  const __grid_constant__ CUtensorMap tmap_a) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int BN = a.BN;
+    const int KC = a.KS / TC_BK;
+    const uint32_t raw_bytes = TC_BM * 128, b_bytes = (uint32_t)BN * 128;
+    uint8_t* smem_b = smem;                                             // [KC][hi | lo][BN][128 B]
+    uint8_t* smem_r = smem + (size_t)KC * 2 * b_bytes;                  // [4][128][128 B] raw fp32 A chunks (TMA, swizzled)
+    uint8_t* smem_stg = smem_r + (size_t)TS_RAW_STAGES * raw_bytes;     // [8 epilogue warps][32 rows][128 B]
+    __shared__ uint64_t raw_full[TS_RAW_STAGES], raw_empty[TS_RAW_STAGES], a_full[TS_A_STAGES], a_empty[TS_A_STAGES];
+    __shared__ uint64_t tmem_full[2], tmem_empty[2];
+    __shared__ uint32_t tmem_base_s;
+    __shared__ __align__(16) float epi_bias[256];
+
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform role index
+    const int lane = threadIdx.x & 31;
+    const int groups = a.n_tiles * a.k_slices;
+    const int gid = blockIdx.x % groups;
+    const int nt = gid % a.n_tiles, k_off = (gid / a.n_tiles) * a.KS;
+    const int mt0 = blockIdx.x / groups, mt_step = gridDim.x / groups;
+    const int my_tiles = mt0 < a.m_tiles ? (a.m_tiles - mt0 + mt_step - 1) / mt_step : 0;
+    const int total = my_tiles * KC;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TS_RAW_STAGES; s++) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], 128); }
+        for (int s = 0; s < TS_A_STAGES; s++) { mbar_init(&a_full[s], 128); mbar_init(&a_empty[s], 1); }
+        for (int b = 0; b < 2; b++) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 32 * TC_EPI_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == TS_MMA_WARP) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    // resident weight tile: split once per CTA
+    {
+        const int k4 = a.KS >> 2;
+        for (int f = threadIdx.x; f < BN * k4; f += TS_THREADS) {
+            const int r = f / k4, kq = f - r * k4;
+            const int kc = kq >> 3, c = kq & 7;
+            const long long j = (long long)nt * BN + r;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (j < a.N) {
+                const float* p = a.B + j * a.sbj + (long long)(k_off + kq * 4) * a.sbi;
+                if (a.sbi == 1) v = __ldg(reinterpret_cast<const float4*>(p));
+                else { v.x = __ldg(p); v.y = __ldg(p + a.sbi); v.z = __ldg(p + 2 * a.sbi); v.w = __ldg(p + 3 * a.sbi); }
+            }
+            float* hi = reinterpret_cast<float*>(smem_b + (size_t)kc * 2 * b_bytes);
+            tc_store_split(hi, hi + BN * 32, r, c, v);
+        }
+        for (int c = threadIdx.x; c < BN; c += TS_THREADS) epi_bias[c] = a.bias ? __ldg(a.bias + (long long)nt * BN + c) : 0.f;
+        fence_async_smem();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp < TC_EPI_WARPS) {
+        tc_epilogue(a, &tmap_c, warp, lane, nt, mt0, mt_step, my_tiles, tmem_base, smem_stg, epi_bias, tmem_full, tmem_empty);
+    } else if (warp == TS_MMA_WARP) {
+        // ===================== MMA issuer: A from tensor memory, B = resident smem weight tile =====================
+        const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+        const uint64_t desc_b0 = tc_smem_desc(smem_u32(smem_b));
+        const uint64_t b_lo_off = (uint64_t)(b_bytes >> 4);
+        const uint32_t idesc = a.idesc;
+        int st = 0;
+        uint32_t ph = 0;
+        for (int it = 0; it < my_tiles; it++) {
+            const int buf = it & 1;
+            mbar_wait(&tmem_empty[buf], ((it >> 1) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_u + (uint32_t)(buf * BN);
+            for (int kc = 0; kc < KC; kc++) {
+                mbar_wait(&a_full[st], ph);
+                tc_fence_after();
+                const uint32_t a_hi = tmem_u + (uint32_t)(TS_A_COL0 + st * 64), a_lo = a_hi + 32u;
+                const uint64_t b_hi = desc_b0 + (uint64_t)((uint32_t)kc * ((2 * b_bytes) >> 4));
+                if (elect_one()) {
+#pragma unroll
+                    for (int ks = 0; ks < TC_BK / 8; ks++) {
+                        const uint64_t adv = (uint64_t)(ks * 2);       // +32 bytes inside the 128B swizzle row of B
+                        const uint32_t ac = (uint32_t)(ks * 8);        // +8 columns of the TMEM operand
+                        tc_mma_ts(tmem_d, a_lo + ac, b_hi + adv, idesc, (kc | ks) != 0);
+                        tc_mma_ts(tmem_d, a_hi + ac, b_hi + b_lo_off + adv, idesc, 1);
+                        tc_mma_ts(tmem_d, a_hi + ac, b_hi + adv, idesc, 1);
+                    }
+                    tc_commit(&a_empty[st]);                       // frees the TMEM operand stage when these MMAs retire
+                    if (kc == KC - 1) tc_commit(&tmem_full[buf]);
+                }
+                __syncwarp();
+                if (++st == TS_A_STAGES) { st = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == TS_TMA_WARP) {
+        // ===================== TMA producer: raw fp32 chunks, 4 in flight =====================
+        if (lane == 0) {
+            int st = 0;
+            uint32_t ph = 0;
+            for (int cc = 0; cc < total; cc++) {
+                const int row0 = (mt0 + (cc / KC) * mt_step) * TC_BM, kcol = k_off + (cc % KC) * TC_BK;
+                mbar_wait(&raw_empty[st], ph ^ 1);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&raw_full[st])),
+                             "r"(raw_bytes) : "memory");
+                asm volatile(
+                    "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                    ::"r"(smem_u32(smem_r + (size_t)st * raw_bytes)), "l"(&tmap_a), "r"(kcol), "r"(row0),
+                      "r"(smem_u32(&raw_full[st]))
+                    : "memory");
+                if (++st == TS_RAW_STAGES) { st = 0; ph ^= 1; }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===================== converters: thread = row; raw smem -> mask -> hi / lo -> tensor memory =====================
+        const int quad = warp & 3;                               // TMEM lane quadrant this warp may access
+        const int r = quad * 32 + lane;                          // my row of the 128-row tile
+        const uint32_t t_lane = (uint32_t)(quad * 32) << 16;
+        const bool has_y = a.relu_y != nullptr;
+        int sr = 0, sa = 0;
+        uint32_t phr = 0, pha = 0;
+        for (int cc = 0; cc < total; cc++) {
+            const int mt = mt0 + (cc / KC) * mt_step, kcol = k_off + (cc % KC) * TC_BK;
+            const long long row = (long long)mt * TC_BM + r;
+            const bool keep = row < a.M && !tc_row_masked(a.a_rowmask, a.a_na, a.a_ne, a.a_mper, row);
+            float4 y[8];
+            if (has_y && keep) {                                 // relu' mask: my 128-byte row segment of the forward output
+                const float* py = a.relu_y + row * a.ldy + kcol;
+#pragma unroll
+                for (int c = 0; c < 8; c++) y[c] = __ldg(reinterpret_cast<const float4*>(py + 4 * c));
+            }
+            mbar_wait(&raw_full[sr], phr);
+            const float* rawrow = reinterpret_cast<const float*>(smem_r + (size_t)sr * raw_bytes) + r * 32;
+            float4 v[8];
+#pragma unroll
+            for (int c = 0; c < 8; c++) v[c] = *reinterpret_cast<const float4*>(rawrow + ((c ^ (r & 7)) << 2));
+            uint32_t hi[32], lo[32];
+#pragma unroll
+            for (int c = 0; c < 8; c++) {
+                float4 x = v[c];
+                if (!keep) x = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (has_y && keep) {
+                    if (!(y[c].x > 0.f)) x.x = 0.f;
+                    if (!(y[c].y > 0.f)) x.y = 0.f;
+                    if (!(y[c].z > 0.f)) x.z = 0.f;
+                    if (!(y[c].w > 0.f)) x.w = 0.f;
+                }
+                const uint32_t hx = __float_as_uint(x.x) & 0xffffe000u, hy = __float_as_uint(x.y) & 0xffffe000u,
+                               hz = __float_as_uint(x.z) & 0xffffe000u, hw = __float_as_uint(x.w) & 0xffffe000u;
+                hi[4 * c] = hx; hi[4 * c + 1] = hy; hi[4 * c + 2] = hz; hi[4 * c + 3] = hw;
+                lo[4 * c] = __float_as_uint(x.x - __uint_as_float(hx));
+                lo[4 * c + 1] = __float_as_uint(x.y - __uint_as_float(hy));
+                lo[4 * c + 2] = __float_as_uint(x.z - __uint_as_float(hz));
+                lo[4 * c + 3] = __float_as_uint(x.w - __uint_as_float(hw));
+            }
+            mbar_arrive(&raw_empty[sr]);                         // my row of the raw chunk is in registers
+            if (++sr == TS_RAW_STAGES) { sr = 0; phr ^= 1; }
+            mbar_wait(&a_empty[sa], pha ^ 1);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + t_lane + (uint32_t)(TS_A_COL0 + sa * 64);
+            tc_tmem_st32(taddr, hi);
+            tc_tmem_st32(taddr + 32u, lo);
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            mbar_arrive(&a_full[sa]);
+            if (++sa == TS_A_STAGES) { sa = 0; pha ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == TS_MMA_WARP) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+    }
+}
+
 // CUtensorMap of C viewed as [M][N] fp32 (row stride ldc) with a (32 columns, 32 rows) box, 128B swizzle
 typedef CUresult (*tc_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static int tc_make_tmap_c(CUtensorMap* tm, const float* C, long long ldc, int M, int N) {
+static tc_encode_fn tc_encoder() {
     static tc_encode_fn enc = nullptr;
     static bool tried = false;
-    memset(tm, 0, sizeof(*tm));
     if (!tried) {
         tried = true;
         void* p = nullptr;
@@ -409,6 +635,12 @@ static int tc_make_tmap_c(CUtensorMap* tm, const float* C, long long ldc, int M,
             q == cudaDriverEntryPointSuccess)
             enc = (tc_encode_fn)p;
     }
+    return enc;
+}
+
+static int tc_make_tmap_c(CUtensorMap* tm, const float* C, long long ldc, int M, int N) {
+    memset(tm, 0, sizeof(*tm));
+    tc_encode_fn enc = tc_encoder();
     if (!enc) return 0;
     const cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)M};
     const cuuint64_t strides[1] = {(cuuint64_t)ldc * 4};
@@ -416,6 +648,21 @@ static int tc_make_tmap_c(CUtensorMap* tm, const float* C, long long ldc, int M,
     const cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)C, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 1 : 0;
+}
+
+// CUtensorMap of A viewed as [M][K] fp32 (row stride lda) with a (32 columns, 128 rows) box, 128B swizzle: one box = one raw
+// 128 x 32 chunk in exactly the K-major swizzled layout the converters (and tcgen05) expect; rows >= M are zero-filled
+static int tc_make_tmap_a(CUtensorMap* tm, const float* A, long long lda, int M, int K) {
+    memset(tm, 0, sizeof(*tm));
+    tc_encode_fn enc = tc_encoder();
+    if (!enc) return 0;
+    const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)M};
+    const cuuint64_t strides[1] = {(cuuint64_t)lda * 4};
+    const cuuint32_t box[2] = {TC_BK, TC_BM};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)A, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 1 : 0;
 }
 
@@ -436,9 +683,9 @@ static int tc_pick_slices(int N, int K) {
 }
 
 // n-tile width: multiple of 32 dividing N, <= 256, with the resident split weight within budget
-static int tc_pick_bn(int N, int KS) {
+static int tc_pick_bn(int N, int KS, int cap = 256) {
     int best = 0;
-    for (int bn = 32; bn <= 256 && bn <= N; bn += 32)
+    for (int bn = 32; bn <= cap && bn <= N; bn += 32)
         if (N % bn == 0 && (long long)2 * bn * KS * 4 <= TC_B_BUDGET) best = bn;
     return best;
 }
@@ -478,7 +725,14 @@ extern "C" int refil_tc_gemm_tn(const float* A, long long lda, const float* relu
     a.KS = K / a.k_slices;
     REFIL_CHECK_ARG(a.k_slices == 1 || (!bias && !relu && !c_row_entity_mask),
                     "tc_gemm_tn: a sliced reduction (K=%d) cannot carry a non-linear epilogue", K);
-    const int BN = tc_pick_bn(N, a.KS);
+    // operand path: "ts" (default) keeps the A operand in tensor memory (TMA-fed raw ring + converter warps), "ss" is the
+    // all-shared-memory kernel; REFIL_TC_MODE=ss selects the latter for A/B comparisons
+    static int mode_ts = -1;
+    if (mode_ts < 0) {
+        const char* e = getenv("REFIL_TC_MODE");
+        mode_ts = (e && e[0] == 's' && e[1] == 's') ? 0 : 1;
+    }
+    const int BN = tc_pick_bn(N, a.KS, mode_ts ? 128 : 256);      // ts: two accumulators + the operand ring share 512 columns
     a.BN = BN;
     a.n_tiles = N / BN;
     a.m_tiles = refil_cdiv(M, TC_BM);
@@ -491,20 +745,23 @@ extern "C" int refil_tc_gemm_tn(const float* A, long long lda, const float* relu
     a.stages = stages;
     // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=tf32, both K-major, N>>3, M>>4
     a.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-    CUtensorMap tmap;
-    if (!tc_make_tmap_c(&tmap, C, ldc, M, N)) {
-        refil_set_error("tc_gemm_tn: cuTensorMapEncodeTiled failed (C=%p ldc=%lld M=%d N=%d)", (const void*)C, ldc, M, N);
+    CUtensorMap tmap, tmap_a;
+    if (!tc_make_tmap_c(&tmap, C, ldc, M, N) || (mode_ts && !tc_make_tmap_a(&tmap_a, A, lda, M, K))) {
+        refil_set_error("tc_gemm_tn: cuTensorMapEncodeTiled failed (A=%p lda=%lld C=%p ldc=%lld M=%d N=%d K=%d)", (const void*)A,
+                        lda, (const void*)C, ldc, M, N, K);
         return REFIL_ERR_CUDA;
     }
-    const size_t smem = b_res + stages * stage_bytes + stg_bytes + 1024;
-    static size_t attr_smem = 0;
-    if (smem > attr_smem) {
-        cudaError_t e = cudaFuncSetAttribute(tc_gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t smem = mode_ts ? b_res + (size_t)TS_RAW_STAGES * TC_BM * 128 + stg_bytes + 1024
+                                : b_res + stages * stage_bytes + stg_bytes + 1024;
+    static size_t attr_smem[2] = {0, 0};
+    if (smem > attr_smem[mode_ts]) {
+        cudaError_t e = mode_ts ? cudaFuncSetAttribute(tc_gemm_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                                : cudaFuncSetAttribute(tc_gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) {
             refil_set_error("tc_gemm_tn: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
             return REFIL_ERR_CUDA;
         }
-        attr_smem = smem;
+        attr_smem[mode_ts] = smem;
     }
     if (a.k_slices > 1) {             // partial tiles are reduce-added into C
         cudaError_t e = cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)N * 4, (size_t)M, stream);
@@ -519,6 +776,11 @@ extern "C" int refil_tc_gemm_tn(const float* A, long long lda, const float* relu
     if (per_g < 1) per_g = 1;
     if (per_g > a.m_tiles) per_g = a.m_tiles;
     const int grid = per_g * groups;
+    if (mode_ts) {
+        tc_gemm_ts_kernel<<<grid, TS_THREADS, smem, stream>>>(a, tmap, tmap_a);
+        REFIL_CHECK_LAUNCH("tc_gemm_tn (ts)");
+        return REFIL_OK;
+    }
     tc_gemm_tn_kernel<<<grid, TC_THREADS, smem, stream>>>(a, tmap);
     REFIL_CHECK_LAUNCH("tc_gemm_tn");
     return REFIL_OK;
