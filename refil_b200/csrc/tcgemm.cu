@@ -409,8 +409,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_tn_kernel(TcArgs a, con
 // per 64-cycle MMA = 128 B/clk) while the producers also have to write the split tiles there.  Here
 //   warp 9      one lane streams RAW fp32 A chunks [128 x 32] into a 4-deep smem ring with TMA tensor loads (128B swizzle,
 //               out-of-range rows zero-filled by the hardware) -- no registers are held while a load is in flight;
-//   warps 10-13 converters, thread = row of the tile: 8 conflict-free LDS.128 of its swizzled row -> row mask / relu' ->
-//               hi/lo split -> two tcgen05.st (32 columns each) into a 4-deep ring of TMEM columns;
+//   warps 10-17 converters, thread = (row of the tile, 16-column half): 4 conflict-free LDS.128 of its swizzled row -> row
+//               mask / relu' -> hi/lo split -> two tcgen05.st (16 columns each) into a 4-deep ring of TMEM columns;
 //   warp 8      issues tcgen05.mma kind::tf32 with [tmem] A and the resident smem weight tile as B;
 //   warps 0-7   the same TMA-store epilogue.
 // Shared-memory traffic per 128 x 32 chunk drops from 144 KB to 80 KB, the A stages leave shared memory entirely
@@ -419,7 +419,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_tn_kernel(TcArgs a, con
 #define TS_MMA_WARP 8
 #define TS_TMA_WARP 9
 #define TS_CONV_WARP0 10
-#define TS_THREADS (32 * 14)
+#define TS_CONV_WARPS 8
+#define TS_THREADS (32 * (TS_CONV_WARP0 + TS_CONV_WARPS))
 #define TS_RAW_STAGES 4
 #define TS_A_STAGES 4
 #define TS_A_COL0 256                     // operand ring: TMEM columns [256, 512), 64 per stage (hi | lo)
@@ -441,6 +442,14 @@ __device__ __forceinline__ void tc_tmem_st32(uint32_t taddr, const uint32_t (&r)
           "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
           "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
           "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+
+__device__ __forceinline__ void tc_tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
         : "memory");
 }
 
@@ -468,8 +477,8 @@ __global__ void __launch_bounds__(TS_THREADS, 1) tc_gemm_ts_kernel(TcArgs a, con
     const int my_tiles = mt0 < a.m_tiles ? (a.m_tiles - mt0 + mt_step - 1) / mt_step : 0;
     const int total = my_tiles * KC;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < TS_RAW_STAGES; s++) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], 128); }
-        for (int s = 0; s < TS_A_STAGES; s++) { mbar_init(&a_full[s], 128); mbar_init(&a_empty[s], 1); }
+        for (int s = 0; s < TS_RAW_STAGES; s++) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], 32 * TS_CONV_WARPS); }
+        for (int s = 0; s < TS_A_STAGES; s++) { mbar_init(&a_full[s], 32 * TS_CONV_WARPS); mbar_init(&a_empty[s], 1); }
         for (int b = 0; b < 2; b++) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 32 * TC_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -540,10 +549,10 @@ __global__ void __launch_bounds__(TS_THREADS, 1) tc_gemm_ts_kernel(TcArgs a, con
     } else if (warp == TS_TMA_WARP) {
         // ===================== TMA producer: raw fp32 chunks, 4 in flight =====================
         if (lane == 0) {
-            int st = 0;
+            int st = 0, kc = 0, mt = mt0;
             uint32_t ph = 0;
             for (int cc = 0; cc < total; cc++) {
-                const int row0 = (mt0 + (cc / KC) * mt_step) * TC_BM, kcol = k_off + (cc % KC) * TC_BK;
+                const int row0 = mt * TC_BM, kcol = k_off + kc * TC_BK;
                 mbar_wait(&raw_empty[st], ph ^ 1);
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&raw_full[st])),
                              "r"(raw_bytes) : "memory");
@@ -552,44 +561,45 @@ __global__ void __launch_bounds__(TS_THREADS, 1) tc_gemm_ts_kernel(TcArgs a, con
                     ::"r"(smem_u32(smem_r + (size_t)st * raw_bytes)), "l"(&tmap_a), "r"(kcol), "r"(row0),
                       "r"(smem_u32(&raw_full[st]))
                     : "memory");
+                if (++kc == KC) { kc = 0; mt += mt_step; }
                 if (++st == TS_RAW_STAGES) { st = 0; ph ^= 1; }
             }
         }
         __syncwarp();
     } else {
-        // ===================== converters: thread = row; raw smem -> mask -> hi / lo -> tensor memory =====================
+        // ===================== converters: thread = (row, 16-column half); raw smem -> mask -> hi / lo -> tensor memory ====
         const int quad = warp & 3;                               // TMEM lane quadrant this warp may access
+        const int half = (warp - TS_CONV_WARP0) >> 2;            // columns [16 half, 16 half + 16) of the 32-wide chunk
         const int r = quad * 32 + lane;                          // my row of the 128-row tile
         const uint32_t t_lane = (uint32_t)(quad * 32) << 16;
         const bool has_y = a.relu_y != nullptr;
-        int sr = 0, sa = 0;
+        const int roff = r * 32, rsw = r & 7;
+        int sr = 0, sa = 0, kc = 0, mt = mt0;
         uint32_t phr = 0, pha = 0;
         for (int cc = 0; cc < total; cc++) {
-            const int mt = mt0 + (cc / KC) * mt_step, kcol = k_off + (cc % KC) * TC_BK;
             const long long row = (long long)mt * TC_BM + r;
             const bool keep = row < a.M && !tc_row_masked(a.a_rowmask, a.a_na, a.a_ne, a.a_mper, row);
-            float4 y[8];
-            if (has_y && keep) {                                 // relu' mask: my 128-byte row segment of the forward output
-                const float* py = a.relu_y + row * a.ldy + kcol;
+            float4 y[4];
 #pragma unroll
-                for (int c = 0; c < 8; c++) y[c] = __ldg(reinterpret_cast<const float4*>(py + 4 * c));
+            for (int c = 0; c < 4; c++) y[c] = make_float4(1.f, 1.f, 1.f, 1.f);
+            if (has_y && keep) {                                 // relu' mask: my 64-byte segment of the forward output row
+                const float* py = a.relu_y + row * a.ldy + k_off + kc * TC_BK + half * 16;
+#pragma unroll
+                for (int c = 0; c < 4; c++) y[c] = __ldg(reinterpret_cast<const float4*>(py + 4 * c));
             }
             mbar_wait(&raw_full[sr], phr);
-            const float* rawrow = reinterpret_cast<const float*>(smem_r + (size_t)sr * raw_bytes) + r * 32;
-            float4 v[8];
+            const float* rawrow = reinterpret_cast<const float*>(smem_r + (size_t)sr * raw_bytes) + roff;
+            float4 v[4];
 #pragma unroll
-            for (int c = 0; c < 8; c++) v[c] = *reinterpret_cast<const float4*>(rawrow + ((c ^ (r & 7)) << 2));
-            uint32_t hi[32], lo[32];
+            for (int c = 0; c < 4; c++) v[c] = *reinterpret_cast<const float4*>(rawrow + (((half * 4 + c) ^ rsw) << 2));
+            uint32_t hi[16], lo[16];
 #pragma unroll
-            for (int c = 0; c < 8; c++) {
+            for (int c = 0; c < 4; c++) {
                 float4 x = v[c];
-                if (!keep) x = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (has_y && keep) {
-                    if (!(y[c].x > 0.f)) x.x = 0.f;
-                    if (!(y[c].y > 0.f)) x.y = 0.f;
-                    if (!(y[c].z > 0.f)) x.z = 0.f;
-                    if (!(y[c].w > 0.f)) x.w = 0.f;
-                }
+                x.x = (keep && y[c].x > 0.f) ? x.x : 0.f;
+                x.y = (keep && y[c].y > 0.f) ? x.y : 0.f;
+                x.z = (keep && y[c].z > 0.f) ? x.z : 0.f;
+                x.w = (keep && y[c].w > 0.f) ? x.w : 0.f;
                 const uint32_t hx = __float_as_uint(x.x) & 0xffffe000u, hy = __float_as_uint(x.y) & 0xffffe000u,
                                hz = __float_as_uint(x.z) & 0xffffe000u, hw = __float_as_uint(x.w) & 0xffffe000u;
                 hi[4 * c] = hx; hi[4 * c + 1] = hy; hi[4 * c + 2] = hz; hi[4 * c + 3] = hw;
@@ -598,17 +608,18 @@ __global__ void __launch_bounds__(TS_THREADS, 1) tc_gemm_ts_kernel(TcArgs a, con
                 lo[4 * c + 2] = __float_as_uint(x.z - __uint_as_float(hz));
                 lo[4 * c + 3] = __float_as_uint(x.w - __uint_as_float(hw));
             }
-            mbar_arrive(&raw_empty[sr]);                         // my row of the raw chunk is in registers
+            mbar_arrive(&raw_empty[sr]);                         // my part of the raw chunk is in registers
             if (++sr == TS_RAW_STAGES) { sr = 0; phr ^= 1; }
             mbar_wait(&a_empty[sa], pha ^ 1);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + t_lane + (uint32_t)(TS_A_COL0 + sa * 64);
-            tc_tmem_st32(taddr, hi);
-            tc_tmem_st32(taddr + 32u, lo);
+            const uint32_t taddr = tmem_base + t_lane + (uint32_t)(TS_A_COL0 + sa * 64 + half * 16);
+            tc_tmem_st16(taddr, hi);
+            tc_tmem_st16(taddr + 32u, lo);
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tc_fence_before();
             mbar_arrive(&a_full[sa]);
             if (++sa == TS_A_STAGES) { sa = 0; pha ^= 1; }
+            if (++kc == KC) { kc = 0; mt += mt_step; }
         }
     }
     tc_fence_before();
