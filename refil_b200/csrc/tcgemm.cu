@@ -677,6 +677,21 @@ static int tc_make_tmap_a(CUtensorMap* tm, const float* A, long long lda, int M,
     return r == CUDA_SUCCESS ? 1 : 0;
 }
 
+// CUtensorMap of a row-major [M][P] fp32 matrix with a (128 columns, 32 rows) box, no swizzle: one raw reduction chunk of
+// the weight-gradient kernel; columns >= P and rows >= M are zero-filled
+static int tc_make_tmap_rows(CUtensorMap* tm, const float* X, long long ldx, int M, int P) {
+    memset(tm, 0, sizeof(*tm));
+    tc_encode_fn enc = tc_encoder();
+    if (!enc) return 0;
+    const cuuint64_t dims[2] = {(cuuint64_t)P, (cuuint64_t)M};
+    const cuuint64_t strides[1] = {(cuuint64_t)ldx * 4};
+    const cuuint32_t box[2] = {128, 32};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)X, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 1 : 0;
+}
+
 // resident split weight tile (2 * BN * KS fp32) must leave room for >= 2 A stages and the staging tiles
 #define TC_B_BUDGET (128 * 1024)
 
@@ -1041,6 +1056,283 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) tc_gemm_wgrad_kernel(TcWArgs a
     }
 }
 
+// =====================================================================================================================
+// TS variant of the weight gradient: X^T is the tcgen05 "A" operand in TENSOR MEMORY.
+// The tensor core wants A as lane = output row (p, a column of X) x column = reduction index (m, a row of X): exactly the
+// transpose of the row-major gradient chunk.  A TMA tensor load drops the raw [32 rows][128 columns] chunk into a smem ring
+// (un-swizzled; columns beyond P and rows beyond M are zero-filled by the hardware), and the four converter warps read it
+// COLUMN-wise -- lane = p, one coalesced 128-byte LDS per row -- apply relu' / the row mask, split hi / lo and tcgen05.st
+// their 32 values as 32 TMEM columns: the transposition costs nothing.  Only Y (the layer input, MN-major hi/lo tiles with
+// the ones-atom for the bias gradient) is staged through registers by the two producer groups, now with the next chunk's
+// loads in flight.  Shared-memory traffic per 32-row chunk: 132 KB instead of 180 KB, and the X path holds no registers
+// while its loads are in flight.
+//   warps 0-3  converters during the main loop, then the epilogue (TMEM partial tile -> vector atomics into dW / db)
+//   warp  4    TMEM allocation + MMA issue ([tmem] A, MN-major smem B)
+//   warp  5    TMA producer (X chunks, and the matching relu_y chunks when the relu' mask is fused)
+//   warps 6-13 two Y producer groups taking alternate chunks
+// =====================================================================================================================
+#define TW_MMA_WARP 4
+#define TW_TMA_WARP 5
+#define TW_Y_WARP0 6
+#define TW_THREADS (32 * 14)
+#define TW_X_STAGES 4                     // TMEM operand ring (64 columns per stage: hi | lo) and max raw smem ring
+#define TW_X_COL0 256
+
+struct TcWGeom {
+    int raw_stages, y_stages;
+};
+
+__global__ void __launch_bounds__(TW_THREADS, 1) tc_wgrad_ts_kernel(TcWArgs a, TcWGeom g, const __grid_constant__ CUtensorMap tmap_x,
+                                                                   const __grid_constant__ CUtensorMap tmap_r) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int BQ = a.BQ, SY = g.y_stages, RS = g.raw_stages;
+    const int ya = BQ / 32;                                   // MN atoms of the Y tile
+    const bool has_r = a.relu_y != nullptr;
+    const uint32_t raw_bytes = 32 * 128 * 4, y_bytes = 32 * (uint32_t)BQ * 4, y_stage_bytes = 2 * y_bytes;
+    uint8_t* smem_x = smem;                                               // [RS][32][128] raw X chunks
+    uint8_t* smem_rl = smem_x + (size_t)RS * raw_bytes;                   // [RS][32][128] raw relu_y chunks (if fused)
+    uint8_t* smem_y = smem_rl + (has_r ? (size_t)RS * raw_bytes : 0);     // [SY][Y_hi | Y_lo]
+    __shared__ uint64_t xr_full[TW_X_STAGES], xr_empty[TW_X_STAGES], xa_full[TW_X_STAGES], xa_empty[TW_X_STAGES];
+    __shared__ uint64_t y_full[TC_MAX_STAGES], y_empty[TC_MAX_STAGES], acc_bar;
+    __shared__ uint32_t tmem_base_s;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform role index
+    const int lane = threadIdx.x & 31;
+    const int ptile = blockIdx.x % a.p_tiles, split = blockIdx.x / a.p_tiles;
+    const int chunks_total = (a.M + 31) / 32;
+    const int c_begin = split * a.chunks_per_split, c_end = min(chunks_total, c_begin + a.chunks_per_split);
+    const int n_chunks = max(0, c_end - c_begin);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TW_X_STAGES; s++) {
+            mbar_init(&xr_full[s], 1); mbar_init(&xr_empty[s], 128);
+            mbar_init(&xa_full[s], 128); mbar_init(&xa_empty[s], 1);
+        }
+        for (int s = 0; s < TC_MAX_STAGES; s++) { mbar_init(&y_full[s], 128); mbar_init(&y_empty[s], 1); }
+        mbar_init(&acc_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == TW_MMA_WARP) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    // constant "ones" atom of every stage's Y tile (hi: column Q = 1, rest 0; lo: 0), written once (bias gradient only)
+    for (int s = 0; s < SY && BQ > a.Q; s++) {
+        float* yhi = reinterpret_cast<float*>(smem_y + (size_t)s * y_stage_bytes);
+        float* ylo = reinterpret_cast<float*>(smem_y + (size_t)s * y_stage_bytes + y_bytes);
+        for (int f = threadIdx.x; f < 32 * 32; f += TW_THREADS) {         // 32 rows x 32 floats of the last MN atom
+            const int r = f >> 5, e = f & 31;
+            const int off = tc_mn_off(r, (ya - 1) * 8 + (e >> 2), ya) + (e & 3);
+            yhi[off] = (e == 0) ? 1.f : 0.f;
+            ylo[off] = 0.f;
+        }
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp < 4) {
+        // ===================== converters: lane = p (column of X); raw chunk read column-wise -> TMEM rows =====================
+        const int pl = warp * 32 + lane;                         // my output row p of the tile = my TMEM lane
+        const uint32_t t_lane = (uint32_t)(warp * 32) << 16;
+        int sr = 0, sa = 0;
+        uint32_t phr = 0, pha = 0;
+        for (int ch = 0; ch < n_chunks; ch++) {
+            const long long m0 = (long long)(c_begin + ch) * 32;
+            // rows of the chunk that survive the row mask (lane k evaluates row m0 + k)
+            const long long myrow = m0 + lane;
+            const uint32_t keep = __ballot_sync(0xffffffffu, myrow < a.M && !tc_row_masked(a.x_rowmask, a.na, a.ne, a.mper, myrow));
+            mbar_wait(&xr_full[sr], phr);
+            const float* xs = reinterpret_cast<const float*>(smem_x + (size_t)sr * raw_bytes) + pl;
+            const float* rs = reinterpret_cast<const float*>(smem_rl + (size_t)sr * raw_bytes) + pl;
+            mbar_wait(&xa_empty[sa], pha ^ 1);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + t_lane + (uint32_t)(TW_X_COL0 + sa * 64);
+#pragma unroll
+            for (int hf = 0; hf < 2; hf++) {
+                float x[16];
+#pragma unroll
+                for (int k = 0; k < 16; k++) x[k] = xs[(hf * 16 + k) * 128];
+                if (has_r) {
+#pragma unroll
+                    for (int k = 0; k < 16; k++)
+                        if (!(rs[(hf * 16 + k) * 128] > 0.f)) x[k] = 0.f;
+                }
+                uint32_t hi[16], lo[16];
+#pragma unroll
+                for (int k = 0; k < 16; k++) {
+                    const float xv = ((keep >> (hf * 16 + k)) & 1u) ? x[k] : 0.f;
+                    const uint32_t h = __float_as_uint(xv) & 0xffffe000u;
+                    hi[k] = h;
+                    lo[k] = __float_as_uint(xv - __uint_as_float(h));
+                }
+                tc_tmem_st16(taddr + (uint32_t)(hf * 16), hi);
+                tc_tmem_st16(taddr + 32u + (uint32_t)(hf * 16), lo);
+            }
+            mbar_arrive(&xr_empty[sr]);                          // my column of the raw chunk has been consumed
+            if (++sr == RS) { sr = 0; phr ^= 1; }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            mbar_arrive(&xa_full[sa]);
+            if (++sa == TW_X_STAGES) { sa = 0; pha ^= 1; }
+        }
+        // ===================== epilogue: TMEM partial tile -> vector atomics into dW / db =====================
+        if (n_chunks > 0) {
+            mbar_wait(&acc_bar, 0);
+            tc_fence_after();
+            const int p = ptile * 128 + pl;
+            const uint32_t tacc = tmem_base + t_lane;
+            for (int c0 = 0; c0 < a.Q + (BQ > a.Q ? 16 : 0); c0 += 16) {
+                uint32_t r[16];
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                    : "r"(tacc + (uint32_t)c0));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (p < a.P) {
+                    if (c0 < a.Q) {
+                        float* dst = a.dW + (long long)p * a.lddw + c0;
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            float4 v = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
+                                                   __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+                            atomicAdd(reinterpret_cast<float4*>(dst + 4 * q), v);
+                        }
+                    } else if (a.db) {
+                        atomicAdd(a.db + p, __uint_as_float(r[0]));       // column Q: sum over rows of g(X)[:, p]
+                    }
+                }
+            }
+        }
+    } else if (warp == TW_MMA_WARP) {
+        // ===================== MMA issuer: A = X^T hi / lo in tensor memory, B = MN-major Y tiles =====================
+        const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+        const uint32_t sy0 = smem_u32(smem_y);
+        const uint32_t idesc = a.idesc;
+        const uint64_t y_step = (uint64_t)((ya * 1024) >> 4), y_lo_off = (uint64_t)(y_bytes >> 4);
+        int sx = 0, sy = 0;
+        uint32_t phx = 0, phy = 0;
+        for (int ch = 0; ch < n_chunks; ch++) {
+            mbar_wait(&xa_full[sx], phx);
+            mbar_wait(&y_full[sy], phy);
+            tc_fence_after();
+            const uint32_t x_hi = tmem_u + (uint32_t)(TW_X_COL0 + sx * 64), x_lo = x_hi + 32u;
+            const uint64_t y_hi = tc_smem_desc_mn(sy0 + (uint32_t)sy * y_stage_bytes, 512, ya * 512);
+            if (elect_one()) {
+#pragma unroll
+                for (int ks = 0; ks < 4; ks++) {                          // 4 MMAs of K = 8 rows each
+                    const uint64_t yo = (uint64_t)ks * y_step;
+                    const uint32_t xc = (uint32_t)(ks * 8);
+                    tc_mma_ts(tmem_u, x_lo + xc, y_hi + yo, idesc, (ch | ks) != 0);
+                    tc_mma_ts(tmem_u, x_hi + xc, y_hi + y_lo_off + yo, idesc, 1);
+                    tc_mma_ts(tmem_u, x_hi + xc, y_hi + yo, idesc, 1);
+                }
+                tc_commit(&xa_empty[sx]);
+                tc_commit(&y_empty[sy]);
+                if (ch == n_chunks - 1) tc_commit(&acc_bar);
+            }
+            __syncwarp();
+            if (++sx == TW_X_STAGES) { sx = 0; phx ^= 1; }
+            if (++sy == SY) { sy = 0; phy ^= 1; }
+        }
+    } else if (warp == TW_TMA_WARP) {
+        // ===================== TMA producer: raw X (and relu_y) chunks =====================
+        if (lane == 0) {
+            int st = 0;
+            uint32_t ph = 0;
+            const uint32_t tx = raw_bytes * (has_r ? 2u : 1u);
+            for (int ch = 0; ch < n_chunks; ch++) {
+                const int m0 = (c_begin + ch) * 32;
+                mbar_wait(&xr_empty[st], ph ^ 1);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&xr_full[st])), "r"(tx)
+                             : "memory");
+                asm volatile(
+                    "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                    ::"r"(smem_u32(smem_x + (size_t)st * raw_bytes)), "l"(&tmap_x), "r"(ptile * 128), "r"(m0),
+                      "r"(smem_u32(&xr_full[st]))
+                    : "memory");
+                if (has_r)
+                    asm volatile(
+                        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                        ::"r"(smem_u32(smem_rl + (size_t)st * raw_bytes)), "l"(&tmap_r), "r"(ptile * 128), "r"(m0),
+                          "r"(smem_u32(&xr_full[st]))
+                        : "memory");
+                if (++st == RS) { st = 0; ph ^= 1; }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===================== Y producers (two groups, alternate chunks, next chunk's loads in flight) =====================
+        const int grp = (warp - TW_Y_WARP0) >> 2;
+        const int pt = (int)threadIdx.x - (TW_Y_WARP0 * 32 + grp * 128);
+        // Y tile: 32 rows x cpr chunks; thread -> fixed chunk cy of rows ry0 + ry_step i  (ry_step = 128 / cpr in {4,8,16})
+        const int cpr = a.Q >> 2, ry0 = pt / cpr, cy = pt - ry0 * cpr, ry_step = 128 / cpr, ny = (32 * cpr) >> 7;
+        const int offy0 = tc_mn_off(ry0, cy, ya), offy_step = (ry_step >> 2) * ya * 128;
+        const float* py = a.Y + cy * 4;
+        auto load_y = [&](int ch, float4 (&vy)[8]) {
+            const long long m0 = (long long)(c_begin + ch) * 32;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                vy[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                const long long row = m0 + ry0 + ry_step * i;
+                if (i < ny && row < a.M) {
+                    if (a.y_shift == 0) vy[i] = __ldg(reinterpret_cast<const float4*>(py + row * a.ldyy));
+                    else if ((((unsigned)row) / (unsigned)a.y_shift) % (unsigned)a.y_period != 0u)
+                        vy[i] = __ldg(reinterpret_cast<const float4*>(py + (row - a.y_shift) * a.ldyy));
+                }
+            }
+        };
+        auto store_y = [&](int ch, const float4 (&vy)[8]) {
+            const int stage = ch % SY;
+            const uint32_t phase = (uint32_t)(ch / SY) & 1u;
+            mbar_wait(&y_empty[stage], phase ^ 1);
+            float* yhi = reinterpret_cast<float*>(smem_y + (size_t)stage * y_stage_bytes) + offy0;
+            float* ylo = yhi + 32 * BQ;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                if (i < ny) {
+                    float4 h, l;
+                    h.x = __uint_as_float(__float_as_uint(vy[i].x) & 0xffffe000u);
+                    h.y = __uint_as_float(__float_as_uint(vy[i].y) & 0xffffe000u);
+                    h.z = __uint_as_float(__float_as_uint(vy[i].z) & 0xffffe000u);
+                    h.w = __uint_as_float(__float_as_uint(vy[i].w) & 0xffffe000u);
+                    l.x = vy[i].x - h.x; l.y = vy[i].y - h.y; l.z = vy[i].z - h.z; l.w = vy[i].w - h.w;
+                    *reinterpret_cast<float4*>(yhi + i * offy_step) = h;
+                    *reinterpret_cast<float4*>(ylo + i * offy_step) = l;
+                }
+            }
+            fence_async_smem();
+            mbar_arrive(&y_full[stage]);
+        };
+        float4 va[8], vb[8];
+        int ch = grp;
+        if (ch < n_chunks) {
+            load_y(ch, va);
+            for (;;) {
+                int cn = ch + 2;
+                if (cn < n_chunks) load_y(cn, vb);
+                store_y(ch, va);
+                ch = cn;
+                if (ch >= n_chunks) break;
+                cn = ch + 2;
+                if (cn < n_chunks) load_y(cn, va);
+                store_y(ch, vb);
+                ch = cn;
+                if (ch >= n_chunks) break;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == TW_MMA_WARP) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+    }
+}
+
 extern "C" int refil_tc_wgrad_supported(int M, int P, int Q) {
     if (M < 32 || P < 4 || P % 4 != 0) return 0;
     return (Q == 32 || Q == 64 || Q == 128) ? 1 : 0;
@@ -1069,6 +1361,42 @@ extern "C" int refil_tc_gemm_wgrad(const float* X, long long ldx, const float* r
     if (splits > chunks_total) splits = chunks_total;
     a.chunks_per_split = refil_cdiv(chunks_total, splits);
     a.splits = refil_cdiv(chunks_total, a.chunks_per_split);
+    static int mode_ts = -1;
+    if (mode_ts < 0) {
+        const char* e = getenv("REFIL_TC_MODE");
+        mode_ts = (e && e[0] == 's' && e[1] == 's') ? 0 : 1;
+    }
+    if (mode_ts) {
+        // X^T operand in tensor memory (K-major by construction), Y tiles MN-major in shared memory
+        a.idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(a.BQ >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        TcWGeom g{};
+        const size_t raw_bytes = 32 * 128 * 4, y_stage = 2 * (size_t)32 * a.BQ * 4;
+        g.raw_stages = relu_y ? 3 : 4;
+        const size_t raw_total = (size_t)g.raw_stages * raw_bytes * (relu_y ? 2 : 1);
+        int ys = (int)((225 * 1024 - raw_total) / y_stage);
+        if (ys > TC_MAX_STAGES) ys = TC_MAX_STAGES;
+        REFIL_CHECK_ARG(ys >= 2, "tc_gemm_wgrad: shared memory budget (Q=%d)", Q);
+        g.y_stages = ys;
+        CUtensorMap tmx, tmr;
+        memset(&tmr, 0, sizeof(tmr));
+        if (!tc_make_tmap_rows(&tmx, X, ldx, M, P) || (relu_y && !tc_make_tmap_rows(&tmr, relu_y, ldy, M, P))) {
+            refil_set_error("tc_gemm_wgrad: cuTensorMapEncodeTiled failed (X=%p ldx=%lld M=%d P=%d)", (const void*)X, ldx, M, P);
+            return REFIL_ERR_CUDA;
+        }
+        const size_t smem = raw_total + (size_t)ys * y_stage + 1024;
+        static size_t attr_smem_ts = 0;
+        if (smem > attr_smem_ts) {
+            cudaError_t e = cudaFuncSetAttribute(tc_wgrad_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) {
+                refil_set_error("tc_gemm_wgrad: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
+                return REFIL_ERR_CUDA;
+            }
+            attr_smem_ts = smem;
+        }
+        tc_wgrad_ts_kernel<<<a.p_tiles * a.splits, TW_THREADS, smem, stream>>>(a, g, tmx, tmr);
+        REFIL_CHECK_LAUNCH("tc_gemm_wgrad (ts)");
+        return REFIL_OK;
+    }
     const size_t stage_bytes = 2 * (size_t)32 * 128 * 4 + 2 * (size_t)32 * a.BQ * 4;
     int stages = (int)((200 * 1024) / stage_bytes);
     if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
