@@ -29,7 +29,7 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --c
   python bench.py --steps 1 --warmup 1 --no-cpu > gpurun_out/${TAG}_ncu_launches.log 2>&1
 if [ "$FULL" = "full" ]; then
   timeout 900 ncu --set full --clock-control none --import-source on \
-    -k regex:'tc_gemm_tn_kernel|attn_fwd_kernel|attn_bwd_kernel|tc_gemm_wgrad_kernel' -s 40 -c 24 \
+    -k regex:'tc_gemm_t._kernel|tc_wgrad_ts_kernel|tc_gemm_wgrad_kernel|attn_fwd_kernel|attn_bwd_kernel|gru_scan' -s 60 -c 16 \
     -o gpurun_out/${TAG}_prof -f python bench.py --steps 1 --warmup 1 --no-cpu > gpurun_out/${TAG}_ncu_full.log 2>&1
   ls -la gpurun_out/
 fi
