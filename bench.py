@@ -177,7 +177,8 @@ def run_reference(a):
         "impl": "reference", "metric": "learner transitions/sec", "value": v, "unit": "transitions/s",
         "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(a.workload, sample_B, T, na, ne), "sample_B": sample_B},
+        "config": {"workload": workload_name(a.workload, B, T, na, ne), "sample_B": sample_B,
+                   "note": "each step is a bounded sample (sample_B episodes) of the workload; transitions/s does not depend on B"},
         "cpu_baseline": {"value": v, "unit": "transitions/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "transitions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
