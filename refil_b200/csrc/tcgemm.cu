@@ -182,6 +182,51 @@ __device__ __forceinline__ void tc_mask_relu(const TcArgs& a, int mt, int kcol, 
     }
 }
 
+// Resident weight tile [KS/32][hi | lo][BN][32]: every global load of the tile is issued before the first split / store
+// (BN * KS <= 16384 elements -> at most 8 float4 per thread), so the prologue of a launch costs one memory latency, not eight
+template <int NTHREADS>
+__device__ __forceinline__ void tc_load_resident_b(const TcArgs& a, uint8_t* smem_b, uint32_t b_bytes, int nt, int k_off) {
+    const int BN = a.BN, k4 = a.KS >> 2, tot = BN * k4;
+    constexpr int MAXIT = 8;
+    float4 v[MAXIT];
+#pragma unroll
+    for (int it = 0; it < MAXIT; it++) {
+        const int f = (int)threadIdx.x + it * NTHREADS;
+        v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (f < tot) {
+            const int r = f / k4, kq = f - r * k4;           // row of the tile, 16-byte chunk along K
+            const long long j = (long long)nt * BN + r;
+            if (j < a.N) {
+                const float* p = a.B + j * a.sbj + (long long)(k_off + kq * 4) * a.sbi;
+                if (a.sbi == 1) v[it] = __ldg(reinterpret_cast<const float4*>(p));
+                else { v[it].x = __ldg(p); v[it].y = __ldg(p + a.sbi); v[it].z = __ldg(p + 2 * a.sbi); v[it].w = __ldg(p + 3 * a.sbi); }
+            }
+        }
+    }
+#pragma unroll
+    for (int it = 0; it < MAXIT; it++) {
+        const int f = (int)threadIdx.x + it * NTHREADS;
+        if (f < tot) {
+            const int r = f / k4, kq = f - r * k4;
+            const int kc = kq >> 3, c = kq & 7;
+            float* hi = reinterpret_cast<float*>(smem_b + (size_t)kc * 2 * b_bytes);
+            tc_store_split(hi, hi + BN * 32, r, c, v[it]);
+        }
+    }
+    for (int f = (int)threadIdx.x + MAXIT * NTHREADS; f < tot; f += NTHREADS) {      // never taken within the smem budget
+        const int r = f / k4, kq = f - r * k4;
+        const int kc = kq >> 3, c = kq & 7;
+        const long long j = (long long)nt * BN + r;
+        float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j < a.N) {
+            const float* p = a.B + j * a.sbj + (long long)(k_off + kq * 4) * a.sbi;
+            w.x = __ldg(p); w.y = __ldg(p + a.sbi); w.z = __ldg(p + 2 * a.sbi); w.w = __ldg(p + 3 * a.sbi);
+        }
+        float* hi = reinterpret_cast<float*>(smem_b + (size_t)kc * 2 * b_bytes);
+        tc_store_split(hi, hi + BN * 32, r, c, w);
+    }
+}
+
 // Epilogue role (warps 0-7; warp w owns TMEM lane quadrant w & 3 and every other 32-column slab, w >> 2):
 // TMEM (lane = row) -> registers -> bias / relu / row mask -> swizzled staging tile -> one TMA store per slab
 __device__ __forceinline__ void tc_epilogue(const TcArgs& a, const CUtensorMap* tmap_c, int warp, int lane, int nt, int mt0,
@@ -300,20 +345,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_tn_kernel(TcArgs a, con
     }
     // resident weight tile: split once per CTA
     {
-        const int k4 = a.KS >> 2;
-        for (int f = threadIdx.x; f < BN * k4; f += TC_THREADS) {
-            const int r = f / k4, kq = f - r * k4;           // row of the tile, 16-byte chunk along K
-            const int kc = kq >> 3, c = kq & 7;
-            const long long j = (long long)nt * BN + r;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (j < a.N) {
-                const float* p = a.B + j * a.sbj + (long long)(k_off + kq * 4) * a.sbi;
-                if (a.sbi == 1) v = __ldg(reinterpret_cast<const float4*>(p));
-                else { v.x = __ldg(p); v.y = __ldg(p + a.sbi); v.z = __ldg(p + 2 * a.sbi); v.w = __ldg(p + 3 * a.sbi); }
-            }
-            float* hi = reinterpret_cast<float*>(smem_b + (size_t)kc * 2 * b_bytes);
-            tc_store_split(hi, hi + BN * 32, r, c, v);
-        }
+        tc_load_resident_b<TC_THREADS>(a, smem_b, b_bytes, nt, k_off);
         for (int c = threadIdx.x; c < BN; c += TC_THREADS) epi_bias[c] = a.bias ? __ldg(a.bias + (long long)nt * BN + c) : 0.f;
         fence_async_smem();
     }
@@ -488,20 +520,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) tc_gemm_ts_kernel(TcArgs a, con
     }
     // resident weight tile: split once per CTA
     {
-        const int k4 = a.KS >> 2;
-        for (int f = threadIdx.x; f < BN * k4; f += TS_THREADS) {
-            const int r = f / k4, kq = f - r * k4;
-            const int kc = kq >> 3, c = kq & 7;
-            const long long j = (long long)nt * BN + r;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (j < a.N) {
-                const float* p = a.B + j * a.sbj + (long long)(k_off + kq * 4) * a.sbi;
-                if (a.sbi == 1) v = __ldg(reinterpret_cast<const float4*>(p));
-                else { v.x = __ldg(p); v.y = __ldg(p + a.sbi); v.z = __ldg(p + 2 * a.sbi); v.w = __ldg(p + 3 * a.sbi); }
-            }
-            float* hi = reinterpret_cast<float*>(smem_b + (size_t)kc * 2 * b_bytes);
-            tc_store_split(hi, hi + BN * 32, r, c, v);
-        }
+        tc_load_resident_b<TS_THREADS>(a, smem_b, b_bytes, nt, k_off);
         for (int c = threadIdx.x; c < BN; c += TS_THREADS) epi_bias[c] = a.bias ? __ldg(a.bias + (long long)nt * BN + c) : 0.f;
         fence_async_smem();
     }
