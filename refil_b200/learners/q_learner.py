@@ -58,6 +58,11 @@ class QLearner:
         self.sumsq = torch.zeros(1, dtype=torch.float64, device=dev)
         self.grad_norm = torch.zeros(1, dtype=torch.float32, device=dev)
 
+    def _side_stream(self):
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        return self._side
+
     def cuda(self):
         self.mac.cuda()
         self.target_mac.cuda()
@@ -92,38 +97,59 @@ class QLearner:
             self.mixer.forward(ch_gt[0], ch_gt[1], ch_gt[2], inp_gt["entities"], inp_gt["last_action"],
                                inp_gt["entity_mask"], T, imagine_masks=mix_gt, xin=inp_gt.get("xin"), ret_ingroup=True)
             gt_ingroup = self.mixer.ingroup.view(B, T)[:, :-1].mean()
-        # online agent on all T steps, 3 mask copies when imagining (q_learner.py:79-109)
+        # Two CUDA streams (args.concurrent_streams, default on): the target networks' forward runs beside the online
+        # forward, and the hypernetworks' backward beside the agent's backward.  The kernels are persistent one-CTA-per-SM
+        # grids, so the two chains do not share an SM at any instant -- what overlaps is every launch's fixed cost (tile
+        # prologue, pipeline fill and drain, tail rounds), ~15 us x 200 launches a step.
+        two = bool(getattr(args, "concurrent_streams", True)) and self.mixer is not None
+        main = torch.cuda.current_stream()
+        side = self._side_stream() if two else main
+        # shared inputs first (entities / last-action index / masks / packed fc1 input), then fork
+        T_all = batch["avail_actions"].shape[1]
+        inp = self.mac._build_inputs(batch, slice(0, T_all))
+        if two:
+            side.wait_stream(main)
+        # ---- side: target agent + target hypernetworks (q_learner.py:111-118,154) ------------------------------------
+        ents, la, em = inp["entities"], inp["last_action"], inp["entity_mask"]
+        with torch.cuda.stream(side):
+            self.target_mac.init_hidden(B)
+            q_tgt, _, _, _ = self.target_mac.forward(batch, None, ret_plan=True, inputs=inp)
+            self.target_mixer.hyper_forward(ents, la, em, T, xin=inp.get("xin"))
+        # ---- main: online agent on all T steps, 3 mask copies when imagining (q_learner.py:79-109) -------------------
         self.mac.init_hidden(B)
-        q_all, spec, mix, inp = self.mac.forward(batch, None, imagine=self.imagine,
-                                                 use_gt_factors=getattr(args, "train_gt_factors", False),
-                                                 use_rand_gt_factors=getattr(args, "train_rand_gt_factors", False),
-                                                 group_bits=group_bits, train=True, ret_plan=True)
+        q_all, spec, mix, _ = self.mac.forward(batch, None, imagine=self.imagine,
+                                               use_gt_factors=getattr(args, "train_gt_factors", False),
+                                               use_rand_gt_factors=getattr(args, "train_rand_gt_factors", False),
+                                               group_bits=group_bits, train=True, ret_plan=True, inputs=inp)
         C = spec.C
         chosen = ops.gather_chosen(q_all, actions, ws.get("chosen", (3, N, na)), C, N * na, A)
-        # target agent + double-Q selection (q_learner.py:111-126)
-        self.target_mac.init_hidden(B)
-        q_tgt, _, _, _ = self.target_mac.forward(batch, None, ret_plan=True, inputs=inp)
-        tgt_max = ops.target_max(q_all[0], q_tgt[0], avail, ws.get("tgt_max", (N, na)), None, N * na, A, args.double_q)
-        # mixers (q_learner.py:129-154)
-        ents, la, em = inp["entities"], inp["last_action"], inp["entity_mask"]
-        qtot, qtot_im = self.mixer.forward(chosen[0], chosen[1] if self.imagine else None,
-                                           chosen[2] if self.imagine else None, ents, la, em, T,
-                                           imagine_masks=mix if self.imagine else None, xin=inp.get("xin"),
-                                           ret_ingroup=log_gt)
+        self.mixer.hyper_forward(ents, la, em, T, imagine_masks=mix if self.imagine else None, xin=inp.get("xin"))
+        qtot, qtot_im = self.mixer.mix(chosen[0], chosen[1] if self.imagine else None,
+                                       chosen[2] if self.imagine else None, ret_ingroup=log_gt)
         ingroup = self.mixer.ingroup.view(B, T)[:, :-1].mean() if log_gt else None
-        tgt_tot, _ = self.target_mixer.forward(tgt_max, None, None, ents, la, em, T, xin=inp.get("xin"))
+        if two:
+            main.wait_stream(side)
+        # double-Q selection and the target mix (q_learner.py:121-126,154)
+        tgt_max = ops.target_max(q_all[0], q_tgt[0], avail, ws.get("tgt_max", (N, na)), None, N * na, A, args.double_q)
+        tgt_tot, _ = self.target_mixer.mix(tgt_max, None, None)
         # targets, TD errors, masked losses as sums (q_learner.py:157-172)
         self.stats64.zero_()
         g_plain = ws.get("g_plain", (N,))
         g_im = ws.get("g_im", (N,)) if self.imagine else None
         ops.td_loss(qtot, qtot_im, tgt_tot, reward, terminated, filled, g_plain, g_im, None, self.stats64, B, T,
                     args.gamma, args.lmbda if self.imagine else 0.0)
-        # backward (q_learner.py:175-176)
+        # backward (q_learner.py:175-176): hypernetworks on the side stream, agent on the main stream
         self.gradbuf.zero_()
-        dq = self.mixer.backward(g_plain, g_im)
+        dq, dhyper = self.mixer.backward_mix(g_plain, g_im)
+        if two:
+            side.wait_stream(main)
+        with torch.cuda.stream(side):
+            self.mixer.backward_hyper(dhyper)
         Ap = self.mac.agent.dq_width()        # one-hot scatter of d(chosen) into (padded) action columns
         dQ = ops.scatter_dq(dq, actions, ws.get("dQ", (C * N * na, Ap)), C, N * na, Ap, T, na)
         self.mac.agent.backward(dQ)
+        if two:
+            main.wait_stream(side)
         # one all-reduce of [grads | stats], then normalise + clip + RMSprop (q_learner.py:177-178)
         ops.pack_stats(self.stats64, self.gradbuf[self.n_params:], N_STATS)
         parallel.all_reduce_sum_(self.gradbuf)

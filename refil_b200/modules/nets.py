@@ -311,15 +311,10 @@ class Mixer:
     def eval(self):
         return self
 
-    def forward(self, q, qW, qI, ents, la, entity_mask, T, imagine_masks=None, xin=None, ret_ingroup=False):
-        """q [N, na] (+ qW, qI when imagine); ents [N, ne, ed]; entity_mask [N, ne].
-        imagine_masks: (copy_W, copy_I) MaskSpec-style copy tuples + group bits, or None.
-        Returns (q_tot [N], q_tot_im [N] or None)."""
-        ws, tag = self.ws, self.tag
-        N = ents.shape[0]
+    def hyper_forward(self, ents, la, entity_mask, T, imagine_masks=None, xin=None):
+        """The heavy part of the mixer: every hypernetwork evaluated on the entity rows (independent of the agent utilities,
+        so the learner may run it concurrently with the agent forward).  -> {name: [rows, me]}"""
         imagine = imagine_masks is not None
-        qtot = ws.get(tag + ".qtot", (N,))
-        qtot_im = ws.get(tag + ".qtot_im", (N,)) if imagine else None
         outs = {}
         if self.kind != 2:
             default = (None, 0, ops.ATTN_DEFAULT)
@@ -330,6 +325,16 @@ class Mixer:
                 else:
                     m = MaskSpec([default], None, entity_mask)
                 outs[h] = net.forward(ents, la, m, T, xin=xin)
+        self._hyper = (outs, ents.shape[0], imagine)
+        return outs
+
+    def mix(self, q, qW, qI, ret_ingroup=False):
+        """q [N, na] (+ qW, qI when imagine) combined with the hypernetwork outputs of the last hyper_forward.
+        Returns (q_tot [N], q_tot_im [N] or None)."""
+        ws, tag = self.ws, self.tag
+        outs, N, imagine = self._hyper
+        qtot = ws.get(tag + ".qtot", (N,))
+        qtot_im = ws.get(tag + ".qtot_im", (N,)) if imagine else None
         w1 = outs.get("hyper_w_1.")
         self.saved = (q, qW, qI, outs, N, imagine)
         self.ingroup = ws.get(tag + ".ingroup", (N,)) if (ret_ingroup and imagine and self.kind == 1) else None
@@ -338,8 +343,15 @@ class Mixer:
                       ingroup=self.ingroup)
         return qtot, qtot_im
 
-    def backward(self, g_plain, g_im):
-        """-> dq, dqW, dqI [N, na]; hypernet parameter gradients are accumulated."""
+    def forward(self, q, qW, qI, ents, la, entity_mask, T, imagine_masks=None, xin=None, ret_ingroup=False):
+        """q [N, na] (+ qW, qI when imagine); ents [N, ne, ed]; entity_mask [N, ne].
+        imagine_masks: (copy_W, copy_I) MaskSpec-style copy tuples + group bits, or None.
+        Returns (q_tot [N], q_tot_im [N] or None)."""
+        self.hyper_forward(ents, la, entity_mask, T, imagine_masks=imagine_masks, xin=xin)
+        return self.mix(q, qW, qI, ret_ingroup=ret_ingroup)
+
+    def backward_mix(self, g_plain, g_im):
+        """Mixer combine backward: -> (dq [3, N, na], {name: d(hypernet output)}); cheap, no parameter gradients."""
         ws, tag = self.ws, self.tag
         q, qW, qI, outs, N, imagine = self.saved
         na = self.na
@@ -350,6 +362,15 @@ class Mixer:
                       d.get("hyper_w_final."), d.get("V."), dq[0], dq[1] if imagine else None,
                       dq[2] if imagine else None, N, na, self.me, 3 if imagine else 1, imagine, self.softmax_w,
                       self.tanh_nl)
+        return dq, d
+
+    def backward_hyper(self, d):
+        """Hypernetwork backward passes (parameter gradients are accumulated); independent of the agent backward."""
         for h, net in self.nets.items():
             net.backward(d[h])
+
+    def backward(self, g_plain, g_im):
+        """-> dq, dqW, dqI [N, na]; hypernet parameter gradients are accumulated."""
+        dq, d = self.backward_mix(g_plain, g_im)
+        self.backward_hyper(d)
         return dq
