@@ -307,12 +307,14 @@ def run_ours(a):
     e2e = trans * a.steps / (ms_e2e * 1e-3)
 
     # ---- per-kernel breakdown (instrumented repeat of the step, events around every launch) -------------------
+    args.concurrent_streams = False          # serialised launches: per-kernel durations are not inflated by overlap
     ops.set_timing(True)
     step_resident(0)
     step_resident(1)
     tsum = ops.timing_summary()
     shapes = ops.shape_timing_summary()
     ops.set_timing(False)
+    args.concurrent_streams = True
     kern = {k: {"launches": v[0] // 2, "ms_per_step": v[1] / 2, "flop_per_step": v[2] / 2, "bytes_per_step": v[3] / 2}
             for k, v in tsum.items()}
     hbm, tf_burst, tf_sus, src = peaks()

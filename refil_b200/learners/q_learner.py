@@ -35,6 +35,8 @@ class QLearner:
             self.mixer = Mixer(args, self.ein, self.device, tag="mixer")
             self.target_mixer = Mixer(args, self.ein, self.device, tag="target_mixer")
             self.target_mixer.load_state_dict(self.mixer.state_dict())
+            names = list(self.mixer.nets.keys())
+            self.mixer.set_scratch_groups([names[:1], names[1:]])      # the two groups run on different streams
         self.target_mac = type(mac)(mac.scheme, mac.groups, args)
         self.target_mac.load_state(mac)
         self._bind_flat()
@@ -58,10 +60,10 @@ class QLearner:
         self.sumsq = torch.zeros(1, dtype=torch.float64, device=dev)
         self.grad_norm = torch.zeros(1, dtype=torch.float32, device=dev)
 
-    def _side_stream(self):
+    def _side_stream(self, i):
         if getattr(self, "_side", None) is None:
-            self._side = torch.cuda.Stream(device=self.device)
-        return self._side
+            self._side = [torch.cuda.Stream(device=self.device) for _ in range(2)]
+        return self._side[i]
 
     def cuda(self):
         self.mac.cuda()
@@ -103,27 +105,36 @@ class QLearner:
         # prologue, pipeline fill and drain, tail rounds), ~15 us x 200 launches a step.
         two = bool(getattr(args, "concurrent_streams", True)) and self.mixer is not None
         main = torch.cuda.current_stream()
-        side = self._side_stream() if two else main
-        # shared inputs first (entities / last-action index / masks / packed fc1 input), then fork
+        side, side2 = (self._side_stream(0), self._side_stream(1)) if two else (main, main)
+        # shared inputs first (entities / last-action index / masks / packed fc1 input) and the mask plan, then fork
         T_all = batch["avail_actions"].shape[1]
         inp = self.mac._build_inputs(batch, slice(0, T_all))
+        use_gt = getattr(args, "train_gt_factors", False)
+        use_rgt = getattr(args, "train_rand_gt_factors", False)
+        if self.imagine and group_bits is None and not use_gt:         # the random partition is drawn ONCE, here
+            group_bits = self.mac.draw_groups(inp["bs"], inp["ne"], inp["entity_mask"].device)
+        _, mix, _ = self.mac.mask_plan(inp, self.imagine, use_gt, use_rgt, group_bits)
         if two:
             side.wait_stream(main)
-        # ---- side: target agent + target hypernetworks (q_learner.py:111-118,154) ------------------------------------
+            side2.wait_stream(main)
         ents, la, em = inp["entities"], inp["last_action"], inp["entity_mask"]
+        # ---- side: target agent + target hypernetworks (q_learner.py:111-118,154) ------------------------------------
         with torch.cuda.stream(side):
             self.target_mac.init_hidden(B)
             q_tgt, _, _, _ = self.target_mac.forward(batch, None, ret_plan=True, inputs=inp)
             self.target_mixer.hyper_forward(ents, la, em, T, xin=inp.get("xin"))
+        # ---- side2: online hypernetworks (they only need the entities and the partition) ---------------------------
+        with torch.cuda.stream(side2):
+            self.mixer.hyper_forward(ents, la, em, T, imagine_masks=mix if self.imagine else None, xin=inp.get("xin"))
         # ---- main: online agent on all T steps, 3 mask copies when imagining (q_learner.py:79-109) -------------------
         self.mac.init_hidden(B)
-        q_all, spec, mix, _ = self.mac.forward(batch, None, imagine=self.imagine,
-                                               use_gt_factors=getattr(args, "train_gt_factors", False),
-                                               use_rand_gt_factors=getattr(args, "train_rand_gt_factors", False),
-                                               group_bits=group_bits, train=True, ret_plan=True, inputs=inp)
+        q_all, spec, _, _ = self.mac.forward(batch, None, imagine=self.imagine, use_gt_factors=use_gt,
+                                             use_rand_gt_factors=use_rgt, group_bits=group_bits, train=True,
+                                             ret_plan=True, inputs=inp)
         C = spec.C
         chosen = ops.gather_chosen(q_all, actions, ws.get("chosen", (3, N, na)), C, N * na, A)
-        self.mixer.hyper_forward(ents, la, em, T, imagine_masks=mix if self.imagine else None, xin=inp.get("xin"))
+        if two:
+            main.wait_stream(side2)
         qtot, qtot_im = self.mixer.mix(chosen[0], chosen[1] if self.imagine else None,
                                        chosen[2] if self.imagine else None, ret_ingroup=log_gt)
         ingroup = self.mixer.ingroup.view(B, T)[:, :-1].mean() if log_gt else None
@@ -138,18 +149,24 @@ class QLearner:
         g_im = ws.get("g_im", (N,)) if self.imagine else None
         ops.td_loss(qtot, qtot_im, tgt_tot, reward, terminated, filled, g_plain, g_im, None, self.stats64, B, T,
                     args.gamma, args.lmbda if self.imagine else 0.0)
-        # backward (q_learner.py:175-176): hypernetworks on the side stream, agent on the main stream
+        # backward (q_learner.py:175-176): hypernetworks on the side streams, agent on the main stream
         self.gradbuf.zero_()
         dq, dhyper = self.mixer.backward_mix(g_plain, g_im)
+        names = list(self.mixer.nets.keys())
+        grp_a, grp_b = names[:1], names[1:]          # hyper_w_1 (3 mask copies when imagining) | the other hypernetworks
         if two:
             side.wait_stream(main)
+            side2.wait_stream(main)
         with torch.cuda.stream(side):
-            self.mixer.backward_hyper(dhyper)
+            self.mixer.backward_hyper(dhyper, grp_a)
+        with torch.cuda.stream(side2):
+            self.mixer.backward_hyper(dhyper, grp_b)
         Ap = self.mac.agent.dq_width()        # one-hot scatter of d(chosen) into (padded) action columns
         dQ = ops.scatter_dq(dq, actions, ws.get("dQ", (C * N * na, Ap)), C, N * na, Ap, T, na)
         self.mac.agent.backward(dQ)
         if two:
             main.wait_stream(side)
+            main.wait_stream(side2)
         # one all-reduce of [grads | stats], then normalise + clip + RMSprop (q_learner.py:177-178)
         ops.pack_stats(self.stats64, self.gradbuf[self.n_params:], N_STATS)
         parallel.all_reduce_sum_(self.gradbuf)

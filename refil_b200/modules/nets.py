@@ -40,6 +40,7 @@ class AttnTrunk:
     def __init__(self, store, prefix, ws, tag, ein, d, n_heads, n_agents, n_actions):
         self.s, self.pre, self.ws, self.tag = store, prefix, ws, tag
         self.ein, self.d, self.H, self.na, self.A = ein, d, n_heads, n_agents, n_actions
+        self.scratch = "scratch"      # tag prefix of the backward scratch buffers: nets that run concurrently use distinct ones
         # attention.py:18-19 registers sqrt(head_dim) as a buffer: keep the key so checkpoints interchange
         store.buffers[prefix + "attn.scale_factor"] = torch.tensor(float(d // n_heads)).sqrt()
 
@@ -86,15 +87,15 @@ class AttnTrunk:
         relu_y = x2 if relu_out else None
         ops.linear_bwd_weight(dx2, att, g[pre + "attn.out_trans.weight"], g[pre + "attn.out_trans.bias"],
                               relu_y=relu_y, row_mask=self.row_mask)
-        datt = ws.get("scratch.datt", (C * N * na, d))
+        datt = ws.get(self.scratch + ".datt", (C * N * na, d))
         ops.linear_bwd_data(dx2, p[pre + "attn.out_trans.weight"], datt, relu_y=relu_y, row_mask=self.row_mask)
-        dqkv = ws.get("scratch.dqkv", (N * ne, 3 * d))
+        dqkv = ws.get(self.scratch + ".dqkv", (N * ne, 3 * d))
         ops.masked_attn_bwd(qkv, datt, dqkv, masks.copies, masks.group_bits, masks.entity_mask, N, T, ne, na, d, self.H)
         ops.linear_bwd_weight(dqkv, x1, g[pre + "attn.in_trans.weight"], None)
-        dx1 = ws.get("scratch.dx1", (N * ne, d))
+        dx1 = ws.get(self.scratch + ".dx1", (N * ne, d))
         ops.linear_bwd_data(dqkv, p[pre + "attn.in_trans.weight"], dx1)
         if xin is not None:
-            dw1p = ws.get("scratch.dw1p", (d, xin.shape[1]), zero=True)
+            dw1p = ws.get(self.scratch + ".dw1p", (d, xin.shape[1]), zero=True)
             ops.linear_bwd_weight(dx1, xin, dw1p, g[pre + "fc1.bias"], relu_y=x1)
             g[pre + "fc1.weight"].add_(dw1p[:, :self.ein])
         else:
@@ -260,7 +261,7 @@ class AttnHyperNet:
         p, g, pre = self.s.p, self.s.g, self.pre
         rm = self.trunk.row_mask
         ops.linear_bwd_weight(dx3, self.x2, g[pre + "fc2.weight"], g[pre + "fc2.bias"], row_mask=rm)
-        dx2 = self.ws.get("scratch.dx2h", (dx3.shape[0], self.he))
+        dx2 = self.ws.get(self.trunk.scratch + ".dx2h", (dx3.shape[0], self.he))
         ops.linear_bwd_data(dx3, p[pre + "fc2.weight"], dx2, row_mask=rm)
         self.trunk.backward(dx2)
 
@@ -310,6 +311,12 @@ class Mixer:
 
     def eval(self):
         return self
+
+    def set_scratch_groups(self, groups):
+        """groups: list of lists of hypernet names that may run concurrently with each other's group -> distinct scratch."""
+        for gi, names in enumerate(groups):
+            for h in names:
+                self.nets[h].trunk.scratch = "scratch%d" % gi
 
     def hyper_forward(self, ents, la, entity_mask, T, imagine_masks=None, xin=None):
         """The heavy part of the mixer: every hypernetwork evaluated on the entity rows (independent of the agent utilities,
@@ -364,10 +371,12 @@ class Mixer:
                       self.tanh_nl)
         return dq, d
 
-    def backward_hyper(self, d):
-        """Hypernetwork backward passes (parameter gradients are accumulated); independent of the agent backward."""
+    def backward_hyper(self, d, names=None):
+        """Hypernetwork backward passes (parameter gradients are accumulated); independent of the agent backward and, given
+        distinct scratch groups, of each other."""
         for h, net in self.nets.items():
-            net.backward(d[h])
+            if names is None or h in names:
+                net.backward(d[h])
 
     def backward(self, g_plain, g_im):
         """-> dq, dqW, dqI [N, na]; hypernet parameter gradients are accumulated."""
