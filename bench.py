@@ -241,12 +241,16 @@ def run_ours(a):
             dist.barrier()
         torch.cuda.synchronize()
 
+    host_ms = [0.0]
+
     def timed(fn, steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        t0 = time.perf_counter()
         for i in range(steps):
             fn(i)
+        host_ms[0] = (time.perf_counter() - t0) * 1e3 / steps      # host time to ENQUEUE one step (no sync inside fn)
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -296,6 +300,7 @@ def run_ours(a):
     clocks.start()
     l0 = ops.launch_count()
     ms = timed(step_resident, a.steps)
+    host_enqueue_ms = host_ms[0]
     launches = ops.launch_count() - l0
     for i in range(2):
         step_e2e(i)
@@ -349,7 +354,7 @@ def run_ours(a):
                    "l2": "working set per step (%.1f GB of activations) exceeds the 126 MB L2" % (learner_bytes(learner, mac) / 1e9)},
         "e2e": {"value": e2e, "unit": "transitions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 32,
                 "ms_per_step": ms_e2e / a.steps},
-        "gpu_launches": launches, "clocks": clk, "roofline": roofline, "roofline_attention": roof_att,
+        "gpu_launches": launches, "host_enqueue_ms_per_step": round(host_enqueue_ms, 3), "clocks": clk, "roofline": roofline, "roofline_attention": roof_att,
         "roofline_wgrad": hbm_roof("tc_gemm_wgrad", "tc_gemm_wgrad_kernel (weight gradients, MN-major tcgen05)"),
         "roofline_attention_bwd": hbm_roof("masked_attn_bwd", "attn_bwd_kernel"), "dominant_kernel": dom[0],
         "kernels_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in sorted(kern.items(), key=lambda kv: -kv[1]["ms_per_step"])},

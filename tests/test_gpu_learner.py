@@ -109,3 +109,37 @@ def test_train_step_matches_oracle_mid_size(alg):
         _close(mac.agent.store.g[k], g, rtol=2e-4, atol=2e-5 * scale, what="grad agent " + k)
     for k, g in ref["grads_mixer"].items():
         _close(learner.mixer.store.g[k], g, rtol=2e-4, atol=2e-5 * scale, what="grad mixer " + k)
+
+
+@pytest.mark.gpu
+def test_concurrent_streams_match_single_stream():
+    """The three-stream schedule of QLearner.train is a pure re-ordering: same loss statistics and gradients as the
+    single-stream schedule (up to the summation order of the fp32 atomics in the weight-gradient kernels)."""
+    import copy
+    import torch
+    from gpu_util import build_product
+    from oracle import learner_oracle as lo
+    gen = torch.Generator().manual_seed(5)
+    B, T, na, ne, ed, A = 6, 9, 8, 24, 39, 14
+    args = lo.default_args()
+    args.n_agents, args.n_actions, args.n_entities, args.entity_shape = na, A, ne, ed
+    args.mac, args.learner, args.agent_output_type, args.action_selector = "entity_mac", "q_learner", "q", "epsilon_greedy"
+    args.target_update_interval, args.learner_log_interval, args.gt_mask_avail = 200, 1, False
+    syn = lo.synthetic_batch(gen, B, T, na, ne, ed, A)
+    ap, mp = lo.init_agent_params(gen, args, ed + A), lo.init_mixer_params(gen, args, ed + A)
+    gb = (torch.rand(B, ne, generator=gen) < 0.5).to(torch.uint8)
+    outs = []
+    for conc in (False, True):
+        a2 = copy.copy(args)
+        a2.concurrent_streams = conc
+        batch, mac, learner, logger = build_product(a2, (B, T, na, ne, ed, A), syn, "cuda:0")
+        mac.agent.load_state_dict(ap)
+        learner.target_mac.agent.load_state_dict(ap)
+        learner.mixer.load_state_dict(mp)
+        learner.target_mixer.load_state_dict(mp)
+        learner.train(batch, t_env=10, episode_num=0, group_bits=gb.to("cuda:0"))
+        torch.cuda.synchronize()
+        outs.append((logger.stats["loss"][0], logger.stats["grad_norm"][0], learner.flat.clone()))
+    assert abs(outs[0][0] - outs[1][0]) <= 1e-6 * max(1.0, abs(outs[0][0]))
+    assert abs(outs[0][1] - outs[1][1]) <= 1e-5 * max(1.0, abs(outs[0][1]))
+    assert torch.allclose(outs[0][2], outs[1][2], rtol=0, atol=1e-6)
