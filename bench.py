@@ -48,18 +48,46 @@ def make_args(alg, na, ne, ed, A):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe).  ONE long-lived
-    `nvidia-smi -lms` child started before the timed region (no fork / driver query from this process while it is timed)."""
+    """SM clocks / throttle reasons / power during the timed region (B200_PROFILING.md recipe), sampled every 20 ms through NVML
+    from a thread of this process (nvidia_ml_py: no fork, no nvidia-smi start-up); falls back to one long-lived
+    `nvidia-smi -lms` child when NVML cannot be imported."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index, enabled=True):
         self.index, self.proc, self.enabled = index, None, enabled
+        self.samples, self.stop_flag, self.thread, self.max_mhz = [], False, None, None
+
+    def _nvml_loop(self, nv, h):
+        bits = (("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
+                ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap))
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                self.samples.append((float(sm), pw, [n for n, b in bits if rs & b]))
+            except Exception:
+                pass
+            time.sleep(0.02)
 
     def start(self):
         if not self.enabled:
             return
+        try:
+            import threading
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].strip().isdigit() else self.index
+            h = nv.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
@@ -71,7 +99,11 @@ class ClockSampler:
         if not self.enabled:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["sampled on rank 0 only"]}
         samples = []
-        if self.proc is not None:
+        if self.thread is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            samples = list(self.samples)
+        elif self.proc is not None:
             try:
                 self.proc.terminate()
                 out, _ = self.proc.communicate(timeout=5)
@@ -80,24 +112,21 @@ class ClockSampler:
             for line in out.strip().splitlines():
                 f = [x.strip() for x in line.split(",")]
                 if len(f) >= 9:
-                    samples.append(f)
+                    try:
+                        self.max_mhz = float(f[2])
+                        samples.append((float(f[1]), float(f[3]), [n for n, v in zip(("hw_slowdown", "hw_thermal_slowdown",
+                                        "sw_thermal_slowdown", "sw_power_cap"), f[5:9]) if v.lower().startswith("active")]))
+                    except ValueError:
+                        pass
         if not samples:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        def num(x):
-            try:
-                return float(x)
-            except ValueError:
-                return 0.0
-        pmax = max(num(s[3]) for s in samples)
-        load = [s for s in samples if num(s[3]) >= 0.6 * pmax] or samples      # samples taken under load
-        sm = sorted(num(s[1]) for s in load)
-        reasons = set()
-        for s in load:
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(samples[0][2]), "reasons": sorted(reasons),
-                "samples": len(samples), "samples_under_load": len(load), "power_w_max": pmax}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock samples (NVML and nvidia-smi unavailable)"]}
+        pmax = max(p for _, p, _ in samples)
+        load = [x for x in samples if x[1] >= 0.6 * pmax] or samples          # samples taken under load
+        sm = sorted(x[0] for x in load)
+        reasons = sorted({r for x in load for r in x[2]})
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(samples),
+                "samples_under_load": len(load), "power_w_max": pmax,
+                "source": "nvml" if self.thread is not None else "nvidia-smi"}
 
 
 def peaks():
@@ -215,6 +244,7 @@ def run_ours(a):
         B = a.batch
     args = make_args(alg, na, ne, ed, A)
     args.device = dev
+    args.cuda_graph = not a.no_graph
 
     class Log:
         class console_logger:
@@ -313,6 +343,7 @@ def run_ours(a):
 
     # ---- per-kernel breakdown (instrumented repeat of the step, events around every launch) -------------------
     args.concurrent_streams = False          # serialised launches: per-kernel durations are not inflated by overlap
+    args.cuda_graph = False                  # ... and enqueued one by one so that events can bracket each of them
     ops.set_timing(True)
     step_resident(0)
     step_resident(1)
@@ -320,6 +351,7 @@ def run_ours(a):
     shapes = ops.shape_timing_summary()
     ops.set_timing(False)
     args.concurrent_streams = True
+    args.cuda_graph = not a.no_graph
     kern = {k: {"launches": v[0] // 2, "ms_per_step": v[1] / 2, "flop_per_step": v[2] / 2, "bytes_per_step": v[3] / 2}
             for k, v in tsum.items()}
     hbm, tf_burst, tf_sus, src = peaks()
@@ -351,6 +383,7 @@ def run_ours(a):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(a.workload, B, T, na, ne), "global_batch_episodes": world * B,
                    "parallelism": "dp%d (episodes sharded, one all-reduce of grads+stats)" % world,
+                   "step_submission": "cuda graph replay" if args.cuda_graph else "eager launches",
                    "l2": "working set per step (%.1f GB of activations) exceeds the 126 MB L2" % (learner_bytes(learner, mac) / 1e9)},
         "e2e": {"value": e2e, "unit": "transitions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 32,
                 "ms_per_step": ms_e2e / a.steps},
@@ -467,6 +500,8 @@ if __name__ == "__main__":
     ap.add_argument("--workload", default="ns", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="episodes per GPU (default: the workload's)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-graph", action="store_true", help="enqueue every kernel from Python instead of replaying the "
+                    "captured CUDA graph of the step (QLearner args.cuda_graph)")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)

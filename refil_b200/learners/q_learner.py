@@ -18,6 +18,29 @@ from ..modules.params import Workspace
 N_STATS = 8
 
 
+class _StaticBatch:
+    """Fixed-address copy of the EpisodeBatch tensors the learner reads: the input side of a captured CUDA graph."""
+
+    def __init__(self, batch, keys):
+        self.batch_size, self.max_seq_length = batch.batch_size, batch.max_seq_length
+        self.data = {}
+        for k in keys:
+            try:
+                t = batch[k]
+            except (KeyError, ValueError, AttributeError):
+                continue
+            self.data[k] = t.contiguous().clone()
+
+    def __getitem__(self, k):
+        return self.data[k]
+
+    def load(self, batch):
+        for k, dst in self.data.items():
+            src = batch[k]
+            if src.data_ptr() != dst.data_ptr():
+                dst.copy_(src, non_blocking=True)
+
+
 class QLearner:
     def __init__(self, mac, scheme, logger, args):
         self.args = args
@@ -42,6 +65,7 @@ class QLearner:
         self._bind_flat()
         self.ws = Workspace(self.device)
         self.log_stats_t = -self.args.learner_log_interval - 1
+        self._graphs = {}
 
     # ---- flat parameter / gradient / optimiser state -----------------------------------------------------------
     def _bind_flat(self):
@@ -78,6 +102,66 @@ class QLearner:
 
     # ---- the training step ---------------------------------------------------------------------------------------
     def train(self, batch, t_env, episode_num, group_bits=None):
+        args = self.args
+        na = args.n_agents
+        will_log = t_env - self.log_stats_t >= args.learner_log_interval
+        log_gt = will_log and self.imagine and getattr(args, "test_gt_factors", False) and args.mixer == "lin_flex_qmix"
+        # the device part of the step: eagerly, or (args.cuda_graph) as ONE replayed CUDA graph per batch shape
+        if getattr(args, "cuda_graph", False) and group_bits is None and not log_gt:
+            ingroup = gt_ingroup = None
+            self._graph_step(batch)
+        else:
+            ingroup, gt_ingroup = self._device_step(batch, group_bits, log_gt)
+
+        if (episode_num - self.last_target_update_episode) / args.target_update_interval >= 1.0:
+            self._update_targets()
+            self.last_target_update_episode = episode_num
+
+        if will_log:
+            st = self.gradbuf[self.n_params:].double().cpu()      # the only host sync of the step
+            m = float(st[0])
+            td, td_im = float(st[1]) / m, float(st[2]) / m
+            loss = (1 - args.lmbda) * td + args.lmbda * td_im if self.imagine else td
+            self.logger.log_stat("loss", loss, t_env)
+            if self.imagine:
+                self.logger.log_stat("im_loss", td_im, t_env)
+            if log_gt:
+                self.logger.log_stat("ingroup_prop", float(ingroup.item()), t_env)
+                self.logger.log_stat("gt_ingroup_prop", float(gt_ingroup.item()), t_env)
+            self.logger.log_stat("grad_norm", float(self.grad_norm.item()), t_env)
+            self.logger.log_stat("td_error_abs", float(st[3]) / m, t_env)
+            self.logger.log_stat("q_taken_mean", float(st[4]) / (m * na), t_env)
+            self.logger.log_stat("target_mean", float(st[5]) / (m * na), t_env)
+            self.log_stats_t = t_env
+
+    # ---- CUDA-graph replay of the device step -------------------------------------------------------------------------
+    _GRAPH_KEYS = ("entities", "obs_mask", "entity_mask", "gt_mask", "actions", "avail_actions", "reward", "terminated",
+                   "filled")
+
+    def _graph_step(self, batch):
+        """First call for a (B, T) shape runs eagerly (sizes every workspace), the second captures the whole step -- all
+        three streams, ~200 kernel launches, the gradient all-reduce -- into one CUDA graph on static input tensors, later
+        calls copy the batch into those tensors (device to device) and replay.  Host cost per step: a dozen copies + 1 launch."""
+        key = (batch.batch_size, batch.max_seq_length)
+        ent = self._graphs.get(key)
+        if ent is None:
+            self._graphs[key] = {"static": None, "graph": None, "launches": 0}
+            self._device_step(batch, None, False)
+            return
+        if ent["graph"] is None:
+            static = _StaticBatch(batch, self._GRAPH_KEYS)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            l0 = ops.launch_count()
+            with torch.cuda.graph(g):
+                self._device_step(static, None, False)
+            ent["static"], ent["graph"], ent["launches"] = static, g, ops.launch_count() - l0
+            ops.add_launches(-ent["launches"])                     # capturing launched nothing
+        ent["static"].load(batch)
+        ent["graph"].replay()
+        ops.add_launches(ent["launches"])
+
+    def _device_step(self, batch, group_bits, log_gt):
         args, ws = self.args, self.ws
         B, T = batch.batch_size, batch.max_seq_length
         na, A = args.n_agents, args.n_actions
@@ -87,10 +171,7 @@ class QLearner:
         reward = batch["reward"].contiguous().view(N)
         terminated = batch["terminated"].contiguous().view(N)
         filled = batch["filled"].contiguous().view(N)
-
-        will_log = t_env - self.log_stats_t >= args.learner_log_interval
-        gt_ingroup = None
-        log_gt = will_log and self.imagine and getattr(args, "test_gt_factors", False) and args.mixer == "lin_flex_qmix"
+        gt_ingroup = ingroup = None
         if log_gt:
             # logging-only pass with the ground-truth factorisation (q_learner.py:98-105,138-147), same weights, no grads
             self.mac.init_hidden(B)
@@ -176,27 +257,7 @@ class QLearner:
                               self.gradbuf[self.n_params:self.n_params + 1], self.sumsq, self.grad_norm,
                               args.grad_norm_clip, args.lr, args.optim_alpha, args.optim_eps,
                               getattr(args, "weight_decay", 0))
-
-        if (episode_num - self.last_target_update_episode) / args.target_update_interval >= 1.0:
-            self._update_targets()
-            self.last_target_update_episode = episode_num
-
-        if will_log:
-            st = self.gradbuf[self.n_params:].double().cpu()      # the only host sync of the step
-            m = float(st[0])
-            td, td_im = float(st[1]) / m, float(st[2]) / m
-            loss = (1 - args.lmbda) * td + args.lmbda * td_im if self.imagine else td
-            self.logger.log_stat("loss", loss, t_env)
-            if self.imagine:
-                self.logger.log_stat("im_loss", td_im, t_env)
-            if log_gt:
-                self.logger.log_stat("ingroup_prop", float(ingroup.item()), t_env)
-                self.logger.log_stat("gt_ingroup_prop", float(gt_ingroup.item()), t_env)
-            self.logger.log_stat("grad_norm", float(self.grad_norm.item()), t_env)
-            self.logger.log_stat("td_error_abs", float(st[3]) / m, t_env)
-            self.logger.log_stat("q_taken_mean", float(st[4]) / (m * na), t_env)
-            self.logger.log_stat("target_mean", float(st[5]) / (m * na), t_env)
-            self.log_stats_t = t_env
+        return ingroup, gt_ingroup
 
     def _update_targets(self):
         self.target_mac.load_state(self.mac)

@@ -15,6 +15,12 @@ def launch_count():
     return _launches
 
 
+def add_launches(n):
+    """Account kernel launches that did not go through _call (CUDA-graph replays of a captured step)."""
+    global _launches
+    _launches += n
+
+
 def _stream():
     return torch.cuda.current_stream().cuda_stream
 

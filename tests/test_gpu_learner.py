@@ -143,3 +143,36 @@ def test_concurrent_streams_match_single_stream():
     assert abs(outs[0][0] - outs[1][0]) <= 1e-6 * max(1.0, abs(outs[0][0]))
     assert abs(outs[0][1] - outs[1][1]) <= 1e-5 * max(1.0, abs(outs[0][1]))
     assert torch.allclose(outs[0][2], outs[1][2], rtol=0, atol=1e-6)
+
+
+@pytest.mark.gpu
+def test_cuda_graph_step_matches_eager():
+    """args.cuda_graph: the captured + replayed step trains exactly like the eager one (same injected partition is not possible
+    under capture, so a non-imagine algorithm is used: qmix_atten has no random partition)."""
+    import copy
+    import torch
+    from gpu_util import build_product
+    from oracle import learner_oracle as lo
+    gen = torch.Generator().manual_seed(7)
+    B, T, na, ne, ed, A = 5, 8, 8, 16, 39, 14
+    args = lo.default_args()
+    args.agent = "entity_attend_rnn"
+    args.n_agents, args.n_actions, args.n_entities, args.entity_shape = na, A, ne, ed
+    args.mac, args.learner, args.agent_output_type, args.action_selector = "entity_mac", "q_learner", "q", "epsilon_greedy"
+    args.target_update_interval, args.learner_log_interval, args.gt_mask_avail = 200, 10 ** 9, False
+    syn = lo.synthetic_batch(gen, B, T, na, ne, ed, A)
+    ap, mp = lo.init_agent_params(gen, args, ed + A), lo.init_mixer_params(gen, args, ed + A)
+    finals = []
+    for graph in (False, True):
+        a2 = copy.copy(args)
+        a2.cuda_graph = graph
+        batch, mac, learner, logger = build_product(a2, (B, T, na, ne, ed, A), syn, "cuda:0")
+        mac.agent.load_state_dict(ap)
+        learner.target_mac.agent.load_state_dict(ap)
+        learner.mixer.load_state_dict(mp)
+        learner.target_mixer.load_state_dict(mp)
+        for step in range(4):                      # eager, capture + replay, replay, replay
+            learner.train(batch, t_env=step, episode_num=step)
+        torch.cuda.synchronize()
+        finals.append(learner.flat.clone())
+    assert torch.allclose(finals[0], finals[1], rtol=0, atol=2e-6), (finals[0] - finals[1]).abs().max().item()
