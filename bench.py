@@ -403,7 +403,13 @@ def run_ours(a):
     if rank == 0:
         print(json.dumps(out))
     if world > 1:
-        dist.destroy_process_group()
+        # every rank is past its last collective (bench_env all-reduces): leave without tearing the communicator down --
+        # ncclCommDestroy has been seen to block for minutes behind captured graphs / side streams on this stack
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def learner_bytes(learner, mac):

@@ -140,8 +140,9 @@ class QLearner:
 
     def _graph_step(self, batch):
         """First call for a (B, T) shape runs eagerly (sizes every workspace), the second captures the whole step -- all
-        three streams, ~200 kernel launches, the gradient all-reduce -- into one CUDA graph on static input tensors, later
-        calls copy the batch into those tensors (device to device) and replay.  Host cost per step: a dozen copies + 1 launch."""
+        three streams, ~200 kernel launches -- into two CUDA graphs on static input tensors (forward + backward | normalise +
+        clip + RMSprop; the NCCL gradient all-reduce between them stays an eager call), later calls copy the batch into those
+        tensors (device to device) and replay.  Host cost per step: a dozen copies + 2 graph launches."""
         key = (batch.batch_size, batch.max_seq_length)
         ent = self._graphs.get(key)
         if ent is None:
@@ -151,17 +152,21 @@ class QLearner:
         if ent["graph"] is None:
             static = _StaticBatch(batch, self._GRAPH_KEYS)
             torch.cuda.synchronize()
-            g = torch.cuda.CUDAGraph()
+            g, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
             l0 = ops.launch_count()
-            with torch.cuda.graph(g):
-                self._device_step(static, None, False)
-            ent["static"], ent["graph"], ent["launches"] = static, g, ops.launch_count() - l0
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                self._device_step(static, None, False, reduce_and_update=False)
+            with torch.cuda.graph(g2, capture_error_mode="thread_local"):
+                self._update_step()
+            ent["static"], ent["graph"], ent["update"], ent["launches"] = static, g, g2, ops.launch_count() - l0
             ops.add_launches(-ent["launches"])                     # capturing launched nothing
         ent["static"].load(batch)
         ent["graph"].replay()
+        parallel.all_reduce_sum_(self.gradbuf)                     # eager: NCCL stays outside the captured graphs
+        ent["update"].replay()
         ops.add_launches(ent["launches"])
 
-    def _device_step(self, batch, group_bits, log_gt):
+    def _device_step(self, batch, group_bits, log_gt, reduce_and_update=True):
         args, ws = self.args, self.ws
         B, T = batch.batch_size, batch.max_seq_length
         na, A = args.n_agents, args.n_actions
@@ -250,14 +255,20 @@ class QLearner:
             main.wait_stream(side2)
         # one all-reduce of [grads | stats], then normalise + clip + RMSprop (q_learner.py:177-178)
         ops.pack_stats(self.stats64, self.gradbuf[self.n_params:], N_STATS)
+        if not reduce_and_update:
+            return ingroup, gt_ingroup
         parallel.all_reduce_sum_(self.gradbuf)
+        self._update_step()
+        return ingroup, gt_ingroup
+
+    def _update_step(self):
+        args = self.args
         self.sumsq.zero_()
         ops.grad_sumsq(self.gradbuf, self.n_params, self.sumsq)
         ops.clip_rmsprop_step(self.flat, self.gradbuf, self.square_avg, self.n_params,
                               self.gradbuf[self.n_params:self.n_params + 1], self.sumsq, self.grad_norm,
                               args.grad_norm_clip, args.lr, args.optim_alpha, args.optim_eps,
                               getattr(args, "weight_decay", 0))
-        return ingroup, gt_ingroup
 
     def _update_targets(self):
         self.target_mac.load_state(self.mac)
