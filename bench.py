@@ -369,9 +369,16 @@ def run_ours(a):
 
     roof_att = hbm_roof("masked_attn_fwd", "attn_fwd_kernel (K2 masked MHA; bytes = 4d(2ne+2na)+na*ne per (b,t,copy))")
     # dominant kernel of the step: the 3xTF32 tcgen05 GEMM behind every dense layer (forward + backward-data)
-    roofline = hbm_roof("tc_gemm_tn", "tc_gemm_tn_kernel (K1 dense layers, tcgen05 kind::tf32 x3, fp32 accumulate in TMEM; "
+    roofline = hbm_roof("tc_gemm_tn", "tc_gemm_ts_kernel (K1 dense layers, tcgen05 kind::tf32 x3 with the A operand in tensor memory, fp32 accumulate in TMEM; "
                         "bytes = 4(M*K + M*N + N*K) per launch)")
     if roofline is not None:
+        # DRAM traffic per launch of the same kernel from the committed ncu capture (never measured under this run)
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            roofline["traffic"] = tj["traffic_bytes_per_launch"]
+            roofline["traffic_source"] = tj["source"]
+            roofline["algorithmic_bytes_per_launch"] = roofline["algorithmic_bytes_per_step"] / max(roofline["launches_per_step"], 1)
         roofline["tensor_frac_of_bf16_peak"] = 3.0 * roofline["algorithmic_tflops"] / tf_sus   # 3 MMAs per product
         roofline["note"] = ("memory-bound by construction (48 flop/B at N=384,K=128); tensor-side: 3 tf32 MMAs per "
                             "product, quoted against the measured bf16 sustained peak for context")
@@ -388,7 +395,7 @@ def run_ours(a):
         "e2e": {"value": e2e, "unit": "transitions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 32,
                 "ms_per_step": ms_e2e / a.steps},
         "gpu_launches": launches, "host_enqueue_ms_per_step": round(host_enqueue_ms, 3), "clocks": clk, "roofline": roofline, "roofline_attention": roof_att,
-        "roofline_wgrad": hbm_roof("tc_gemm_wgrad", "tc_gemm_wgrad_kernel (weight gradients, MN-major tcgen05)"),
+        "roofline_wgrad": hbm_roof("tc_gemm_wgrad", "tc_wgrad_ts_kernel (weight gradients: X^T in tensor memory, MN-major Y tiles)"),
         "roofline_attention_bwd": hbm_roof("masked_attn_bwd", "attn_bwd_kernel"), "dominant_kernel": dom[0],
         "kernels_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in sorted(kern.items(), key=lambda kv: -kv[1]["ms_per_step"])},
         # dense-layer kernels by shape [M x N x K]: (launches per step, us per launch)
