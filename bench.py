@@ -404,6 +404,11 @@ def run_ours(a):
     # ---- env kernel in the same run ---------------------------------------------------------------------------
     if rank == 0 or world > 1:
         out["env"] = bench_env(dev, world, rank, a, hbm, src)
+    if rank == 0 and world == 1:
+        try:
+            out["env"]["rollout"] = bench_rollout(dev, rank)
+        except Exception as e:                    # the rollout leg is informational: never lose the bench line over it
+            out["env"]["rollout"] = {"error": "%s: %s" % (type(e).__name__, e)}
     if rank == 0 and world == 1 and not a.no_cpu:
         out["cpu_baseline"] = cpu_reference_rate(alg, T, na, ne, ed, A, sample_B=4 if a.workload != "gm" else 64)
         out["env"]["cpu_baseline"] = cpu_env_rate(8)
@@ -502,6 +507,60 @@ def bench_env(dev, world, rank, a, hbm, src):
                       "reset + 50 step launches per rollout, rollout tensors written in place",
             "roofline": {"kernel": "gm_step_kernel (K0)", "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s",
                          "frac": ach / hbm, "traffic": None, "bytes_per_env_step": bytes_per_step, "peak_source": src}}
+
+
+def bench_rollout(dev, rank, n_envs=4096, n_agents=4):
+    """Full on-device rollouts through the reference runner interface (ParallelRunner.run: agent forward + epsilon-greedy
+    selection + env kernel + EpisodeBatch writes per timestep): BASELINE.json config 2 -- group_matching, 4 agents,
+    refil_group_matching (FF imagine agent, d=64), 4096 parallel envs on one GPU."""
+    import torch
+    from types import SimpleNamespace
+    from refil_b200.components.episode_buffer import EpisodeBatch
+    from refil_b200.config import build_config
+    from refil_b200.controllers import REGISTRY as mac_REGISTRY
+    from refil_b200.runners import REGISTRY as r_REGISTRY
+    from refil_b200.utils.synthetic import entity_scheme
+
+    class Log:
+        class console_logger:
+            @staticmethod
+            def info(*x, **k):
+                pass
+
+        def log_stat(self, *x, **k):
+            pass
+
+    cfg = build_config("group_matching", "refil_group_matching", ["batch_size_run=%d" % n_envs, "env_args.n_agents=%d" % n_agents])
+    cfg["env_args"]["seed"] = 0
+    args = SimpleNamespace(**cfg)
+    args.device, args.rank = dev, rank
+    runner = r_REGISTRY[args.runner](args=args, logger=Log())
+    info = runner.get_env_info()
+    args.n_agents, args.n_actions, args.entity_shape, args.n_entities = (info["n_agents"], info["n_actions"],
+                                                                         info["entity_shape"], info["n_entities"])
+    args.gt_mask_avail, args.entity_scheme = True, True
+    scheme, groups, preprocess = entity_scheme(args.n_agents, args.n_entities, args.entity_shape, args.n_actions, gt_mask=True)
+    proto = EpisodeBatch(scheme, groups, 1, 2, preprocess=preprocess, device=dev)
+    torch.manual_seed(0)
+    mac = mac_REGISTRY[args.mac](proto.scheme, groups, args)
+    runner.setup(scheme=scheme, groups=groups, preprocess=preprocess, mac=mac)
+    for _ in range(2):
+        runner.run(test_mode=False)
+    torch.cuda.synchronize()
+    t0_env = runner.t_env
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 3
+    e0.record()
+    for _ in range(reps):
+        runner.run(test_mode=False)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    steps = runner.t_env - t0_env
+    return {"metric": "GroupMatching env-steps/sec through ParallelRunner.run (agent forward + epsilon-greedy + env kernel)",
+            "value": steps / (ms * 1e-3), "unit": "env-steps/s", "n_envs": n_envs, "n_agents": n_agents,
+            "ms_per_rollout": ms / reps, "env_steps_per_rollout": steps / reps,
+            "config": "group_matching %d agents, refil_group_matching, %d parallel envs, epsilon-greedy training rollouts" % (n_agents, n_envs)}
 
 
 if __name__ == "__main__":

@@ -103,16 +103,16 @@ __device__ __forceinline__ void att_tma_load_rows(float* tile, const float* src,
 }
 
 // one TMA tensor copy of the whole K|V tile of unit n: box (2d, ne, 1) of the [N][ne][3d] tensor at column d
-__device__ __forceinline__ void att_tma_load_tile(float* tile, const CUtensorMap* tmap, int d, int ne, long long n,
-                                                  uint64_t* bar, int lane) {
+__device__ __forceinline__ void att_tma_load_tile(float* tile, const CUtensorMap* tmap, int col, int ne, long long n,
+                                                  uint64_t* bar, int lane, int box_cols) {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
     if (lane == 0) {
-        const uint32_t bytes = (uint32_t)(ne * 2 * d) * 4u;
+        const uint32_t bytes = (uint32_t)(ne * box_cols) * 4u;
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(att_smem_u32(bar)), "r"(bytes) : "memory");
         asm volatile(
             "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-            ::"r"(att_smem_u32(tile)), "l"(tmap), "r"(d), "r"(0), "r"((int)n), "r"(att_smem_u32(bar))
+            ::"r"(att_smem_u32(tile)), "l"(tmap), "r"(col), "r"(0), "r"((int)n), "r"(att_smem_u32(bar))
             : "memory");
     }
 }
@@ -212,18 +212,32 @@ __global__ void __launch_bounds__(32 * ATT_MAX_WARPS) attn_fwd_kernel(AttnArgs a
     // 128-byte aligned base, derived by pointer arithmetic on the __shared__ symbol so that every access below is
     // provably shared memory (LDS / STS, not generic LD / ST)
     float* smem = smem_raw_ + (((128u - (att_smem_u32(smem_raw_) & 127u)) & 127u) >> 2);
-    constexpr int NCH = HD / 4, d = HD * H, ldk = 2 * d;   // compile-time row strides: tile offsets become immediates
+    constexpr int NCH = HD / 4, d = HD * H;               // compile-time row stride: tile offsets become immediates
     const int ne = a.ne, nq = a.nq;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
-    float* kv = smem + (size_t)warp * warp_floats;                       // [NEB][ldk]: K | V rows of the current unit
-    float* lgs = kv + tile_floats + lane;                                // [NEB][32]: my row of logits, lgs[j * 32]
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + (size_t)wpc * warp_floats) + warp;
+    // The K tile and the V tile of a unit are separate TMA transactions with separate barriers: K of the NEXT unit is
+    // requested as soon as the logits of this unit are done (it lands during the softmax / PV phase), V of the next unit at
+    // the end (it lands during the next unit's logits) -- the tile latency is hidden without a second tile buffer.
+    float* kt = smem + (size_t)warp * warp_floats;                       // [NEB][d]: K rows of the current unit
+    float* vt = kt + NEB * d;                                            // [NEB][d]: V rows
+    float* lgs = kt + tile_floats + lane;                                // [NEB][32]: my row of logits, lgs[j * 32]
+    uint64_t* bark = reinterpret_cast<uint64_t*>(smem + (size_t)wpc * warp_floats) + 2 * warp;
+    uint64_t* barv = bark + 1;
     if (lane == 0) {
-        att_mbar_init(bar, 1);
+        att_mbar_init(bark, 1);
+        att_mbar_init(barv, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int f = ne * ldk + lane; f < NEB * ldk; f += 32) kv[f] = 0.f;   // padding rows stay zero
+    for (int f = ne * d + lane; f < NEB * d; f += 32) { kt[f] = 0.f; vt[f] = 0.f; }   // padding rows stay zero
     __syncwarp();
+    auto load_k = [&](long long n) {
+        if (use_tmap) att_tma_load_tile(kt, &tmap, d, ne, n, bark, lane, d);
+        else att_tma_load_rows(kt, a.qkv + ((size_t)n * ne) * 3 * d + d, 3 * d, ne, d, d, bark, lane);
+    };
+    auto load_v = [&](long long n) {
+        if (use_tmap) att_tma_load_tile(vt, &tmap, 2 * d, ne, n, barv, lane, d);
+        else att_tma_load_rows(vt, a.qkv + ((size_t)n * ne) * 3 * d + 2 * d, 3 * d, ne, d, d, barv, lane);
+    };
     constexpr int ipp = 32 / H;
     const int h = lane % H, il = lane / H;
     int rot[NCH];                                        // float offset of my kc-th chunk inside a row (head-rotated)
@@ -241,12 +255,12 @@ __global__ void __launch_bounds__(32 * ATT_MAX_WARPS) attn_fwd_kernel(AttnArgs a
     AttMeta mn;
     float4 qn[NCH];
     if (gw < a.N) {
+        load_k(gw);
+        load_v(gw);
         att_meta_load(a, gw, lane, 0, mn);
         load_q(gw, il < nq ? il : 0, qn);
     }
     for (long long n = gw; n < a.N; n += GW) {
-        if (use_tmap) att_tma_load_tile(kv, &tmap, d, ne, n, bar, lane);
-        else att_tma_load_rows(kv, a.qkv + ((size_t)n * ne) * 3 * d + d, 3 * d, ne, 2 * d, ldk, bar, lane);
         const AttMeta mc = mn;
         float4 qc[NCH];
 #pragma unroll
@@ -278,15 +292,17 @@ __global__ void __launch_bounds__(32 * ATT_MAX_WARPS) attn_fwd_kernel(AttnArgs a
                     q[4 * kc] = qt[kc].x; q[4 * kc + 1] = qt[kc].y; q[4 * kc + 2] = qt[kc].z; q[4 * kc + 3] = qt[kc].w;
                 }
             }
-            if (!waited) { att_mbar_wait(bar, parity); parity ^= 1; waited = true; }
-            const float* kbase = kv;
+            const bool last_pass = ib + ipp >= nq;
+            if (!waited) att_mbar_wait(bark, parity);
+            const float* kbase = kt;
+            const float* vbase = vt;
             float mx[ATT_MAX_COPIES] = {-INFINITY, -INFINITY, -INFINITY};
 #pragma unroll 4
             for (int j = 0; j < NEB; j++) {
                 float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
                 for (int kc = 0; kc < NCH; kc++) {
-                    const float4 k4 = *reinterpret_cast<const float4*>(kbase + j * ldk + rot[kc]);
+                    const float4 k4 = *reinterpret_cast<const float4*>(kbase + j * d + rot[kc]);
                     s0 = fmaf(q[4 * kc], k4.x, s0);
                     s1 = fmaf(q[4 * kc + 1], k4.y, s1);
                     s2 = fmaf(q[4 * kc + 2], k4.z, s2);
@@ -298,6 +314,11 @@ __global__ void __launch_bounds__(32 * ATT_MAX_WARPS) attn_fwd_kernel(AttnArgs a
                 for (int c = 0; c < ATT_MAX_COPIES; c++)
                     if (!((mb[c] >> j) & 1u)) mx[c] = fmaxf(mx[c], lg);
             }
+            if (last_pass) {                      // every lane is done with K: the next unit's K tile may land
+                __syncwarp();
+                if (n + GW < a.N) load_k(n + GW);
+            }
+            if (!waited) { att_mbar_wait(barv, parity); parity ^= 1; waited = true; }
 #pragma unroll
             for (int c = 0; c < ATT_MAX_COPIES; c++) {
                 if (c < a.C) {
@@ -313,7 +334,7 @@ __global__ void __launch_bounds__(32 * ATT_MAX_WARPS) attn_fwd_kernel(AttnArgs a
                         ssum += e;
 #pragma unroll
                         for (int kc = 0; kc < NCH; kc++) {
-                            const float4 v4 = *reinterpret_cast<const float4*>(kbase + j * ldk + d + rot[kc]);
+                            const float4 v4 = *reinterpret_cast<const float4*>(vbase + j * d + rot[kc]);
                             acc[4 * kc] = fmaf(e, v4.x, acc[4 * kc]);
                             acc[4 * kc + 1] = fmaf(e, v4.y, acc[4 * kc + 1]);
                             acc[4 * kc + 2] = fmaf(e, v4.z, acc[4 * kc + 2]);
@@ -331,7 +352,8 @@ __global__ void __launch_bounds__(32 * ATT_MAX_WARPS) attn_fwd_kernel(AttnArgs a
                 }
             }
         }
-        __syncwarp();          // every lane is done with the tile before the next unit's copies land in it
+        __syncwarp();          // every lane is done with V before the next unit's copy lands in it
+        if (n + GW < a.N) load_v(n + GW);
     }
 }
 
@@ -383,7 +405,7 @@ __global__ void __launch_bounds__(32 * ATT_MAX_WARPS) attn_bwd_kernel(AttnArgs a
     }
     for (long long n = gw; n < a.N; n += GW) {
         for (int f = ne * ldk + lane; f < NEB * ldk; f += 32) kv[f] = 0.f;   // padding rows (the tile is reused for dK|dV)
-        if (use_tmap) att_tma_load_tile(kv, &tmap, d, ne, n, bar, lane);
+        if (use_tmap) att_tma_load_tile(kv, &tmap, d, ne, n, bar, lane, 2 * d);
         else att_tma_load_rows(kv, a.qkv + ((size_t)n * ne) * 3 * d + d, 3 * d, ne, 2 * d, ldk, bar, lane);
         const AttMeta mc = mn;
         float4 qc[NCH];
@@ -712,14 +734,15 @@ extern "C" int refil_masked_attn_fwd(const float* qkv, float* out, const uint8_t
     REFIL_CHECK_ARG(out != nullptr, "masked_attn_fwd: out is null");
     a.out = out;
     const int hd = embed_dim / n_heads, neb = (n_entities + 7) / 8 * 8;
-    const int tile_floats = neb * 2 * embed_dim;
+    const int tile_floats = neb * 2 * embed_dim;              // K tile | V tile, [neb][d] each
     const int warp_floats = tile_floats + neb * 32;           // multiples of 32 floats: every warp tile is 128-byte aligned
     CUtensorMap tmap;
-    const int use_tmap = attn_make_tmap(&tmap, qkv, N, n_entities, embed_dim);
+    const int use_tmap = attn_make_tmap_box(&tmap, qkv, N, n_entities, embed_dim, embed_dim, n_entities);
     int warps, grid;
     size_t smem;
     rc = attn_geometry("masked_attn_fwd", N, warp_floats, &warps, &grid, &smem);
     if (rc) return rc;
+    smem += (size_t)warps * 8;                                // two mbarriers per warp (K tile, V tile)
     ATT_DISPATCH(attn_fwd_kernel, "masked_attn_fwd", hd, n_heads, a, smem, grid, warps, stream, "masked_attn_fwd", neb, tile_floats, warp_floats, tmap, use_tmap)
 }
 
