@@ -20,12 +20,16 @@
 //   part I (mode&3 == 2): masked iff    i, j are in the same random group and both present at t = 0
 // A row whose entities are all masked yields zeros (attention.py:58-60).
 //
-// Work decomposition: every WARP is an independent persistent worker that walks (b, t) units.  The K|V rows of a unit
-// (ne x 2d floats) are staged in the warp's shared-memory tile by TMA bulk copies (cp.async.bulk + mbarrier); Q rows are
-// read straight from global into registers.  Lane = (agent i, head h): each thread owns one attention row, so logits,
-// the masked softmax and the weighted sum over V never leave its registers (no shuffles, no shared-memory round trips);
-// the masks are resolved once per row with warp ballots (lane = entity j).  Threads of different heads read K/V chunks
-// in a head-rotated order so that the four distinct broadcast addresses of a warp load hit different banks.
+// Work decomposition: every WARP is an independent persistent worker that walks (b, t) units.  The K and V rows of a unit
+// (ne x d floats each) are staged in the warp's shared-memory tile by TMA tensor copies (cp.async.bulk.tensor + mbarrier);
+// in the forward kernel K and V are separate transactions so that the next unit's K lands while this unit's softmax / PV
+// phase runs and its V while the next logits run.  The Q row and the mask bytes of the next unit are requested one unit
+// ahead into registers.  Lane = (agent i, head h): each thread owns one attention row, so logits, the masked softmax and
+// the weighted sum over V never leave its registers (no shuffles, no shared-memory round trips); the masks are resolved
+// once per unit as entity sets with warp ballots (lane = entity j).  Threads of different heads read K/V chunks in a
+// head-rotated order so that the four distinct broadcast addresses of a warp load hit different banks.  The tile pointer
+// is derived by pointer arithmetic on the __shared__ symbol and the head count is a template parameter, so every tile
+// access is an LDS.128 with an immediate offset.
 #include <cuda.h>   // CUtensorMap (the encode function is fetched through cudaGetDriverEntryPoint, libcuda is not linked)
 
 #include <string.h>
@@ -48,21 +52,6 @@ struct AttnArgs {
     const uint8_t* entity_mask;  // [N, ne] (N = B*T) or null
     int N, T, ne, nq, d, H, C;
 };
-
-__device__ __forceinline__ bool att_masked(const AttnArgs& a, int c, int n, int i, int j, int gi, int gj, int ina_i,
-                                           int ina_j, int em_i, int em_j) {
-    bool m = false;
-    if (a.mask[c]) m = a.mask[c][(size_t)n * a.mask_stride_n[c] + (size_t)i * a.ne + j] != 0;
-    const int mode = a.mode[c];
-    const int part = mode & 3;
-    if (part) {
-        bool same = (gi == gj) && !ina_i && !ina_j;
-        m = m || (part == 1 ? !same : same);
-    }
-    if (mode & 4) m = m || ina_i || ina_j;
-    if (mode & 8) m = m || em_i || em_j;
-    return m;
-}
 
 
 #define ATT_MAX_WARPS 8

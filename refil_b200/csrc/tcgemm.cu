@@ -13,8 +13,13 @@
 //   A*B ~= A_lo*B_hi + A_hi*B_lo + A_hi*B_hi   accumulated in fp32 in tensor memory,
 // which leaves ~2^-21 relative error per product -- fp32 grade.
 //
-// Structure (one persistent CTA per SM, 17 warps, warp-specialised; the role index is made warp-uniform with a shuffle
-// so that the MMA warp's descriptors live in uniform registers -- no per-instruction R2UR waterfall):
+// Two operand paths share the epilogue, the resident weight tile and the host entry point (REFIL_TC_MODE=ss|ts, default ts):
+//   TS  tc_gemm_ts_kernel / tc_wgrad_ts_kernel (further down): the A operand lives in TENSOR MEMORY -- raw fp32 chunks arrive by
+//       TMA, converter warps split them into TMEM columns, the MMA reads only the resident weight tile from shared memory.
+//   SS  tc_gemm_tn_kernel / tc_gemm_wgrad_kernel: both operands in shared memory (the predecessor, kept for A/B runs).
+//
+// Structure of the SS kernel (one persistent CTA per SM, 17 warps, warp-specialised; the role index is made warp-uniform with
+// a shuffle so that the MMA warp's descriptors live in uniform registers -- no per-instruction R2UR waterfall):
 //   warps 0-7   epilogue: warp w owns TMEM lane quadrant w & 3 (rows) and every other 32-column slab (w >> 2):
 //               tcgen05.ld 32 x 32 fp32 (lane = row) -> bias / relu / row mask -> 128B-swizzled 4 KB staging tile ->
 //               ONE TMA tensor store (cp.async.bulk.tensor, or cp.reduce...add for split-K partials) per slab
@@ -463,17 +468,6 @@ __device__ __forceinline__ void tc_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
         ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc)
-        : "memory");
-}
-
-__device__ __forceinline__ void tc_tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
-        "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
-        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
-          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
-          "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
-          "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
         : "memory");
 }
 
