@@ -502,11 +502,28 @@ __global__ void __launch_bounds__(TS_THREADS, 1) tc_gemm_ts_kernel(TcArgs a, con
     const int mt0 = blockIdx.x / groups, mt_step = gridDim.x / groups;
     const int my_tiles = mt0 < a.m_tiles ? (a.m_tiles - mt0 + mt_step - 1) / mt_step : 0;
     const int total = my_tiles * KC;
-    if (threadIdx.x == 0) {
+    // The TMA lane initialises the barriers and puts the first raw A chunks in flight at once: they do not depend on the weight
+    // tile, so their latency overlaps the prologue below instead of following it
+    auto tma_chunk = [&](int st, int mt, int kc) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&raw_full[st])), "r"(raw_bytes)
+                     : "memory");
+        asm volatile(
+            "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+            ::"r"(smem_u32(smem_r + (size_t)st * raw_bytes)), "l"(&tmap_a), "r"(k_off + kc * TC_BK), "r"(mt * TC_BM),
+              "r"(smem_u32(&raw_full[st]))
+            : "memory");
+    };
+    const int pre = min(total, TS_RAW_STAGES);                 // chunks requested before the prologue
+    if (threadIdx.x == TS_TMA_WARP * 32) {
         for (int s = 0; s < TS_RAW_STAGES; s++) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], 32 * TS_CONV_WARPS); }
         for (int s = 0; s < TS_A_STAGES; s++) { mbar_init(&a_full[s], 32 * TS_CONV_WARPS); mbar_init(&a_empty[s], 1); }
         for (int b = 0; b < 2; b++) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 32 * TC_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        int kc = 0, mt = mt0;
+        for (int cc = 0; cc < pre; cc++) {
+            tma_chunk(cc, mt, kc);
+            if (++kc == KC) { kc = 0; mt += mt_step; }
+        }
     }
     if (warp == TS_MMA_WARP) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512u));
@@ -562,18 +579,11 @@ __global__ void __launch_bounds__(TS_THREADS, 1) tc_gemm_ts_kernel(TcArgs a, con
     } else if (warp == TS_TMA_WARP) {
         // ===================== TMA producer: raw fp32 chunks, 4 in flight =====================
         if (lane == 0) {
-            int st = 0, kc = 0, mt = mt0;
-            uint32_t ph = 0;
-            for (int cc = 0; cc < total; cc++) {
-                const int row0 = mt * TC_BM, kcol = k_off + kc * TC_BK;
+            int st = pre % TS_RAW_STAGES, kc = pre % KC, mt = mt0 + (pre / KC) * mt_step;
+            uint32_t ph = (uint32_t)(pre / TS_RAW_STAGES) & 1u;
+            for (int cc = pre; cc < total; cc++) {
                 mbar_wait(&raw_empty[st], ph ^ 1);
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&raw_full[st])),
-                             "r"(raw_bytes) : "memory");
-                asm volatile(
-                    "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                    ::"r"(smem_u32(smem_r + (size_t)st * raw_bytes)), "l"(&tmap_a), "r"(kcol), "r"(row0),
-                      "r"(smem_u32(&raw_full[st]))
-                    : "memory");
+                tma_chunk(st, mt, kc);
                 if (++kc == KC) { kc = 0; mt += mt_step; }
                 if (++st == TS_RAW_STAGES) { st = 0; ph ^= 1; }
             }
@@ -1116,7 +1126,24 @@ __global__ void __launch_bounds__(TW_THREADS, 1) tc_wgrad_ts_kernel(TcWArgs a, T
     const int c_begin = split * a.chunks_per_split, c_end = min(chunks_total, c_begin + a.chunks_per_split);
     const int n_chunks = max(0, c_end - c_begin);
 
-    if (threadIdx.x == 0) {
+    // the TMA lane initialises the barriers and requests the first raw chunks before the rest of the prologue
+    auto tma_chunk = [&](int st, int ch) {
+        const int m0 = (c_begin + ch) * 32;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&xr_full[st])),
+                     "r"(raw_bytes * (has_r ? 2u : 1u)) : "memory");
+        asm volatile(
+            "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+            ::"r"(smem_u32(smem_x + (size_t)st * raw_bytes)), "l"(&tmap_x), "r"(ptile * 128), "r"(m0), "r"(smem_u32(&xr_full[st]))
+            : "memory");
+        if (has_r)
+            asm volatile(
+                "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                ::"r"(smem_u32(smem_rl + (size_t)st * raw_bytes)), "l"(&tmap_r), "r"(ptile * 128), "r"(m0),
+                  "r"(smem_u32(&xr_full[st]))
+                : "memory");
+    };
+    const int pre = min(n_chunks, RS);
+    if (threadIdx.x == TW_TMA_WARP * 32) {
         for (int s = 0; s < TW_X_STAGES; s++) {
             mbar_init(&xr_full[s], 1); mbar_init(&xr_empty[s], 128);
             mbar_init(&xa_full[s], 128); mbar_init(&xa_empty[s], 1);
@@ -1124,6 +1151,7 @@ __global__ void __launch_bounds__(TW_THREADS, 1) tc_wgrad_ts_kernel(TcWArgs a, T
         for (int s = 0; s < TC_MAX_STAGES; s++) { mbar_init(&y_full[s], 128); mbar_init(&y_empty[s], 1); }
         mbar_init(&acc_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int ch = 0; ch < pre; ch++) tma_chunk(ch, ch);
     }
     if (warp == TW_MMA_WARP) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512u));
@@ -1254,25 +1282,11 @@ __global__ void __launch_bounds__(TW_THREADS, 1) tc_wgrad_ts_kernel(TcWArgs a, T
     } else if (warp == TW_TMA_WARP) {
         // ===================== TMA producer: raw X (and relu_y) chunks =====================
         if (lane == 0) {
-            int st = 0;
-            uint32_t ph = 0;
-            const uint32_t tx = raw_bytes * (has_r ? 2u : 1u);
-            for (int ch = 0; ch < n_chunks; ch++) {
-                const int m0 = (c_begin + ch) * 32;
+            int st = pre % RS;
+            uint32_t ph = (uint32_t)(pre / RS) & 1u;
+            for (int ch = pre; ch < n_chunks; ch++) {
                 mbar_wait(&xr_empty[st], ph ^ 1);
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&xr_full[st])), "r"(tx)
-                             : "memory");
-                asm volatile(
-                    "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                    ::"r"(smem_u32(smem_x + (size_t)st * raw_bytes)), "l"(&tmap_x), "r"(ptile * 128), "r"(m0),
-                      "r"(smem_u32(&xr_full[st]))
-                    : "memory");
-                if (has_r)
-                    asm volatile(
-                        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                        ::"r"(smem_u32(smem_rl + (size_t)st * raw_bytes)), "l"(&tmap_r), "r"(ptile * 128), "r"(m0),
-                          "r"(smem_u32(&xr_full[st]))
-                        : "memory");
+                tma_chunk(st, ch);
                 if (++st == RS) { st = 0; ph ^= 1; }
             }
         }

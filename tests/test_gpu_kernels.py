@@ -76,7 +76,8 @@ def test_linear_row_mask_and_embed():
     _close(db, b1r.grad, rtol=2e-4, atol=2e-4, what="embed db")
 
 
-@pytest.mark.parametrize("ne,na,d,H", [(5, 3, 32, 2), (4, 4, 32, 4), (24, 8, 128, 4), (32, 32, 64, 4), (1, 1, 32, 2)])
+@pytest.mark.parametrize("ne,na,d,H", [(5, 3, 32, 2), (4, 4, 32, 4), (24, 8, 128, 4), (32, 32, 64, 4), (1, 1, 32, 2),
+                                      (12, 12, 32, 2), (6, 4, 64, 8), (4, 2, 32, 1), (17, 9, 64, 4)])
 def test_masked_attention_fwd_bwd(ne, na, d, H):
     from oracle import learner_oracle as lo
     from refil_b200 import ops
