@@ -404,11 +404,25 @@ def run_ours(a):
     # ---- env kernel in the same run ---------------------------------------------------------------------------
     if rank == 0 or world > 1:
         out["env"] = bench_env(dev, world, rank, a, hbm, src)
-    if rank == 0 and world == 1:
+    if rank == 0 and world == 1 and not a.no_extra:
         try:
             out["env"]["rollout"] = bench_rollout(dev, rank)
         except Exception as e:                    # the rollout leg is informational: never lose the bench line over it
             out["env"]["rollout"] = {"error": "%s: %s" % (type(e).__name__, e)}
+    if rank == 0 and world == 1 and a.workload == "ns" and not a.no_extra:
+        # the other BASELINE.json learner configs, each in its own process (own workspaces): configs[1]'s learner side
+        # (group_matching 4 agents, refil_group_matching, 4096 episodes of 4096 parallel envs) and configs[2] (qmix_atten)
+        out["other_workloads"] = {}
+        for w in ("gm", "cfg3"):
+            try:
+                r = subprocess.run([sys.executable, os.path.abspath(__file__), "--workload", w, "--steps", "5", "--warmup", "3",
+                                    "--no-cpu", "--no-extra"], capture_output=True, text=True, timeout=240)
+                line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1]
+                d = json.loads(line)
+                out["other_workloads"][w] = {"workload": d["config"]["workload"], "value": d["value"], "unit": d["unit"],
+                                             "ms_per_step": d["ms_per_step"], "e2e": d["e2e"]["value"]}
+            except Exception as e:
+                out["other_workloads"][w] = {"error": "%s: %s" % (type(e).__name__, e)}
     if rank == 0 and world == 1 and not a.no_cpu:
         out["cpu_baseline"] = cpu_reference_rate(alg, T, na, ne, ed, A, sample_B=4 if a.workload != "gm" else 64)
         out["env"]["cpu_baseline"] = cpu_env_rate(8)
@@ -572,6 +586,7 @@ if __name__ == "__main__":
     ap.add_argument("--workload", default="ns", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="episodes per GPU (default: the workload's)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extra", action="store_true", help="skip the other-workload and rollout legs")
     ap.add_argument("--no-graph", action="store_true", help="enqueue every kernel from Python instead of replaying the "
                     "captured CUDA graph of the step (QLearner args.cuda_graph)")
     a = ap.parse_args()

@@ -26,10 +26,10 @@ EOF
 kill $SMI 2>/dev/null
 # launch list of one short run (cold-cache, serialised: shares only)
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${TAG}_ncu_launches.csv \
-  python bench.py --steps 1 --warmup 1 --no-cpu --no-graph > gpurun_out/${TAG}_ncu_launches.log 2>&1
+  python bench.py --steps 1 --warmup 1 --no-cpu --no-graph --no-extra > gpurun_out/${TAG}_ncu_launches.log 2>&1
 if [ "$FULL" = "full" ]; then
   timeout 900 ncu --set full --clock-control none --import-source on \
     -k regex:'tc_gemm_t._kernel|tc_wgrad_ts_kernel|tc_gemm_wgrad_kernel|attn_fwd_kernel|attn_bwd_kernel|gru_scan' -s 60 -c 16 \
-    -o gpurun_out/${TAG}_prof -f python bench.py --steps 1 --warmup 1 --no-cpu --no-graph > gpurun_out/${TAG}_ncu_full.log 2>&1
+    -o gpurun_out/${TAG}_prof -f python bench.py --steps 1 --warmup 1 --no-cpu --no-graph --no-extra > gpurun_out/${TAG}_ncu_full.log 2>&1
   ls -la gpurun_out/
 fi
