@@ -340,3 +340,82 @@ def test_tc_wgrad_without_bias_gradient(M, P, Q):
     scale = (dC.abs().double().t() @ A.abs().double()).max().item()
     err = (dW.cpu().double() - ref_w).abs().max().item()
     assert err <= 4e-6 * scale, (err, scale)
+
+
+# ---- full north-star sizes (B=128, T=60, ne=24, d=128): size-independent properties + float64 spot checks ------------------
+NS_ROWS = 128 * 60 * 24
+
+
+def test_full_size_dense_forward_against_float64_rows():
+    """in_trans at the benchmark size on the tensor-memory path: 4096 sampled rows against float64, and the whole output against
+    the independent fp32 FFMA kernel."""
+    from refil_b200 import ops
+    g = torch.Generator(device=DEV).manual_seed(1)
+    M, N, K = NS_ROWS, 384, 128
+    A = torch.randn(M, K, device=DEV, generator=g)
+    W = torch.randn(N, K, device=DEV, generator=g) * 0.2
+    out_tc = torch.empty(M, N, device=DEV)
+    ops.linear_fwd(A, W, None, out_tc)
+    rows = torch.randint(0, M, (4096,), device=DEV, generator=g)
+    ref = A[rows].double() @ W.double().t()
+    scale = (A[rows].abs().double() @ W.abs().double().t()).max().item()
+    assert (out_tc[rows].double() - ref).abs().max().item() <= 4e-6 * scale
+    old = ops.USE_TENSOR_CORES
+    try:
+        ops.USE_TENSOR_CORES = False
+        out_ff = torch.empty(M, N, device=DEV)
+        ops.linear_fwd(A, W, None, out_ff)
+    finally:
+        ops.USE_TENSOR_CORES = old
+    assert (out_tc - out_ff).abs().max().item() <= 1e-5 * scale
+
+
+def test_full_size_split_k_backward_and_weight_gradient():
+    """Backward-data of in_trans (K = 3d, k-sliced reduce-add) is linear in the upstream gradient, and the weight gradient at
+    full size matches float64."""
+    from refil_b200 import ops
+    g = torch.Generator(device=DEV).manual_seed(2)
+    M, N, K = NS_ROWS, 384, 128
+    W = torch.randn(N, K, device=DEV, generator=g) * 0.2
+    d1 = torch.randn(M, N, device=DEV, generator=g)
+    d2 = torch.randn(M, N, device=DEV, generator=g)
+    o1, o2, o12 = (torch.empty(M, K, device=DEV) for _ in range(3))
+    ops.linear_bwd_data(d1, W, o1)
+    ops.linear_bwd_data(d2, W, o2)
+    ops.linear_bwd_data(d1 + d2, W, o12)
+    scale = o12.abs().max().item()
+    assert (o12 - (o1 + o2)).abs().max().item() <= 2e-5 * scale
+    X = torch.randn(M, K, device=DEV, generator=g)
+    dW = torch.zeros(N, K, device=DEV)
+    ops.linear_bwd_weight(d1, X, dW, None)
+    ref = d1.double().t() @ X.double()
+    scale = (d1.abs().double().t() @ X.abs().double()).max().item()      # fp32 accumulation over 184 320 rows
+    assert (dW.double() - ref).abs().max().item() <= 4e-6 * scale
+
+
+def test_full_size_attention_copies_are_independent():
+    """One launch with three mask copies equals three single-copy launches (forward and backward), at the benchmark size."""
+    from refil_b200 import ops
+    g = torch.Generator(device=DEV).manual_seed(3)
+    B, T, ne, na, d, H = 128, 60, 24, 8, 128, 4
+    N = B * T
+    qkv = torch.randn(N * ne, 3 * d, device=DEV, generator=g)
+    obs = (torch.rand(N, ne, ne, device=DEV, generator=g) < 0.2).to(torch.uint8)
+    em = (torch.rand(B, 1, ne, device=DEV, generator=g) < 0.1).to(torch.uint8).expand(B, T, ne).contiguous().view(N, ne)
+    gb = (torch.rand(B, ne, device=DEV, generator=g) < 0.5).to(torch.uint8)
+    copies = [(obs, ne * ne, 0), (obs, ne * ne, 1), (obs, ne * ne, 2)]
+    out3 = torch.empty(3, N, na, d, device=DEV)
+    ops.masked_attn_fwd(qkv, out3, copies, gb, em, N, T, ne, na, d, H)
+    dout = torch.randn(3, N, na, d, device=DEV, generator=g)
+    dq3 = torch.empty(N * ne, 3 * d, device=DEV)
+    ops.masked_attn_bwd(qkv, dout, dq3, copies, gb, em, N, T, ne, na, d, H)
+    acc = torch.zeros_like(dq3)
+    for c in range(3):
+        o1 = torch.empty(1, N, na, d, device=DEV)
+        ops.masked_attn_fwd(qkv, o1, [copies[c]], gb, em, N, T, ne, na, d, H)
+        assert torch.equal(o1[0], out3[c])
+        dq1 = torch.empty(N * ne, 3 * d, device=DEV)
+        ops.masked_attn_bwd(qkv, dout[c:c + 1].contiguous(), dq1, [copies[c]], gb, em, N, T, ne, na, d, H)
+        acc += dq1
+    assert torch.isfinite(out3).all()
+    assert (acc - dq3).abs().max().item() <= 1e-4 * dq3.abs().max().item()
