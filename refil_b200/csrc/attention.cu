@@ -195,8 +195,9 @@ __device__ __forceinline__ void att_meta_resolve(const AttnArgs& a, long long n,
     }
 }
 
+// head dim <= 16 (d = 64 configs: small units, latency-bound): registers capped so that two CTAs share an SM
 template <int HD, int H>
-__global__ void __launch_bounds__(32 * ATT_MAX_WARPS) attn_fwd_kernel(AttnArgs a, int NEB, int tile_floats, int warp_floats, const __grid_constant__ CUtensorMap tmap, int use_tmap) {
+__global__ void __launch_bounds__(32 * ATT_MAX_WARPS, (HD <= 16) ? 2 : 1) attn_fwd_kernel(AttnArgs a, int NEB, int tile_floats, int warp_floats, const __grid_constant__ CUtensorMap tmap, int use_tmap) {
     extern __shared__ __align__(128) float smem_raw_[];
     // 128-byte aligned base, derived by pointer arithmetic on the __shared__ symbol so that every access below is
     // provably shared memory (LDS / STS, not generic LD / ST)
@@ -352,7 +353,7 @@ __global__ void __launch_bounds__(32 * ATT_MAX_WARPS) attn_fwd_kernel(AttnArgs a
 //   phase 2, lane = (entity j, head h): dK_j = sum_{c,i} dlogit_ij Q_i, dV_j = sum_{c,i} w_ij dO_i (Q / dO rows come
 //            back through L1), written over the K|V tile, which is then streamed out as the K|V columns of dQKV.
 template <int HD, int H>
-__global__ void __launch_bounds__(32 * ATT_MAX_WARPS) attn_bwd_kernel(AttnArgs a, int NEB, int tile_floats, int warp_floats, const __grid_constant__ CUtensorMap tmap, int use_tmap) {
+__global__ void __launch_bounds__(32 * ATT_MAX_WARPS, (HD <= 16) ? 2 : 1) attn_bwd_kernel(AttnArgs a, int NEB, int tile_floats, int warp_floats, const __grid_constant__ CUtensorMap tmap, int use_tmap) {
     extern __shared__ __align__(128) float smem_raw_[];
     // 128-byte aligned base, derived by pointer arithmetic on the __shared__ symbol so that every access below is
     // provably shared memory (LDS / STS, not generic LD / ST)
@@ -693,7 +694,7 @@ static int attn_make_tmap(CUtensorMap* tm, const float* qkv, int N, int ne, int 
     return attn_make_tmap_box(tm, qkv, N, ne, d, 2 * d, ne);
 }
 
-static int attn_geometry(const char* name, int N, int warp_floats, int* warps, int* grid, size_t* smem) {
+static int attn_geometry(const char* name, int N, int warp_floats, int* warps, int* grid, size_t* smem, int ctas_per_sm = 1) {
     const size_t per_warp = (size_t)warp_floats * sizeof(float);
     int w = (int)((220 * 1024) / (per_warp + 8));
     if (w > ATT_MAX_WARPS) w = ATT_MAX_WARPS;
@@ -703,7 +704,8 @@ static int attn_geometry(const char* name, int N, int warp_floats, int* warps, i
     }
     *warps = w;
     *smem = (size_t)w * per_warp + (size_t)w * 8 + 16 + 128;
-    int g = refil_num_sms();
+    if (ctas_per_sm > 1 && (*smem + 1024) * ctas_per_sm > 227 * 1024) ctas_per_sm = 1;   // the tiles of two CTAs must fit
+    int g = refil_num_sms() * ctas_per_sm;
     const int need = refil_cdiv(N, w);
     if (g > need) g = need;
     *grid = g;
@@ -729,7 +731,7 @@ extern "C" int refil_masked_attn_fwd(const float* qkv, float* out, const uint8_t
     const int use_tmap = attn_make_tmap_box(&tmap, qkv, N, n_entities, embed_dim, embed_dim, n_entities);
     int warps, grid;
     size_t smem;
-    rc = attn_geometry("masked_attn_fwd", N, warp_floats, &warps, &grid, &smem);
+    rc = attn_geometry("masked_attn_fwd", N, warp_floats, &warps, &grid, &smem, hd <= 16 ? 2 : 1);
     if (rc) return rc;
     smem += (size_t)warps * 8;                                // two mbarriers per warp (K tile, V tile)
     ATT_DISPATCH(attn_fwd_kernel, "masked_attn_fwd", hd, n_heads, a, smem, grid, warps, stream, "masked_attn_fwd", neb, tile_floats, warp_floats, tmap, use_tmap)
@@ -757,7 +759,7 @@ extern "C" int refil_masked_attn_bwd(const float* qkv, const float* dout, float*
     const int use_tmap = attn_make_tmap(&tmap, qkv, N, n_entities, embed_dim);
     int warps, grid;
     size_t smem;
-    rc = attn_geometry("masked_attn_bwd", N, warp_floats, &warps, &grid, &smem);
+    rc = attn_geometry("masked_attn_bwd", N, warp_floats, &warps, &grid, &smem, hd <= 16 ? 2 : 1);
     if (rc) return rc;
     ATT_DISPATCH(attn_bwd_kernel, "masked_attn_bwd", hd, n_heads, a, smem, grid, warps, stream, "masked_attn_bwd", neb, tile_floats, warp_floats, tmap, use_tmap)
 }
