@@ -106,6 +106,8 @@ int refil_last_action_index(const long long* actions, int32_t* la, int B, int T,
  *      C[M,N] = [rowmask_c][relu]( g(A)[M,K] B[N,K]^T + bias ),  B[j,i] = B[j*b_stride_n + i*b_stride_k],
  *      g = relu'(relu_y) and/or row mask on A (backward-data use).  refil_tc_gemm_supported() != 0 iff the shape
  *      can run here (K % 32 == 0, N % 32 == 0, ...); otherwise use refil_linear_fwd / refil_linear_bwd_data.
+ *      Operand path: the A operand of tcgen05.mma lives in tensor memory (TMA-fed, "ts"); REFIL_TC_MODE=ss in the environment
+ *      selects the all-shared-memory predecessor for A/B comparisons.
  *      refil_tc_gemm_k_slices() > 1: the reduction is too long for a resident weight tile and is cut into k-slices whose
  *      partial tiles are reduce-added into a zeroed C -- only for a linear epilogue (no bias / relu / output row mask). */
 int refil_tc_gemm_supported(int M, int N, int K);
@@ -126,7 +128,8 @@ int refil_tc_gemm_wgrad(const float* X, long long ldx, const float* relu_y, long
                         int P, int Q, cudaStream_t stream);
 
 /* ---- masked multi-head attention over entities: modules/layers/attention.py:43-64 with the mask algebra of
- *      agents/entity_rnn_agent.py:79-124 resolved on the fly.  QKV [N, ne, 3d]; OUT / dOUT [C, N, nq, d]. */
+ *      agents/entity_rnn_agent.py:79-124 resolved on the fly.  QKV [N, ne, 3d]; OUT / dOUT [C, N, nq, d].
+ *      Instantiated for head dim in {8, 16, 32} and heads in {1, 2, 4, 8}, ne <= 32; other shapes return REFIL_ERR_UNSUPPORTED. */
 int refil_masked_attn_fwd(const float* qkv, float* out, const uint8_t* mask0, const uint8_t* mask1,
                           const uint8_t* mask2, long long mask_stride0, long long mask_stride1,
                           long long mask_stride2, int mode0, int mode1, int mode2, const uint8_t* group_bits,
