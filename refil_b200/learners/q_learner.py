@@ -149,15 +149,27 @@ class QLearner:
             self._graphs[key] = {"static": None, "graph": None, "launches": 0}
             self._device_step(batch, None, False)
             return
+        if ent.get("failed"):
+            self._device_step(batch, None, False)
+            return
         if ent["graph"] is None:
             static = _StaticBatch(batch, self._GRAPH_KEYS)
             torch.cuda.synchronize()
             g, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
             l0 = ops.launch_count()
-            with torch.cuda.graph(g, capture_error_mode="thread_local"):
-                self._device_step(static, None, False, reduce_and_update=False)
-            with torch.cuda.graph(g2, capture_error_mode="thread_local"):
-                self._update_step()
+            try:
+                with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                    self._device_step(static, None, False, reduce_and_update=False)
+                with torch.cuda.graph(g2, capture_error_mode="thread_local"):
+                    self._update_step()
+            except Exception as e:           # capture is an optimisation of the submission path only: never lose the step
+                ops.add_launches(l0 - ops.launch_count())
+                ent["failed"] = True
+                torch.cuda.synchronize()
+                if self.logger is not None:
+                    self.logger.console_logger.info("CUDA graph capture failed (%s: %s); training eagerly" % (type(e).__name__, e))
+                self._device_step(batch, None, False)
+                return
             ent["static"], ent["graph"], ent["update"], ent["launches"] = static, g, g2, ops.launch_count() - l0
             ops.add_launches(-ent["launches"])                     # capturing launched nothing
         ent["static"].load(batch)
