@@ -122,3 +122,21 @@ def test_param_store_views_and_state_dict():
     assert float(flat[23:26].sum()) == 3.0
     with pytest.raises(KeyError):
         a.load_state_dict({"w": torch.ones(3, 5)})
+
+
+def test_bench_reference_arm_schema():
+    """`bench.py --impl reference` (the CPU restatement timed on the host cores) prints ONE JSON line with the contract's keys."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-500:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "transitions/s" and d["value"] > 0 and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert "B=128" in d["config"]["workload"]
