@@ -192,6 +192,10 @@ __device__ __forceinline__ void tc_mask_relu(const TcArgs& a, int mt, int kcol, 
 template <int NTHREADS>
 __device__ __forceinline__ void tc_load_resident_b(const TcArgs& a, uint8_t* smem_b, uint32_t b_bytes, int nt, int k_off) {
     const int BN = a.BN, k4 = a.KS >> 2, tot = BN * k4;
+    // element f of the tile -> (row r = output column j, 16-byte chunk kq along K).  Forward (sbi == 1, rows of W contiguous along
+    // K): kq fastest, one float4 per thread.  Backward-data (B = W^T by strides, sbj == 1: contiguous along j): r fastest, so that
+    // the four scalar loads of a warp are four coalesced 128-byte rows instead of 128 scattered sectors.
+    const bool k_contig = a.sbi == 1;
     constexpr int MAXIT = 8;
     float4 v[MAXIT];
 #pragma unroll
@@ -199,11 +203,11 @@ __device__ __forceinline__ void tc_load_resident_b(const TcArgs& a, uint8_t* sme
         const int f = (int)threadIdx.x + it * NTHREADS;
         v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (f < tot) {
-            const int r = f / k4, kq = f - r * k4;           // row of the tile, 16-byte chunk along K
+            const int r = k_contig ? f / k4 : f % BN, kq = k_contig ? f - r * k4 : f / BN;
             const long long j = (long long)nt * BN + r;
             if (j < a.N) {
                 const float* p = a.B + j * a.sbj + (long long)(k_off + kq * 4) * a.sbi;
-                if (a.sbi == 1) v[it] = __ldg(reinterpret_cast<const float4*>(p));
+                if (k_contig) v[it] = __ldg(reinterpret_cast<const float4*>(p));
                 else { v[it].x = __ldg(p); v[it].y = __ldg(p + a.sbi); v[it].z = __ldg(p + 2 * a.sbi); v[it].w = __ldg(p + 3 * a.sbi); }
             }
         }
@@ -212,7 +216,7 @@ __device__ __forceinline__ void tc_load_resident_b(const TcArgs& a, uint8_t* sme
     for (int it = 0; it < MAXIT; it++) {
         const int f = (int)threadIdx.x + it * NTHREADS;
         if (f < tot) {
-            const int r = f / k4, kq = f - r * k4;
+            const int r = k_contig ? f / k4 : f % BN, kq = k_contig ? f - r * k4 : f / BN;
             const int kc = kq >> 3, c = kq & 7;
             float* hi = reinterpret_cast<float*>(smem_b + (size_t)kc * 2 * b_bytes);
             tc_store_split(hi, hi + BN * 32, r, c, v[it]);
