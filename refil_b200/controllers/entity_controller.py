@@ -77,7 +77,9 @@ class EntityMAC(BasicMAC):
         plain = (obs, obs_stride, 0)
         if not imagine:
             return MaskSpec([plain], None, em), None, None
-        if group_bits is None and not use_gt_factors:
+        # the RNN agent ignores use_gt_factors / use_rand_gt_factors (entity_rnn_agent.py:83 takes **kwargs) and always
+        # draws a random partition; the FF agent skips the draw only for the pure ground-truth factorisation
+        if group_bits is None and (is_rnn or not use_gt_factors):
             group_bits = self.draw_groups(inp["bs"], ne, em.device)
         if is_rnn or not (use_gt_factors or use_rand_gt_factors):
             spec = MaskSpec([plain, (obs, obs_stride, ops.ATTN_PART_WITHIN), (obs, obs_stride, ops.ATTN_PART_INTERACT)],

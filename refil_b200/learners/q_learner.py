@@ -84,6 +84,14 @@ class QLearner:
         self.sumsq = torch.zeros(1, dtype=torch.float64, device=dev)
         self.grad_norm = torch.zeros(1, dtype=torch.float32, device=dev)
 
+    def sync_replicas(self, src=0):
+        """Multi-GPU: broadcast rank `src`'s parameters, optimiser state and target networks (no-op on one rank)."""
+        bufs = [self.flat, self.square_avg, self.target_mac.agent.store.flat]
+        if self.mixer is not None:
+            bufs.append(self.target_mixer.store.flat)
+        for b in bufs:
+            parallel.broadcast_(b, src=src)
+
     def _side_stream(self, i):
         if getattr(self, "_side", None) is None:
             self._side = [torch.cuda.Stream(device=self.device) for _ in range(2)]
@@ -144,10 +152,21 @@ class QLearner:
         clip + RMSprop; the NCCL gradient all-reduce between them stays an eager call), later calls copy the batch into those
         tensors (device to device) and replay.  Host cost per step: a dozen copies + 2 graph launches."""
         key = (batch.batch_size, batch.max_seq_length)
-        ent = self._graphs.get(key)
+        gen = self._ws_generation()
+        if gen != getattr(self, "_graphs_gen", gen):
+            self._graphs.clear()               # a workspace grew and moved: every captured address is stale
+        self._graphs_gen = gen
+        ent = self._graphs.pop(key, None)
+        if ent is not None:
+            self._graphs[key] = ent            # most recently used last
         if ent is None:
-            self._graphs[key] = {"static": None, "graph": None, "launches": 0}
+            while len(self._graphs) >= self.MAX_GRAPHS:      # LRU bound: each entry pins a static batch + two graphs
+                self._graphs.pop(next(iter(self._graphs)))
             self._device_step(batch, None, False)
+            if self._ws_generation() != gen:   # this shape grew a workspace: graphs of the other shapes are stale too
+                self._graphs.clear()
+                self._graphs_gen = self._ws_generation()
+            self._graphs[key] = {"static": None, "graph": None, "launches": 0}
             return
         if ent.get("failed"):
             self._device_step(batch, None, False)
@@ -177,6 +196,14 @@ class QLearner:
         parallel.all_reduce_sum_(self.gradbuf)                     # eager: NCCL stays outside the captured graphs
         ent["update"].replay()
         ops.add_launches(ent["launches"])
+
+    MAX_GRAPHS = 8
+
+    def _ws_generation(self):
+        wss = [self.ws, self.mac.agent.ws, self.target_mac.agent.ws]
+        if self.mixer is not None:
+            wss += [self.mixer.ws, self.target_mixer.ws]
+        return sum(w.generation for w in wss)
 
     def _device_step(self, batch, group_bits, log_gt, reduce_and_update=True):
         args, ws = self.args, self.ws
@@ -209,7 +236,7 @@ class QLearner:
         inp = self.mac._build_inputs(batch, slice(0, T_all))
         use_gt = getattr(args, "train_gt_factors", False)
         use_rgt = getattr(args, "train_rand_gt_factors", False)
-        if self.imagine and group_bits is None and not use_gt:         # the random partition is drawn ONCE, here
+        if self.imagine and group_bits is None and (self.mac.agent.rnn or not use_gt):   # the partition is drawn ONCE, here
             group_bits = self.mac.draw_groups(inp["bs"], inp["ne"], inp["entity_mask"].device)
         _, mix, _ = self.mac.mask_plan(inp, self.imagine, use_gt, use_rgt, group_bits)
         if two:

@@ -124,7 +124,9 @@ class EntityAttnAgent:
         self.ws = ws if ws is not None else Workspace(device)
         self.tag = tag
         self.trunk = AttnTrunk(self.store, "", self.ws, tag, self.ein, self.d, self.H, self.na, self.A)
-        gen = torch.Generator().manual_seed(int(seed) if seed is not None else torch.initial_seed() % (2 ** 31))
+        # like nn.Linear, draw from the GLOBAL torch RNG (a private generator seeded with torch.initial_seed() made the
+        # agent's and the mixer's first layers bit-identical whenever their shapes matched)
+        gen = torch.Generator().manual_seed(int(seed)) if seed is not None else None
         self.trunk.init(gen)
         p = self.store.p
         if self.rnn:
@@ -286,7 +288,7 @@ class Mixer:
         self.store = ParamStore(specs, device)
         self.nets = OrderedDict((h, AttnHyperNet(self.store, h, self.ws, tag + "." + h, args, ein))
                                 for h in self.HYPERS[args.mixer])
-        gen = torch.Generator().manual_seed(int(seed) if seed is not None else torch.initial_seed() % (2 ** 31))
+        gen = torch.Generator().manual_seed(int(seed)) if seed is not None else None      # None: the global torch RNG
         for n in self.nets.values():
             n.init(gen)
 

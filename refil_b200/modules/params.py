@@ -97,22 +97,31 @@ def init_uniform_(gen, t, bound):
 
 
 class Workspace:
-    """Shape-keyed cache of device scratch tensors: the same address is returned for the same (tag, shape) so a whole
-    training step can be captured in a CUDA graph and re-launched."""
+    """Tag-keyed cache of device scratch tensors.  A tag owns ONE allocation sized for the largest request seen so far and
+    hands out a view of its head, so (a) the same (tag, shape) always returns the same address -- a whole training step can be
+    captured in a CUDA graph and re-launched -- and (b) a run whose batches change length (run.py truncates every sample to
+    its longest filled episode) holds one activation set, not one per distinct T.  `generation` counts re-allocations: an
+    address that moved invalidates every graph captured against it (QLearner drops its graph cache when it changes).
+    Requests of different shapes under one tag alias each other: tags are only shared by uses that are ordered on one
+    stream and do not outlive the step."""
 
     def __init__(self, device):
         self.device = torch.device(device)
         self._bufs = {}
+        self.generation = 0
 
     def get(self, tag, shape, dtype=torch.float32, zero=False):
-        key = (tag, tuple(int(s) for s in shape), dtype)
-        t = self._bufs.get(key)
-        if t is None:
-            t = torch.empty(key[1], dtype=dtype, device=self.device)
-            self._bufs[key] = t
-            if zero:
-                t.zero_()
-        elif zero:
+        shape = tuple(int(s) for s in shape)
+        n = _numel(shape)
+        key = (tag, dtype)
+        buf = self._bufs.get(key)
+        if buf is None or buf.numel() < n:
+            if buf is not None:
+                self.generation += 1
+            buf = torch.empty(max(n, 1), dtype=dtype, device=self.device)
+            self._bufs[key] = buf
+        t = buf[:n].view(shape)
+        if zero:
             t.zero_()
         return t
 

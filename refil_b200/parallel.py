@@ -53,3 +53,23 @@ def broadcast_(flat, src=0):
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.broadcast(flat, src=src)
     return flat
+
+
+def all_reduce_sum_int(value, device=None):
+    """Sum of a host integer over the ranks (rollout step counts: `t_env` must be the same on every rank, or the ranks leave
+    the training loop at different iterations and dead-lock in the gradient all-reduce)."""
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+        return int(value)
+    dev = device if dist.get_backend() == "nccl" else "cpu"
+    t = torch.tensor([int(value)], dtype=torch.int64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return int(t.item())
+
+
+def all_reduce_max_int(value, device=None):
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+        return int(value)
+    dev = device if dist.get_backend() == "nccl" else "cpu"
+    t = torch.tensor([int(value)], dtype=torch.int64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return int(t.item())

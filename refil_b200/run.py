@@ -12,6 +12,7 @@ from types import SimpleNamespace
 import numpy as np
 import torch
 
+from . import parallel
 from .components.episode_buffer import ReplayBuffer
 from .components.transforms import OneHot
 from .controllers import REGISTRY as mac_REGISTRY
@@ -37,11 +38,28 @@ def run(config, console, jsonl_path=None):
     args.device = "cuda:%d" % local_rank
     args.rank = int(os.environ.get("RANK", "0"))
     torch.cuda.set_device(local_rank)
-    logger = Logger(console, jsonl_path)
+    # torchrun: one process per GPU.  Env instances and replay episodes are sharded by rank, the learner's ONE all-reduce
+    # joins the gradients (parallel.py); only rank 0 writes stats and checkpoints.  gloo is used on a CUDA-less test box.
+    args.rank, args.world_size = parallel.init_distributed(device=args.device)
+    if args.world_size > 1 and args.batch_size % args.world_size:
+        raise ValueError("batch_size=%d is not divisible by WORLD_SIZE=%d (episodes are sharded over the ranks)"
+                         % (args.batch_size, args.world_size))
+    logger = Logger(console, jsonl_path if args.rank == 0 else None)
     console.info("Experiment Parameters:\n\n" + pprint.pformat(config, indent=4, width=1) + "\n")
     args.unique_token = "{}__{}".format(getattr(args, "name", "run"), datetime.datetime.now().strftime("%Y-%m-%d_%H-%M-%S"))
     run_sequential(args, logger)
     console.info("Exiting Main")
+    if args.world_size > 1:
+        # every rank is past its last collective: leave together without tearing the communicator down (ncclCommDestroy has
+        # been seen to block behind captured graphs / side streams on this stack; the reference ends with os._exit too,
+        # src/main.py:37)
+        import sys
+        import torch.distributed as dist
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def evaluate_sequential(args, runner):
@@ -73,13 +91,16 @@ def run_sequential(args, logger):
     groups = {"agents": args.n_agents, "entities": args.n_entities}
     preprocess = {"actions": ("actions_onehot", [OneHot(out_dim=args.n_actions)])}
 
-    buffer = ReplayBuffer(scheme, groups, args.buffer_size, env_info["episode_limit"] + 1, preprocess=preprocess,
-                          device=args.device)                 # device-resident: the env kernel feeds it without a host hop
+    world = int(getattr(args, "world_size", 1))
+    local_bs = args.batch_size // world                       # replay is sharded by episode: each rank samples B / world
+    buffer = ReplayBuffer(scheme, groups, max(args.buffer_size // world, local_bs), env_info["episode_limit"] + 1,
+                          preprocess=preprocess, device=args.device)   # device-resident: fed by the env kernel, no host hop
     mac = mac_REGISTRY[args.mac](buffer.scheme, groups, args)
     runner.setup(scheme=scheme, groups=groups, preprocess=preprocess, mac=mac)
     learner = le_REGISTRY[args.learner](mac, buffer.scheme, logger, args)
     if args.use_cuda:
         learner.cuda()
+    learner.sync_replicas()                                   # every replica starts from rank 0's parameters
 
     if args.checkpoint_path != "":
         if not os.path.isdir(args.checkpoint_path):
@@ -94,6 +115,7 @@ def run_sequential(args, logger):
         model_path = os.path.join(args.checkpoint_path, str(step))
         logger.console_logger.info("Loading model from {}".format(model_path))
         learner.load_models(model_path, evaluate=args.evaluate)
+        learner.sync_replicas()
         runner.t_env = step
         if args.evaluate or args.save_replay:
             evaluate_sequential(args, runner)
@@ -105,10 +127,14 @@ def run_sequential(args, logger):
     while runner.t_env <= args.t_max:
         episode_batch = runner.run(test_mode=False)
         buffer.insert_episode_batch(episode_batch)
-        if buffer.can_sample(args.batch_size):
+        if buffer.can_sample(local_bs):                        # same insert count on every rank -> same decision
             for _ in range(args.training_iters):
-                sample = buffer.sample(args.batch_size)
-                max_ep_t = int(sample.max_t_filled())          # truncate to the longest filled episode (run.py:269-270)
+                sample = buffer.sample(local_bs)
+                # truncate to the longest filled episode (run.py:269-270) -- over ALL ranks, rounded up to a multiple of 8
+                # steps so that the learner sees a handful of shapes (workspaces, CUDA graphs); the extra steps are
+                # unfilled and carry zero loss weight
+                max_ep_t = parallel.all_reduce_max_int(int(sample.max_t_filled()), args.device)
+                max_ep_t = min((max_ep_t + 7) // 8 * 8, sample.max_seq_length)
                 sample = sample[:, :max_ep_t]
                 learner.train(sample, runner.t_env, episode)
         n_test_runs = max(1, args.test_nepisode // runner.batch_size)
@@ -121,11 +147,12 @@ def run_sequential(args, logger):
         if args.save_model and (runner.t_env - model_save_time >= args.save_model_interval or model_save_time == 0
                                 or runner.t_env > args.t_max):
             model_save_time = runner.t_env
-            save_path = os.path.join(args.local_results_path, "models", args.unique_token, str(runner.t_env))
-            os.makedirs(save_path, exist_ok=True)
-            logger.console_logger.info("Saving models to {}".format(save_path))
-            learner.save_models(save_path)
-        episode += args.batch_size_run
+            if args.rank == 0:                                  # replicas are identical: one writer
+                save_path = os.path.join(args.local_results_path, "models", args.unique_token, str(runner.t_env))
+                os.makedirs(save_path, exist_ok=True)
+                logger.console_logger.info("Saving models to {}".format(save_path))
+                learner.save_models(save_path)
+        episode += args.batch_size_run * world
         if (runner.t_env - last_log_T) >= args.log_interval:
             logger.log_stat("episode", episode, runner.t_env)
             logger.print_recent_stats()

@@ -15,6 +15,7 @@ from functools import partial
 import numpy as np
 import torch
 
+from .. import parallel
 from ..components.episode_buffer import EpisodeBatch
 from ..envs import BATCHED_REGISTRY
 from ..envs.group_matching import F_LIMIT, F_SOLVED
@@ -84,7 +85,9 @@ class ParallelRunner:
         returns = env.ep_ret.cpu().numpy()
         lengths, flags = est[3], est[2]
         if not test_mode:
-            self.env_steps_this_run = int(lengths.sum())
+            # t_env counts the env steps of ALL ranks' instances, so every rank sees the same value (loop exit, target
+            # updates, epsilon schedule and logging decisions stay in lock-step under torchrun)
+            self.env_steps_this_run = parallel.all_reduce_sum_int(int(lengths.sum()), self.args.device)
             self.t_env += self.env_steps_this_run
 
         cur_stats = self.test_stats if test_mode else self.train_stats

@@ -49,6 +49,8 @@ def _gloo_worker(rank, world, port, out):
     flat = torch.arange(4.0) + rank
     parallel.broadcast_(flat, src=0)
     assert torch.equal(flat, torch.arange(4.0))
+    # host-integer reductions the CLI loop relies on (run.py: global t_env, common truncation length)
+    assert parallel.all_reduce_sum_int(10 + rank) == 21 and parallel.all_reduce_max_int(5 * rank) == 5
     if rank == 0:
         torch.save({"grad": buf[:-8] / buf[-8], "msum": buf[-8]}, out)
     dist.destroy_process_group()
@@ -114,3 +116,24 @@ def test_two_gpu_step_equals_single_gpu_step(tmp_path):
     assert abs(got["loss"] - c.stats["loss"]) <= 1e-4 * max(1.0, abs(c.stats["loss"]))
     assert abs(got["grad_norm"] - c.stats["grad_norm"]) <= 1e-4 * max(1.0, c.stats["grad_norm"])
     assert float((got["flat"] - learner.flat.cpu()).abs().max()) <= 2e-5
+
+
+@pytest.mark.gpu
+def test_cli_under_torchrun_two_gpus(tmp_path):
+    """src/main.py under torchrun: both ranks stay in lock-step (global t_env), train ONE model (identical replicas) and only
+    rank 0 writes the checkpoint."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    import glob
+    import subprocess
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29547", os.path.join(ROOT, "src", "main.py"), "--env-config=group_matching",
+           "--config=refil_group_matching", "with", "env_args.n_agents=4", "batch_size_run=16", "batch_size=8", "t_max=3000",
+           "seed=3", "test_interval=100000", "test_nepisode=16", "save_model=True", "save_model_interval=100000",
+           "local_results_path=%s" % tmp_path, "cuda_graph=True"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    tokens = glob.glob(os.path.join(str(tmp_path), "models", "*"))
+    assert len(tokens) == 1, tokens                     # one writer, one run directory
+    steps = sorted(os.listdir(tokens[0]))
+    assert steps and all(os.path.exists(os.path.join(tokens[0], s, "agent.th")) for s in steps)
