@@ -338,6 +338,18 @@ def td_loss(agent_p, mixer_p, tgt_agent_p, tgt_mixer_p, batch, args, group_a=Non
     if imagine:
         groups = [g[:, :-1] for g in groups]
         q_tot_im = mix(mixer_p, args, caq_imagine, m_e, m_m, imagine_groups=groups)
+        if getattr(args, "test_gt_factors", False) and args.mixer == "lin_flex_qmix":
+            # logging-only pass of q_learner.py:98-105,138-147: the share of the mixing weight that stays inside each agent's
+            # own group, for the partition used in training and for the ground-truth factorisation
+            with torch.no_grad():
+                aux["ingroup_prop"] = lin_flex_mixer(mixer_p, args, caq_imagine, m_e, m_m, imagine_groups=groups,
+                                                     ret_ingroup_prop=True)[1]
+                gt_out, gt_groups = agent_forward(agent_p, args, batch, imagine=True, group_a=group_a, use_gt_factors=True)
+                gt_chosen = torch.gather(gt_out[:, :-1], 3, actions.repeat(3, 1, 1, 1)).squeeze(3)
+                _, gt_w, gt_i = gt_chosen.chunk(3, dim=0)
+                gt_groups = [g[:, :-1] for g in gt_groups]
+                aux["gt_ingroup_prop"] = lin_flex_mixer(mixer_p, args, torch.cat([gt_w, gt_i], dim=2), m_e, m_m,
+                                                        imagine_groups=gt_groups, ret_ingroup_prop=True)[1]
     with torch.no_grad():
         tgt_tot = mix(tgt_mixer_p, args, tgt_max, t_e, t_m)
     targets = rewards + args.gamma * (1 - terminated) * tgt_tot

@@ -238,6 +238,7 @@ class QLearner:
         use_rgt = getattr(args, "train_rand_gt_factors", False)
         if self.imagine and group_bits is None and (self.mac.agent.rnn or not use_gt):   # the partition is drawn ONCE, here
             group_bits = self.mac.draw_groups(inp["bs"], inp["ne"], inp["entity_mask"].device)
+        self.last_group_bits = group_bits        # under graph replay: the static tensor the captured draw writes (tests read it)
         _, mix, _ = self.mac.mask_plan(inp, self.imagine, use_gt, use_rgt, group_bits)
         if two:
             side.wait_stream(main)

@@ -111,7 +111,9 @@ def _t2n(d):
     return {k: v.detach().cpu().numpy().copy() for k, v in d.items()}
 
 
-def make_learner_case(name, alg, B, T, na, ne, ed, A, seed, gt=False, **over):
+def make_learner_case(name, alg, B, T, na, ne, ed, A, seed, gt=False, compact=False, **over):
+    """compact=True (cases at the real layer widths, ~0.4 M parameters): the perturbed target parameters and the post-step
+    parameters are not stored; golden_util.load_learner_case re-creates the target perturbation from the stored seed."""
     from components.episode_buffer import EpisodeBatch
     from components.transforms import OneHot
     from controllers import REGISTRY as mac_REGISTRY
@@ -151,7 +153,8 @@ def make_learner_case(name, alg, B, T, na, ne, ed, A, seed, gt=False, **over):
     for k, v in syn.items():
         batch.data.transition_data[k][:] = v
 
-    out = {"meta_alg": np.array(alg), "meta_dims": np.array([B, T, na, ne, ed, A], np.int64)}
+    out = {"meta_alg": np.array(alg), "meta_dims": np.array([B, T, na, ne, ed, A], np.int64),
+           "meta_seed": np.int64(seed), "meta_compact": np.int64(int(compact))}
     for k, v in vars(args).items():
         if isinstance(v, (int, float, bool, str)) or v is None:
             out["arg_" + k] = np.array("None" if v is None else v)
@@ -159,13 +162,15 @@ def make_learner_case(name, alg, B, T, na, ne, ed, A, seed, gt=False, **over):
         out["in_" + k] = v.numpy()
     for k, v in _t2n(mac.agent.state_dict()).items():
         out["agent_" + k] = v
-    for k, v in _t2n(learner.target_mac.agent.state_dict()).items():
-        out["tagent_" + k] = v
+    if not compact:
+        for k, v in _t2n(learner.target_mac.agent.state_dict()).items():
+            out["tagent_" + k] = v
     if learner.mixer is not None:
         for k, v in _t2n(learner.mixer.state_dict()).items():
             out["mixer_" + k] = v
-        for k, v in _t2n(learner.target_mixer.state_dict()).items():
-            out["tmixer_" + k] = v
+        if not compact:
+            for k, v in _t2n(learner.target_mixer.state_dict()).items():
+                out["tmixer_" + k] = v
 
     imagine = "imagine" in args.agent
     rng_seed = seed + 7
@@ -205,18 +210,34 @@ def make_learner_case(name, alg, B, T, na, ne, ed, A, seed, gt=False, **over):
         out["stat_" + k] = np.float64(v[0])
     for k, p in mac.agent.named_parameters():
         out["grad_agent_" + k] = p.grad.numpy().copy()
-        out["new_agent_" + k] = p.detach().numpy().copy()
+        if not compact:
+            out["new_agent_" + k] = p.detach().numpy().copy()
     if learner.mixer is not None:
         for k, p in learner.mixer.named_parameters():
             out["grad_mixer_" + k] = p.grad.numpy().copy()
-            out["new_mixer_" + k] = p.detach().numpy().copy()
+            if not compact:
+                out["new_mixer_" + k] = p.detach().numpy().copy()
     np.savez_compressed(os.path.join(HERE, "learner_%s.npz" % name), **out)
     print("learner_%s.npz: loss=%.6f grad_norm=%.6f" % (name, out["stat_loss"], out["stat_grad_norm"]))
 
 
 SMALL = dict(attn_embed_dim=32, attn_n_heads=2, hypernet_embed=32, mixing_embed_dim=8, rnn_hidden_dim=16)
 
+NEW_ONLY = "--new" in sys.argv          # only (re)write the cases added after round 1
+
 if __name__ == "__main__":
+    # round 2: the benchmark's layer widths (d=128, 4 heads, 8 agents, 24 entities, 53 input features, 14 actions) with
+    # B*T*na = 256 agent rows and 768 entity rows, so the tcgen05 GEMM / weight-gradient kernels and the <32,4>
+    # attention instantiation are compared with reference outputs directly
+    make_learner_case("refil_ns", "refil", B=4, T=8, na=8, ne=24, ed=39, A=14, seed=21, compact=True)
+    # ground-truth factorisation modes (entity_ff_agent.py:34-35,93-95) and an RNN agent with the flag set (ignored, :83)
+    make_learner_case("refil_gm_gt", "refil_group_matching", B=3, T=5, na=4, ne=4, ed=12, A=3, seed=19, gt=True,
+                      train_gt_factors=True, attn_embed_dim=32, attn_n_heads=4, hypernet_embed=32, mixing_embed_dim=8)
+    make_learner_case("qmix_atten_gm_gtobs", "qmix_atten_group_matching", B=3, T=5, na=4, ne=4, ed=12, A=3, seed=20, gt=True,
+                      gt_obs_mask=True, attn_embed_dim=32, attn_n_heads=4, hypernet_embed=32, mixing_embed_dim=8)
+    make_learner_case("refil_gtflag", "refil", B=2, T=4, na=3, ne=5, ed=6, A=4, seed=22, train_gt_factors=True, **SMALL)
+    if NEW_ONLY:
+        sys.exit(0)
     make_env_transcripts()
     make_learner_case("refil", "refil", B=3, T=6, na=3, ne=5, ed=6, A=4, seed=11, **SMALL)
     make_learner_case("qmix_atten", "qmix_atten", B=3, T=5, na=3, ne=5, ed=6, A=4, seed=12, **SMALL)

@@ -29,9 +29,19 @@ def load_learner_case(name):
     def grab(prefix):
         return {k[len(prefix):]: torch.from_numpy(z[k].copy()) for k in z.files if k.startswith(prefix)}
 
+    agent, mixer = grab("agent_"), grab("mixer_")
+    tagent, tmixer = grab("tagent_"), grab("tmixer_")
+    if "meta_compact" in z.files and int(z["meta_compact"]):
+        # compact fixture: the target networks are the online ones plus the generator's seeded perturbation
+        # (make_golden.py: 0.05 * randn, parameter order of target_mac then target_mixer, generator seed + 99)
+        gen = torch.Generator().manual_seed(int(z["meta_seed"]) + 99)
+        tagent, tmixer = {}, {}
+        for src, dst in ((agent, tagent), (mixer, tmixer)):
+            for k, v in src.items():
+                dst[k] = v.clone() if k.endswith("scale_factor") else v + 0.05 * torch.randn(v.shape, generator=gen)
     case = SimpleNamespace(
-        name=name, args=args, dims=(B, T, na, ne, ed, A),
-        batch=grab("in_"), agent=grab("agent_"), tagent=grab("tagent_"), mixer=grab("mixer_"), tmixer=grab("tmixer_"),
+        name=name, args=args, dims=(B, T, na, ne, ed, A), compact="meta_compact" in z.files and bool(int(z["meta_compact"])),
+        batch=grab("in_"), agent=agent, tagent=tagent, mixer=mixer, tmixer=tmixer,
         group_a=torch.from_numpy(z["group_a"].copy()),
         fwd=grab("fwd_"), greedy_actions=torch.from_numpy(z["greedy_actions"].copy()),
         greedy_q=torch.from_numpy(z["greedy_q"].copy()),

@@ -15,7 +15,9 @@ def _close(a, b, rtol=1e-5, atol=1e-6):
 
 
 def test_have_cases():
-    assert {"refil", "qmix_atten", "refil_gm", "qmix_atten_gm", "refil_vdn", "vdn_atten"} <= set(CASES)
+    assert {"refil", "qmix_atten", "refil_gm", "qmix_atten_gm", "refil_vdn", "vdn_atten", "refil_ns", "refil_gm_gt",
+            "qmix_atten_gm_gtobs", "refil_gtflag"} <= set(CASES)
+    assert "ingroup_prop" in load_learner_case("refil_gm").stats and "gt_ingroup_prop" in load_learner_case("refil_gm_gt").stats
 
 
 @pytest.mark.parametrize("name", CASES)
@@ -54,6 +56,9 @@ def test_train_step_matches_reference(name):
     assert abs(float(out["grad_norm"]) - s["grad_norm"]) <= 1e-4 * max(1.0, s["grad_norm"])
     for k in ("td_error_abs", "q_taken_mean", "target_mean"):
         assert abs(float(out["aux"][k]) - s[k]) <= 1e-5 * max(1.0, abs(s[k])), k
+    for k in ("ingroup_prop", "gt_ingroup_prop"):          # test_gt_factors logging pass (q_learner.py:98-105,138-147)
+        if k in s:
+            assert abs(float(out["aux"][k]) - s[k]) <= 1e-6, k
     for k, g in c.grad_agent.items():
         _close(out["grads_agent"][k], g, rtol=1e-4, atol=1e-6)
     for k, g in c.grad_mixer.items():
