@@ -1,15 +1,18 @@
 #!/usr/bin/env python
 """Benchmark of the REFIL hot path on B200 (contract: see the task's bench.py section).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload ns|cfg3|gm]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload ns|ns-strong|cfg5|cfg3|gm]
 
 One "step" = one QLearner.train pass (online + target forward, TD loss, hand-written backward, clip + RMSprop, and the
 gradient all-reduce when N > 1) over one synthetic replay batch.  Default workload = BASELINE.json's north-star shape
 (REFIL, B=128 episodes per GPU, T=60, 8 agents, 24 entities, d=128).  `value` = learner transitions/s with the batch
 resident in HBM; `e2e` = the same through the public API with the batch in pinned HOST memory (H2D copy of every input
 tensor + D2H read of the loss inside the timed region).  The Group Matching env kernel is measured in the same run and
-reported under "env".  `--impl reference` times the CPU restatement of the reference (oracle/, torch-CPU, all host
-threads) on a bounded sample of the same workload.
+reported under "env" (kernel alone, and full rollouts through ParallelRunner.run for BASELINE configs 2 and 4).  The headline
+line is WEAK scaling (B=128 per GPU); the "strong" sub-record re-runs the named GLOBAL batch sharded B/N per rank for the
+north-star shape and for BASELINE config 5 (sc2 3-8csz replay shape: B=128, T=120, 8 agents, 16 entities).
+`--impl reference` times the reference's OWN QLearner.train (sources staged by oracle/stage_ref.py into oracle/_ref, all
+host threads; falls back to the torch-CPU restatement in oracle/ when nothing is staged) on the same workload.
 """
 import argparse
 import json
@@ -22,10 +25,12 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: (alg, B per GPU, T, na, ne, ed, A, overrides)
-    "ns": ("refil", 128, 60, 8, 24, 39, 14, {}),
-    "cfg3": ("qmix_atten", 64, 60, 8, 16, 39, 14, {}),
-    "gm": ("refil_group_matching", 4096, 51, 4, 4, 12, 3, {}),
+    # name: (alg, B, T, na, ne, ed, A, scaling)   weak: B episodes PER GPU; strong: B episodes in total, B / N per GPU
+    "ns": ("refil", 128, 60, 8, 24, 39, 14, "weak"),
+    "ns-strong": ("refil", 128, 60, 8, 24, 39, 14, "strong"),
+    "cfg5": ("refil", 128, 120, 8, 16, 39, 14, "strong"),       # BASELINE.json configs[4]: sc2custom 3-8csz replay shape
+    "cfg3": ("qmix_atten", 64, 60, 8, 16, 39, 14, "weak"),
+    "gm": ("refil_group_matching", 4096, 51, 4, 4, 12, 3, "weak"),
 }
 
 
@@ -138,39 +143,97 @@ def peaks():
 
 
 # --------------------------------------------------------------------------------------------------------------------
-def cpu_reference_rate(alg, T, na, ne, ed, A, budget_s=15.0, sample_B=4, seed=0):
-    """Reference algorithm on the host cores: torch-CPU restatement in oracle/ (kind "port"), bounded sample."""
-    import torch
-    from oracle import learner_oracle as lo
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    args = make_args(alg, na, ne, ed, A)
-    gen = torch.Generator().manual_seed(seed)
-    ein = ed + (A if args.entity_last_action else 0)
-    syn = lo.synthetic_batch(gen, sample_B, T, na, ne, ed, A, pad=ne > na)
-    ap, mp = lo.init_agent_params(gen, args, ein), lo.init_mixer_params(gen, args, ein)
-    group_a = (torch.rand(sample_B, ne, generator=gen) < 0.5).to(torch.uint8)
-    lo.train_step(ap, mp, ap, mp, syn, args, group_a=group_a)          # warm-up
+# CPU arm: the reference's own code (oracle/_ref, staged by oracle/stage_ref.py) or, when nothing is staged, the torch-CPU
+# restatement (oracle/learner_oracle.py).  bench.py is one of the three places allowed to execute oracle/.
+def _syn_for(alg, B, T, na, ne, ed, A, seed):
+    from refil_b200.utils.synthetic import synthetic_replay
+    gm = alg == "refil_group_matching"
+    return synthetic_replay(B, T, na, ne, ed, A, seed=seed, gt_mask=gm, pad=ne > na)
+
+
+class CpuLearnerArm:
+    """One QLearner.train step of the reference on the host cores, on B episodes of a workload."""
+
+    def __init__(self, alg, B, T, na, ne, ed, A, seed=0):
+        import torch
+        from oracle import stage_ref
+        self.cores = os.cpu_count() or 1
+        torch.set_num_threads(self.cores)
+        self.B, self.T = B, T
+        syn = _syn_for(alg, B, T, na, ne, ed, A, seed)
+        gm = alg == "refil_group_matching"
+        if stage_ref.available():
+            self.kind = "reference"
+            self.learner, self.batch, _ = stage_ref.build_reference_learner(
+                alg, syn, (B, T, na, ne, ed, A), gt=gm, seed=seed, learner_log_interval=10 ** 12)
+            self.what = "the reference's own EntityMAC + QLearner.train (oracle/_ref, staged from /root/reference/src)"
+            self._i = 0
+        else:
+            from oracle import learner_oracle as lo
+            self.kind = "port"
+            self.lo, self.args = lo, make_args(alg, na, ne, ed, A)
+            gen = torch.Generator().manual_seed(seed)
+            ein = ed + (A if self.args.entity_last_action else 0)
+            self.syn = syn
+            self.ap, self.mp = lo.init_agent_params(gen, self.args, ein), lo.init_mixer_params(gen, self.args, ein)
+            self.group_a = (torch.rand(B, ne, generator=gen) < 0.5).to(torch.uint8)
+            self.what = "torch-CPU restatement of QLearner.train (oracle/learner_oracle.py)"
+
+    def step(self):
+        if self.kind == "reference":
+            self._i += 1
+            self.learner.train(self.batch, t_env=self._i, episode_num=self._i)
+        else:
+            self.lo.train_step(self.ap, self.mp, self.ap, self.mp, self.syn, self.args, group_a=self.group_a)
+
+    def transitions(self):
+        return self.B * (self.T - 1)
+
+
+def cpu_reference_rate(alg, T, na, ne, ed, A, budget_s=20.0, sample_B=16, seed=0):
+    """cpu_baseline leg of our arm: a BOUNDED sample (sample_B episodes, ~budget_s seconds) on rank 0 at N=1."""
+    arm = CpuLearnerArm(alg, sample_B, T, na, ne, ed, A, seed)
+    arm.step()                                                   # warm-up
     times = []
     t_end = time.perf_counter() + budget_s
-    while len(times) < 3 or (time.perf_counter() < t_end and len(times) < 50):
+    while len(times) < 3 or (time.perf_counter() < t_end and len(times) < 30):
         t0 = time.perf_counter()
-        lo.train_step(ap, mp, ap, mp, syn, args, group_a=group_a)
+        arm.step()
         times.append(time.perf_counter() - t0)
-    best = sorted(times)[len(times) // 2]
-    return {"value": sample_B * (T - 1) / best, "unit": "transitions/s", "cores": cores, "kind": "port",
-            "sample": "%d timed QLearner.train steps (median) of the torch-CPU oracle on B=%d episodes of the same "
-                      "(T=%d, agents=%d, entities=%d) workload, %d torch threads" % (len(times), sample_B, T, na, ne, cores),
-            "ms_per_step": best * 1e3}
+    med = sorted(times)[len(times) // 2]
+    return {"value": arm.transitions() / med, "unit": "transitions/s", "cores": arm.cores, "kind": arm.kind,
+            "sample": "%d timed steps (median) of %s on B=%d episodes of the same (T=%d, agents=%d, entities=%d) workload, "
+                      "%d torch threads" % (len(times), arm.what, sample_B, T, na, ne, arm.cores),
+            "ms_per_step": med * 1e3}
 
 
 def cpu_env_rate(na, budget_s=5.0):
+    """Group Matching on one host core: the reference class itself when staged (step + get_avail_actions + get_masks +
+    get_entities per step = what env_worker does, parallel_runner.py:253-280), else the C restatement."""
+    from oracle import stage_ref
+    cfg = dict(n_agents=na, n_states=6, n_groups=2, rand_trans=0.1, episode_limit=50)
+    if stage_ref.available():
+        import numpy as np
+        env = stage_ref.group_matching_env(seed=0, **cfg)
+        rng = np.random.RandomState(0)
+        env.reset()
+        n, t0 = 0, time.perf_counter()
+        while time.perf_counter() - t0 < budget_s:
+            for _ in range(200):
+                _, done, _ = env.step(rng.randint(0, 3, size=na))
+                env.get_avail_actions(); env.get_masks(); env.get_entities()
+                n += 1
+                if done:
+                    env.reset()
+        dt = time.perf_counter() - t0
+        return {"value": n / dt, "unit": "env-steps/s", "cores": 1, "kind": "reference",
+                "sample": "%d steps of the reference GroupMatching class (step + avail + masks + entities, reset on done), "
+                          "1 process; the reference runs one such process per env" % n}
     from oracle.gm_env_oracle import GroupMatchingOracle
-    env = GroupMatchingOracle(n_agents=na, n_states=6, n_groups=2, rand_trans=0.1, episode_limit=50, seed=0)
+    env = GroupMatchingOracle(seed=0, **cfg)
     env.reset()
-    n = 200000
     t0 = time.perf_counter()
-    done = env.bench_loop(n)
+    done = env.bench_loop(200000)
     dt = time.perf_counter() - t0
     return {"value": done / dt, "unit": "env-steps/s", "cores": 1, "kind": "port",
             "sample": "%d steps of the C oracle (step + entities + masks), 1 thread" % done}
@@ -178,93 +241,93 @@ def cpu_env_rate(na, budget_s=5.0):
 
 # --------------------------------------------------------------------------------------------------------------------
 def run_reference(a):
+    """`--impl reference`: the reference's own CPU path on this box's host cores, same workload / metric / unit.  Each step is
+    the workload's own batch when that fits the time budget, else the largest power-of-two sample of it that does (a
+    calibration step decides; config.sample_B says which)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    alg, B, T, na, ne, ed, A, _ = WORKLOADS[a.workload]
-    sample_B = 4 if a.workload != "gm" else 64
-    import torch
-    from oracle import learner_oracle as lo
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    args = make_args(alg, na, ne, ed, A)
-    gen = torch.Generator().manual_seed(0)
-    ein = ed + (A if args.entity_last_action else 0)
-    syn = lo.synthetic_batch(gen, sample_B, T, na, ne, ed, A, pad=ne > na)
-    ap, mp = lo.init_agent_params(gen, args, ein), lo.init_mixer_params(gen, args, ein)
-    group_a = (torch.rand(sample_B, ne, generator=gen) < 0.5).to(torch.uint8)
-    for _ in range(max(1, min(a.warmup, 2))):
-        lo.train_step(ap, mp, ap, mp, syn, args, group_a=group_a)
+    alg, B, T, na, ne, ed, A, scaling = WORKLOADS[a.workload]
+    if a.batch:
+        B = a.batch
+    budget_s = float(os.environ.get("REFIL_REF_BUDGET_S", "110"))
+    n_steps = a.steps + max(1, min(a.warmup, 1))
+    # calibration on a small sample: seconds per episode-step of this workload on this box
+    cal_B = min(B, 8 if a.workload != "gm" else 128)
+    cal = CpuLearnerArm(alg, cal_B, T, na, ne, ed, A)
+    cal.step()
+    t0 = time.perf_counter()
+    cal.step()
+    per_ep = (time.perf_counter() - t0) / cal_B
+    sample_B = B
+    while sample_B > cal_B and per_ep * sample_B * n_steps > budget_s:
+        sample_B //= 2
+    arm = cal if sample_B == cal_B else CpuLearnerArm(alg, sample_B, T, na, ne, ed, A)
+    del cal
+    for _ in range(max(1, min(a.warmup, 1))):
+        arm.step()
     t0 = time.perf_counter()
     for _ in range(a.steps):
-        lo.train_step(ap, mp, ap, mp, syn, args, group_a=group_a)
+        arm.step()
     dt = (time.perf_counter() - t0) / a.steps
-    v = sample_B * (T - 1) / dt
-    sample = ("each step = one torch-CPU QLearner.train restatement (oracle/learner_oracle.py) on B=%d episodes of the "
-              "(T=%d, agents=%d, entities=%d, d=128) workload, %d threads" % (sample_B, T, na, ne, cores))
+    v = arm.transitions() / dt
+    sample = ("each step = %s on B=%d episodes of the (T=%d, agents=%d, entities=%d) workload, %d torch threads"
+              % (arm.what, sample_B, T, na, ne, arm.cores))
     print(json.dumps({
         "impl": "reference", "metric": "learner transitions/sec", "value": v, "unit": "transitions/s",
         "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(a.workload, B, T, na, ne), "sample_B": sample_B,
-                   "note": "each step is a bounded sample (sample_B episodes) of the workload; transitions/s does not depend on B"},
-        "cpu_baseline": {"value": v, "unit": "transitions/s", "cores": cores, "kind": "port", "sample": sample},
+        "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a.workload, B, T, na, ne), "sample_B": sample_B, "same_batch": sample_B == B,
+                   "note": "CPU arm runs on rank 0's host cores only, whatever --gpus says; a step is the workload's own "
+                           "batch when (steps + warm-up) x step time fits %.0f s, else a power-of-two sample of it" % budget_s},
+        "cpu_baseline": {"value": v, "unit": "transitions/s", "cores": arm.cores, "kind": arm.kind, "sample": sample},
         "e2e": {"value": v, "unit": "transitions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
 def workload_name(w, B, T, na, ne):
-    alg = WORKLOADS[w][0]
-    return "%s learner step, synthetic replay (B=%d per GPU, T=%d, agents=%d, entities=%d, d=%d)" % (
-        alg, B, T, na, ne, 64 if w == "gm" else 128)
+    alg, scaling = WORKLOADS[w][0], WORKLOADS[w][7]
+    return "%s learner step, synthetic replay (B=%d %s, T=%d, agents=%d, entities=%d, d=%d)" % (
+        alg, B, "per GPU" if scaling == "weak" else "in total, sharded over the GPUs", T, na, ne, 64 if w == "gm" else 128)
+
+
+class _Log:
+    class console_logger:
+        @staticmethod
+        def info(*x, **k):
+            pass
+
+    def log_stat(self, *x, **k):
+        pass
 
 
 # --------------------------------------------------------------------------------------------------------------------
-def run_ours(a):
+def bench_learner(w, B, a, dev, rank, world, do_e2e=True, do_breakdown=False, steps=None):
+    """Time `steps` QLearner.train steps of workload `w` with B episodes on THIS rank (max over ranks).  -> dict."""
     import torch
     import torch.distributed as dist
     from refil_b200 import ops
     from refil_b200.components.episode_buffer import EpisodeBatch
     from refil_b200.controllers import REGISTRY as mac_REGISTRY
-    from refil_b200.envs.group_matching import GroupMatchingBatch
     from refil_b200.learners import REGISTRY as le_REGISTRY
     from refil_b200.utils.synthetic import entity_scheme, synthetic_replay
 
-    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = "cuda:%d" % local
-    if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
-            os.environ.pop("NCCL_DEBUG")               # those levels print the NCCL banner on stdout: keep it to the JSON line
-        from refil_b200 import parallel
-        parallel.init_distributed(backend="nccl", device=dev)
-    alg, B, T, na, ne, ed, A, _ = WORKLOADS[a.workload]
-    if a.batch:
-        B = a.batch
+    alg, _, T, na, ne, ed, A, scaling = WORKLOADS[w]
+    steps = steps or a.steps
     args = make_args(alg, na, ne, ed, A)
     args.device = dev
     args.cuda_graph = not a.no_graph
-
-    class Log:
-        class console_logger:
-            @staticmethod
-            def info(*x, **k):
-                pass
-
-        def log_stat(self, *x, **k):
-            pass
-
-    scheme, groups, preprocess = entity_scheme(na, ne, ed, A, gt_mask=(a.workload == "gm"))
-    syn = synthetic_replay(B, T, na, ne, ed, A, seed=1000 + rank, gt_mask=(a.workload == "gm"), pad=ne > na)
-    args.gt_mask_avail = a.workload == "gm"
+    gm = w == "gm"
+    scheme, groups, preprocess = entity_scheme(na, ne, ed, A, gt_mask=gm)
+    syn = synthetic_replay(B, T, na, ne, ed, A, seed=1000 + rank, gt_mask=gm, pad=ne > na)
+    args.gt_mask_avail = gm
     batch = EpisodeBatch(scheme, groups, B, T, preprocess=preprocess, device=dev)
     host = {k: v.pin_memory() for k, v in syn.items()}
     for k, v in host.items():
         batch.data.transition_data[k].copy_(v)
     torch.manual_seed(0)                       # identical initial weights on every rank
     mac = mac_REGISTRY[args.mac](batch.scheme, groups, args)
-    learner = le_REGISTRY[args.learner](mac, batch.scheme, Log(), args)
+    learner = le_REGISTRY[args.learner](mac, batch.scheme, _Log(), args)
 
     def barrier():
         if world > 1:
@@ -273,20 +336,20 @@ def run_ours(a):
 
     host_ms = [0.0]
 
-    def timed(fn, steps):
+    def timed(fn, n):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         t0 = time.perf_counter()
-        for i in range(steps):
+        for i in range(n):
             fn(i)
-        host_ms[0] = (time.perf_counter() - t0) * 1e3 / steps      # host time to ENQUEUE one step (no sync inside fn)
+        host_ms[0] = (time.perf_counter() - t0) * 1e3 / n      # host time to ENQUEUE one step (no sync inside fn)
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
             if os.environ.get("REFIL_BENCH_DEBUG"):
-                print("rank %d: %.3f ms for %d steps" % (rank, float(ms.item()), steps), file=sys.stderr)
+                print("rank %d: %.3f ms for %d steps" % (rank, float(ms.item()), n), file=sys.stderr)
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
@@ -297,63 +360,95 @@ def run_ours(a):
         learner.train(batch, t_env=ep[0], episode_num=ep[0])
 
     h2d = sum(v.numel() * v.element_size() for v in host.values())
-
-    # end to end through the public API: every step's inputs come from pinned host memory and its loss statistics go back to
-    # the host.  Two device-side EpisodeBatch buffers: the H2D copy of step i+1 runs on a copy stream while step i trains.
-    batch_b = EpisodeBatch(scheme, groups, B, T, preprocess=preprocess, device=dev)
-    bufs = [batch, batch_b]
-    copy_stream = torch.cuda.Stream(device=dev)
-    ev_copied = [torch.cuda.Event(), torch.cuda.Event()]
-    ev_trained = [torch.cuda.Event(), torch.cuda.Event()]
-
-    def copy_async(slot):
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(ev_trained[slot])           # the step that last read this buffer is done
-            for k, v in host.items():
-                bufs[slot].data.transition_data[k].copy_(v, non_blocking=True)
-            ev_copied[slot].record(copy_stream)
-
-    def step_e2e(i):
-        slot = i % 2
-        if i == 0:
-            copy_async(0)
-        torch.cuda.current_stream().wait_event(ev_copied[slot])
-        ep[0] += 1
-        learner.train(bufs[slot], t_env=ep[0], episode_num=ep[0])
-        ev_trained[slot].record()
-        copy_async(slot ^ 1)                                   # next step's inputs, overlapped with this step's kernels
-        learner.gradbuf[learner.n_params:].cpu()          # D2H read of the step's loss statistics (syncs)
-
     for i in range(max(a.warmup, 3)):
         step_resident(i)
+    l0 = ops.launch_count()
+    ms = timed(step_resident, steps)
+    res = {"workload": workload_name(w, B * world if scaling == "strong" else B, T, na, ne), "episodes_per_gpu": B,
+           "ms_per_step": ms / steps, "host_enqueue_ms_per_step": round(host_ms[0], 3),
+           "gpu_launches": ops.launch_count() - l0, "launches_per_step": (ops.launch_count() - l0) / steps,
+           "transitions_per_step": world * B * (T - 1), "value": world * B * (T - 1) * steps / (ms * 1e-3),
+           "activation_bytes": learner_bytes(learner, mac), "args": args, "dims": (B, T, na, ne, ed, A)}
+
+    if do_e2e:
+        # end to end through the public API: every step's inputs come from pinned host memory and its loss statistics go back
+        # to the host.  Two device-side EpisodeBatch buffers: the H2D copy of step i+1 runs on a copy stream while step i trains.
+        batch_b = EpisodeBatch(scheme, groups, B, T, preprocess=preprocess, device=dev)
+        bufs = [batch, batch_b]
+        copy_stream = torch.cuda.Stream(device=dev)
+        ev_copied = [torch.cuda.Event(), torch.cuda.Event()]
+        ev_trained = [torch.cuda.Event(), torch.cuda.Event()]
+
+        def copy_async(slot):
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(ev_trained[slot])           # the step that last read this buffer is done
+                for k, v in host.items():
+                    bufs[slot].data.transition_data[k].copy_(v, non_blocking=True)
+                ev_copied[slot].record(copy_stream)
+
+        def step_e2e(i):
+            slot = i % 2
+            if i == 0:
+                copy_async(0)
+            torch.cuda.current_stream().wait_event(ev_copied[slot])
+            ep[0] += 1
+            learner.train(bufs[slot], t_env=ep[0], episode_num=ep[0])
+            ev_trained[slot].record()
+            copy_async(slot ^ 1)                                   # next step's inputs, overlapped with this step's kernels
+            learner.gradbuf[learner.n_params:].cpu()          # D2H read of the step's loss statistics (syncs)
+
+        for i in range(2):
+            step_e2e(i)
+        torch.cuda.synchronize()
+        ms_e2e = timed(step_e2e, steps)
+        res["e2e"] = {"value": world * B * (T - 1) * steps / (ms_e2e * 1e-3), "unit": "transitions/s",
+                      "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 32, "ms_per_step": ms_e2e / steps}
+
+    if do_breakdown:
+        # per-kernel breakdown (instrumented repeat of the step, events around every launch)
+        args.concurrent_streams = False          # serialised launches: per-kernel durations are not inflated by overlap
+        args.cuda_graph = False                  # ... and enqueued one by one so that events can bracket each of them
+        ops.set_timing(True)
+        step_resident(0)
+        step_resident(1)
+        tsum = ops.timing_summary()
+        shapes = ops.shape_timing_summary()
+        ops.set_timing(False)
+        res["kern"] = {k: {"launches": v[0] // 2, "ms_per_step": v[1] / 2, "flop_per_step": v[2] / 2,
+                           "bytes_per_step": v[3] / 2} for k, v in tsum.items()}
+        res["shapes"] = shapes
+    del learner, mac, batch
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    return res
+
+
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = "cuda:%d" % local
+    if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+            os.environ.pop("NCCL_DEBUG")               # those levels print the NCCL banner on stdout: keep it to the JSON line
+        from refil_b200 import parallel
+        parallel.init_distributed(backend="nccl", device=dev)
+    alg, B, T, na, ne, ed, A, scaling = WORKLOADS[a.workload]
+    if a.batch:
+        B = a.batch
+    if scaling == "strong":
+        if B % world:
+            raise SystemExit("workload %s: global batch %d is not divisible by %d GPUs" % (a.workload, B, world))
+        B //= world
     clocks = ClockSampler(local, enabled=(rank == 0))
     clocks.start()
-    l0 = ops.launch_count()
-    ms = timed(step_resident, a.steps)
-    host_enqueue_ms = host_ms[0]
-    launches = ops.launch_count() - l0
-    for i in range(2):
-        step_e2e(i)
-    torch.cuda.synchronize()
-    ms_e2e = timed(step_e2e, a.steps)
+    head = bench_learner(a.workload, B, a, dev, rank, world, do_e2e=True, do_breakdown=True)
     clk = clocks.summary()           # sampled across both timed regions (resident + e2e)
-    trans = world * B * (T - 1)
-    value = trans * a.steps / (ms * 1e-3)
-    e2e = trans * a.steps / (ms_e2e * 1e-3)
-
-    # ---- per-kernel breakdown (instrumented repeat of the step, events around every launch) -------------------
-    args.concurrent_streams = False          # serialised launches: per-kernel durations are not inflated by overlap
-    args.cuda_graph = False                  # ... and enqueued one by one so that events can bracket each of them
-    ops.set_timing(True)
-    step_resident(0)
-    step_resident(1)
-    tsum = ops.timing_summary()
-    shapes = ops.shape_timing_summary()
-    ops.set_timing(False)
-    args.concurrent_streams = True
-    args.cuda_graph = not a.no_graph
-    kern = {k: {"launches": v[0] // 2, "ms_per_step": v[1] / 2, "flop_per_step": v[2] / 2, "bytes_per_step": v[3] / 2}
-            for k, v in tsum.items()}
+    args = head["args"]
+    kern, shapes = head["kern"], head["shapes"]
     hbm, tf_burst, tf_sus, src = peaks()
     timing_note = "per-launch CUDA events on an instrumented repeat of the step (2 steps averaged)"
 
@@ -382,32 +477,56 @@ def run_ours(a):
         roofline["tensor_frac_of_bf16_peak"] = 3.0 * roofline["algorithmic_tflops"] / tf_sus   # 3 MMAs per product
         roofline["note"] = ("memory-bound by construction (48 flop/B at N=384,K=128); tensor-side: 3 tf32 MMAs per "
                             "product, quoted against the measured bf16 sustained peak for context")
+        # whole-step view (fused K1 accounting): what the step HAS to move if every trunk were one fused kernel
+        roofline["step_algorithmic_bytes_all_kernels"] = sum(k["bytes_per_step"] for k in kern.values())
+        roofline["step_bytes_over_hbm_peak_ms"] = roofline["step_algorithmic_bytes_all_kernels"] / (hbm * 1e9) * 1e3
     dom = max(kern.items(), key=lambda kv: kv[1]["ms_per_step"])
 
     out = {
-        "metric": "learner transitions/sec", "value": value, "unit": "transitions/s", "n_gpus": world, "steps": a.steps,
-        "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
+        "metric": "learner transitions/sec", "value": head["value"], "unit": "transitions/s", "n_gpus": world, "steps": a.steps,
+        "warmup": max(a.warmup, 3), "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": scaling,
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(a.workload, B, T, na, ne), "global_batch_episodes": world * B,
+        "config": {"workload": head["workload"], "global_batch_episodes": world * B,
                    "parallelism": "dp%d (episodes sharded, one all-reduce of grads+stats)" % world,
-                   "step_submission": "cuda graph replay" if args.cuda_graph else "eager launches",
-                   "l2": "working set per step (%.1f GB of activations) exceeds the 126 MB L2" % (learner_bytes(learner, mac) / 1e9)},
-        "e2e": {"value": e2e, "unit": "transitions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 32,
-                "ms_per_step": ms_e2e / a.steps},
-        "gpu_launches": launches, "host_enqueue_ms_per_step": round(host_enqueue_ms, 3), "clocks": clk, "roofline": roofline, "roofline_attention": roof_att,
+                   "step_submission": "cuda graph replay" if not a.no_graph else "eager launches",
+                   "l2": "working set per step (%.1f GB of activations) exceeds the 126 MB L2" % (head["activation_bytes"] / 1e9)},
+        "e2e": head["e2e"],
+        "gpu_launches": head["gpu_launches"], "launches_per_step": head["launches_per_step"],
+        "host_enqueue_ms_per_step": head["host_enqueue_ms_per_step"], "clocks": clk, "roofline": roofline, "roofline_attention": roof_att,
         "roofline_wgrad": hbm_roof("tc_gemm_wgrad", "tc_wgrad_ts_kernel (weight gradients: X^T in tensor memory, MN-major Y tiles)"),
         "roofline_attention_bwd": hbm_roof("masked_attn_bwd", "attn_bwd_kernel"), "dominant_kernel": dom[0],
         "kernels_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in sorted(kern.items(), key=lambda kv: -kv[1]["ms_per_step"])},
         # dense-layer kernels by shape [M x N x K]: (launches per step, us per launch)
         "dense_shapes_us": {k: [v[0] // 2, round(1e3 * v[1] / max(v[0], 1), 1)] for k, v in sorted(shapes.items(), key=lambda kv: -kv[1][1])},
     }
+    # ---- strong scaling of the NAMED global batches (every rank takes part; B / N episodes per GPU) -----------------
+    if a.workload == "ns" and not a.no_extra:
+        strong = {}
+        for w in ("ns-strong", "cfg5"):
+            gB = WORKLOADS[w][1]
+            if gB % world:
+                strong[w] = {"error": "global batch %d not divisible by %d GPUs" % (gB, world)}
+                continue
+            if w == "ns-strong" and world == 1:          # one GPU: the strong and the weak workload are the same run
+                r = head
+            else:
+                r = bench_learner(w, gB // world, a, dev, rank, world, do_e2e=False, do_breakdown=False, steps=min(a.steps, 10))
+            strong[w] = {"workload": r["workload"], "value": r["value"], "unit": "transitions/s", "scaling": "strong",
+                         "episodes_per_gpu": r["episodes_per_gpu"], "ms_per_step": r["ms_per_step"],
+                         "launches_per_step": r["launches_per_step"], "host_enqueue_ms_per_step": r["host_enqueue_ms_per_step"]}
+        out["strong"] = strong
     # ---- env kernel in the same run ---------------------------------------------------------------------------
     if rank == 0 or world > 1:
         out["env"] = bench_env(dev, world, rank, a, hbm, src)
+    if not a.no_extra and a.workload == "ns":
+        try:          # BASELINE configs[3]: group_matching 8 agents / 24 entity slots, REFIL (RNN agent), 4096 envs PER GPU
+            out["env"]["rollout_cfg4"] = bench_rollout(dev, rank, world, "refil", 4096, 8, 24)
+        except Exception as e:                    # the rollout legs are informational: never lose the bench line over them
+            out["env"]["rollout_cfg4"] = {"error": "%s: %s" % (type(e).__name__, e)}
     if rank == 0 and world == 1 and not a.no_extra:
-        try:
-            out["env"]["rollout"] = bench_rollout(dev, rank)
-        except Exception as e:                    # the rollout leg is informational: never lose the bench line over it
+        try:          # BASELINE configs[1]: group_matching 4 agents, refil_group_matching, 4096 envs on one GPU
+            out["env"]["rollout"] = bench_rollout(dev, rank, world, "refil_group_matching", 4096, 4, 4)
+        except Exception as e:
             out["env"]["rollout"] = {"error": "%s: %s" % (type(e).__name__, e)}
     if rank == 0 and world == 1 and a.workload == "ns" and not a.no_extra:
         # the other BASELINE.json learner configs, each in its own process (own workspaces): configs[1]'s learner side
@@ -424,7 +543,7 @@ def run_ours(a):
             except Exception as e:
                 out["other_workloads"][w] = {"error": "%s: %s" % (type(e).__name__, e)}
     if rank == 0 and world == 1 and not a.no_cpu:
-        out["cpu_baseline"] = cpu_reference_rate(alg, T, na, ne, ed, A, sample_B=4 if a.workload != "gm" else 64)
+        out["cpu_baseline"] = cpu_reference_rate(alg, T, na, ne, ed, A, sample_B=16 if a.workload != "gm" else 256)
         out["env"]["cpu_baseline"] = cpu_env_rate(8)
     if rank == 0:
         print(json.dumps(out))
@@ -523,11 +642,13 @@ def bench_env(dev, world, rank, a, hbm, src):
                          "frac": ach / hbm, "traffic": None, "bytes_per_env_step": bytes_per_step, "peak_source": src}}
 
 
-def bench_rollout(dev, rank, n_envs=4096, n_agents=4):
+def bench_rollout(dev, rank, world, alg, n_envs, n_agents, n_entities):
     """Full on-device rollouts through the reference runner interface (ParallelRunner.run: agent forward + epsilon-greedy
-    selection + env kernel + EpisodeBatch writes per timestep): BASELINE.json config 2 -- group_matching, 4 agents,
-    refil_group_matching (FF imagine agent, d=64), 4096 parallel envs on one GPU."""
+    selection + env kernel + EpisodeBatch writes per timestep), `n_envs` instances PER GPU, env instances sharded by index with
+    no collective.  BASELINE.json configs[1] = (refil_group_matching, 4 agents, FF imagine agent, d=64);
+    configs[3] = (refil, 8 agents in 24 entity slots, RNN agent + flex_qmix dims of refil.yaml, d=128)."""
     import torch
+    import torch.distributed as dist
     from types import SimpleNamespace
     from refil_b200.components.episode_buffer import EpisodeBatch
     from refil_b200.config import build_config
@@ -535,20 +656,15 @@ def bench_rollout(dev, rank, n_envs=4096, n_agents=4):
     from refil_b200.runners import REGISTRY as r_REGISTRY
     from refil_b200.utils.synthetic import entity_scheme
 
-    class Log:
-        class console_logger:
-            @staticmethod
-            def info(*x, **k):
-                pass
-
-        def log_stat(self, *x, **k):
-            pass
-
-    cfg = build_config("group_matching", "refil_group_matching", ["batch_size_run=%d" % n_envs, "env_args.n_agents=%d" % n_agents])
+    over = ["batch_size_run=%d" % n_envs, "env_args.n_agents=%d" % n_agents]
+    if n_entities != n_agents:
+        over.append("env_args.n_entities=%d" % n_entities)
+    cfg = build_config("group_matching", alg, over)
     cfg["env_args"]["seed"] = 0
     args = SimpleNamespace(**cfg)
     args.device, args.rank = dev, rank
-    runner = r_REGISTRY[args.runner](args=args, logger=Log())
+    args.rollout_graph = not bool(os.environ.get("REFIL_NO_ROLLOUT_GRAPH"))
+    runner = r_REGISTRY[args.runner](args=args, logger=_Log())
     info = runner.get_env_info()
     args.n_agents, args.n_actions, args.entity_shape, args.n_entities = (info["n_agents"], info["n_actions"],
                                                                          info["entity_shape"], info["n_entities"])
@@ -558,9 +674,11 @@ def bench_rollout(dev, rank, n_envs=4096, n_agents=4):
     torch.manual_seed(0)
     mac = mac_REGISTRY[args.mac](proto.scheme, groups, args)
     runner.setup(scheme=scheme, groups=groups, preprocess=preprocess, mac=mac)
-    for _ in range(2):
+    for _ in range(3):
         runner.run(test_mode=False)
     torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
     t0_env = runner.t_env
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     reps = 3
@@ -569,12 +687,19 @@ def bench_rollout(dev, rank, n_envs=4096, n_agents=4):
         runner.run(test_mode=False)
     e1.record()
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
-    steps = runner.t_env - t0_env
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    steps = runner.t_env - t0_env                # under torchrun the runner already sums env steps over the ranks
+    del runner, mac
+    torch.cuda.empty_cache()
     return {"metric": "GroupMatching env-steps/sec through ParallelRunner.run (agent forward + epsilon-greedy + env kernel)",
-            "value": steps / (ms * 1e-3), "unit": "env-steps/s", "n_envs": n_envs, "n_agents": n_agents,
+            "value": steps / (ms * 1e-3), "unit": "env-steps/s", "n_envs": n_envs * world, "n_envs_per_gpu": n_envs,
+            "n_agents": n_agents, "n_entities": n_entities,
             "ms_per_rollout": ms / reps, "env_steps_per_rollout": steps / reps,
-            "config": "group_matching %d agents, refil_group_matching, %d parallel envs, epsilon-greedy training rollouts" % (n_agents, n_envs)}
+            "config": "group_matching %d agents / %d entity slots, %s, %d parallel envs per GPU x %d GPUs, epsilon-greedy "
+                      "training rollouts" % (n_agents, n_entities, alg, n_envs, world)}
 
 
 if __name__ == "__main__":
