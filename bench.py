@@ -162,7 +162,7 @@ class CpuLearnerArm:
         self.B, self.T = B, T
         syn = _syn_for(alg, B, T, na, ne, ed, A, seed)
         gm = alg == "refil_group_matching"
-        if stage_ref.available():
+        if stage_ref.available() and not os.environ.get("REFIL_REF_FORCE_PORT"):
             self.kind = "reference"
             self.learner, self.batch, _ = stage_ref.build_reference_learner(
                 alg, syn, (B, T, na, ne, ed, A), gt=gm, seed=seed, learner_log_interval=10 ** 12)

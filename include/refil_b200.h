@@ -64,7 +64,9 @@ int refil_gm_env_reset(uint32_t* mt_key, int32_t* mt_pos, int32_t* loc, uint32_t
 /* step(actions[:, ts]): group_matching.py:19-53 + the post/pre-transition writes of runners/parallel_runner.py:140-197 */
 int refil_gm_env_step(uint32_t* mt_key, int32_t* mt_pos, int32_t* loc, uint32_t* grp, int32_t* est, double* ep_ret,
                       const long long* actions, float* entities, uint8_t* obs_mask, uint8_t* entity_mask,
-                      int32_t* avail_actions, float* reward, uint8_t* terminated, long long* filled,
+                      uint8_t* gt_mask /* null: not rewritten after reset (ParallelRunner); else every step
+                      (runners/episode_runner.py:66-67) */, int32_t* avail_actions, float* reward, uint8_t* terminated,
+                      long long* filled,
                       unsigned long long* step_counter, int n_envs, int n_agents, int n_entities, int n_states,
                       int n_groups, double rand_trans, int episode_limit, int T, int ts, int env_offset,
                       cudaStream_t stream);

@@ -275,7 +275,9 @@ __global__ void __launch_bounds__(GM_THREADS) gm_step_kernel(GmParams p, GmBuffe
         }
     }
     __syncthreads();
-    if (b.entities) gm_write_obs(p, b, ts + 1, e0, n_env, s_loc, s_grp, s_write, false);
+    // gt_mask at ts + 1 only when the caller passes the tensor: EpisodeRunner stores it every step (episode_runner.py:66-67),
+    // ParallelRunner at reset only (parallel_runner.py:140-150 drops the workers' per-step gt_mask)
+    if (b.entities) gm_write_obs(p, b, ts + 1, e0, n_env, s_loc, s_grp, s_write, b.gt_mask != nullptr);
     if (threadIdx.x == 0 && b.step_counter && s_count) atomicAdd(b.step_counter, (unsigned long long)s_count);
 }
 
@@ -317,7 +319,8 @@ extern "C" int refil_gm_env_reset(uint32_t* mt_key, int32_t* mt_pos, int32_t* lo
 
 extern "C" int refil_gm_env_step(uint32_t* mt_key, int32_t* mt_pos, int32_t* loc, uint32_t* grp, int32_t* est,
                                  double* ep_ret, const long long* actions, float* entities, uint8_t* obs_mask,
-                                 uint8_t* entity_mask, int32_t* avail_actions, float* reward, uint8_t* terminated,
+                                 uint8_t* entity_mask, uint8_t* gt_mask, int32_t* avail_actions, float* reward,
+                                 uint8_t* terminated,
                                  long long* filled, unsigned long long* step_counter, int n_envs, int n_agents,
                                  int n_entities, int n_states, int n_groups, double rand_trans, int episode_limit,
                                  int T, int ts, int env_offset, cudaStream_t stream) {
@@ -327,7 +330,7 @@ extern "C" int refil_gm_env_step(uint32_t* mt_key, int32_t* mt_pos, int32_t* loc
     REFIL_CHECK_ARG(actions != nullptr, "gm_env_step: actions is null");
     GmParams p{n_envs, n_agents, n_entities, n_states, n_groups, n_states + n_groups + n_agents, episode_limit, T,
                rand_trans, 0, env_offset};
-    GmBuffers b{mt_key, mt_pos, loc, grp, est, ep_ret, entities, obs_mask, entity_mask, nullptr, avail_actions,
+    GmBuffers b{mt_key, mt_pos, loc, grp, est, ep_ret, entities, obs_mask, entity_mask, gt_mask, avail_actions,
                 reward, terminated, filled, actions, step_counter};
     gm_step_kernel<<<refil_cdiv(n_envs, GM_THREADS), GM_THREADS, 0, stream>>>(p, b, ts);
     REFIL_CHECK_LAUNCH("gm_env_step");

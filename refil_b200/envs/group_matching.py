@@ -72,9 +72,9 @@ class GroupMatchingBatch:
                   torch.cuda.current_stream().cuda_stream)
         ops._launches += 1
 
-    def step(self, batch, ts, env_offset=0):
+    def step(self, batch, ts, env_offset=0, write_gt=False):
         """Advance every live instance with batch['actions'][:, ts]; writes reward / terminated at ts and the
-        observation rows at ts + 1."""
+        observation rows at ts + 1 (plus gt_mask when write_gt: the EpisodeRunner's per-step pre-transition data)."""
         T = batch["entities"].shape[1]
         _lib.call("gm_env_step", self.mt_key.data_ptr(), self.mt_pos.data_ptr(), self.loc.data_ptr(),
                   self.grp.data_ptr(), self.est.data_ptr(), self.ep_ret.data_ptr(), self._ptr(batch, "actions"),

@@ -22,6 +22,8 @@ from ..envs.group_matching import F_LIMIT, F_SOLVED
 
 
 class ParallelRunner:
+    write_gt_every_step = False          # ParallelRunner: gt_mask at reset only (SURVEY.md section 3.2 quirk iv)
+
     def __init__(self, args, logger):
         self.args = args
         self.logger = logger
@@ -77,7 +79,7 @@ class ParallelRunner:
             self.mac.action_selector.select_action(q, batch["avail_actions"][:, t], self.t_env, test_mode=test_mode,
                                                    est_flags=env.flags, out=actions)
             batch.update({"actions": actions.unsqueeze(1)}, ts=t, mark_filled=False)
-            env.step(batch, t)              # reward / terminated at t, observations + filled at t + 1
+            env.step(batch, t, write_gt=self.write_gt_every_step)   # reward / terminated at t, observations + filled at t + 1
             self.t = t + 1
             if (t & 7) == 7 and not bool(env.alive().any()):
                 break
@@ -117,3 +119,10 @@ class ParallelRunner:
             if k != "n_episodes":
                 self.logger.log_stat(prefix + k + "_mean", v / stats["n_episodes"], self.t_env)
         stats.clear()
+
+
+class EpisodeRunner(ParallelRunner):
+    """`runner: episode` (runners/episode_runner.py:8-139): the same device loop, with the one data difference between the two
+    reference runners kept -- the episode runner stores gt_mask in its pre-transition data at EVERY step (:52-67), so
+    `train_gt_factors` sees the ground-truth factorisation on all timesteps."""
+    write_gt_every_step = True
