@@ -143,6 +143,19 @@ int refil_masked_attn_bwd(const float* qkv, const float* dout, float* dqkv, cons
                           const uint8_t* entity_mask, int N, int T, int n_entities, int n_queries, int embed_dim,
                           int n_heads, int n_copies, cudaStream_t stream);
 
+/* ---- EntityPoolingLayer (`pooling_type: mean | max`): modules/layers/attention.py:82-132, same mask interface as the attention
+ *      kernels.  E [N, ne, d] = in_trans(x1); OUT / dOUT [C, N, nq, d]; dE [N, ne, d] (overwritten).  pool_type 0 = mean (masked
+ *      entities count as zeros, divisor ne), 1 = max (zeros of masked entities take part; gradient to the first arg-max). */
+int refil_entity_pool_fwd(const float* E, float* out, const uint8_t* mask0, const uint8_t* mask1, const uint8_t* mask2,
+                          long long mask_stride0, long long mask_stride1, long long mask_stride2, int mode0, int mode1,
+                          int mode2, const uint8_t* group_bits, const uint8_t* entity_mask, int N, int T, int n_entities,
+                          int n_queries, int embed_dim, int n_copies, int pool_type, cudaStream_t stream);
+int refil_entity_pool_bwd(const float* E, const float* dout, float* dE, const uint8_t* mask0, const uint8_t* mask1,
+                          const uint8_t* mask2, long long mask_stride0, long long mask_stride1, long long mask_stride2,
+                          int mode0, int mode1, int mode2, const uint8_t* group_bits, const uint8_t* entity_mask, int N,
+                          int T, int n_entities, int n_queries, int embed_dim, int n_copies, int pool_type,
+                          cudaStream_t stream);
+
 /* ---- GRU scan: the `for t` loop of agents/entity_rnn_agent.py:51-55 (torch.nn.GRUCell, gates r,z,n) ------------
  * rows = (seq-batch, t, agent); GI [R, 3r] = x W_ih^T + b_ih; gates [R, 4r] (saved for BPTT, may be null). */
 int refil_gru_scan_fwd(const float* GI, const float* Whh, const float* bhh, const float* h0, float* HS, float* gates,

@@ -49,6 +49,26 @@ def entity_attention(x, w_in, w_out, b_out, pre_mask, post_mask, n_heads):
     return o.masked_fill(post_mask.bool().unsqueeze(-1), 0.0)
 
 
+def entity_pooling(x, w_in, b_in, w_out, b_out, pre_mask, post_mask, pooling_type):
+    """EntityPoolingLayer.forward, modules/layers/attention.py:95-132: in_trans (with bias), masked entities set to ZERO (they
+    still count in the mean's divisor and take part in the max), pool over entities per agent, out_trans, post-mask."""
+    nq = post_mask.shape[1]
+    e = x @ w_in.t() + b_in
+    rep = e.unsqueeze(1).repeat(1, nq, 1, 1).masked_fill(pre_mask[:, :nq].bool().unsqueeze(3), 0.0)
+    pooled = rep.max(dim=2)[0] if pooling_type == "max" else rep.mean(dim=2)
+    o = pooled @ w_out.t() + b_out
+    return o.masked_fill(post_mask.bool().unsqueeze(-1), 0.0)
+
+
+def entity_layer(p, args, x1, pre_mask, post_mask):
+    """`self.attn` of the agents / hypernetworks: attention unless args.pooling_type is set (entity_rnn_agent.py:13-22)."""
+    if getattr(args, "pooling_type", None) is None:
+        return entity_attention(x1, p["attn.in_trans.weight"], p["attn.out_trans.weight"], p["attn.out_trans.bias"],
+                                pre_mask, post_mask, args.attn_n_heads)
+    return entity_pooling(x1, p["attn.in_trans.weight"], p["attn.in_trans.bias"], p["attn.out_trans.weight"],
+                          p["attn.out_trans.bias"], pre_mask, post_mask, args.pooling_type)
+
+
 def _sub(p, prefix):
     return {k[len(prefix):]: v for k, v in p.items() if k.startswith(prefix)}
 
@@ -81,8 +101,7 @@ def rnn_agent_forward(p, args, entities, obs_mask, entity_mask, h0):
     em = entity_mask.reshape(bs * ts, ne)
     am = em[:, :na]
     x1 = F.relu(e @ p["fc1.weight"].t() + p["fc1.bias"])
-    x2 = entity_attention(x1, p["attn.in_trans.weight"], p["attn.out_trans.weight"], p["attn.out_trans.bias"],
-                          om, am, args.attn_n_heads)
+    x2 = entity_layer(p, args, x1, om, am)
     x3 = F.relu(x2 @ p["fc2.weight"].t() + p["fc2.bias"]).reshape(bs, ts, na, r)
     h = h0.reshape(-1, r)
     hs = []
@@ -108,8 +127,7 @@ def ff_agent_forward(p, args, entities, obs_mask, entity_mask, gt_mask=None):
     em = entity_mask.reshape(bs * ts, ne)
     am = em[:, :na]
     x1 = F.relu(e @ p["fc1.weight"].t() + p["fc1.bias"])
-    x2 = F.relu(entity_attention(x1, p["attn.in_trans.weight"], p["attn.out_trans.weight"],
-                                 p["attn.out_trans.bias"], om, am, args.attn_n_heads))
+    x2 = F.relu(entity_layer(p, args, x1, om, am))
     q = x2 @ p["fc2.weight"].t() + p["fc2.bias"]
     q = q.reshape(bs, ts, na, -1).masked_fill(am.reshape(bs, ts, na, 1).bool(), 0.0)
     return q, x2
@@ -211,8 +229,7 @@ def hypernet(p, args, entities, entity_mask, attn_mask, mode):
     am = entity_mask[:, :na]
     if attn_mask is None:
         attn_mask = (am.bool().unsqueeze(2) | entity_mask.bool().unsqueeze(1)).to(torch.uint8)
-    x2 = entity_attention(x1, p["attn.in_trans.weight"], p["attn.out_trans.weight"], p["attn.out_trans.bias"],
-                          attn_mask, am, args.attn_n_heads)
+    x2 = entity_layer(p, args, x1, attn_mask, am)
     x3 = x2 @ p["fc2.weight"].t() + p["fc2.bias"]
     x3 = x3.masked_fill(am.bool().unsqueeze(2), 0.0)
     if mode == "vector":
@@ -449,7 +466,10 @@ def init_agent_params(gen, args, ein):
     d, r, A = args.attn_embed_dim, args.rnn_hidden_dim, args.n_actions
     p = {}
     p["fc1.weight"], p["fc1.bias"] = init_linear(gen, d, ein)
-    p["attn.in_trans.weight"], _ = init_linear(gen, 3 * d, d, bias=False)
+    if getattr(args, "pooling_type", None) is None:
+        p["attn.in_trans.weight"], _ = init_linear(gen, 3 * d, d, bias=False)
+    else:
+        p["attn.in_trans.weight"], p["attn.in_trans.bias"] = init_linear(gen, d, d)
     p["attn.out_trans.weight"], p["attn.out_trans.bias"] = init_linear(gen, d, d)
     if "rnn" in args.agent:
         p["fc2.weight"], p["fc2.bias"] = init_linear(gen, r, d)
@@ -468,7 +488,10 @@ def init_hypernet_params(gen, args, ein, prefix):
     he, me = args.hypernet_embed, args.mixing_embed_dim
     p = {}
     p[prefix + "fc1.weight"], p[prefix + "fc1.bias"] = init_linear(gen, he, ein)
-    p[prefix + "attn.in_trans.weight"], _ = init_linear(gen, 3 * he, he, bias=False)
+    if getattr(args, "pooling_type", None) is None:
+        p[prefix + "attn.in_trans.weight"], _ = init_linear(gen, 3 * he, he, bias=False)
+    else:
+        p[prefix + "attn.in_trans.weight"], p[prefix + "attn.in_trans.bias"] = init_linear(gen, he, he)
     p[prefix + "attn.out_trans.weight"], p[prefix + "attn.out_trans.bias"] = init_linear(gen, he, he)
     p[prefix + "fc2.weight"], p[prefix + "fc2.bias"] = init_linear(gen, me, he)
     return p

@@ -616,6 +616,156 @@ static int attn_fill(AttnArgs& a, const float* qkv, const uint8_t* m0, const uin
     return REFIL_OK;
 }
 
+// =====================================================================================================================
+// EntityPoolingLayer (/root/reference/src/modules/layers/attention.py:82-132): the `pooling_type` ablation of the attention
+// layer, with the SAME mask interface (explicit tensors + closed-form partition modes, up to 3 copies).
+//   E [N, ne, d] = in_trans(x1) (dense kernels);   OUT[c, n, i, :] = pool_j ( masked_c(n, i, j) ? 0 : E[n, j, :] )
+//   mean divides by ne, masked entities contribute zeros (:118-124); max takes the elementwise maximum INCLUDING those zeros
+//   and its gradient goes to the first maximal entity (torch.max(dim) index rule) unless that entity is a masked zero.
+// One warp per (b, t) unit; lane = 4 consecutive columns of a 128-column chunk (coalesced 512-byte row reads); the mask words
+// of the unit's query rows are resolved once (lane = query row) and broadcast with shuffles.
+// =====================================================================================================================
+#define POOL_MEAN 0
+#define POOL_MAX 1
+
+__global__ void __launch_bounds__(128) entity_pool_fwd_kernel(AttnArgs a, const float* __restrict__ E, int pool_type) {
+    const int lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
+    const long long gw = (long long)blockIdx.x * wpc + (threadIdx.x >> 5), GW = (long long)gridDim.x * wpc;
+    const int ne = a.ne, nq = a.nq, d = a.d;
+    const float inv_ne = 1.f / (float)ne;
+    for (long long n = gw; n < a.N; n += GW) {
+        AttMeta m;
+        uint32_t mb[ATT_MAX_COPIES];
+        att_meta_load(a, n, lane, 0, m);
+        att_meta_resolve(a, n, lane, 0, 32, lane, m, mb);          // lane = query row: its mask word per copy
+        const float* e0 = E + (size_t)n * ne * d;
+        for (int col = lane * 4; col < d; col += 128) {
+            for (int c = 0; c < a.C; c++) {
+                for (int i = 0; i < nq; i++) {
+                    const uint32_t word = __shfl_sync(0xffffffffu, mb[c], i);
+                    float4 acc = pool_type == POOL_MAX ? make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY)
+                                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int j = 0; j < ne; j++) {
+                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (!((word >> j) & 1u)) v = __ldg(reinterpret_cast<const float4*>(e0 + (size_t)j * d + col));
+                        if (pool_type == POOL_MAX) {
+                            acc.x = fmaxf(acc.x, v.x); acc.y = fmaxf(acc.y, v.y); acc.z = fmaxf(acc.z, v.z); acc.w = fmaxf(acc.w, v.w);
+                        } else {
+                            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+                        }
+                    }
+                    if (pool_type == POOL_MEAN) { acc.x *= inv_ne; acc.y *= inv_ne; acc.z *= inv_ne; acc.w *= inv_ne; }
+                    *reinterpret_cast<float4*>(a.out + (((size_t)c * a.N + n) * nq + i) * d + col) = acc;
+                }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) entity_pool_bwd_kernel(AttnArgs a, const float* __restrict__ E, float* __restrict__ dE,
+                                                             int pool_type) {
+    const int lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
+    const long long gw = (long long)blockIdx.x * wpc + (threadIdx.x >> 5), GW = (long long)gridDim.x * wpc;
+    const int ne = a.ne, nq = a.nq, d = a.d;
+    const float inv_ne = 1.f / (float)ne;
+    for (long long n = gw; n < a.N; n += GW) {
+        AttMeta m;
+        uint32_t mb[ATT_MAX_COPIES];
+        att_meta_load(a, n, lane, 0, m);
+        att_meta_resolve(a, n, lane, 0, 32, lane, m, mb);
+        const float* e0 = E + (size_t)n * ne * d;
+        float* de0 = dE + (size_t)n * ne * d;
+        for (int col = lane * 4; col < d; col += 128) {
+            float4 acc[ATT_MAX_NE];                                 // gradient of my 4 columns of every entity row
+#pragma unroll
+            for (int j = 0; j < ATT_MAX_NE; j++) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int c = 0; c < a.C; c++) {
+                for (int i = 0; i < nq; i++) {
+                    const uint32_t word = __shfl_sync(0xffffffffu, mb[c], i);
+                    const float4 g = __ldg(reinterpret_cast<const float4*>(a.dout + (((size_t)c * a.N + n) * nq + i) * d + col));
+                    if (pool_type == POOL_MEAN) {
+#pragma unroll
+                        for (int j = 0; j < ATT_MAX_NE; j++)
+                            if (j < ne && !((word >> j) & 1u)) {
+                                acc[j].x += g.x * inv_ne; acc[j].y += g.y * inv_ne; acc[j].z += g.z * inv_ne; acc[j].w += g.w * inv_ne;
+                            }
+                    } else {
+                        // recompute the first arg-max per column; -1 = the maximum is a masked zero (no gradient)
+                        float4 best = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+                        int jx = -1, jy = -1, jz = -1, jw = -1;
+                        for (int j = 0; j < ne; j++) {
+                            const bool mk = (word >> j) & 1u;
+                            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (!mk) v = __ldg(reinterpret_cast<const float4*>(e0 + (size_t)j * d + col));
+                            const int id = mk ? -1 : j;
+                            if (v.x > best.x) { best.x = v.x; jx = id; }
+                            if (v.y > best.y) { best.y = v.y; jy = id; }
+                            if (v.z > best.z) { best.z = v.z; jz = id; }
+                            if (v.w > best.w) { best.w = v.w; jw = id; }
+                        }
+#pragma unroll
+                        for (int j = 0; j < ATT_MAX_NE; j++) {
+                            if (jx == j) acc[j].x += g.x;
+                            if (jy == j) acc[j].y += g.y;
+                            if (jz == j) acc[j].z += g.z;
+                            if (jw == j) acc[j].w += g.w;
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < ATT_MAX_NE; j++)
+                if (j < ne) *reinterpret_cast<float4*>(de0 + (size_t)j * d + col) = acc[j];
+        }
+    }
+}
+
+static int pool_fill(AttnArgs& a, const char* name, const float* E, const uint8_t* m0, const uint8_t* m1, const uint8_t* m2,
+                     long long s0, long long s1, long long s2, int mode0, int mode1, int mode2, const uint8_t* group_bits,
+                     const uint8_t* entity_mask, int N, int T, int ne, int nq, int d, int C, int pool_type) {
+    REFIL_CHECK_ARG(pool_type == POOL_MEAN || pool_type == POOL_MAX, "%s: pooling type %d (0 = mean, 1 = max)", name, pool_type);
+    REFIL_CHECK_ARG(d >= 4 && d % 4 == 0, "%s: embed dim %d must be a multiple of 4", name, d);
+    // same mask contract as the attention kernels (checked there with a formal head count of d / 8)
+    return attn_fill(a, E, m0, m1, m2, s0, s1, s2, mode0, mode1, mode2, group_bits, entity_mask, N, T, ne, nq, 8, 1, C) ||
+           ((a.d = d), REFIL_OK);
+}
+
+extern "C" int refil_entity_pool_fwd(const float* E, float* out, const uint8_t* mask0, const uint8_t* mask1,
+                                     const uint8_t* mask2, long long mask_stride0, long long mask_stride1,
+                                     long long mask_stride2, int mode0, int mode1, int mode2, const uint8_t* group_bits,
+                                     const uint8_t* entity_mask, int N, int T, int n_entities, int n_queries, int embed_dim,
+                                     int n_copies, int pool_type, cudaStream_t stream) {
+    AttnArgs a{};
+    int rc = pool_fill(a, "entity_pool_fwd", E, mask0, mask1, mask2, mask_stride0, mask_stride1, mask_stride2, mode0, mode1,
+                       mode2, group_bits, entity_mask, N, T, n_entities, n_queries, embed_dim, n_copies, pool_type);
+    if (rc) return rc;
+    REFIL_CHECK_ARG(out && ((uintptr_t)out % 16) == 0, "entity_pool_fwd: out is null / unaligned");
+    a.out = out;
+    int grid = refil_cdiv(N, 4);
+    if (grid > 8 * refil_num_sms()) grid = 8 * refil_num_sms();
+    entity_pool_fwd_kernel<<<grid, 128, 0, stream>>>(a, E, pool_type);
+    REFIL_CHECK_LAUNCH("entity_pool_fwd");
+    return REFIL_OK;
+}
+
+extern "C" int refil_entity_pool_bwd(const float* E, const float* dout, float* dE, const uint8_t* mask0, const uint8_t* mask1,
+                                     const uint8_t* mask2, long long mask_stride0, long long mask_stride1,
+                                     long long mask_stride2, int mode0, int mode1, int mode2, const uint8_t* group_bits,
+                                     const uint8_t* entity_mask, int N, int T, int n_entities, int n_queries, int embed_dim,
+                                     int n_copies, int pool_type, cudaStream_t stream) {
+    AttnArgs a{};
+    int rc = pool_fill(a, "entity_pool_bwd", E, mask0, mask1, mask2, mask_stride0, mask_stride1, mask_stride2, mode0, mode1,
+                       mode2, group_bits, entity_mask, N, T, n_entities, n_queries, embed_dim, n_copies, pool_type);
+    if (rc) return rc;
+    REFIL_CHECK_ARG(dout && dE && ((uintptr_t)dout % 16) == 0 && ((uintptr_t)dE % 16) == 0, "entity_pool_bwd: dout / dE");
+    a.dout = dout;
+    int grid = refil_cdiv(N, 4);
+    if (grid > 8 * refil_num_sms()) grid = 8 * refil_num_sms();
+    entity_pool_bwd_kernel<<<grid, 128, 0, stream>>>(a, E, dE, pool_type);
+    REFIL_CHECK_LAUNCH("entity_pool_bwd");
+    return REFIL_OK;
+}
+
 template <class K, class... Extra>
 static int attn_launch(K kernel, const AttnArgs& a, size_t smem, int grid, int warps, cudaStream_t stream,
                        const char* name, Extra... extra) {

@@ -79,7 +79,8 @@ class GroupMatchingBatch:
         _lib.call("gm_env_step", self.mt_key.data_ptr(), self.mt_pos.data_ptr(), self.loc.data_ptr(),
                   self.grp.data_ptr(), self.est.data_ptr(), self.ep_ret.data_ptr(), self._ptr(batch, "actions"),
                   self._ptr(batch, "entities"), self._ptr(batch, "obs_mask"), self._ptr(batch, "entity_mask"),
-                  self._ptr(batch, "avail_actions"), self._ptr(batch, "reward"), self._ptr(batch, "terminated"),
+                  self._ptr(batch, "gt_mask") if write_gt else None, self._ptr(batch, "avail_actions"),
+                  self._ptr(batch, "reward"), self._ptr(batch, "terminated"),
                   self._ptr(batch, "filled"), self.step_counter.data_ptr(), self.E, self.n_agents, self.n_entities,
                   self.n_states, self.n_groups, self.rand_trans, self.episode_limit, T, int(ts), int(env_offset),
                   torch.cuda.current_stream().cuda_stream)

@@ -37,23 +37,30 @@ class AttnTrunk:
     """x1 = relu(fc1([ents | onehot(last action)])); QKV = in_trans(x1); masked MHA for C mask copies;
     x2 = [relu] out_trans(.) with inactive-agent rows zeroed."""
 
-    def __init__(self, store, prefix, ws, tag, ein, d, n_heads, n_agents, n_actions):
+    def __init__(self, store, prefix, ws, tag, ein, d, n_heads, n_agents, n_actions, pooling_type=None):
         self.s, self.pre, self.ws, self.tag = store, prefix, ws, tag
         self.ein, self.d, self.H, self.na, self.A = ein, d, n_heads, n_agents, n_actions
+        self.pool = pooling_type      # None: EntityAttentionLayer; "mean" / "max": EntityPoolingLayer (attention.py:82-132)
         self.scratch = "scratch"      # tag prefix of the backward scratch buffers: nets that run concurrently use distinct ones
-        # attention.py:18-19 registers sqrt(head_dim) as a buffer: keep the key so checkpoints interchange
-        store.buffers[prefix + "attn.scale_factor"] = torch.tensor(float(d // n_heads)).sqrt()
+        if self.pool is None:
+            # attention.py:18-19 registers sqrt(head_dim) as a buffer: keep the key so checkpoints interchange
+            store.buffers[prefix + "attn.scale_factor"] = torch.tensor(float(d // n_heads)).sqrt()
 
     @staticmethod
-    def specs(prefix, ein, d):
-        return OrderedDict([(prefix + "fc1.weight", (d, ein)), (prefix + "fc1.bias", (d,)),
-                            (prefix + "attn.in_trans.weight", (3 * d, d)),
-                            (prefix + "attn.out_trans.weight", (d, d)), (prefix + "attn.out_trans.bias", (d,))])
+    def specs(prefix, ein, d, pooling_type=None):
+        if pooling_type is not None:      # EntityPoolingLayer: in_trans is d -> d WITH a bias (attention.py:92)
+            if pooling_type not in ops.POOL_TYPES:
+                raise ValueError("pooling_type %r not in %s" % (pooling_type, sorted(ops.POOL_TYPES)))
+            mid = [(prefix + "attn.in_trans.weight", (d, d)), (prefix + "attn.in_trans.bias", (d,))]
+        else:
+            mid = [(prefix + "attn.in_trans.weight", (3 * d, d))]
+        return OrderedDict([(prefix + "fc1.weight", (d, ein)), (prefix + "fc1.bias", (d,))] + mid +
+                           [(prefix + "attn.out_trans.weight", (d, d)), (prefix + "attn.out_trans.bias", (d,))])
 
     def init(self, gen):
         p, pre = self.s.p, self.pre
         init_linear_(gen, p[pre + "fc1.weight"], p[pre + "fc1.bias"])
-        init_linear_(gen, p[pre + "attn.in_trans.weight"])
+        init_linear_(gen, p[pre + "attn.in_trans.weight"], p.get(pre + "attn.in_trans.bias"))
         init_linear_(gen, p[pre + "attn.out_trans.weight"], p[pre + "attn.out_trans.bias"])
 
     def forward(self, ents, la, masks, T, relu_out=False, xin=None):
@@ -69,10 +76,15 @@ class AttnTrunk:
             ops.linear_fwd(xin, w1p, p[pre + "fc1.bias"], x1, relu=True)
         else:
             ops.embed_fwd(ents, la, self.A, p[pre + "fc1.weight"], p[pre + "fc1.bias"], x1, relu=True)
-        qkv = ws.get(tag + ".qkv", (N * ne, 3 * d))
-        ops.linear_fwd(x1, p[pre + "attn.in_trans.weight"], None, qkv)
         att = ws.get(tag + ".att", (C * N * na, d))
-        ops.masked_attn_fwd(qkv, att, masks.copies, masks.group_bits, masks.entity_mask, N, T, ne, na, d, self.H)
+        if self.pool is None:
+            qkv = ws.get(tag + ".qkv", (N * ne, 3 * d))
+            ops.linear_fwd(x1, p[pre + "attn.in_trans.weight"], None, qkv)
+            ops.masked_attn_fwd(qkv, att, masks.copies, masks.group_bits, masks.entity_mask, N, T, ne, na, d, self.H)
+        else:                               # pooling ablation: qkv holds E = in_trans(x1) [N*ne, d]
+            qkv = ws.get(tag + ".qkv", (N * ne, d))
+            ops.linear_fwd(x1, p[pre + "attn.in_trans.weight"], p[pre + "attn.in_trans.bias"], qkv)
+            ops.entity_pool_fwd(qkv, att, masks.copies, masks.group_bits, masks.entity_mask, N, T, ne, na, d, self.pool)
         x2 = ws.get(tag + ".x2", (C * N * na, d))
         self.row_mask = (masks.entity_mask, na, N * na) if masks.entity_mask is not None else None
         ops.linear_fwd(att, p[pre + "attn.out_trans.weight"], p[pre + "attn.out_trans.bias"], x2, relu=relu_out,
@@ -89,9 +101,14 @@ class AttnTrunk:
                               relu_y=relu_y, row_mask=self.row_mask)
         datt = ws.get(self.scratch + ".datt", (C * N * na, d))
         ops.linear_bwd_data(dx2, p[pre + "attn.out_trans.weight"], datt, relu_y=relu_y, row_mask=self.row_mask)
-        dqkv = ws.get(self.scratch + ".dqkv", (N * ne, 3 * d))
-        ops.masked_attn_bwd(qkv, datt, dqkv, masks.copies, masks.group_bits, masks.entity_mask, N, T, ne, na, d, self.H)
-        ops.linear_bwd_weight(dqkv, x1, g[pre + "attn.in_trans.weight"], None)
+        if self.pool is None:
+            dqkv = ws.get(self.scratch + ".dqkv", (N * ne, 3 * d))
+            ops.masked_attn_bwd(qkv, datt, dqkv, masks.copies, masks.group_bits, masks.entity_mask, N, T, ne, na, d, self.H)
+            ops.linear_bwd_weight(dqkv, x1, g[pre + "attn.in_trans.weight"], None)
+        else:
+            dqkv = ws.get(self.scratch + ".dqkv", (N * ne, d))
+            ops.entity_pool_bwd(qkv, datt, dqkv, masks.copies, masks.group_bits, masks.entity_mask, N, T, ne, na, d, self.pool)
+            ops.linear_bwd_weight(dqkv, x1, g[pre + "attn.in_trans.weight"], g[pre + "attn.in_trans.bias"])
         dx1 = ws.get(self.scratch + ".dx1", (N * ne, d))
         ops.linear_bwd_data(dqkv, p[pre + "attn.in_trans.weight"], dx1)
         if xin is not None:
@@ -112,7 +129,8 @@ class EntityAttnAgent:
         self.ein, self.d, self.H = int(input_shape), int(args.attn_embed_dim), int(args.attn_n_heads)
         self.na, self.A, self.r = int(args.n_agents), int(args.n_actions), int(args.rnn_hidden_dim)
         self.one_hot_la = bool(args.entity_last_action)
-        specs = AttnTrunk.specs("", self.ein, self.d)
+        self.pool = getattr(args, "pooling_type", None)
+        specs = AttnTrunk.specs("", self.ein, self.d, self.pool)
         if self.rnn:
             specs.update(OrderedDict([("fc2.weight", (self.r, self.d)), ("fc2.bias", (self.r,)),
                                       ("rnn.weight_ih", (3 * self.r, self.r)), ("rnn.weight_hh", (3 * self.r, self.r)),
@@ -123,7 +141,7 @@ class EntityAttnAgent:
         self.store = ParamStore(specs, device)
         self.ws = ws if ws is not None else Workspace(device)
         self.tag = tag
-        self.trunk = AttnTrunk(self.store, "", self.ws, tag, self.ein, self.d, self.H, self.na, self.A)
+        self.trunk = AttnTrunk(self.store, "", self.ws, tag, self.ein, self.d, self.H, self.na, self.A, self.pool)
         # like nn.Linear, draw from the GLOBAL torch RNG (a private generator seeded with torch.initial_seed() made the
         # agent's and the mixer's first layers bit-identical whenever their shapes matched)
         gen = torch.Generator().manual_seed(int(seed)) if seed is not None else None
@@ -239,11 +257,12 @@ class AttnHyperNet:
     def __init__(self, store, prefix, ws, tag, args, ein):
         self.s, self.pre, self.ws, self.tag = store, prefix, ws, tag
         self.he, self.me, self.na = int(args.hypernet_embed), int(args.mixing_embed_dim), int(args.n_agents)
-        self.trunk = AttnTrunk(store, prefix, ws, tag, ein, self.he, int(args.attn_n_heads), self.na, int(args.n_actions))
+        self.trunk = AttnTrunk(store, prefix, ws, tag, ein, self.he, int(args.attn_n_heads), self.na, int(args.n_actions),
+                               getattr(args, "pooling_type", None))
 
     @staticmethod
-    def specs(prefix, ein, he, me):
-        s = AttnTrunk.specs(prefix, ein, he)
+    def specs(prefix, ein, he, me, pooling_type=None):
+        s = AttnTrunk.specs(prefix, ein, he, pooling_type)
         s.update(OrderedDict([(prefix + "fc2.weight", (me, he)), (prefix + "fc2.bias", (me,))]))
         return s
 
@@ -284,7 +303,8 @@ class Mixer:
         self.tag = tag
         specs = OrderedDict()
         for h in self.HYPERS[args.mixer]:
-            specs.update(AttnHyperNet.specs(h, ein, int(args.hypernet_embed), self.me))  # vdn: no hypernets
+            specs.update(AttnHyperNet.specs(h, ein, int(args.hypernet_embed), self.me,
+                                            getattr(args, "pooling_type", None)))  # vdn: no hypernets
         self.store = ParamStore(specs, device)
         self.nets = OrderedDict((h, AttnHyperNet(self.store, h, self.ws, tag + "." + h, args, ein))
                                 for h in self.HYPERS[args.mixer])

@@ -221,6 +221,24 @@ def masked_attn_bwd(qkv, dout, dqkv, copies, group_bits, entity_mask, N, T, ne, 
     return dqkv
 
 
+POOL_TYPES = {"mean": 0, "max": 1}
+
+
+def entity_pool_fwd(E, out, copies, group_bits, entity_mask, N, T, ne, nq, d, pool_type):
+    """EntityPoolingLayer between in_trans and out_trans (attention.py:111-124): E [N*ne, d] -> out [C*N*nq, d]."""
+    _account("entity_pool_fwd", 0.0, 4.0 * d * (ne + nq * len(copies)) * N)
+    _call("entity_pool_fwd", _p(E, F32), _p(out, F32), *_copies(copies), _p(group_bits, U8), _p(entity_mask, U8),
+          N, T, ne, nq, d, len(copies), POOL_TYPES[pool_type])
+    return out
+
+
+def entity_pool_bwd(E, dout, dE, copies, group_bits, entity_mask, N, T, ne, nq, d, pool_type):
+    _account("entity_pool_bwd", 0.0, 4.0 * d * (2 * ne + nq * len(copies)) * N)
+    _call("entity_pool_bwd", _p(E, F32), _p(dout, F32), _p(dE, F32), *_copies(copies), _p(group_bits, U8),
+          _p(entity_mask, U8), N, T, ne, nq, d, len(copies), POOL_TYPES[pool_type])
+    return dE
+
+
 # ---------------------------------------------------------------------------------------------------- GRU
 def gru_scan_fwd(GI, Whh, bhh, h0, HS, gates, n_seq, T, na):
     r = Whh.shape[1]

@@ -236,6 +236,11 @@ if __name__ == "__main__":
     make_learner_case("qmix_atten_gm_gtobs", "qmix_atten_group_matching", B=3, T=5, na=4, ne=4, ed=12, A=3, seed=20, gt=True,
                       gt_obs_mask=True, attn_embed_dim=32, attn_n_heads=4, hypernet_embed=32, mixing_embed_dim=8)
     make_learner_case("refil_gtflag", "refil", B=2, T=4, na=3, ne=5, ed=6, A=4, seed=22, train_gt_factors=True, **SMALL)
+    # EntityPoolingLayer ablations (modules/layers/attention.py:82-132; `pooling_type` of config/default.yaml:43)
+    make_learner_case("refil_pool_mean", "refil", B=3, T=5, na=3, ne=5, ed=6, A=4, seed=23, pooling_type="mean", **SMALL)
+    make_learner_case("qmix_atten_pool_max", "qmix_atten", B=3, T=5, na=3, ne=5, ed=6, A=4, seed=24, pooling_type="max", **SMALL)
+    make_learner_case("refil_gm_pool_max", "refil_group_matching", B=3, T=5, na=4, ne=4, ed=12, A=3, seed=25, gt=True,
+                      pooling_type="max", attn_embed_dim=32, attn_n_heads=4, hypernet_embed=32, mixing_embed_dim=8)
     if NEW_ONLY:
         sys.exit(0)
     make_env_transcripts()

@@ -152,3 +152,33 @@ def test_bench_reference_arm_schema():
 def test_bench_reference_arm_port_fallback():
     d = _run_reference_arm({"REFIL_REF_FORCE_PORT": "1"})
     assert d["cpu_baseline"]["kind"] == "port" and d["value"] > 0
+
+
+def test_python_call_sites_match_header_arity():
+    """Every `_lib.call("name", ...)` / `ops._call("name", ...)` site in the host package passes as many arguments as the C
+    prototype declares (ctypes only complains at run time, i.e. on the GPU box)."""
+    import ast
+    import glob
+    from refil_b200 import _lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    checked = 0
+    for path in glob.glob(os.path.join(root, "refil_b200", "**", "*.py"), recursive=True):
+        tree = ast.parse(open(path).read())
+        for node in ast.walk(tree):
+            if not isinstance(node, ast.Call) or not node.args or not isinstance(node.args[0], ast.Constant):
+                continue
+            f = node.func
+            fname = f.attr if isinstance(f, ast.Attribute) else getattr(f, "id", "")
+            if fname not in ("call", "_call") or not isinstance(node.args[0].value, str):
+                continue
+            proto = _lib.PROTOS.get("refil_" + node.args[0].value)
+            if proto is None:
+                continue
+            n = len(node.args) - 1 + (1 if fname == "_call" else 0)      # ops._call appends the stream
+            star = sum(isinstance(x, ast.Starred) for x in node.args)
+            if star:
+                n += star * (9 - 1)                                       # ops._copies(): 3 masks + 3 strides + 3 modes
+            assert n == len(proto[1]), "%s:%d refil_%s: %d args passed, header declares %d" % (
+                os.path.relpath(path, root), node.lineno, node.args[0].value, n, len(proto[1]))
+            checked += 1
+    assert checked >= 25

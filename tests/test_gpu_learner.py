@@ -77,12 +77,23 @@ def test_train_step_matches_reference(name):
         assert float((learner.mixer.store.p[k].cpu() - p).abs().max()) <= 1e-4, k
 
 
-@pytest.mark.parametrize("alg", ["refil", "qmix_atten", "refil_gm"])
+@pytest.mark.parametrize("alg", ["refil", "qmix_atten", "refil_gm", "refil_pool_mean", "refil_pool_max", "refil_cfg5"])
 def test_train_step_matches_oracle_mid_size(alg):
-    """Same seeded inputs through the CUDA path and the CPU oracle at a size the oracle finishes in seconds."""
+    """Same seeded inputs through the CUDA path and the CPU oracle at a size the oracle finishes in seconds.  `refil_cfg5` is
+    BASELINE config 5's shape (sc2 3-8csz: 16 entities, T = 120) on 2 episodes; `refil_pool_*` the EntityPoolingLayer ablation at
+    the real layer widths."""
     from oracle import learner_oracle as lo
     gen = torch.Generator().manual_seed(123)
-    if alg == "refil_gm":
+    pool = alg.split("_pool_")[1] if "_pool_" in alg else None
+    if alg == "refil_cfg5":
+        B, T, na, ne, ed, A = 2, 120, 8, 16, 39, 14
+        args = lo.default_args(agent="imagine_entity_attend_rnn")
+        alg = "refil"
+    elif pool:
+        B, T, na, ne, ed, A = 5, 12, 8, 24, 39, 14
+        args = lo.default_args(agent="imagine_entity_attend_rnn", pooling_type=pool)
+        alg = "refil"
+    elif alg == "refil_gm":
         B, T, na, ne, ed, A = 6, 9, 4, 4, 12, 3
         args = lo.default_args(agent="imagine_entity_attend_ff", mixer="lin_flex_qmix", attn_embed_dim=64,
                                hypernet_embed=64, entity_last_action=False)
