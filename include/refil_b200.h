@@ -116,9 +116,11 @@ int refil_tc_gemm_supported(int M, int N, int K);
 int refil_tc_gemm_k_slices(int N, int K);
 int refil_tc_gemm_tn(const float* A, long long lda, const float* relu_y, long long ldy,
                      const uint8_t* a_row_entity_mask, int a_na, int a_ne, int a_rows_per_copy, const float* B,
-                     long long b_stride_n, long long b_stride_k, const float* bias, int relu,
-                     const uint8_t* c_row_entity_mask, int c_na, int c_ne, int c_rows_per_copy, float* C,
-                     long long ldc, int M, int N, int K, cudaStream_t stream);
+                     long long b_stride_n, long long b_stride_k,
+                     int b_k_valid /* B is taken as zero for reduction indices >= b_k_valid (0: K): a weight whose true fan-in is
+                     not a multiple of 32 (fc1: 53, action head: 14) is read in place, no padded copy */,
+                     const float* bias, int relu, const uint8_t* c_row_entity_mask, int c_na, int c_ne, int c_rows_per_copy,
+                     float* C, long long ldc, int M, int N, int K, cudaStream_t stream);
 
 /* weight gradient on the tensor cores: dW[P,Q] += g(X)[M,P]^T Y[M,Q]; db[P] += colsum g(X) (db may be null).
  * y_shift_rows > 0: Y row m is read from row m - y_shift_rows and is zero where (m / y_shift_rows) % y_period == 0
@@ -126,8 +128,9 @@ int refil_tc_gemm_tn(const float* A, long long lda, const float* relu_y, long lo
 int refil_tc_wgrad_supported(int M, int P, int Q);
 int refil_tc_gemm_wgrad(const float* X, long long ldx, const float* relu_y, long long ldy,
                         const uint8_t* x_row_entity_mask, int na, int ne, int rows_per_copy, const float* Y,
-                        long long ldyy, int y_shift_rows, int y_period, float* dW, long long lddw, float* db, int M,
-                        int P, int Q, cudaStream_t stream);
+                        long long ldyy, int y_shift_rows, int y_period, float* dW, long long lddw,
+                        int q_valid /* dW has q_valid <= Q columns (0: Q); the rest of Y is zero padding */, float* db,
+                        int M, int P, int Q, cudaStream_t stream);
 
 /* ---- masked multi-head attention over entities: modules/layers/attention.py:43-64 with the mask algebra of
  *      agents/entity_rnn_agent.py:79-124 resolved on the fly.  QKV [N, ne, 3d]; OUT / dOUT [C, N, nq, d].

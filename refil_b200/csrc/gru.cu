@@ -10,6 +10,8 @@
 //   GI [R, 3r]  HS [R, r]  GATES [R, 4r] = (r | z | n | W_hn h + b_hn)   dHS [R, r]  dGI [R, 3r]  dGH [R, 3r]
 // Thread mapping: 128 threads = (128/r) groups x r features; every thread owns feature j of 4 sequences, so the
 // recurrent mat-vec runs 12 FMAs per 3 conflict-free weight loads + 1 broadcast 128-bit state load.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 #define GRU_THREADS 128
@@ -363,6 +365,334 @@ __global__ void __launch_bounds__(R) gru_scan_bwd8_kernel(const float* __restric
     }
 }
 
+static bool gru_use_mma() {
+    static int mode = -1;
+    if (mode < 0) {
+        const char* e = getenv("REFIL_GRU_MODE");
+        mode = (e && e[0] == 'f') ? 0 : 1;
+    }
+    return mode == 1;
+}
+
+static int gru_set_smem_attr(const void* kernel, size_t smem, const char* name) {
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) {
+            refil_set_error("%s: cudaFuncSetAttribute: %s", name, cudaGetErrorString(e));
+            return REFIL_ERR_CUDA;
+        }
+    }
+    return REFIL_OK;
+}
+
+// =====================================================================================================================
+// Tensor-core scans (hidden size 32 / 64): the per-step recurrent product is a small GEMM -- [16 sequences x R] x [R x 3R]
+// forward, [16 x 3R] x [3R x R] backward -- issued as warp-level mma.sync m16n8k8 TF32 with the same 3xTF32 hi/lo split as the
+// dense layers (fp32-grade: ~2^-21 relative per product).  The FFMA scans above spend ~780 warp instructions per (sequence,
+// step) and ~3 us per step however few sequences a CTA holds (ncu r2d: one warp per scheduler, stalled on shared-memory
+// latency); here
+//   * W_hh lives in REGISTERS as pre-split B fragments (warp w owns features [8w, 8w+8) of all three gates: 96 registers at
+//     R = 64), loaded once per launch;
+//   * the state h (forward) / the gate gradients (backward) of the CTA's 16 x MT sequences sit in a double-buffered
+//     shared-memory tile, padded so that the A-fragment reads of a warp hit 32 distinct banks; ONE __syncthreads per step;
+//   * the accumulator fragment of a thread -- rows gid, gid + 8, features 8w + 2 tig, + 1 -- is exactly the set of
+//     (sequence, feature) pairs whose gate math it does, so the MMA result never leaves registers;
+//   * the global inputs of step t + 1 are requested before step t is computed.
+// 72 x MT mma per warp and step; a 16-episode shard (384 sequences) runs on 24 CTAs in ~0.5 us per step.
+// =====================================================================================================================
+__device__ __forceinline__ void gru_mma_tf32(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                             uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void gru_split(float x, uint32_t& hi, uint32_t& lo) {
+    hi = __float_as_uint(x) & 0xffffe000u;
+    lo = __float_as_uint(x - __uint_as_float(hi));
+}
+// acc += A (4 fp32 fragment values) x B (pre-split fragment), three TF32 passes
+__device__ __forceinline__ void gru_mma3(float (&c)[4], const float (&a)[4], const uint32_t (&bh)[2], const uint32_t (&bl)[2]) {
+    uint32_t ah[4], al[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) gru_split(a[i], ah[i], al[i]);
+    gru_mma_tf32(c, al[0], al[1], al[2], al[3], bh[0], bh[1]);
+    gru_mma_tf32(c, ah[0], ah[1], ah[2], ah[3], bl[0], bl[1]);
+    gru_mma_tf32(c, ah[0], ah[1], ah[2], ah[3], bh[0], bh[1]);
+}
+
+template <int R, int MT>
+__global__ void __launch_bounds__(R * 4, 1) gru_scan_fwd_mma_kernel(const float* __restrict__ GI, const float* __restrict__ Whh,
+                                                                    const float* __restrict__ bhh, const float* __restrict__ h0,
+                                                                    float* __restrict__ HS, float* __restrict__ GATES, int n_seq,
+                                                                    int T, int na) {
+    constexpr int KT = R / 8, LD = R + 4, NT = R * 4;      // R / 8 warps, one per 8 features
+    __shared__ float hsm[2][MT * 16][LD];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gid = lane >> 2, tig = lane & 3;
+    const int f0 = 8 * warp + 2 * tig;                     // my two features f0, f0 + 1 (accumulator columns 2 tig, 2 tig + 1)
+    // B fragments: B[k][n] = Whh[g * R + 8 warp + n][k]; b0: k = 8 kt + tig, b1: k + 4; n = gid
+    uint32_t bh[KT][3][2], bl[KT][3][2];
+#pragma unroll
+    for (int kt = 0; kt < KT; kt++)
+#pragma unroll
+        for (int g = 0; g < 3; g++)
+#pragma unroll
+            for (int h = 0; h < 2; h++)
+                gru_split(__ldg(Whh + (size_t)(g * R + 8 * warp + gid) * R + 8 * kt + tig + 4 * h), bh[kt][g][h], bl[kt][g][h]);
+    float bias[3][2];
+#pragma unroll
+    for (int g = 0; g < 3; g++) { bias[g][0] = __ldg(bhh + g * R + f0); bias[g][1] = __ldg(bhh + g * R + f0 + 1); }
+    // my sequences: rows gid and gid + 8 of every 16-row m-tile
+    long long row0[MT][2];
+    bool valid[MT][2];
+    float hreg[MT][2][2];
+    const int sbase = blockIdx.x * (MT * 16);
+#pragma unroll
+    for (int m = 0; m < MT; m++)
+#pragma unroll
+        for (int hr = 0; hr < 2; hr++) {
+            const int s = sbase + m * 16 + gid + 8 * hr;
+            valid[m][hr] = s < n_seq;
+            const int cb = valid[m][hr] ? s / na : 0, a = valid[m][hr] ? s - cb * na : 0;
+            row0[m][hr] = ((long long)cb * T) * na + a;
+            float2 hv = make_float2(0.f, 0.f);
+            if (valid[m][hr] && h0) hv = __ldg(reinterpret_cast<const float2*>(h0 + (size_t)s * R + f0));
+            hreg[m][hr][0] = hv.x; hreg[m][hr][1] = hv.y;
+            hsm[0][m * 16 + gid + 8 * hr][f0] = hv.x;
+            hsm[0][m * 16 + gid + 8 * hr][f0 + 1] = hv.y;
+        }
+    float2 gn[MT][2][3];                                   // input projections of the next step
+    auto load_gi = [&](int t) {
+#pragma unroll
+        for (int m = 0; m < MT; m++)
+#pragma unroll
+            for (int hr = 0; hr < 2; hr++) {
+                const float* g = GI + (size_t)(row0[m][hr] + (long long)t * na) * 3 * R + f0;
+#pragma unroll
+                for (int gg = 0; gg < 3; gg++)
+                    gn[m][hr][gg] = valid[m][hr] ? __ldg(reinterpret_cast<const float2*>(g + gg * R)) : make_float2(0.f, 0.f);
+            }
+    };
+    load_gi(0);
+    __syncthreads();
+    int cur = 0;
+    for (int t = 0; t < T; t++) {
+        float2 gi[MT][2][3];
+#pragma unroll
+        for (int m = 0; m < MT; m++)
+#pragma unroll
+            for (int hr = 0; hr < 2; hr++)
+#pragma unroll
+                for (int gg = 0; gg < 3; gg++) gi[m][hr][gg] = gn[m][hr][gg];
+        if (t + 1 < T) load_gi(t + 1);
+        float acc[MT][3][4];
+#pragma unroll
+        for (int m = 0; m < MT; m++)
+#pragma unroll
+            for (int g = 0; g < 3; g++) { acc[m][g][0] = bias[g][0]; acc[m][g][1] = bias[g][1]; acc[m][g][2] = bias[g][0]; acc[m][g][3] = bias[g][1]; }
+#pragma unroll
+        for (int kt = 0; kt < KT; kt++) {
+#pragma unroll
+            for (int m = 0; m < MT; m++) {
+                const float* hb = &hsm[cur][m * 16][0];
+                float a[4];
+                a[0] = hb[gid * LD + 8 * kt + tig];
+                a[1] = hb[(gid + 8) * LD + 8 * kt + tig];
+                a[2] = hb[gid * LD + 8 * kt + tig + 4];
+                a[3] = hb[(gid + 8) * LD + 8 * kt + tig + 4];
+#pragma unroll
+                for (int g = 0; g < 3; g++) gru_mma3(acc[m][g], a, bh[kt][g], bl[kt][g]);
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < MT; m++)
+#pragma unroll
+            for (int hr = 0; hr < 2; hr++) {
+                float hn[2], rgv[2], zgv[2], ngv[2], anv[2];
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    const float ar = acc[m][0][2 * hr + e], az = acc[m][1][2 * hr + e], an = acc[m][2][2 * hr + e];
+                    const float gir = e ? gi[m][hr][0].y : gi[m][hr][0].x, giz = e ? gi[m][hr][1].y : gi[m][hr][1].x,
+                                gin = e ? gi[m][hr][2].y : gi[m][hr][2].x;
+                    const float rg = sigmoidf_(gir + ar), zg = sigmoidf_(giz + az);
+                    const float ng = tanhf(gin + rg * an);
+                    hn[e] = (hreg[m][hr][e] - ng) * zg + ng;
+                    hreg[m][hr][e] = hn[e];
+                    rgv[e] = rg; zgv[e] = zg; ngv[e] = ng; anv[e] = an;
+                }
+                float* hw = &hsm[cur ^ 1][m * 16 + gid + 8 * hr][f0];
+                hw[0] = hn[0]; hw[1] = hn[1];
+                if (valid[m][hr]) {
+                    const size_t row = (size_t)(row0[m][hr] + (long long)t * na);
+                    *reinterpret_cast<float2*>(HS + row * R + f0) = make_float2(hn[0], hn[1]);
+                    if (GATES) {
+                        float* g = GATES + row * 4 * R + f0;
+                        *reinterpret_cast<float2*>(g) = make_float2(rgv[0], rgv[1]);
+                        *reinterpret_cast<float2*>(g + R) = make_float2(zgv[0], zgv[1]);
+                        *reinterpret_cast<float2*>(g + 2 * R) = make_float2(ngv[0], ngv[1]);
+                        *reinterpret_cast<float2*>(g + 3 * R) = make_float2(anv[0], anv[1]);
+                    }
+                }
+            }
+        __syncthreads();
+        cur ^= 1;
+    }
+    (void)NT;
+}
+
+template <int R, int MT>
+__global__ void __launch_bounds__(R * 4, 1) gru_scan_bwd_mma_kernel(const float* __restrict__ dHS, const float* __restrict__ GATES,
+                                                                    const float* __restrict__ HS, const float* __restrict__ h0,
+                                                                    const float* __restrict__ Whh, float* __restrict__ dGI,
+                                                                    float* __restrict__ dGH, int n_seq, int T, int na) {
+    constexpr int KT = 3 * R / 8, LD = 3 * R + 4;          // reduction over the 3R gate rows of W_hh
+    extern __shared__ __align__(16) float smem_g[];        // [2][MT * 16][LD]: (d_r | d_z | d_nh) of the CTA's sequences
+    float (*sg)[LD] = reinterpret_cast<float (*)[LD]>(smem_g);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gid = lane >> 2, tig = lane & 3;
+    const int f0 = 8 * warp + 2 * tig;
+    // B fragments: B[k = gj][n] = Whh[gj][8 warp + n]; b0: gj = 8 kt + tig, b1: gj + 4; n = gid
+    uint32_t bh[KT][2], bl[KT][2];
+#pragma unroll
+    for (int kt = 0; kt < KT; kt++)
+#pragma unroll
+        for (int h = 0; h < 2; h++)
+            gru_split(__ldg(Whh + (size_t)(8 * kt + tig + 4 * h) * R + 8 * warp + gid), bh[kt][h], bl[kt][h]);
+    long long row0[MT][2];
+    bool valid[MT][2];
+    int sidx[MT][2];
+    float dh[MT][2][2];
+    const int sbase = blockIdx.x * (MT * 16);
+#pragma unroll
+    for (int m = 0; m < MT; m++)
+#pragma unroll
+        for (int hr = 0; hr < 2; hr++) {
+            const int s = sbase + m * 16 + gid + 8 * hr;
+            valid[m][hr] = s < n_seq;
+            sidx[m][hr] = s;
+            const int cb = valid[m][hr] ? s / na : 0, a = valid[m][hr] ? s - cb * na : 0;
+            row0[m][hr] = ((long long)cb * T) * na + a;
+            dh[m][hr][0] = 0.f; dh[m][hr][1] = 0.f;
+        }
+    // inputs of one step: gates (r, z, n, W_hn h + b_hn), previous state, upstream gradient
+    float2 nx[MT][2][6];
+    auto load_step = [&](int t) {
+#pragma unroll
+        for (int m = 0; m < MT; m++)
+#pragma unroll
+            for (int hr = 0; hr < 2; hr++) {
+#pragma unroll
+                for (int q = 0; q < 6; q++) nx[m][hr][q] = make_float2(0.f, 0.f);
+                if (valid[m][hr]) {
+                    const size_t row = (size_t)(row0[m][hr] + (long long)t * na);
+                    const float* g = GATES + row * 4 * R + f0;
+#pragma unroll
+                    for (int q = 0; q < 4; q++) nx[m][hr][q] = __ldg(reinterpret_cast<const float2*>(g + q * R));
+                    if (t > 0) nx[m][hr][4] = __ldg(reinterpret_cast<const float2*>(HS + (row - na) * R + f0));
+                    else if (h0) nx[m][hr][4] = __ldg(reinterpret_cast<const float2*>(h0 + (size_t)sidx[m][hr] * R + f0));
+                    nx[m][hr][5] = __ldg(reinterpret_cast<const float2*>(dHS + row * R + f0));
+                }
+            }
+    };
+    load_step(T - 1);
+    int cur = 0;
+    for (int t = T - 1; t >= 0; t--) {
+        float keep[MT][2][2];
+        float (*sc)[LD] = sg + cur * (MT * 16);
+#pragma unroll
+        for (int m = 0; m < MT; m++)
+#pragma unroll
+            for (int hr = 0; hr < 2; hr++) {
+                float dr[2], dz_[2], dn[2], dnh[2];
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    const float rg = e ? nx[m][hr][0].y : nx[m][hr][0].x, zg = e ? nx[m][hr][1].y : nx[m][hr][1].x,
+                                ng = e ? nx[m][hr][2].y : nx[m][hr][2].x, hn = e ? nx[m][hr][3].y : nx[m][hr][3].x,
+                                hp = e ? nx[m][hr][4].y : nx[m][hr][4].x, du = e ? nx[m][hr][5].y : nx[m][hr][5].x;
+                    const float d = dh[m][hr][e] + du;
+                    // h' = (hp - n) z + n
+                    const float dz = d * (hp - ng);
+                    const float dnn = d * (1.f - zg);
+                    keep[m][hr][e] = valid[m][hr] ? d * zg : 0.f;
+                    dn[e] = valid[m][hr] ? dnn * (1.f - ng * ng) : 0.f;
+                    dnh[e] = dn[e] * rg;
+                    dr[e] = dn[e] * hn * rg * (1.f - rg);
+                    dz_[e] = valid[m][hr] ? dz * zg * (1.f - zg) : 0.f;
+                }
+                float* srow = &sc[m * 16 + gid + 8 * hr][f0];
+                srow[0] = dr[0]; srow[1] = dr[1];
+                srow[R] = dz_[0]; srow[R + 1] = dz_[1];
+                srow[2 * R] = dnh[0]; srow[2 * R + 1] = dnh[1];
+                if (valid[m][hr]) {
+                    const size_t row = (size_t)(row0[m][hr] + (long long)t * na);
+                    float* o = dGI + row * 3 * R + f0;
+                    *reinterpret_cast<float2*>(o) = make_float2(dr[0], dr[1]);
+                    *reinterpret_cast<float2*>(o + R) = make_float2(dz_[0], dz_[1]);
+                    *reinterpret_cast<float2*>(o + 2 * R) = make_float2(dn[0], dn[1]);
+                    float* o2 = dGH + row * 3 * R + f0;
+                    *reinterpret_cast<float2*>(o2) = make_float2(dr[0], dr[1]);
+                    *reinterpret_cast<float2*>(o2 + R) = make_float2(dz_[0], dz_[1]);
+                    *reinterpret_cast<float2*>(o2 + 2 * R) = make_float2(dnh[0], dnh[1]);
+                }
+            }
+        if (t > 0) load_step(t - 1);                  // next step's inputs in flight during the product below
+        __syncthreads();
+        // dh_prev[seq][k] = keep + sum_gj (d_r | d_z | d_nh)[seq][gj] * Whh[gj][k]; three independent accumulator chains
+        float acc[MT][3][4];
+#pragma unroll
+        for (int m = 0; m < MT; m++) {
+#pragma unroll
+            for (int c = 0; c < 3; c++)
+#pragma unroll
+                for (int e = 0; e < 4; e++) acc[m][c][e] = 0.f;
+            acc[m][0][0] = keep[m][0][0]; acc[m][0][1] = keep[m][0][1]; acc[m][0][2] = keep[m][1][0]; acc[m][0][3] = keep[m][1][1];
+        }
+#pragma unroll
+        for (int kt = 0; kt < KT; kt++) {
+#pragma unroll
+            for (int m = 0; m < MT; m++) {
+                const float* ab = &sc[m * 16][0];
+                float a[4];
+                a[0] = ab[gid * LD + 8 * kt + tig];
+                a[1] = ab[(gid + 8) * LD + 8 * kt + tig];
+                a[2] = ab[gid * LD + 8 * kt + tig + 4];
+                a[3] = ab[(gid + 8) * LD + 8 * kt + tig + 4];
+                gru_mma3(acc[m][kt % 3], a, bh[kt], bl[kt]);
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < MT; m++) {
+            dh[m][0][0] = acc[m][0][0] + acc[m][1][0] + acc[m][2][0];
+            dh[m][0][1] = acc[m][0][1] + acc[m][1][1] + acc[m][2][1];
+            dh[m][1][0] = acc[m][0][2] + acc[m][1][2] + acc[m][2][2];
+            dh[m][1][1] = acc[m][0][3] + acc[m][1][3] + acc[m][2][3];
+        }
+        cur ^= 1;                                     // the other buffer is written next step: one barrier per step
+    }
+}
+
+// MT = m16 tiles (16 sequences each) per CTA: one while the sequences fit one wave of CTAs, else two
+template <int R>
+static int gru_launch_mma(bool fwd, const float* a0, const float* a1, const float* a2, const float* a3, const float* a4,
+                          float* o0, float* o1, int n_seq, int T, int na, cudaStream_t stream) {
+    const int mt = refil_cdiv(n_seq, 16) > refil_num_sms() ? 2 : 1;
+    const int grid = refil_cdiv(n_seq, 16 * mt);
+    if (fwd) {
+        if (mt == 1) gru_scan_fwd_mma_kernel<R, 1><<<grid, R * 4, 0, stream>>>(a0, a1, a2, a3, o0, o1, n_seq, T, na);
+        else gru_scan_fwd_mma_kernel<R, 2><<<grid, R * 4, 0, stream>>>(a0, a1, a2, a3, o0, o1, n_seq, T, na);
+        return REFIL_OK;
+    }
+    const size_t smem = (size_t)2 * mt * 16 * (3 * R + 4) * sizeof(float);
+    if (mt == 1) {
+        int rc = gru_set_smem_attr((const void*)gru_scan_bwd_mma_kernel<R, 1>, smem, "gru_scan_bwd");
+        if (rc) return rc;
+        gru_scan_bwd_mma_kernel<R, 1><<<grid, R * 4, smem, stream>>>(a0, a1, a2, a3, a4, o0, o1, n_seq, T, na);
+    } else {
+        int rc = gru_set_smem_attr((const void*)gru_scan_bwd_mma_kernel<R, 2>, smem, "gru_scan_bwd");
+        if (rc) return rc;
+        gru_scan_bwd_mma_kernel<R, 2><<<grid, R * 4, smem, stream>>>(a0, a1, a2, a3, a4, o0, o1, n_seq, T, na);
+    }
+    return REFIL_OK;
+}
+
 static int gru_check(const char* name, int n_seq, int T, int na, int r, size_t* smem, size_t extra_rows) {
     REFIL_CHECK_ARG(n_seq > 0 && T > 0 && na > 0 && n_seq % na == 0, "%s: bad n_seq=%d T=%d na=%d", name, n_seq, T, na);
     REFIL_CHECK_ARG(r >= 8 && r <= GRU_THREADS && (r & (r - 1)) == 0, "%s: rnn_hidden_dim %d must be a power of two in [8,128]", name, r);
@@ -389,6 +719,13 @@ extern "C" int refil_gru_scan_fwd(const float* GI, const float* Whh, const float
     int rc = gru_check("gru_scan_fwd", n_seq, T, n_agents, r, &smem, 2);
     if (rc) return rc;
     REFIL_CHECK_ARG(GI && Whh && bhh && HS, "gru_scan_fwd: null pointer");
+    if ((r == 64 || r == 32) && gru_use_mma()) {    // tensor-core scan (REFIL_GRU_MODE=ffma selects the FFMA scans below)
+        rc = r == 64 ? gru_launch_mma<64>(true, GI, Whh, bhh, h0, nullptr, HS, gates, n_seq, T, n_agents, stream)
+                     : gru_launch_mma<32>(true, GI, Whh, bhh, h0, nullptr, HS, gates, n_seq, T, n_agents, stream);
+        if (rc) return rc;
+        REFIL_CHECK_LAUNCH("gru_scan_fwd (mma)");
+        return REFIL_OK;
+    }
     if (r == 64 || r == 32 || r == 128) {           // specialised scan: 128 threads, 4 sequences per thread
 #define GRU_FWDT(RV, NGV)                                                                                                  \
     {                                                                                                                      \
@@ -419,6 +756,13 @@ extern "C" int refil_gru_scan_bwd(const float* dHS, const float* gates, const fl
     int rc = gru_check("gru_scan_bwd", n_seq, T, n_agents, r, &smem, 3);
     if (rc) return rc;
     REFIL_CHECK_ARG(dHS && gates && HS && Whh && dGI && dGH, "gru_scan_bwd: null pointer");
+    if ((r == 64 || r == 32) && gru_use_mma()) {
+        rc = r == 64 ? gru_launch_mma<64>(false, dHS, gates, HS, h0, Whh, dGI, dGH, n_seq, T, n_agents, stream)
+                     : gru_launch_mma<32>(false, dHS, gates, HS, h0, Whh, dGI, dGH, n_seq, T, n_agents, stream);
+        if (rc) return rc;
+        REFIL_CHECK_LAUNCH("gru_scan_bwd (mma)");
+        return REFIL_OK;
+    }
     if (r == 64 || r == 32 || r == 128) {
         const size_t sm8 = ((size_t)3 * r * r + 3 * (size_t)r * GRU8) * sizeof(float);
         const int grid8 = refil_cdiv(n_seq, GRU8);

@@ -54,6 +54,7 @@ struct TcArgs {
     const float* relu_y; long long ldy;      // optional: A element is zeroed where relu_y <= 0
     const uint8_t* a_rowmask; int a_na, a_ne, a_mper;   // optional: A row zeroed (stack of [C, N, na] rows)
     const float* B; long long sbj, sbi;      // B[j, i] = B[j*sbj + i*sbi], j < N (output col), i < K (reduction)
+    int kb_valid, b_vec;                     // B is zero for i >= kb_valid (zero-padded reduction); b_vec: 16-byte row loads allowed
     const float* bias; int relu;
     const uint8_t* c_rowmask; int c_na, c_ne, c_mper;
     int M, N, K;                             // K = whole reduction length
@@ -197,6 +198,8 @@ __device__ __forceinline__ void tc_load_resident_b(const TcArgs& a, uint8_t* sme
     // the four scalar loads of a warp are four coalesced 128-byte rows instead of 128 scattered sectors.
     const bool k_contig = a.sbi == 1;
     constexpr int MAXIT = 8;
+    const int kv = a.kb_valid;
+    const bool vec = k_contig && a.b_vec;
     float4 v[MAXIT];
 #pragma unroll
     for (int it = 0; it < MAXIT; it++) {
@@ -206,9 +209,15 @@ __device__ __forceinline__ void tc_load_resident_b(const TcArgs& a, uint8_t* sme
             const int r = k_contig ? f / k4 : f % BN, kq = k_contig ? f - r * k4 : f / BN;
             const long long j = (long long)nt * BN + r;
             if (j < a.N) {
-                const float* p = a.B + j * a.sbj + (long long)(k_off + kq * 4) * a.sbi;
-                if (k_contig) v[it] = __ldg(reinterpret_cast<const float4*>(p));
-                else { v[it].x = __ldg(p); v[it].y = __ldg(p + a.sbi); v[it].z = __ldg(p + 2 * a.sbi); v[it].w = __ldg(p + 3 * a.sbi); }
+                const int k0 = k_off + kq * 4;
+                const float* p = a.B + j * a.sbj + (long long)k0 * a.sbi;
+                if (vec && k0 + 4 <= kv) v[it] = __ldg(reinterpret_cast<const float4*>(p));
+                else {                       // strided (W^T), unaligned rows (lda = 53) or the zero-padded tail of the reduction
+                    if (k0 < kv) v[it].x = __ldg(p);
+                    if (k0 + 1 < kv) v[it].y = __ldg(p + a.sbi);
+                    if (k0 + 2 < kv) v[it].z = __ldg(p + 2 * a.sbi);
+                    if (k0 + 3 < kv) v[it].w = __ldg(p + 3 * a.sbi);
+                }
             }
         }
     }
@@ -228,8 +237,12 @@ __device__ __forceinline__ void tc_load_resident_b(const TcArgs& a, uint8_t* sme
         const long long j = (long long)nt * BN + r;
         float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
         if (j < a.N) {
-            const float* p = a.B + j * a.sbj + (long long)(k_off + kq * 4) * a.sbi;
-            w.x = __ldg(p); w.y = __ldg(p + a.sbi); w.z = __ldg(p + 2 * a.sbi); w.w = __ldg(p + 3 * a.sbi);
+            const int k0 = k_off + kq * 4;
+            const float* p = a.B + j * a.sbj + (long long)k0 * a.sbi;
+            if (k0 < kv) w.x = __ldg(p);
+            if (k0 + 1 < kv) w.y = __ldg(p + a.sbi);
+            if (k0 + 2 < kv) w.z = __ldg(p + 2 * a.sbi);
+            if (k0 + 3 < kv) w.w = __ldg(p + 3 * a.sbi);
         }
         float* hi = reinterpret_cast<float*>(smem_b + (size_t)kc * 2 * b_bytes);
         tc_store_split(hi, hi + BN * 32, r, c, w);
@@ -758,16 +771,18 @@ extern "C" int refil_tc_gemm_k_slices(int N, int K) {
 
 extern "C" int refil_tc_gemm_tn(const float* A, long long lda, const float* relu_y, long long ldy,
                                 const uint8_t* a_row_entity_mask, int a_na, int a_ne, int a_rows_per_copy,
-                                const float* B, long long b_stride_n, long long b_stride_k, const float* bias,
-                                int relu, const uint8_t* c_row_entity_mask, int c_na, int c_ne, int c_rows_per_copy,
-                                float* C, long long ldc, int M, int N, int K, cudaStream_t stream) {
+                                const float* B, long long b_stride_n, long long b_stride_k, int b_k_valid,
+                                const float* bias, int relu, const uint8_t* c_row_entity_mask, int c_na, int c_ne,
+                                int c_rows_per_copy, float* C, long long ldc, int M, int N, int K, cudaStream_t stream) {
     REFIL_CHECK_ARG(A && B && C, "tc_gemm_tn: null pointer");
     REFIL_CHECK_ARG(refil_tc_gemm_supported(M, N, K), "tc_gemm_tn: unsupported shape M=%d N=%d K=%d", M, N, K);
     REFIL_CHECK_ARG((lda % 4) == 0 && (ldc % 4) == 0 && ((uintptr_t)A % 16) == 0 && ((uintptr_t)C % 16) == 0,
                     "tc_gemm_tn: A / C must be 16-byte aligned with leading dimensions divisible by 4");
     REFIL_CHECK_ARG(!relu_y || ((ldy % 4) == 0 && ((uintptr_t)relu_y % 16) == 0), "tc_gemm_tn: relu_y alignment");
-    REFIL_CHECK_ARG(b_stride_k != 1 || ((b_stride_n % 4) == 0 && ((uintptr_t)B % 16) == 0), "tc_gemm_tn: B alignment");
+    REFIL_CHECK_ARG(b_k_valid >= 0 && b_k_valid <= K, "tc_gemm_tn: b_k_valid=%d outside [0, K=%d]", b_k_valid, K);
     TcArgs a{};
+    a.kb_valid = b_k_valid > 0 ? b_k_valid : K;
+    a.b_vec = (b_stride_k == 1 && (b_stride_n % 4) == 0 && ((uintptr_t)B % 16) == 0) ? 1 : 0;
     a.A = A; a.lda = lda; a.relu_y = relu_y; a.ldy = ldy;
     a.a_rowmask = a_row_entity_mask; a.a_na = a_na > 0 ? a_na : 1; a.a_ne = a_ne; a.a_mper = a_rows_per_copy > 0 ? a_rows_per_copy : 1;
     a.B = B; a.sbj = b_stride_n; a.sbi = b_stride_k;
@@ -827,6 +842,16 @@ extern "C" int refil_tc_gemm_tn(const float* A, long long lda, const float* relu
     const int groups = a.n_tiles * a.k_slices;
     int per_g = sms / groups;                    // CTAs per (n-tile, k-slice)
     if (per_g < 1) per_g = 1;
+    // every CTA pays a fixed prologue (split of its resident weight tile, pipeline fill): give it at least `min_tiles` m-tiles, so
+    // that a small problem (a 16-episode shard) leaves SMs to the independent networks running on the other streams
+    static int min_tiles = -1;
+    if (min_tiles < 0) {
+        const char* e = getenv("REFIL_TC_MIN_TILES");
+        min_tiles = e ? atoi(e) : 6;
+        if (min_tiles < 1) min_tiles = 1;
+    }
+    const int want = refil_cdiv(a.m_tiles, min_tiles);
+    if (per_g > want) per_g = want;
     if (per_g > a.m_tiles) per_g = a.m_tiles;
     const int grid = per_g * groups;
     if (mode_ts) {
@@ -859,6 +884,7 @@ struct TcWArgs {
     float* dW; long long lddw;
     float* db;
     int M, P, Q, BQ, p_tiles, splits, stages, chunks_per_split;
+    int q_valid, dw_vec;                 // columns >= q_valid of dW do not exist (zero-padded Y); dw_vec: 16-byte atomics allowed
     uint32_t idesc;
 };
 
@@ -939,11 +965,17 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) tc_gemm_wgrad_kernel(TcWArgs a
                 if (p < a.P) {
                     if (c0 < a.Q) {
                         float* dst = a.dW + (long long)p * a.lddw + c0;
+                        if (a.dw_vec) {
 #pragma unroll
-                        for (int q = 0; q < 4; q++) {
-                            float4 v = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
-                                                   __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
-                            atomicAdd(reinterpret_cast<float4*>(dst + 4 * q), v);
+                            for (int q = 0; q < 4; q++) {
+                                float4 v = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
+                                                       __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+                                atomicAdd(reinterpret_cast<float4*>(dst + 4 * q), v);
+                            }
+                        } else {             // dW rows are not 16-byte aligned (fc1: 53 columns) or end inside this slab
+#pragma unroll
+                            for (int q = 0; q < 16; q++)
+                                if (c0 + q < a.q_valid) atomicAdd(dst + q, __uint_as_float(r[q]));
                         }
                     } else if (a.db) {
                         atomicAdd(a.db + p, __uint_as_float(r[0]));       // column Q: sum over rows of g(X)[:, p]
@@ -1240,11 +1272,17 @@ __global__ void __launch_bounds__(TW_THREADS, 1) tc_wgrad_ts_kernel(TcWArgs a, T
                 if (p < a.P) {
                     if (c0 < a.Q) {
                         float* dst = a.dW + (long long)p * a.lddw + c0;
+                        if (a.dw_vec) {
 #pragma unroll
-                        for (int q = 0; q < 4; q++) {
-                            float4 v = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
-                                                   __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
-                            atomicAdd(reinterpret_cast<float4*>(dst + 4 * q), v);
+                            for (int q = 0; q < 4; q++) {
+                                float4 v = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
+                                                       __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+                                atomicAdd(reinterpret_cast<float4*>(dst + 4 * q), v);
+                            }
+                        } else {             // dW rows are not 16-byte aligned (fc1: 53 columns) or end inside this slab
+#pragma unroll
+                            for (int q = 0; q < 16; q++)
+                                if (c0 + q < a.q_valid) atomicAdd(dst + q, __uint_as_float(r[q]));
                         }
                     } else if (a.db) {
                         atomicAdd(a.db + p, __uint_as_float(r[0]));       // column Q: sum over rows of g(X)[:, p]
@@ -1365,18 +1403,19 @@ __global__ void __launch_bounds__(TW_THREADS, 1) tc_wgrad_ts_kernel(TcWArgs a, T
 }
 
 extern "C" int refil_tc_wgrad_supported(int M, int P, int Q) {
-    if (M < 32 || P < 4 || P % 4 != 0) return 0;
+    if (M < 32 || P < 1) return 0;       // P: valid columns of X (its row stride only has to be a multiple of 4 floats)
     return (Q == 32 || Q == 64 || Q == 128) ? 1 : 0;
 }
 
 extern "C" int refil_tc_gemm_wgrad(const float* X, long long ldx, const float* relu_y, long long ldy,
                                    const uint8_t* x_row_entity_mask, int na, int ne, int rows_per_copy,
                                    const float* Y, long long ldyy, int y_shift_rows, int y_period, float* dW,
-                                   long long lddw, float* db, int M, int P, int Q, cudaStream_t stream) {
+                                   long long lddw, int q_valid, float* db, int M, int P, int Q, cudaStream_t stream) {
     REFIL_CHECK_ARG(X && Y && dW, "tc_gemm_wgrad: null pointer");
     REFIL_CHECK_ARG(refil_tc_wgrad_supported(M, P, Q), "tc_gemm_wgrad: unsupported shape M=%d P=%d Q=%d", M, P, Q);
-    REFIL_CHECK_ARG((ldx % 4) == 0 && (ldyy % 4) == 0 && (lddw % 4) == 0 && ((uintptr_t)X % 16) == 0 &&
-                    ((uintptr_t)Y % 16) == 0 && ((uintptr_t)dW % 16) == 0, "tc_gemm_wgrad: alignment");
+    REFIL_CHECK_ARG((ldx % 4) == 0 && (ldyy % 4) == 0 && ((uintptr_t)X % 16) == 0 && ((uintptr_t)Y % 16) == 0 &&
+                    ((uintptr_t)dW % 4) == 0, "tc_gemm_wgrad: alignment");
+    REFIL_CHECK_ARG(q_valid >= 0 && q_valid <= Q && ldx >= (P + 3) / 4 * 4, "tc_gemm_wgrad: q_valid=%d / ldx=%lld", q_valid, ldx);
     REFIL_CHECK_ARG(!relu_y || ((ldy % 4) == 0 && ((uintptr_t)relu_y % 16) == 0), "tc_gemm_wgrad: relu_y alignment");
     TcWArgs a{};
     a.X = X; a.ldx = ldx; a.relu_y = relu_y; a.ldy = ldy;
@@ -1384,11 +1423,21 @@ extern "C" int refil_tc_gemm_wgrad(const float* X, long long ldx, const float* r
     a.Y = Y; a.ldyy = ldyy; a.dW = dW; a.lddw = lddw; a.db = db;
     a.y_shift = y_shift_rows > 0 ? y_shift_rows : 0; a.y_period = y_period > 0 ? y_period : 1;
     a.M = M; a.P = P; a.Q = Q;
+    a.q_valid = q_valid > 0 ? q_valid : Q;
+    a.dw_vec = (a.q_valid == Q && (lddw % 4) == 0 && ((uintptr_t)dW % 16) == 0) ? 1 : 0;
     a.BQ = db ? Q + 32 : Q;              // the bias gradient rides as one extra 32-wide atom whose first column is 1
     a.p_tiles = refil_cdiv(P, 128);
     const int chunks_total = refil_cdiv(M, 32);
     int splits = refil_num_sms() / a.p_tiles;
     if (splits < 1) splits = 1;
+    // every split ends with a [128 x Q] tile of atomics: at least `min_chunks` 32-row chunks of reduction per split
+    static int min_chunks = -1;
+    if (min_chunks < 0) {
+        const char* e = getenv("REFIL_TC_MIN_CHUNKS");
+        min_chunks = e ? atoi(e) : 24;
+        if (min_chunks < 1) min_chunks = 1;
+    }
+    if (splits > refil_cdiv(chunks_total, min_chunks)) splits = refil_cdiv(chunks_total, min_chunks);
     if (splits > chunks_total) splits = chunks_total;
     a.chunks_per_split = refil_cdiv(chunks_total, splits);
     a.splits = refil_cdiv(chunks_total, a.chunks_per_split);

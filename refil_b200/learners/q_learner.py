@@ -59,7 +59,7 @@ class QLearner:
             self.target_mixer = Mixer(args, self.ein, self.device, tag="target_mixer")
             self.target_mixer.load_state_dict(self.mixer.state_dict())
             names = list(self.mixer.nets.keys())
-            self.mixer.set_scratch_groups([names[:1], names[1:]])      # the two groups run on different streams
+            self.mixer.set_scratch_groups([[h] for h in names])        # every hypernetwork's backward runs on its own stream
         self.target_mac = type(mac)(mac.scheme, mac.groups, args)
         self.target_mac.load_state(mac)
         self._bind_flat()
@@ -92,9 +92,11 @@ class QLearner:
         for b in bufs:
             parallel.broadcast_(b, src=src)
 
+    N_SIDE = 9       # target agent | 4 online hypernetworks | 4 target hypernetworks
+
     def _side_stream(self, i):
         if getattr(self, "_side", None) is None:
-            self._side = [torch.cuda.Stream(device=self.device) for _ in range(2)]
+            self._side = [torch.cuda.Stream(device=self.device) for _ in range(self.N_SIDE)]
         return self._side[i]
 
     def cuda(self):
@@ -224,13 +226,18 @@ class QLearner:
             self.mixer.forward(ch_gt[0], ch_gt[1], ch_gt[2], inp_gt["entities"], inp_gt["last_action"],
                                inp_gt["entity_mask"], T, imagine_masks=mix_gt, xin=inp_gt.get("xin"), ret_ingroup=True)
             gt_ingroup = self.mixer.ingroup.view(B, T)[:, :-1].mean()
-        # Two CUDA streams (args.concurrent_streams, default on): the target networks' forward runs beside the online
-        # forward, and the hypernetworks' backward beside the agent's backward.  The kernels are persistent one-CTA-per-SM
-        # grids, so the two chains do not share an SM at any instant -- what overlaps is every launch's fixed cost (tile
-        # prologue, pipeline fill and drain, tail rounds), ~15 us x 200 launches a step.
+        # One CUDA stream per network (args.concurrent_streams, default on): the online agent on the main stream, the target agent,
+        # the online hypernetworks and the target hypernetworks each on their own.  The dense kernels size their grids to the
+        # problem (a small shard does not occupy every SM), so independent networks really run side by side; for large
+        # batches, where every kernel fills the GPU, what overlaps is each launch's fixed cost (tile prologue, pipeline fill
+        # and drain, tail rounds).  Under CUDA-graph capture the forks and joins become the graph's parallel branches.
         two = bool(getattr(args, "concurrent_streams", True)) and self.mixer is not None
         main = torch.cuda.current_stream()
-        side, side2 = (self._side_stream(0), self._side_stream(1)) if two else (main, main)
+        n_h = len(self.mixer.nets) if self.mixer is not None else 0
+        s_tgt = self._side_stream(0) if two else main
+        s_hyp = [self._side_stream(1 + i) for i in range(n_h)] if two else None
+        s_thyp = [self._side_stream(1 + n_h + i) for i in range(n_h)] if two else None
+        side_all = ([s_tgt] + s_hyp + s_thyp) if two else []
         # shared inputs first (entities / last-action index / masks / packed fc1 input) and the mask plan, then fork
         T_all = batch["avail_actions"].shape[1]
         inp = self.mac._build_inputs(batch, slice(0, T_all))
@@ -240,18 +247,16 @@ class QLearner:
             group_bits = self.mac.draw_groups(inp["bs"], inp["ne"], inp["entity_mask"].device)
         self.last_group_bits = group_bits        # under graph replay: the static tensor the captured draw writes (tests read it)
         _, mix, _ = self.mac.mask_plan(inp, self.imagine, use_gt, use_rgt, group_bits)
-        if two:
-            side.wait_stream(main)
-            side2.wait_stream(main)
+        for st in side_all:
+            st.wait_stream(main)
         ents, la, em = inp["entities"], inp["last_action"], inp["entity_mask"]
-        # ---- side: target agent + target hypernetworks (q_learner.py:111-118,154) ------------------------------------
-        with torch.cuda.stream(side):
+        # ---- target agent + target hypernetworks (q_learner.py:111-118,154) ------------------------------------------
+        with torch.cuda.stream(s_tgt):
             self.target_mac.init_hidden(B)
             q_tgt, _, _, _ = self.target_mac.forward(batch, None, ret_plan=True, inputs=inp)
-            self.target_mixer.hyper_forward(ents, la, em, T, xin=inp.get("xin"))
-        # ---- side2: online hypernetworks (they only need the entities and the partition) ---------------------------
-        with torch.cuda.stream(side2):
-            self.mixer.hyper_forward(ents, la, em, T, imagine_masks=mix if self.imagine else None, xin=inp.get("xin"))
+        self.target_mixer.hyper_forward(ents, la, em, T, xin=inp.get("xin"), streams=s_thyp)
+        # ---- online hypernetworks (they only need the entities and the partition) -----------------------------------
+        self.mixer.hyper_forward(ents, la, em, T, imagine_masks=mix if self.imagine else None, xin=inp.get("xin"), streams=s_hyp)
         # ---- main: online agent on all T steps, 3 mask copies when imagining (q_learner.py:79-109) -------------------
         self.mac.init_hidden(B)
         q_all, spec, _, _ = self.mac.forward(batch, None, imagine=self.imagine, use_gt_factors=use_gt,
@@ -259,13 +264,13 @@ class QLearner:
                                              ret_plan=True, inputs=inp)
         C = spec.C
         chosen = ops.gather_chosen(q_all, actions, ws.get("chosen", (3, N, na)), C, N * na, A)
-        if two:
-            main.wait_stream(side2)
+        for st in (s_hyp or []):
+            main.wait_stream(st)
         qtot, qtot_im = self.mixer.mix(chosen[0], chosen[1] if self.imagine else None,
                                        chosen[2] if self.imagine else None, ret_ingroup=log_gt)
         ingroup = self.mixer.ingroup.view(B, T)[:, :-1].mean() if log_gt else None
-        if two:
-            main.wait_stream(side)
+        for st in ([s_tgt] + s_thyp if two else []):
+            main.wait_stream(st)
         # double-Q selection and the target mix (q_learner.py:121-126,154)
         tgt_max = ops.target_max(q_all[0], q_tgt[0], avail, ws.get("tgt_max", (N, na)), None, N * na, A, args.double_q)
         tgt_tot, _ = self.target_mixer.mix(tgt_max, None, None)
@@ -278,21 +283,14 @@ class QLearner:
         # backward (q_learner.py:175-176): hypernetworks on the side streams, agent on the main stream
         self.gradbuf.zero_()
         dq, dhyper = self.mixer.backward_mix(g_plain, g_im)
-        names = list(self.mixer.nets.keys())
-        grp_a, grp_b = names[:1], names[1:]          # hyper_w_1 (3 mask copies when imagining) | the other hypernetworks
-        if two:
-            side.wait_stream(main)
-            side2.wait_stream(main)
-        with torch.cuda.stream(side):
-            self.mixer.backward_hyper(dhyper, grp_a)
-        with torch.cuda.stream(side2):
-            self.mixer.backward_hyper(dhyper, grp_b)
+        for st in (s_hyp or []):
+            st.wait_stream(main)
+        self.mixer.backward_hyper(dhyper, streams=s_hyp)
         Ap = self.mac.agent.dq_width()        # one-hot scatter of d(chosen) into (padded) action columns
         dQ = ops.scatter_dq(dq, actions, ws.get("dQ", (C * N * na, Ap)), C, N * na, Ap, T, na)
         self.mac.agent.backward(dQ)
-        if two:
-            main.wait_stream(side)
-            main.wait_stream(side2)
+        for st in (s_hyp or []):
+            main.wait_stream(st)
         # one all-reduce of [grads | stats], then normalise + clip + RMSprop (q_learner.py:177-178)
         ops.pack_stats(self.stats64, self.gradbuf[self.n_params:], N_STATS)
         if not reduce_and_update:

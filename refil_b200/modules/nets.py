@@ -70,10 +70,8 @@ class AttnTrunk:
         N, ne = ents.shape[0], ents.shape[1]
         C, d, na = masks.C, self.d, self.na
         x1 = ws.get(tag + ".x1", (N * ne, d))
-        if xin is not None:
-            w1p = ws.get(tag + ".w1p", (d, xin.shape[1]), zero=True)
-            w1p[:, :self.ein].copy_(p[pre + "fc1.weight"])
-            ops.linear_fwd(xin, w1p, p[pre + "fc1.bias"], x1, relu=True)
+        if xin is not None:          # packed [entities | onehot | 0] input: the (d, ein) weight is read in place, K zero-padded
+            ops.linear_fwd(xin, p[pre + "fc1.weight"], p[pre + "fc1.bias"], x1, relu=True)
         else:
             ops.embed_fwd(ents, la, self.A, p[pre + "fc1.weight"], p[pre + "fc1.bias"], x1, relu=True)
         att = ws.get(tag + ".att", (C * N * na, d))
@@ -112,9 +110,7 @@ class AttnTrunk:
         dx1 = ws.get(self.scratch + ".dx1", (N * ne, d))
         ops.linear_bwd_data(dqkv, p[pre + "attn.in_trans.weight"], dx1)
         if xin is not None:
-            dw1p = ws.get(self.scratch + ".dw1p", (d, xin.shape[1]), zero=True)
-            ops.linear_bwd_weight(dx1, xin, dw1p, g[pre + "fc1.bias"], relu_y=x1)
-            g[pre + "fc1.weight"].add_(dw1p[:, :self.ein])
+            ops.linear_bwd_weight(dx1, xin, g[pre + "fc1.weight"], g[pre + "fc1.bias"], relu_y=x1)
         else:
             ops.embed_bwd_weight(dx1, x1, ents, la, self.A, g[pre + "fc1.weight"], g[pre + "fc1.bias"])
 
@@ -224,18 +220,10 @@ class EntityAttnAgent:
         inp = hs if self.rnn else x2
         width = self.r if self.rnn else self.d
         dhead = ws.get("scratch.dhs", (R, self.r)) if self.rnn else dx2
-        if Ap != self.A:      # padded head: zero-padded copy of the output weight, gradient through a padded temp
-            wp = ws.get(self.tag + ".wheadp", (Ap, width), zero=True)
-            wp[:self.A].copy_(p[wl])
-            dwp = ws.get("scratch.dwheadp", (Ap, width), zero=True)
-            dbp = ws.get("scratch.dbheadp", (Ap,), zero=True)
-            ops.linear_bwd_weight(dq, inp, dwp, dbp, row_mask=rm)
-            g[wl].add_(dwp[:self.A])
-            g[key].add_(dbp[:self.A])
-            ops.linear_bwd_data(dq, wp, dhead, row_mask=rm)
-        else:
-            ops.linear_bwd_weight(dq, inp, g[wl], g[key], row_mask=rm)
-            ops.linear_bwd_data(dq, p[wl], dhead, row_mask=rm)
+        # dq may be padded to 32 columns (dq_width): the (A, width) head weight and its gradient are used in place, the
+        # kernels take the missing rows / columns as zero
+        ops.linear_bwd_weight(dq, inp, g[wl], g[key], row_mask=rm)
+        ops.linear_bwd_data(dq, p[wl], dhead, row_mask=rm)
         if self.rnn:
             dhs = dhead
             dgi = ws.get("scratch.dgi", (R, 3 * self.r))
@@ -340,20 +328,26 @@ class Mixer:
             for h in names:
                 self.nets[h].trunk.scratch = "scratch%d" % gi
 
-    def hyper_forward(self, ents, la, entity_mask, T, imagine_masks=None, xin=None):
+    def hyper_forward(self, ents, la, entity_mask, T, imagine_masks=None, xin=None, streams=None):
         """The heavy part of the mixer: every hypernetwork evaluated on the entity rows (independent of the agent utilities,
-        so the learner may run it concurrently with the agent forward).  -> {name: [rows, me]}"""
+        so the learner may run it concurrently with the agent forward).  streams: optional list of CUDA streams, hypernetwork i
+        is enqueued on streams[i % len] (the nets are independent of each other; every net has its own activations).
+        -> {name: [rows, me]}"""
         imagine = imagine_masks is not None
         outs = {}
         if self.kind != 2:
             default = (None, 0, ops.ATTN_DEFAULT)
-            for h, net in self.nets.items():
+            for i, (h, net) in enumerate(self.nets.items()):
                 if h == "hyper_w_1." and imagine:
                     copies, gbits = imagine_masks
                     m = MaskSpec([default] + list(copies), gbits, entity_mask)
                 else:
                     m = MaskSpec([default], None, entity_mask)
-                outs[h] = net.forward(ents, la, m, T, xin=xin)
+                if streams:
+                    with torch.cuda.stream(streams[i % len(streams)]):
+                        outs[h] = net.forward(ents, la, m, T, xin=xin)
+                else:
+                    outs[h] = net.forward(ents, la, m, T, xin=xin)
         self._hyper = (outs, ents.shape[0], imagine)
         return outs
 
@@ -393,12 +387,16 @@ class Mixer:
                       self.tanh_nl)
         return dq, d
 
-    def backward_hyper(self, d, names=None):
+    def backward_hyper(self, d, names=None, streams=None):
         """Hypernetwork backward passes (parameter gradients are accumulated); independent of the agent backward and, given
-        distinct scratch groups, of each other."""
-        for h, net in self.nets.items():
+        distinct scratch groups (set_scratch_groups), of each other: net i goes to streams[i % len] when streams are given."""
+        for i, (h, net) in enumerate(self.nets.items()):
             if names is None or h in names:
-                net.backward(d[h])
+                if streams:
+                    with torch.cuda.stream(streams[i % len(streams)]):
+                        net.backward(d[h])
+                else:
+                    net.backward(d[h])
 
     def backward(self, g_plain, g_im):
         """-> dq, dqW, dqI [N, na]; hypernet parameter gradients are accumulated."""

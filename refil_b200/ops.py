@@ -113,21 +113,25 @@ def _tc_ok(M, N, K):
     return USE_TENSOR_CORES and M >= TC_MIN_ROWS and _lib.load().refil_tc_gemm_supported(M, N, K) != 0
 
 
-def tc_gemm_tn(A, B, sbn, sbk, out, N, K, bias=None, relu=False, relu_y=None, a_row_mask=None, c_row_mask=None):
+def tc_gemm_tn(A, B, sbn, sbk, out, N, K, bias=None, relu=False, relu_y=None, a_row_mask=None, c_row_mask=None, k_valid=0):
     M = A.shape[0]
     aem, ana, ane, amper = _rm(a_row_mask)
     cem, cna, cne, cmper = _rm(c_row_mask)
     _account("tc_gemm_tn", 2.0 * M * N * K, 4.0 * (M * K * (2 if relu_y is not None else 1) + M * N + N * K))
     _call("tc_gemm_tn", _p(A, F32), A.shape[1], _p(relu_y, F32), A.shape[1], aem, ana, ane, amper, _p(B, F32), sbn, sbk,
-          _p(bias, F32), int(relu), cem, cna, cne, cmper, _p(out, F32), out.shape[1], M, N, K, shape=(M, N, K))
+          int(k_valid), _p(bias, F32), int(relu), cem, cna, cne, cmper, _p(out, F32), out.shape[1], M, N, K, shape=(M, N, K))
     return out
 
 
 def linear_fwd(A, W, bias, out, relu=False, row_mask=None):
+    """out = [rowmask][relu](A W^T + bias).  A may be wider than W (zero-padded input columns, e.g. the packed fc1 input of 64
+    columns against the 53-column weight): the weight is read in place with the tail of the reduction taken as zero."""
     M, K = A.shape
-    N = W.shape[0]
+    N, Kw = W.shape
     if _tc_ok(M, N, K) and (_lib.load().refil_tc_gemm_k_slices(N, K) == 1 or (bias is None and not relu and row_mask is None)):
-        return tc_gemm_tn(A, W, K, 1, out, N, K, bias=bias, relu=relu, c_row_mask=row_mask)
+        return tc_gemm_tn(A, W, Kw, 1, out, N, K, bias=bias, relu=relu, c_row_mask=row_mask, k_valid=Kw if Kw != K else 0)
+    if Kw != K:
+        raise _lib.RefilError("linear_fwd: input has %d columns, weight %d (only the tensor-core path takes a padded input)" % (K, Kw))
     em, na, ne, mper = _rm(row_mask)
     _call("linear_fwd", _p(A, F32), K, _p(W, F32), W.shape[1], _p(bias, F32), _p(out, F32), N, M, N, K, int(relu),
           em, na, ne, mper)
@@ -143,24 +147,32 @@ def embed_fwd(entities, last_action, n_actions, W, bias, out, relu=True):
 
 
 def linear_bwd_data(dC, W, dA, relu_y=None, row_mask=None):
+    """dA = g(dC) W.  dC may be wider than W has rows (zero-padded output columns, e.g. the 14-action head in 32 columns)."""
     M, N = dC.shape
-    K = W.shape[1]
+    Nw, K = W.shape
     if _tc_ok(M, K, N):      # dA[M,K] = g(dC)[M,N] W[N,K]: "B"[j=k, i=n] = W[n*K + k]
-        return tc_gemm_tn(dC, W, 1, K, dA, K, N, relu_y=relu_y, a_row_mask=row_mask)
+        return tc_gemm_tn(dC, W, 1, K, dA, K, N, relu_y=relu_y, a_row_mask=row_mask, k_valid=Nw if Nw != N else 0)
+    if Nw != N:
+        raise _lib.RefilError("linear_bwd_data: gradient has %d columns, weight %d rows" % (N, Nw))
     em, na, ne, mper = _rm(row_mask)
     _call("linear_bwd_data", _p(dC, F32), N, _p(relu_y, F32), N, em, na, ne, mper, _p(W, F32), K, _p(dA, F32), K, M, N, K)
     return dA
 
 
 def linear_bwd_weight(dC, A, dW, db, relu_y=None, row_mask=None):
+    """dW[P, Q] += g(dC)^T A, db += colsum g(dC).  dW may be narrower than A (zero-padded input columns: fc1) and have fewer
+    rows than dC has columns (zero-padded output columns: the action head); it is accumulated in place."""
     M, N = dC.shape
     K = A.shape[1]
+    P, Qv = dW.shape
     em, na, ne, mper = _rm(row_mask)
-    if USE_TENSOR_CORES and M >= TC_MIN_ROWS and _lib.load().refil_tc_wgrad_supported(M, N, K) != 0:
+    if USE_TENSOR_CORES and M >= TC_MIN_ROWS and N % 4 == 0 and _lib.load().refil_tc_wgrad_supported(M, P, K) != 0:
         _account("tc_gemm_wgrad", 2.0 * M * N * K, 4.0 * (M * N * (2 if relu_y is not None else 1) + M * K + N * K))
-        _call("tc_gemm_wgrad", _p(dC, F32), N, _p(relu_y, F32), N, em, na, ne, mper, _p(A, F32), K, 0, 1, _p(dW, F32), K,
-              _p(db, F32), M, N, K, shape=(M, N, K))
+        _call("tc_gemm_wgrad", _p(dC, F32), N, _p(relu_y, F32), N, em, na, ne, mper, _p(A, F32), K, 0, 1, _p(dW, F32), Qv,
+              Qv if Qv != K else 0, _p(db, F32), M, P, K, shape=(M, N, K))
         return
+    if (P, Qv) != (N, K):
+        raise _lib.RefilError("linear_bwd_weight: padded operands need the tensor-core path")
     _call("linear_bwd_weight", _p(dC, F32), N, _p(relu_y, F32), N, em, na, ne, mper, _p(A, F32), K, _p(dW, F32), K,
           _p(db, F32), M, N, K)
 
@@ -175,7 +187,7 @@ def gru_bwd_weight_hh(dGH, HS, n_agents, T, dWhh, dbhh):
     M, r = HS.shape
     if USE_TENSOR_CORES and M >= TC_MIN_ROWS and _lib.load().refil_tc_wgrad_supported(M, 3 * r, r) != 0:
         _call("tc_gemm_wgrad", _p(dGH, F32), 3 * r, None, 3 * r, None, 1, 1, 1, _p(HS, F32), r, n_agents, T,
-              _p(dWhh, F32), r, _p(dbhh, F32), M, 3 * r, r)
+              _p(dWhh, F32), r, 0, _p(dbhh, F32), M, 3 * r, r)
         return
     _call("gru_bwd_weight_hh", _p(dGH, F32), _p(HS, F32), n_agents, T, _p(dWhh, F32), _p(dbhh, F32), M, r)
 

@@ -122,7 +122,10 @@ def test_masked_attention_fwd_bwd(ne, na, d, H):
         _close(dqkv, dqkv_ref.reshape(N * ne, 3 * d), what="%s dqkv" % name)
 
 
-@pytest.mark.parametrize("r,na,CB,T", [(16, 3, 9, 6), (64, 8, 5, 7), (32, 1, 1, 1), (128, 2, 3, 3)])
+@pytest.mark.parametrize("r,na,CB,T", [(16, 3, 9, 6), (64, 8, 5, 7), (32, 1, 1, 1), (128, 2, 3, 3),
+                                       (64, 8, 48, 12),      # 384 sequences = the 16-episode shard: 24 CTAs of the mma scan
+                                       (64, 8, 300, 5),      # 2400 sequences: two m16 tiles per CTA
+                                       (32, 5, 7, 9), (64, 3, 7, 20)])   # ragged: 35 / 21 sequences (partial m16 tiles)
 def test_gru_scan_fwd_bwd(r, na, CB, T):
     from oracle import learner_oracle as lo
     from refil_b200 import ops
