@@ -74,6 +74,7 @@ int refil_gm_env_step(uint32_t* mt_key, int32_t* mt_pos, int32_t* loc, uint32_t*
 /* ---- acting: components/action_selectors.py:45-63 (EpsilonGreedyActionSelector.select_action) ---------------- */
 int refil_select_actions(const float* q, long long q_stride_b, const int32_t* avail, long long avail_stride_b,
                          const float* u_pick, const float* u_act, const int32_t* est_flags, float epsilon,
+                         const float* epsilon_dev /* optional device scalar that overrides `epsilon` (graph-captured rollouts) */,
                          long long* actions_out, long long out_stride_b, int B, int n_agents, int n_actions,
                          cudaStream_t stream);
 

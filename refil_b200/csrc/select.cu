@@ -8,10 +8,13 @@
 __global__ void select_actions_kernel(const float* __restrict__ q, long long q_stride_b,
                                       const int32_t* __restrict__ avail, long long avail_stride_b,
                                       const float* __restrict__ u_pick, const float* __restrict__ u_act,
-                                      const int32_t* __restrict__ est_flags, float eps, long long* __restrict__ out,
+                                      const int32_t* __restrict__ est_flags, float eps_host,
+                                      const float* __restrict__ eps_dev, long long* __restrict__ out,
                                       long long out_stride_b, int B, int na, int A) {
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= B * na) return;
+    // a device-resident epsilon lets one captured CUDA graph of a rollout serve every point of the schedule (and test mode: 0)
+    const float eps = eps_dev ? __ldg(eps_dev) : eps_host;
     int b = idx / na, a = idx - b * na;
     if (est_flags && !(est_flags[b] & 2)) return;  // env not in the runner's envs_not_terminated list
     const float* qr = q + (size_t)b * q_stride_b + (size_t)a * A;
@@ -36,15 +39,15 @@ __global__ void select_actions_kernel(const float* __restrict__ q, long long q_s
 
 extern "C" int refil_select_actions(const float* q, long long q_stride_b, const int32_t* avail,
                                     long long avail_stride_b, const float* u_pick, const float* u_act,
-                                    const int32_t* est_flags, float epsilon, long long* actions_out,
-                                    long long out_stride_b, int B, int n_agents, int n_actions,
+                                    const int32_t* est_flags, float epsilon, const float* epsilon_dev,
+                                    long long* actions_out, long long out_stride_b, int B, int n_agents, int n_actions,
                                     cudaStream_t stream) {
     REFIL_CHECK_ARG(q && avail && actions_out && B > 0 && n_agents > 0 && n_actions > 0, "select_actions: bad arguments");
-    REFIL_CHECK_ARG(epsilon <= 0.f || (u_pick && u_act), "select_actions: epsilon > 0 needs u_pick and u_act");
+    REFIL_CHECK_ARG((epsilon <= 0.f && !epsilon_dev) || (u_pick && u_act), "select_actions: epsilon > 0 needs u_pick and u_act");
     int n = B * n_agents;
     select_actions_kernel<<<refil_cdiv(n, 128), 128, 0, stream>>>(q, q_stride_b, avail, avail_stride_b, u_pick, u_act,
-                                                                  est_flags, epsilon, actions_out, out_stride_b, B,
-                                                                  n_agents, n_actions);
+                                                                  est_flags, epsilon, epsilon_dev, actions_out,
+                                                                  out_stride_b, B, n_agents, n_actions);
     REFIL_CHECK_LAUNCH("select_actions");
     return REFIL_OK;
 }

@@ -92,7 +92,7 @@ class QLearner:
         for b in bufs:
             parallel.broadcast_(b, src=src)
 
-    N_SIDE = 9       # target agent | 4 online hypernetworks | 4 target hypernetworks
+    N_SIDE = 14      # target agent | 4 online hypernetworks | 4 target hypernetworks | weight-gradient companions (agent + 4)
 
     def _side_stream(self, i):
         if getattr(self, "_side", None) is None:
@@ -285,10 +285,12 @@ class QLearner:
         dq, dhyper = self.mixer.backward_mix(g_plain, g_im)
         for st in (s_hyp or []):
             st.wait_stream(main)
-        self.mixer.backward_hyper(dhyper, streams=s_hyp)
-        Ap = self.mac.agent.dq_width()        # one-hot scatter of d(chosen) into (padded) action columns
+        # weight-gradient kernels leave the data-gradient chains: one companion stream per network
+        s_w = [self._side_stream(1 + 2 * n_h + i) for i in range(n_h + 1)] if two else None
+        self.mixer.backward_hyper(dhyper, streams=s_hyp, wstreams=s_w[1:] if two else None)
+        Ap = self.mac.agent.dq_width(C * N * na)        # one-hot scatter of d(chosen) into (padded) action columns
         dQ = ops.scatter_dq(dq, actions, ws.get("dQ", (C * N * na, Ap)), C, N * na, Ap, T, na)
-        self.mac.agent.backward(dQ)
+        self.mac.agent.backward(dQ, wstream=s_w[0] if two else None)
         for st in (s_hyp or []):
             main.wait_stream(st)
         # one all-reduce of [grads | stats], then normalise + clip + RMSprop (q_learner.py:177-178)

@@ -33,6 +33,18 @@ class MaskSpec:
         return len(self.copies)
 
 
+def _on_side(wstream, fn):
+    """Enqueue fn() on `wstream` behind everything already enqueued on the current stream (None: run it inline).  Used for the
+    weight-gradient kernels of a backward pass: they read what the data-gradient chain has produced so far but nothing
+    downstream waits for them, so they leave the chain's critical path; the caller joins `wstream` when the pass is done."""
+    if wstream is None:
+        fn()
+        return
+    wstream.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(wstream):
+        fn()
+
+
 class AttnTrunk:
     """x1 = relu(fc1([ents | onehot(last action)])); QKV = in_trans(x1); masked MHA for C mask copies;
     x2 = [relu] out_trans(.) with inactive-agent rows zeroed."""
@@ -90,23 +102,24 @@ class AttnTrunk:
         self.saved = (ents, la, masks, T, relu_out, x1, qkv, att, x2, N, ne, xin)
         return x2
 
-    def backward(self, dx2):
+    def backward(self, dx2, wstream=None):
         p, g, pre, ws = self.s.p, self.s.g, self.pre, self.ws
         ents, la, masks, T, relu_out, x1, qkv, att, x2, N, ne, xin = self.saved
         C, d, na = masks.C, self.d, self.na
         relu_y = x2 if relu_out else None
-        ops.linear_bwd_weight(dx2, att, g[pre + "attn.out_trans.weight"], g[pre + "attn.out_trans.bias"],
-                              relu_y=relu_y, row_mask=self.row_mask)
+        _on_side(wstream, lambda: ops.linear_bwd_weight(dx2, att, g[pre + "attn.out_trans.weight"], g[pre + "attn.out_trans.bias"],
+                                                        relu_y=relu_y, row_mask=self.row_mask))
         datt = ws.get(self.scratch + ".datt", (C * N * na, d))
         ops.linear_bwd_data(dx2, p[pre + "attn.out_trans.weight"], datt, relu_y=relu_y, row_mask=self.row_mask)
         if self.pool is None:
             dqkv = ws.get(self.scratch + ".dqkv", (N * ne, 3 * d))
             ops.masked_attn_bwd(qkv, datt, dqkv, masks.copies, masks.group_bits, masks.entity_mask, N, T, ne, na, d, self.H)
-            ops.linear_bwd_weight(dqkv, x1, g[pre + "attn.in_trans.weight"], None)
+            _on_side(wstream, lambda: ops.linear_bwd_weight(dqkv, x1, g[pre + "attn.in_trans.weight"], None))
         else:
             dqkv = ws.get(self.scratch + ".dqkv", (N * ne, d))
             ops.entity_pool_bwd(qkv, datt, dqkv, masks.copies, masks.group_bits, masks.entity_mask, N, T, ne, na, d, self.pool)
-            ops.linear_bwd_weight(dqkv, x1, g[pre + "attn.in_trans.weight"], g[pre + "attn.in_trans.bias"])
+            _on_side(wstream, lambda: ops.linear_bwd_weight(dqkv, x1, g[pre + "attn.in_trans.weight"],
+                                                            g[pre + "attn.in_trans.bias"]))
         dx1 = ws.get(self.scratch + ".dx1", (N * ne, d))
         ops.linear_bwd_data(dqkv, p[pre + "attn.in_trans.weight"], dx1)
         if xin is not None:
@@ -204,13 +217,15 @@ class EntityAttnAgent:
         self.saved = (x2, None, None, None, None, B, T, C)
         return q.view(C, N, na, self.A), x2
 
-    def dq_width(self):
-        """Row width of the dQ buffer the learner scatters into: padded to 32 columns on the tensor-core path so that
-        the fc3 / fc2 backward GEMMs have an aligned K (the padding columns are zero)."""
-        return 32 if (ops.USE_TENSOR_CORES and self.A <= 32) else self.A
+    def dq_width(self, rows):
+        """Row width of the dQ buffer the learner scatters into: padded to 32 columns when the head's backward GEMMs run on the
+        tensor cores (>= TC_MIN_ROWS rows; aligned reduction, the padding columns are zero), else the plain A columns."""
+        width = self.r if self.rnn else self.d
+        return 32 if (self.A <= 32 and ops.tc_head_ok(rows, self.A, width)) else self.A
 
-    def backward(self, dq):
-        """dq [C*N*na, dq_width()] -> accumulates into the gradient views of the store."""
+    def backward(self, dq, wstream=None):
+        """dq [C*N*na, dq_width()] -> accumulates into the gradient views of the store.  wstream: optional companion stream for
+        the weight-gradient kernels (joined before returning)."""
         p, g, ws = self.store.p, self.store.g, self.ws
         x2, x3, hs, gates, h0, B, T, C = self.saved
         na, rm = self.na, self.trunk.row_mask
@@ -218,24 +233,28 @@ class EntityAttnAgent:
         dx2 = ws.get("scratch.dx2", (R, self.d))
         wl, key = ("fc3.weight", "fc3.bias") if self.rnn else ("fc2.weight", "fc2.bias")
         inp = hs if self.rnn else x2
-        width = self.r if self.rnn else self.d
         dhead = ws.get("scratch.dhs", (R, self.r)) if self.rnn else dx2
         # dq may be padded to 32 columns (dq_width): the (A, width) head weight and its gradient are used in place, the
         # kernels take the missing rows / columns as zero
-        ops.linear_bwd_weight(dq, inp, g[wl], g[key], row_mask=rm)
+        _on_side(wstream, lambda: ops.linear_bwd_weight(dq, inp, g[wl], g[key], row_mask=rm))
         ops.linear_bwd_data(dq, p[wl], dhead, row_mask=rm)
         if self.rnn:
             dhs = dhead
             dgi = ws.get("scratch.dgi", (R, 3 * self.r))
             dgh = ws.get("scratch.dgh", (R, 3 * self.r))
             ops.gru_scan_bwd(dhs, gates, hs, h0, p["rnn.weight_hh"], dgi, dgh, C * B * na, T, na)
-            ops.linear_bwd_weight(dgi, x3, g["rnn.weight_ih"], g["rnn.bias_ih"])
-            ops.gru_bwd_weight_hh(dgh, hs, na, T, g["rnn.weight_hh"], g["rnn.bias_hh"])
+
+            def rnn_wgrads():
+                ops.linear_bwd_weight(dgi, x3, g["rnn.weight_ih"], g["rnn.bias_ih"])
+                ops.gru_bwd_weight_hh(dgh, hs, na, T, g["rnn.weight_hh"], g["rnn.bias_hh"])
+            _on_side(wstream, rnn_wgrads)
             dx3 = ws.get("scratch.dx3", (R, self.r))
             ops.linear_bwd_data(dgi, p["rnn.weight_ih"], dx3)
-            ops.linear_bwd_weight(dx3, x2, g["fc2.weight"], g["fc2.bias"], relu_y=x3)
+            _on_side(wstream, lambda: ops.linear_bwd_weight(dx3, x2, g["fc2.weight"], g["fc2.bias"], relu_y=x3))
             ops.linear_bwd_data(dx3, p["fc2.weight"], dx2, relu_y=x3)
-        self.trunk.backward(dx2)
+        self.trunk.backward(dx2, wstream=wstream)
+        if wstream is not None:
+            torch.cuda.current_stream().wait_stream(wstream)
 
 
 class AttnHyperNet:
@@ -266,13 +285,15 @@ class AttnHyperNet:
         self.x2 = x2
         return x3
 
-    def backward(self, dx3):
+    def backward(self, dx3, wstream=None):
         p, g, pre = self.s.p, self.s.g, self.pre
         rm = self.trunk.row_mask
-        ops.linear_bwd_weight(dx3, self.x2, g[pre + "fc2.weight"], g[pre + "fc2.bias"], row_mask=rm)
+        _on_side(wstream, lambda: ops.linear_bwd_weight(dx3, self.x2, g[pre + "fc2.weight"], g[pre + "fc2.bias"], row_mask=rm))
         dx2 = self.ws.get(self.trunk.scratch + ".dx2h", (dx3.shape[0], self.he))
         ops.linear_bwd_data(dx3, p[pre + "fc2.weight"], dx2, row_mask=rm)
-        self.trunk.backward(dx2)
+        self.trunk.backward(dx2, wstream=wstream)
+        if wstream is not None:
+            torch.cuda.current_stream().wait_stream(wstream)
 
 
 class Mixer:
@@ -387,14 +408,15 @@ class Mixer:
                       self.tanh_nl)
         return dq, d
 
-    def backward_hyper(self, d, names=None, streams=None):
+    def backward_hyper(self, d, names=None, streams=None, wstreams=None):
         """Hypernetwork backward passes (parameter gradients are accumulated); independent of the agent backward and, given
-        distinct scratch groups (set_scratch_groups), of each other: net i goes to streams[i % len] when streams are given."""
+        distinct scratch groups (set_scratch_groups), of each other: net i goes to streams[i % len] when streams are given, its
+        weight-gradient kernels to the companion wstreams[i % len]."""
         for i, (h, net) in enumerate(self.nets.items()):
             if names is None or h in names:
                 if streams:
                     with torch.cuda.stream(streams[i % len(streams)]):
-                        net.backward(d[h])
+                        net.backward(d[h], wstream=wstreams[i % len(wstreams)] if wstreams else None)
                 else:
                     net.backward(d[h])
 

@@ -113,6 +113,11 @@ def _tc_ok(M, N, K):
     return USE_TENSOR_CORES and M >= TC_MIN_ROWS and _lib.load().refil_tc_gemm_supported(M, N, K) != 0
 
 
+def tc_head_ok(rows, n_out, width):
+    """Can the backward of an [n_out <= 32, width] output head run on the tensor cores with its gradient padded to 32 columns?"""
+    return _tc_ok(rows, width, 32) and _lib.load().refil_tc_wgrad_supported(rows, n_out, width) != 0
+
+
 def tc_gemm_tn(A, B, sbn, sbk, out, N, K, bias=None, relu=False, relu_y=None, a_row_mask=None, c_row_mask=None, k_valid=0):
     M = A.shape[0]
     aem, ana, ane, amper = _rm(a_row_mask)
@@ -316,7 +321,12 @@ def clip_rmsprop_step(params, grads, square_avg, n_params, mask_sum, sumsq, grad
 
 
 # ---------------------------------------------------------------------------------------------------- acting / env
-def select_actions(q, avail, u_pick, u_act, est_flags, epsilon, actions_out, B, na, A):
-    _call("select_actions", _p(q, F32), na * A, _p(avail, I32), na * A, _p(u_pick, F32), _p(u_act, F32),
-          _p(est_flags, I32), float(epsilon), _p(actions_out, I64), na, B, na, A)
+def select_actions(q, avail, u_pick, u_act, est_flags, epsilon, actions_out, B, na, A, eps_dev=None):
+    """q [B, na, A] contiguous; avail / actions_out may be time slices of EpisodeBatch tensors (row stride taken from them)."""
+    if avail.stride(-1) != 1 or avail.stride(-2) != A or actions_out.stride(-1) != 1:
+        raise _lib.RefilError("select_actions: avail / actions_out must be contiguous in their last two dimensions")
+    if not (avail.is_cuda and actions_out.is_cuda and avail.dtype == I32 and actions_out.dtype == I64):
+        raise _lib.RefilError("select_actions: avail int32 / actions int64 CUDA tensors expected")
+    _call("select_actions", _p(q, F32), na * A, avail.data_ptr(), avail.stride(0), _p(u_pick, F32), _p(u_act, F32),
+          _p(est_flags, I32), float(epsilon), _p(eps_dev, F32), actions_out.data_ptr(), actions_out.stride(0), B, na, A)
     return actions_out

@@ -44,6 +44,7 @@ class ParallelRunner:
         self.train_returns, self.test_returns = [], []
         self.train_stats, self.test_stats = {}, {}
         self.log_train_stats_t = -100000
+        self._graph_state = None
 
     def setup(self, scheme, groups, preprocess, mac):
         self.new_batch = partial(EpisodeBatch, scheme, groups, self.batch_size, self.episode_limit + 1,
@@ -66,23 +67,77 @@ class ParallelRunner:
         self.t = 0
         self.env_steps_this_run = 0
 
-    def run(self, test_mode=False, test_scen=None, index=None, vid_writer=None):
-        assert vid_writer is None, "Writing videos not supported for ParallelRunner"
-        self.reset()
+    # ---- the rollout body: everything between reset and the statistics, enqueued without a host sync -------------------
+    def _rollout_steps(self, batch, eps_dev=None, test_mode=False, early_exit=False):
+        """mac.forward -> epsilon-greedy selection (written straight into batch["actions"][:, t]) -> env step, for every
+        timestep.  With eps_dev (device scalar) the sequence contains no host-dependent value and can be captured once."""
+        env = self.env
         self.mac.init_hidden(batch_size=self.batch_size)
-        self.mac.eval()
-        batch, env = self.batch, self.env
-        actions = torch.zeros(self.batch_size, self.args.n_agents, dtype=torch.int64, device=self.args.device)
+        avail, acts = batch["avail_actions"], batch["actions"]
         for t in range(self.episode_limit):
             q = self.mac.forward(batch, t, test_mode=test_mode)
-            actions.zero_()
-            self.mac.action_selector.select_action(q, batch["avail_actions"][:, t], self.t_env, test_mode=test_mode,
-                                                   est_flags=env.flags, out=actions)
-            batch.update({"actions": actions.unsqueeze(1)}, ts=t, mark_filled=False)
+            self.mac.action_selector.select_action(q, avail[:, t], self.t_env, test_mode=test_mode, est_flags=env.flags,
+                                                   out=acts[:, t, :, 0], eps_dev=eps_dev)
             env.step(batch, t, write_gt=self.write_gt_every_step)   # reward / terminated at t, observations + filled at t + 1
             self.t = t + 1
-            if (t & 7) == 7 and not bool(env.alive().any()):
+            if early_exit and (t & 7) == 7 and not bool(env.alive().any()):
                 break
+        # actions_onehot (the scheme's preprocess of `actions`, episode_buffer.py:88-95) once for the whole rollout
+        batch.update({"actions": acts}, mark_filled=False)
+
+    def _run_graph(self, test_mode):
+        """args.rollout_graph: the whole rollout -- reset, `episode_limit` x (agent forward, selection, env step) -- is ONE CUDA
+        graph on a static EpisodeBatch, replayed per run (the uniforms come from torch's graph-safe philox state, epsilon from a
+        device scalar); the result is copied into a fresh EpisodeBatch, as `run` must return one the caller may keep.  The first
+        run is eager (sizes the workspaces), the second captures."""
+        st = self._graph_state
+        if st is None:
+            st = self._graph_state = {"runs": 0, "graph": None, "failed": False}
+        eps = 0.0 if test_mode else self.mac.action_selector.schedule.eval(self.t_env)
+        self.mac.action_selector.epsilon = eps
+        if st["failed"] or st["runs"] == 0:
+            st["runs"] += 1
+            self.reset()
+            self._rollout_steps(self.batch, test_mode=test_mode, early_exit=True)
+            return
+        if st["graph"] is None:
+            st["static"] = self.new_batch()
+            st["eps"] = torch.zeros(1, dtype=torch.float32, device=self.args.device)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            from .. import ops
+            l0 = ops.launch_count()
+            try:
+                with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                    for v in st["static"].data.transition_data.values():
+                        v.zero_()
+                    self.env.reset(st["static"])
+                    self._rollout_steps(st["static"], eps_dev=st["eps"])
+            except Exception as e:      # capture only changes how the work is submitted: never lose the rollout over it
+                st["failed"] = True
+                torch.cuda.synchronize()
+                self.logger.console_logger.info("rollout graph capture failed (%s: %s); running eagerly" % (type(e).__name__, e))
+                return self._run_graph(test_mode)
+            st["graph"], st["launches"] = g, ops.launch_count() - l0
+            ops.add_launches(-st["launches"])
+        st["eps"].fill_(eps)
+        st["graph"].replay()
+        from .. import ops
+        ops.add_launches(st["launches"])
+        self.batch = self.new_batch()
+        for k, v in st["static"].data.transition_data.items():
+            self.batch.data.transition_data[k].copy_(v)
+        self.t = self.episode_limit
+
+    def run(self, test_mode=False, test_scen=None, index=None, vid_writer=None):
+        assert vid_writer is None, "Writing videos not supported for ParallelRunner"
+        self.mac.eval()
+        if getattr(self.args, "rollout_graph", False):
+            self._run_graph(test_mode)
+        else:
+            self.reset()
+            self._rollout_steps(self.batch, test_mode=test_mode, early_exit=True)
+        batch, env = self.batch, self.env
         est = env.est.cpu().numpy()
         returns = env.ep_ret.cpu().numpy()
         lengths, flags = est[3], est[2]

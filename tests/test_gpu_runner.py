@@ -135,3 +135,73 @@ def test_learner_checkpoint_roundtrip(tmp_path):
     sd = torch.load(str(tmp_path / "agent.th"))
     gru = torch.nn.GRUCell(c.args.rnn_hidden_dim, c.args.rnn_hidden_dim)
     gru.load_state_dict({k[4:]: v for k, v in sd.items() if k.startswith("rnn.")})
+
+
+@pytest.mark.parametrize("alg", ["refil_group_matching", "refil"])
+def test_graph_rollout_equals_eager_rollout(alg):
+    """args.rollout_graph: the whole rollout replayed as ONE CUDA graph.  Greedy (test-mode) rollouts are deterministic given the
+    env seeds, so the graph path must reproduce the eager path bit for bit -- entities, actions, rewards, flags, filled -- run
+    after run (run 1 is eager, run 2 captures + replays, runs 3-4 replay); and the env RNG stream continues across resets."""
+    outs = []
+    for graph in (False, True):
+        args, runner, mac, logger, _ = _setup(alg, n_envs=40, seed=21, rollout_graph=graph)
+        runs = []
+        for _ in range(4):
+            b = runner.run(test_mode=True)
+            runs.append({k: v.clone() for k, v in b.data.transition_data.items()})
+        outs.append(runs)
+        if graph:
+            assert runner._graph_state["graph"] is not None, "the rollout was not captured"
+    for r, (a, b) in enumerate(zip(*outs)):
+        for k in a:
+            assert torch.equal(a[k], b[k]), (r, k)
+    assert not torch.equal(outs[0][0]["entities"], outs[0][1]["entities"])     # a new episode every run
+
+
+def test_graph_rollout_training_mode_explores_and_counts_steps():
+    """Training-mode graph rollouts: epsilon comes from a device scalar (schedule value of the run), the uniforms are re-drawn at
+    every replay, t_env / returns follow the transcript exactly as in the eager path."""
+    from oracle.gm_env_oracle import GroupMatchingOracle
+    args, runner, mac, logger, _ = _setup("refil_group_matching", n_envs=48, seed=5, rollout_graph=True)
+    acts = []
+    for rep in range(4):
+        t0 = runner.t_env
+        batch = runner.run(test_mode=False)
+        h = {k: v.cpu() for k, v in batch.data.transition_data.items()}
+        lengths = h["filled"].sum(1)[:, 0] - 1
+        assert runner.t_env - t0 == int(lengths.sum())
+        acts.append(h["actions"].clone())
+        assert torch.equal(h["actions_onehot"].argmax(-1)[h["filled"][:, :, 0] == 1], h["actions"][..., 0][h["filled"][:, :, 0] == 1])
+    env_args = dict(args.env_args)
+    seed = env_args.pop("seed")
+    env_args.pop("entity_scheme")
+    # the last batch replays against the CPU env: seeds continue over the 4 resets of each instance
+    for i in range(0, 48, 7):
+        o = GroupMatchingOracle(seed=seed + i, **env_args)
+        for _ in range(3):
+            o.reset()
+        o.reset()
+        done, ts = False, 0
+        assert np.array_equal(np.stack(o.get_entities()), h["entities"][i, 0].numpy())
+        while not done:
+            r, done, info = o.step(h["actions"][i, ts, :, 0].numpy())
+            assert np.float32(r) == h["reward"][i, ts, 0].item()
+            ts += 1
+    assert 0.9 < mac.action_selector.epsilon <= 1.0
+    assert not torch.equal(acts[1], acts[2]) and not torch.equal(acts[2], acts[3])      # fresh exploration noise per replay
+
+
+def test_episode_runner_writes_gt_mask_every_step():
+    """`runner: episode` keeps the reference EpisodeRunner's pre-transition data: gt_mask at EVERY filled step
+    (runners/episode_runner.py:52-67); the parallel runner stores it at reset only (SURVEY.md section 3.2 quirk iv)."""
+    for kind, every in (("episode", True), ("parallel", False)):
+        args, runner, mac, logger, _ = _setup("refil_group_matching", n_envs=6, seed=3, runner=kind)
+        b = runner.run(test_mode=True)
+        gt, filled = b["gt_mask"].cpu(), b["filled"].cpu()[:, :, 0] == 1
+        assert bool(gt[:, 0].any())
+        for e in range(6):
+            for t in range(1, int(filled[e].sum())):
+                if every:
+                    assert torch.equal(gt[e, t], gt[e, 0]), (kind, e, t)
+                else:
+                    assert not bool(gt[e, t].any()), (kind, e, t)
