@@ -365,14 +365,16 @@ __global__ void __launch_bounds__(R) gru_scan_bwd8_kernel(const float* __restric
     }
 }
 
-static bool gru_use_mma() {
+// REFIL_GRU_MODE: "v3" (default) register-resident FFMA scans, "mma" the mma.sync 3xTF32 scans, "ffma" the first-generation scans
+static int gru_mode() {
     static int mode = -1;
     if (mode < 0) {
         const char* e = getenv("REFIL_GRU_MODE");
-        mode = (e && e[0] == 'f') ? 0 : 1;
+        mode = (e && e[0] == 'f') ? 0 : (e && e[0] == 'm') ? 1 : 2;
     }
-    return mode == 1;
+    return mode;
 }
+static bool gru_use_mma() { return gru_mode() == 1; }
 
 static int gru_set_smem_attr(const void* kernel, size_t smem, const char* name) {
     if (smem > 48 * 1024) {
@@ -669,6 +671,259 @@ __global__ void __launch_bounds__(R * 4, 1) gru_scan_bwd_mma_kernel(const float*
     }
 }
 
+// =====================================================================================================================
+// Register-resident FFMA scans (default for hidden size 32 / 64).  Measured on B200 (profiles/r2f): the legacy mma.sync
+// TF32 path retires one m16n8k8 per ~3.2 cycles per SM, i.e. ~107 MAC/clk/SM after the three passes of the 3xTF32 split --
+// below the 128 FMA/clk/SM of the fp32 pipe -- so the recurrence gains nothing from it; what it needs is a SHORT step on as
+// many SMs as there are sequences to spread.  Here
+//   * W_hh never leaves the registers: lane = (feature j of a 16-feature group, half kh of the reduction), 96 weights per
+//     thread at R = 64, loaded once per launch -- the inner loop is 12 FMAs per 128-bit broadcast load of the state;
+//   * the two halves of a reduction meet with ONE shuffle per (gate, sequence), no shared-memory partials;
+//   * the state (forward) / gate gradients (backward) of the CTA's sequences are double-buffered in shared memory: one
+//     __syncthreads per step; the global inputs of step t + 1 are requested before step t is computed;
+//   * a CTA takes S = 2 x SB x NB sequences, chosen so that the grid is a single wave: 4 sequences per CTA for a 16-episode shard
+//     (384 sequences on 96 SMs, ~0.5 us per step), 24 for the full north-star batch (3072 sequences on 128 SMs).
+// =====================================================================================================================
+__device__ __forceinline__ float gru_sel(bool hi, float a, float b) { return hi ? b : a; }
+
+template <int R, int SB, int NB>
+__global__ void __launch_bounds__(R * 4, 1) gru_scan_fwd_v3_kernel(const float* __restrict__ GI, const float* __restrict__ Whh,
+                                                                   const float* __restrict__ bhh, const float* __restrict__ h0,
+                                                                   float* __restrict__ HS, float* __restrict__ GATES, int n_seq,
+                                                                   int T, int na) {
+    constexpr int KH = R / 2, FG = R / 16, S = 2 * SB * NB, PP = SB / 2;
+    __shared__ __align__(16) float hbuf[2][S][R];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, jl = lane & 15, kh = lane >> 4;
+    const int fg = warp % FG, sgp = warp / FG, j = 16 * fg + jl;
+    float w[3][KH];
+#pragma unroll
+    for (int g = 0; g < 3; g++)
+#pragma unroll
+        for (int kk = 0; kk < KH; kk += 4) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(Whh + (size_t)(g * R + j) * R + KH * kh + kk));
+            w[g][kk] = v.x; w[g][kk + 1] = v.y; w[g][kk + 2] = v.z; w[g][kk + 3] = v.w;
+        }
+    const float br = __ldg(bhh + j), bz = __ldg(bhh + R + j), bn = __ldg(bhh + 2 * R + j);
+    // my (sequence, feature j) pairs: block b = sgp * NB + nb holds local sequences [b SB, b SB + SB); mine are kh + 2 p
+    long long row0[NB][PP];
+    bool valid[NB][PP];
+    float hreg[NB][PP];
+    const int sbase = blockIdx.x * S;
+#pragma unroll
+    for (int nb = 0; nb < NB; nb++)
+#pragma unroll
+        for (int p = 0; p < PP; p++) {
+            const int ls = (sgp * NB + nb) * SB + kh + 2 * p, sq = sbase + ls;
+            valid[nb][p] = sq < n_seq;
+            const int cb = valid[nb][p] ? sq / na : 0, a = valid[nb][p] ? sq - cb * na : 0;
+            row0[nb][p] = ((long long)cb * T) * na + a;
+            hreg[nb][p] = (valid[nb][p] && h0) ? __ldg(h0 + (size_t)sq * R + j) : 0.f;
+            hbuf[0][ls][j] = hreg[nb][p];
+        }
+    float gn[NB][PP][3];
+    auto load_gi = [&](int t) {
+#pragma unroll
+        for (int nb = 0; nb < NB; nb++)
+#pragma unroll
+            for (int p = 0; p < PP; p++) {
+                const float* g = GI + (size_t)(row0[nb][p] + (long long)t * na) * 3 * R + j;
+#pragma unroll
+                for (int gg = 0; gg < 3; gg++) gn[nb][p][gg] = valid[nb][p] ? __ldg(g + gg * R) : 0.f;
+            }
+    };
+    load_gi(0);
+    __syncthreads();
+    int cur = 0;
+    for (int t = 0; t < T; t++) {
+        float gi[NB][PP][3];
+#pragma unroll
+        for (int nb = 0; nb < NB; nb++)
+#pragma unroll
+            for (int p = 0; p < PP; p++)
+#pragma unroll
+                for (int gg = 0; gg < 3; gg++) gi[nb][p][gg] = gn[nb][p][gg];
+        if (t + 1 < T) load_gi(t + 1);
+#pragma unroll
+        for (int nb = 0; nb < NB; nb++) {
+            float acc[3][SB];
+#pragma unroll
+            for (int g = 0; g < 3; g++)
+#pragma unroll
+                for (int q = 0; q < SB; q++) acc[g][q] = 0.f;
+            const float* hb = &hbuf[cur][(sgp * NB + nb) * SB][KH * kh];
+#pragma unroll
+            for (int kk = 0; kk < KH; kk += 4) {
+#pragma unroll
+                for (int q = 0; q < SB; q++) {
+                    const float4 hv = *reinterpret_cast<const float4*>(hb + q * R + kk);
+#pragma unroll
+                    for (int g = 0; g < 3; g++) {
+                        acc[g][q] = fmaf(hv.x, w[g][kk], acc[g][q]);
+                        acc[g][q] = fmaf(hv.y, w[g][kk + 1], acc[g][q]);
+                        acc[g][q] = fmaf(hv.z, w[g][kk + 2], acc[g][q]);
+                        acc[g][q] = fmaf(hv.w, w[g][kk + 3], acc[g][q]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int p = 0; p < PP; p++) {
+                // my pair is sequence kh + 2p of the block: I send my partner the partial sums of ITS sequence and add the
+                // partner's partial sums of mine
+                float sum[3];
+#pragma unroll
+                for (int g = 0; g < 3; g++) {
+                    const float send = gru_sel(kh != 0, acc[g][2 * p + 1], acc[g][2 * p]);
+                    const float mine = gru_sel(kh != 0, acc[g][2 * p], acc[g][2 * p + 1]);
+                    sum[g] = mine + __shfl_xor_sync(0xffffffffu, send, 16);
+                }
+                const float an = sum[2] + bn;
+                const float rg = sigmoidf_(gi[nb][p][0] + sum[0] + br);
+                const float zg = sigmoidf_(gi[nb][p][1] + sum[1] + bz);
+                const float ng = tanhf(gi[nb][p][2] + rg * an);
+                const float hn = (hreg[nb][p] - ng) * zg + ng;
+                hreg[nb][p] = hn;
+                hbuf[cur ^ 1][(sgp * NB + nb) * SB + kh + 2 * p][j] = hn;
+                if (valid[nb][p]) {
+                    const size_t row = (size_t)(row0[nb][p] + (long long)t * na);
+                    HS[row * R + j] = hn;
+                    if (GATES) {
+                        float* g = GATES + row * 4 * R;
+                        g[j] = rg; g[R + j] = zg; g[2 * R + j] = ng; g[3 * R + j] = an;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        cur ^= 1;
+    }
+}
+
+template <int R, int SB, int NB>
+__global__ void __launch_bounds__(R * 4, 1) gru_scan_bwd_v3_kernel(const float* __restrict__ dHS, const float* __restrict__ GATES,
+                                                                   const float* __restrict__ HS, const float* __restrict__ h0,
+                                                                   const float* __restrict__ Whh, float* __restrict__ dGI,
+                                                                   float* __restrict__ dGH, int n_seq, int T, int na) {
+    constexpr int GH = 3 * R / 2, FG = R / 16, S = 2 * SB * NB, PP = SB / 2;
+    __shared__ __align__(16) float abuf[2][S][3 * R];          // (d_r | d_z | d_nh) of the CTA's sequences
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, jl = lane & 15, kh = lane >> 4;
+    const int fg = warp % FG, sgp = warp / FG, j = 16 * fg + jl;
+    float w[GH];                                               // Whh[gj][j] for my half of the 3R gate rows
+#pragma unroll
+    for (int i = 0; i < GH; i++) w[i] = __ldg(Whh + (size_t)(GH * kh + i) * R + j);
+    long long row0[NB][PP];
+    bool valid[NB][PP];
+    int sidx[NB][PP];
+    float dh[NB][PP];
+    const int sbase = blockIdx.x * S;
+#pragma unroll
+    for (int nb = 0; nb < NB; nb++)
+#pragma unroll
+        for (int p = 0; p < PP; p++) {
+            const int ls = (sgp * NB + nb) * SB + kh + 2 * p, sq = sbase + ls;
+            valid[nb][p] = sq < n_seq;
+            sidx[nb][p] = sq;
+            const int cb = valid[nb][p] ? sq / na : 0, a = valid[nb][p] ? sq - cb * na : 0;
+            row0[nb][p] = ((long long)cb * T) * na + a;
+            dh[nb][p] = 0.f;
+        }
+    float nx[NB][PP][6];                                       // r, z, n, W_hn h + b_hn, h_{t-1}, dHS of the next step
+    auto load_step = [&](int t) {
+#pragma unroll
+        for (int nb = 0; nb < NB; nb++)
+#pragma unroll
+            for (int p = 0; p < PP; p++) {
+#pragma unroll
+                for (int q = 0; q < 6; q++) nx[nb][p][q] = 0.f;
+                if (valid[nb][p]) {
+                    const size_t row = (size_t)(row0[nb][p] + (long long)t * na);
+                    const float* g = GATES + row * 4 * R + j;
+#pragma unroll
+                    for (int q = 0; q < 4; q++) nx[nb][p][q] = __ldg(g + q * R);
+                    if (t > 0) nx[nb][p][4] = __ldg(HS + (row - na) * R + j);
+                    else if (h0) nx[nb][p][4] = __ldg(h0 + (size_t)sidx[nb][p] * R + j);
+                    nx[nb][p][5] = __ldg(dHS + row * R + j);
+                }
+            }
+    };
+    load_step(T - 1);
+    int cur = 0;
+    for (int t = T - 1; t >= 0; t--) {
+        float keep[NB][PP];
+#pragma unroll
+        for (int nb = 0; nb < NB; nb++)
+#pragma unroll
+            for (int p = 0; p < PP; p++) {
+                const float rg = nx[nb][p][0], zg = nx[nb][p][1], ng = nx[nb][p][2], hn = nx[nb][p][3], hp = nx[nb][p][4];
+                const float d = dh[nb][p] + nx[nb][p][5];
+                // h' = (hp - n) z + n
+                const float dz = d * (hp - ng);
+                const float dnn = d * (1.f - zg);
+                const bool ok = valid[nb][p];
+                keep[nb][p] = ok ? d * zg : 0.f;
+                const float d_n = ok ? dnn * (1.f - ng * ng) : 0.f;
+                const float d_nh = d_n * rg;
+                const float d_r = d_n * hn * rg * (1.f - rg);
+                const float d_z = ok ? dz * zg * (1.f - zg) : 0.f;
+                float* ar = &abuf[cur][(sgp * NB + nb) * SB + kh + 2 * p][j];
+                ar[0] = d_r; ar[R] = d_z; ar[2 * R] = d_nh;
+                if (ok) {
+                    const size_t row = (size_t)(row0[nb][p] + (long long)t * na);
+                    float* o = dGI + row * 3 * R;
+                    o[j] = d_r; o[R + j] = d_z; o[2 * R + j] = d_n;
+                    float* o2 = dGH + row * 3 * R;
+                    o2[j] = d_r; o2[R + j] = d_z; o2[2 * R + j] = d_nh;
+                }
+            }
+        if (t > 0) load_step(t - 1);                  // next step's inputs in flight during the product below
+        __syncthreads();
+        // dh_prev[seq][j] = keep + sum_gj (d_r | d_z | d_nh)[seq][gj] * Whh[gj][j]
+#pragma unroll
+        for (int nb = 0; nb < NB; nb++) {
+            float acc[SB];
+#pragma unroll
+            for (int q = 0; q < SB; q++) acc[q] = 0.f;
+            const float* ab = &abuf[cur][(sgp * NB + nb) * SB][GH * kh];
+#pragma unroll
+            for (int i = 0; i < GH; i += 4) {
+#pragma unroll
+                for (int q = 0; q < SB; q++) {
+                    const float4 av = *reinterpret_cast<const float4*>(ab + q * 3 * R + i);
+                    acc[q] = fmaf(av.x, w[i], acc[q]);
+                    acc[q] = fmaf(av.y, w[i + 1], acc[q]);
+                    acc[q] = fmaf(av.z, w[i + 2], acc[q]);
+                    acc[q] = fmaf(av.w, w[i + 3], acc[q]);
+                }
+            }
+#pragma unroll
+            for (int p = 0; p < PP; p++) {
+                const float send = gru_sel(kh != 0, acc[2 * p + 1], acc[2 * p]);
+                const float mine = gru_sel(kh != 0, acc[2 * p], acc[2 * p + 1]);
+                dh[nb][p] = keep[nb][p] + mine + __shfl_xor_sync(0xffffffffu, send, 16);
+            }
+        }
+        cur ^= 1;                                     // the other buffer is written next step: one barrier per step
+    }
+}
+
+// sequences per CTA S = 2 SB NB in {4, 8, 16, 24}: the smallest that keeps the grid within one wave of CTAs
+template <int R>
+static void gru_launch_v3(bool fwd, const float* a0, const float* a1, const float* a2, const float* a3, const float* a4,
+                          float* o0, float* o1, int n_seq, int T, int na, cudaStream_t stream) {
+    const int sms = refil_num_sms();
+    int S = 24;
+    if (refil_cdiv(n_seq, 4) <= sms) S = 4;
+    else if (refil_cdiv(n_seq, 8) <= sms) S = 8;
+    else if (refil_cdiv(n_seq, 16) <= sms) S = 16;
+    const int grid = refil_cdiv(n_seq, S);
+#define GRU_V3(SBV, NBV)                                                                                                 \
+    {                                                                                                                    \
+        if (fwd) gru_scan_fwd_v3_kernel<R, SBV, NBV><<<grid, R * 4, 0, stream>>>(a0, a1, a2, a3, o0, o1, n_seq, T, na);   \
+        else gru_scan_bwd_v3_kernel<R, SBV, NBV><<<grid, R * 4, 0, stream>>>(a0, a1, a2, a3, a4, o0, o1, n_seq, T, na);   \
+    }
+    if (S == 4) GRU_V3(2, 1) else if (S == 8) GRU_V3(4, 1) else if (S == 16) GRU_V3(4, 2) else GRU_V3(4, 3)
+#undef GRU_V3
+}
+
 // MT = m16 tiles (16 sequences each) per CTA: one while the sequences fit one wave of CTAs, else two
 template <int R>
 static int gru_launch_mma(bool fwd, const float* a0, const float* a1, const float* a2, const float* a3, const float* a4,
@@ -719,6 +974,12 @@ extern "C" int refil_gru_scan_fwd(const float* GI, const float* Whh, const float
     int rc = gru_check("gru_scan_fwd", n_seq, T, n_agents, r, &smem, 2);
     if (rc) return rc;
     REFIL_CHECK_ARG(GI && Whh && bhh && HS, "gru_scan_fwd: null pointer");
+    if ((r == 64 || r == 32) && gru_mode() == 2) {
+        if (r == 64) gru_launch_v3<64>(true, GI, Whh, bhh, h0, nullptr, HS, gates, n_seq, T, n_agents, stream);
+        else gru_launch_v3<32>(true, GI, Whh, bhh, h0, nullptr, HS, gates, n_seq, T, n_agents, stream);
+        REFIL_CHECK_LAUNCH("gru_scan_fwd (v3)");
+        return REFIL_OK;
+    }
     if ((r == 64 || r == 32) && gru_use_mma()) {    // tensor-core scan (REFIL_GRU_MODE=ffma selects the FFMA scans below)
         rc = r == 64 ? gru_launch_mma<64>(true, GI, Whh, bhh, h0, nullptr, HS, gates, n_seq, T, n_agents, stream)
                      : gru_launch_mma<32>(true, GI, Whh, bhh, h0, nullptr, HS, gates, n_seq, T, n_agents, stream);
@@ -756,6 +1017,12 @@ extern "C" int refil_gru_scan_bwd(const float* dHS, const float* gates, const fl
     int rc = gru_check("gru_scan_bwd", n_seq, T, n_agents, r, &smem, 3);
     if (rc) return rc;
     REFIL_CHECK_ARG(dHS && gates && HS && Whh && dGI && dGH, "gru_scan_bwd: null pointer");
+    if ((r == 64 || r == 32) && gru_mode() == 2) {
+        if (r == 64) gru_launch_v3<64>(false, dHS, gates, HS, h0, Whh, dGI, dGH, n_seq, T, n_agents, stream);
+        else gru_launch_v3<32>(false, dHS, gates, HS, h0, Whh, dGI, dGH, n_seq, T, n_agents, stream);
+        REFIL_CHECK_LAUNCH("gru_scan_bwd (v3)");
+        return REFIL_OK;
+    }
     if ((r == 64 || r == 32) && gru_use_mma()) {
         rc = r == 64 ? gru_launch_mma<64>(false, dHS, gates, HS, h0, Whh, dGI, dGH, n_seq, T, n_agents, stream)
                      : gru_launch_mma<32>(false, dHS, gates, HS, h0, Whh, dGI, dGH, n_seq, T, n_agents, stream);

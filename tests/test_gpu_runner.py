@@ -163,7 +163,7 @@ def test_graph_rollout_training_mode_explores_and_counts_steps():
     every replay, t_env / returns follow the transcript exactly as in the eager path."""
     from oracle.gm_env_oracle import GroupMatchingOracle
     args, runner, mac, logger, _ = _setup("refil_group_matching", n_envs=48, seed=5, rollout_graph=True)
-    acts = []
+    acts, hs = [], []
     for rep in range(4):
         t0 = runner.t_env
         batch = runner.run(test_mode=False)
@@ -171,22 +171,24 @@ def test_graph_rollout_training_mode_explores_and_counts_steps():
         lengths = h["filled"].sum(1)[:, 0] - 1
         assert runner.t_env - t0 == int(lengths.sum())
         acts.append(h["actions"].clone())
+        hs.append(h)
         assert torch.equal(h["actions_onehot"].argmax(-1)[h["filled"][:, :, 0] == 1], h["actions"][..., 0][h["filled"][:, :, 0] == 1])
     env_args = dict(args.env_args)
     seed = env_args.pop("seed")
     env_args.pop("entity_scheme")
-    # the last batch replays against the CPU env: seeds continue over the 4 resets of each instance
+    # every instance replays its four consecutive episodes (eager, capture + replay, replay, replay) against the CPU env: the
+    # MT19937 stream of an instance runs on across resets and graph replays
     for i in range(0, 48, 7):
         o = GroupMatchingOracle(seed=seed + i, **env_args)
-        for _ in range(3):
+        for h in hs:
             o.reset()
-        o.reset()
-        done, ts = False, 0
-        assert np.array_equal(np.stack(o.get_entities()), h["entities"][i, 0].numpy())
-        while not done:
-            r, done, info = o.step(h["actions"][i, ts, :, 0].numpy())
-            assert np.float32(r) == h["reward"][i, ts, 0].item()
-            ts += 1
+            done, ts = False, 0
+            assert np.array_equal(np.stack(o.get_entities()), h["entities"][i, 0].numpy())
+            while not done:
+                r, done, info = o.step(h["actions"][i, ts, :, 0].numpy())
+                assert np.float32(r) == h["reward"][i, ts, 0].item()
+                ts += 1
+            assert int(h["filled"][i].sum()) == ts + 1
     assert 0.9 < mac.action_selector.epsilon <= 1.0
     assert not torch.equal(acts[1], acts[2]) and not torch.equal(acts[2], acts[3])      # fresh exploration noise per replay
 
