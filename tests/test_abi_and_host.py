@@ -182,3 +182,20 @@ def test_python_call_sites_match_header_arity():
                 os.path.relpath(path, root), node.lineno, node.args[0].value, n, len(proto[1]))
             checked += 1
     assert checked >= 25
+
+
+def test_sass_histogram_has_blackwell_native_instructions():
+    """The dense hot path is tcgen05 + TMEM + TMA, the attention kernels stage their tiles with TMA: asserted on the SASS of the
+    built library (scripts/sass_histogram.py; the committed table is profiles/sass_histogram.md)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("sass_histogram", os.path.join(ROOT, "scripts", "sass_histogram.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    h = mod.histogram()
+    ts, wg = h["tc_gemm_ts_kernel"], h["tc_wgrad_ts_kernel"]
+    for k in (ts, wg):
+        assert k["UTCHMMA"] >= 12 and k["LDTM"] >= 1 and k["STTM"] >= 2 and k["UTMALDG"] >= 1 and k["UTCBAR"] >= 2, dict(k)
+    assert ts["UTMASTG"] >= 1 and ts["UTMAREDG"] >= 1                      # TMA tensor store / reduce-add epilogue
+    att = [c for n, c in h.items() if n.startswith("attn_fwd_kernel<32, 4>") or n.startswith("attn_bwd_kernel<32, 4>")]
+    assert len(att) == 2 and all(c["UTMALDG"] >= 1 and c["FFMA"] > 100 for c in att)
+    assert not any(c["HMMA"] for n, c in h.items() if n.startswith("tc_"))   # no legacy mma.sync on the dense path
