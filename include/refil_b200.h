@@ -123,6 +123,21 @@ int refil_tc_gemm_tn(const float* A, long long lda, const float* relu_y, long lo
                      const float* bias, int relu, const uint8_t* c_row_entity_mask, int c_na, int c_ne, int c_rows_per_copy,
                      float* C, long long ldc, int M, int N, int K, cudaStream_t stream);
 
+/* Grouped launch: up to 8 independent problems of ONE (N, K) geometry -- the same layer of several networks (the eight
+ * hypernetworks of the online and target mixers, the agent and its target) -- as a single kernel launch (blockIdx.y = problem).
+ * Field meaning as the arguments of refil_tc_gemm_tn. */
+typedef struct RefilGemmDesc {
+    const float* A; long long lda;
+    const float* relu_y; long long ldy;
+    const uint8_t* a_row_entity_mask; int a_na, a_ne, a_rows_per_copy;
+    const float* B; long long b_stride_n, b_stride_k; int b_k_valid;
+    const float* bias; int relu;
+    const uint8_t* c_row_entity_mask; int c_na, c_ne, c_rows_per_copy;
+    float* C; long long ldc;
+    int M;
+} RefilGemmDesc;
+int refil_tc_gemm_tn_group(const RefilGemmDesc* descs, int n_problems, int N, int K, cudaStream_t stream);
+
 /* weight gradient on the tensor cores: dW[P,Q] += g(X)[M,P]^T Y[M,Q]; db[P] += colsum g(X) (db may be null).
  * y_shift_rows > 0: Y row m is read from row m - y_shift_rows and is zero where (m / y_shift_rows) % y_period == 0
  * (the h_{t-1} view of the GRU state stack for dW_hh: shift = n_agents, period = T) */
@@ -132,6 +147,18 @@ int refil_tc_gemm_wgrad(const float* X, long long ldx, const float* relu_y, long
                         long long ldyy, int y_shift_rows, int y_period, float* dW, long long lddw,
                         int q_valid /* dW has q_valid <= Q columns (0: Q); the rest of Y is zero padding */, float* db,
                         int M, int P, int Q, cudaStream_t stream);
+
+/* grouped weight gradients: up to 8 problems of one (P, Q) geometry in a single launch; fields as refil_tc_gemm_wgrad */
+typedef struct RefilWgradDesc {
+    const float* X; long long ldx;
+    const float* relu_y; long long ldy;
+    const uint8_t* x_row_entity_mask; int na, ne, rows_per_copy;
+    const float* Y; long long ldyy; int y_shift_rows, y_period;
+    float* dW; long long lddw; int q_valid;
+    float* db;
+    int M;
+} RefilWgradDesc;
+int refil_tc_gemm_wgrad_group(const RefilWgradDesc* descs, int n_problems, int P, int Q, cudaStream_t stream);
 
 /* ---- masked multi-head attention over entities: modules/layers/attention.py:43-64 with the mask algebra of
  *      agents/entity_rnn_agent.py:79-124 resolved on the fly.  QKV [N, ne, 3d]; OUT / dOUT [C, N, nq, d].
@@ -146,6 +173,21 @@ int refil_masked_attn_bwd(const float* qkv, const float* dout, float* dqkv, cons
                           long long mask_stride2, int mode0, int mode1, int mode2, const uint8_t* group_bits,
                           const uint8_t* entity_mask, int N, int T, int n_entities, int n_queries, int embed_dim,
                           int n_heads, int n_copies, cudaStream_t stream);
+
+/* grouped attention: up to 8 problems of one geometry (N, T, ne, nq, d, heads) -- the attention of several networks over the same
+ * (b, t) units -- in a single launch; fields as the arguments of refil_masked_attn_fwd / bwd (out: forward; dout, dqkv: backward) */
+typedef struct RefilAttnDesc {
+    const float* qkv; float* out; const float* dout; float* dqkv;
+    const uint8_t* mask0; const uint8_t* mask1; const uint8_t* mask2;
+    long long mask_stride0, mask_stride1, mask_stride2;
+    int mode0, mode1, mode2;
+    const uint8_t* group_bits; const uint8_t* entity_mask;
+    int n_copies;
+} RefilAttnDesc;
+int refil_masked_attn_fwd_group(const RefilAttnDesc* descs, int n_problems, int N, int T, int n_entities, int n_queries,
+                                int embed_dim, int n_heads, cudaStream_t stream);
+int refil_masked_attn_bwd_group(const RefilAttnDesc* descs, int n_problems, int N, int T, int n_entities, int n_queries,
+                                int embed_dim, int n_heads, cudaStream_t stream);
 
 /* ---- EntityPoolingLayer (`pooling_type: mean | max`): modules/layers/attention.py:82-132, same mask interface as the attention
  *      kernels.  E [N, ne, d] = in_trans(x1); OUT / dOUT [C, N, nq, d]; dE [N, ne, d] (overwritten).  pool_type 0 = mean (masked

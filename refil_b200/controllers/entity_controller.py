@@ -36,13 +36,17 @@ class EntityMAC(BasicMAC):
         inp["entities"] = ents.contiguous().view(bs * ts, ne, -1)
         la = None
         if args.entity_last_action:
-            la = torch.full((bs, ts, ne), -1, dtype=torch.int32, device=ents.device)
             acts = batch["actions"]
-            if t.start == 0:
-                if t.stop > 1:
-                    la[:, 1:, :args.n_agents] = acts[:, 0:t.stop - 1, :, 0].to(torch.int32)
-            else:
-                la[:, :, :args.n_agents] = acts[:, t.start - 1:t.stop - 1, :, 0].to(torch.int32)
+            if t.start == 0 and t.stop == acts.shape[1] and acts.is_contiguous():
+                # whole sequence (the learner): one kernel -- la[b, t, e] = actions[b, t-1, e] for agents at t > 0, else -1
+                la = ops.last_action_index(acts, torch.empty((bs, ts, ne), dtype=torch.int32, device=ents.device), ne)
+            else:                          # an acting slice of a few rows: index plumbing with torch ops
+                la = torch.full((bs, ts, ne), -1, dtype=torch.int32, device=ents.device)
+                if t.start == 0:
+                    if t.stop > 1:
+                        la[:, 1:, :args.n_agents] = acts[:, 0:t.stop - 1, :, 0].to(torch.int32)
+                else:
+                    la[:, :, :args.n_agents] = acts[:, t.start - 1:t.stop - 1, :, 0].to(torch.int32)
             la = la.view(bs * ts, ne)
         inp["last_action"] = la
         inp["obs_mask"] = batch["obs_mask"][:, t].contiguous().view(bs * ts, ne, ne)

@@ -55,6 +55,11 @@ struct AttnArgs {
 
 
 #define ATT_MAX_WARPS 8
+#define ATT_MAX_GROUP 8
+// a launch carries up to ATT_MAX_GROUP independent problems of one geometry (the attention of several networks over the same
+// (b, t) units): blockIdx.y selects the problem
+struct AttnGroup { AttnArgs a[ATT_MAX_GROUP]; };
+struct AttnMaps { CUtensorMap m[ATT_MAX_GROUP]; };
 
 __device__ __forceinline__ uint32_t att_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void att_mbar_init(uint64_t* bar, uint32_t count) {
@@ -197,7 +202,9 @@ __device__ __forceinline__ void att_meta_resolve(const AttnArgs& a, long long n,
 
 // head dim <= 16 (d = 64 configs: small units, latency-bound): registers capped so that two CTAs share an SM
 template <int HD, int H>
-__global__ void __launch_bounds__(32 * ATT_MAX_WARPS, (HD <= 16) ? 2 : 1) attn_fwd_kernel(AttnArgs a, int NEB, int tile_floats, int warp_floats, const __grid_constant__ CUtensorMap tmap, int use_tmap) {
+__global__ void __launch_bounds__(32 * ATT_MAX_WARPS, (HD <= 16) ? 2 : 1) attn_fwd_kernel(const __grid_constant__ AttnGroup grp, int NEB, int tile_floats, int warp_floats, const __grid_constant__ AttnMaps maps, int use_tmap) {
+    const AttnArgs& a = grp.a[blockIdx.y];                 // blockIdx.y = problem of a grouped launch (one network each)
+    const CUtensorMap& tmap = maps.m[blockIdx.y];
     extern __shared__ __align__(128) float smem_raw_[];
     // 128-byte aligned base, derived by pointer arithmetic on the __shared__ symbol so that every access below is
     // provably shared memory (LDS / STS, not generic LD / ST)
@@ -353,7 +360,9 @@ __global__ void __launch_bounds__(32 * ATT_MAX_WARPS, (HD <= 16) ? 2 : 1) attn_f
 //   phase 2, lane = (entity j, head h): dK_j = sum_{c,i} dlogit_ij Q_i, dV_j = sum_{c,i} w_ij dO_i (Q / dO rows come
 //            back through L1), written over the K|V tile, which is then streamed out as the K|V columns of dQKV.
 template <int HD, int H>
-__global__ void __launch_bounds__(32 * ATT_MAX_WARPS, (HD <= 16) ? 2 : 1) attn_bwd_kernel(AttnArgs a, int NEB, int tile_floats, int warp_floats, const __grid_constant__ CUtensorMap tmap, int use_tmap) {
+__global__ void __launch_bounds__(32 * ATT_MAX_WARPS, (HD <= 16) ? 2 : 1) attn_bwd_kernel(const __grid_constant__ AttnGroup grp, int NEB, int tile_floats, int warp_floats, const __grid_constant__ AttnMaps maps, int use_tmap) {
+    const AttnArgs& a = grp.a[blockIdx.y];                 // blockIdx.y = problem of a grouped launch (one network each)
+    const CUtensorMap& tmap = maps.m[blockIdx.y];
     extern __shared__ __align__(128) float smem_raw_[];
     // 128-byte aligned base, derived by pointer arithmetic on the __shared__ symbol so that every access below is
     // provably shared memory (LDS / STS, not generic LD / ST)
@@ -767,7 +776,7 @@ extern "C" int refil_entity_pool_bwd(const float* E, const float* dout, float* d
 }
 
 template <class K, class... Extra>
-static int attn_launch(K kernel, const AttnArgs& a, size_t smem, int grid, int warps, cudaStream_t stream,
+static int attn_launch(K kernel, const AttnGroup& a, int n_problems, size_t smem, int grid, int warps, cudaStream_t stream,
                        const char* name, Extra... extra) {
     if (smem > 227 * 1024) {
         refil_set_error("%s: tile needs %zu bytes of shared memory (> 227 KB)", name, smem);
@@ -780,7 +789,7 @@ static int attn_launch(K kernel, const AttnArgs& a, size_t smem, int grid, int w
             return REFIL_ERR_CUDA;
         }
     }
-    kernel<<<grid, 32 * warps, smem, stream>>>(a, extra...);
+    kernel<<<dim3(grid, n_problems), 32 * warps, smem, stream>>>(a, extra...);
     REFIL_CHECK_LAUNCH(name);
     return REFIL_OK;
 }
@@ -862,29 +871,77 @@ static int attn_geometry(const char* name, int N, int warp_floats, int* warps, i
     return REFIL_OK;
 }
 
+// fwd = true: forward (out), else backward (dout, dqkv)
+static int attn_group_launch(bool fwd, const RefilAttnDesc* descs, int n_problems, int N, int T, int n_entities, int n_queries,
+                             int embed_dim, int n_heads, cudaStream_t stream) {
+    const char* name = fwd ? "masked_attn_fwd" : "masked_attn_bwd";
+    REFIL_CHECK_ARG(descs && n_problems >= 1 && n_problems <= ATT_MAX_GROUP, "%s: 1..%d problems (got %d)", name, ATT_MAX_GROUP,
+                    n_problems);
+    AttnGroup grp{};
+    AttnMaps maps{};
+    int max_c = 1, use_tmap = 1;
+    for (int g = 0; g < n_problems; g++) {
+        const RefilAttnDesc& d = descs[g];
+        AttnArgs& a = grp.a[g];
+        int rc = attn_fill(a, d.qkv, d.mask0, d.mask1, d.mask2, d.mask_stride0, d.mask_stride1, d.mask_stride2, d.mode0, d.mode1,
+                           d.mode2, d.group_bits, d.entity_mask, N, T, n_entities, n_queries, embed_dim, n_heads, d.n_copies);
+        if (rc) return rc;
+        if (fwd) {
+            REFIL_CHECK_ARG(d.out != nullptr, "masked_attn_fwd: out is null");
+            a.out = d.out;
+            use_tmap &= attn_make_tmap_box(&maps.m[g], d.qkv, N, n_entities, embed_dim, embed_dim, n_entities);
+        } else {
+            REFIL_CHECK_ARG(d.dout && d.dqkv, "masked_attn_bwd: dout / dqkv is null");
+            REFIL_CHECK_ARG(((uintptr_t)d.dout % 16) == 0 && ((uintptr_t)d.dqkv % 16) == 0, "masked_attn_bwd: alignment");
+            a.dout = d.dout;
+            a.dqkv = d.dqkv;
+            use_tmap &= attn_make_tmap(&maps.m[g], d.qkv, N, n_entities, embed_dim);
+        }
+        if (d.n_copies > max_c) max_c = d.n_copies;
+    }
+    const int hd = embed_dim / n_heads, neb = (n_entities + 7) / 8 * 8;
+    const int tile_floats = neb * 2 * embed_dim;              // K tile | V tile, [neb][d] each
+    int warp_floats;
+    if (fwd) {
+        warp_floats = tile_floats + neb * 32;                 // multiples of 32 floats: every warp tile is 128-byte aligned
+    } else {
+        const int ipp = 32 / n_heads, nqp = (n_queries + ipp - 1) / ipp * ipp;
+        warp_floats = (tile_floats + 2 * max_c * neb * n_heads * nqp + neb * 32 + 31) / 32 * 32;
+    }
+    int warps, grid;
+    size_t smem;
+    int rc = attn_geometry(name, N, warp_floats, &warps, &grid, &smem, hd <= 16 ? 2 : 1);
+    if (rc) return rc;
+    if (fwd) smem += (size_t)warps * 8;                       // two mbarriers per warp (K tile, V tile)
+    if (n_problems > 1) {                                     // the group shares one wave of CTAs
+        const int share = refil_cdiv(refil_num_sms() * (hd <= 16 ? 2 : 1), n_problems);
+        if (grid > share) grid = share;
+    }
+    if (fwd) {
+        ATT_DISPATCH(attn_fwd_kernel, "masked_attn_fwd", hd, n_heads, grp, n_problems, smem, grid, warps, stream, "masked_attn_fwd", neb, tile_floats, warp_floats, maps, use_tmap)
+    }
+    ATT_DISPATCH(attn_bwd_kernel, "masked_attn_bwd", hd, n_heads, grp, n_problems, smem, grid, warps, stream, "masked_attn_bwd", neb, tile_floats, warp_floats, maps, use_tmap)
+}
+
+extern "C" int refil_masked_attn_fwd_group(const RefilAttnDesc* descs, int n_problems, int N, int T, int n_entities,
+                                           int n_queries, int embed_dim, int n_heads, cudaStream_t stream) {
+    return attn_group_launch(true, descs, n_problems, N, T, n_entities, n_queries, embed_dim, n_heads, stream);
+}
+
+extern "C" int refil_masked_attn_bwd_group(const RefilAttnDesc* descs, int n_problems, int N, int T, int n_entities,
+                                           int n_queries, int embed_dim, int n_heads, cudaStream_t stream) {
+    return attn_group_launch(false, descs, n_problems, N, T, n_entities, n_queries, embed_dim, n_heads, stream);
+}
+
 extern "C" int refil_masked_attn_fwd(const float* qkv, float* out, const uint8_t* mask0, const uint8_t* mask1,
                                      const uint8_t* mask2, long long mask_stride0, long long mask_stride1,
                                      long long mask_stride2, int mode0, int mode1, int mode2,
                                      const uint8_t* group_bits, const uint8_t* entity_mask, int N, int T,
                                      int n_entities, int n_queries, int embed_dim, int n_heads, int n_copies,
                                      cudaStream_t stream) {
-    AttnArgs a{};
-    int rc = attn_fill(a, qkv, mask0, mask1, mask2, mask_stride0, mask_stride1, mask_stride2, mode0, mode1, mode2,
-                       group_bits, entity_mask, N, T, n_entities, n_queries, embed_dim, n_heads, n_copies);
-    if (rc) return rc;
-    REFIL_CHECK_ARG(out != nullptr, "masked_attn_fwd: out is null");
-    a.out = out;
-    const int hd = embed_dim / n_heads, neb = (n_entities + 7) / 8 * 8;
-    const int tile_floats = neb * 2 * embed_dim;              // K tile | V tile, [neb][d] each
-    const int warp_floats = tile_floats + neb * 32;           // multiples of 32 floats: every warp tile is 128-byte aligned
-    CUtensorMap tmap;
-    const int use_tmap = attn_make_tmap_box(&tmap, qkv, N, n_entities, embed_dim, embed_dim, n_entities);
-    int warps, grid;
-    size_t smem;
-    rc = attn_geometry("masked_attn_fwd", N, warp_floats, &warps, &grid, &smem, hd <= 16 ? 2 : 1);
-    if (rc) return rc;
-    smem += (size_t)warps * 8;                                // two mbarriers per warp (K tile, V tile)
-    ATT_DISPATCH(attn_fwd_kernel, "masked_attn_fwd", hd, n_heads, a, smem, grid, warps, stream, "masked_attn_fwd", neb, tile_floats, warp_floats, tmap, use_tmap)
+    RefilAttnDesc d{qkv, out, nullptr, nullptr, mask0, mask1, mask2, mask_stride0, mask_stride1, mask_stride2, mode0, mode1, mode2,
+                    group_bits, entity_mask, n_copies};
+    return attn_group_launch(true, &d, 1, N, T, n_entities, n_queries, embed_dim, n_heads, stream);
 }
 
 extern "C" int refil_masked_attn_bwd(const float* qkv, const float* dout, float* dqkv, const uint8_t* mask0,
@@ -893,23 +950,7 @@ extern "C" int refil_masked_attn_bwd(const float* qkv, const float* dout, float*
                                      const uint8_t* group_bits, const uint8_t* entity_mask, int N, int T,
                                      int n_entities, int n_queries, int embed_dim, int n_heads, int n_copies,
                                      cudaStream_t stream) {
-    AttnArgs a{};
-    int rc = attn_fill(a, qkv, mask0, mask1, mask2, mask_stride0, mask_stride1, mask_stride2, mode0, mode1, mode2,
-                       group_bits, entity_mask, N, T, n_entities, n_queries, embed_dim, n_heads, n_copies);
-    if (rc) return rc;
-    REFIL_CHECK_ARG(dout && dqkv, "masked_attn_bwd: dout / dqkv is null");
-    REFIL_CHECK_ARG(((uintptr_t)dout % 16) == 0 && ((uintptr_t)dqkv % 16) == 0, "masked_attn_bwd: alignment");
-    a.dout = dout;
-    a.dqkv = dqkv;
-    const int hd = embed_dim / n_heads, neb = (n_entities + 7) / 8 * 8;
-    const int tile_floats = neb * 2 * embed_dim;
-    const int ipp = 32 / n_heads, nqp = (n_queries + ipp - 1) / ipp * ipp;
-    const int warp_floats = (tile_floats + 2 * n_copies * neb * n_heads * nqp + neb * 32 + 31) / 32 * 32;
-    CUtensorMap tmap;
-    const int use_tmap = attn_make_tmap(&tmap, qkv, N, n_entities, embed_dim);
-    int warps, grid;
-    size_t smem;
-    rc = attn_geometry("masked_attn_bwd", N, warp_floats, &warps, &grid, &smem, hd <= 16 ? 2 : 1);
-    if (rc) return rc;
-    ATT_DISPATCH(attn_bwd_kernel, "masked_attn_bwd", hd, n_heads, a, smem, grid, warps, stream, "masked_attn_bwd", neb, tile_floats, warp_floats, tmap, use_tmap)
+    RefilAttnDesc d{qkv, nullptr, dout, dqkv, mask0, mask1, mask2, mask_stride0, mask_stride1, mask_stride2, mode0, mode1, mode2,
+                    group_bits, entity_mask, n_copies};
+    return attn_group_launch(false, &d, 1, N, T, n_entities, n_queries, embed_dim, n_heads, stream);
 }

@@ -496,8 +496,19 @@ __device__ __forceinline__ void tc_tmem_st16(uint32_t taddr, const uint32_t (&r)
         : "memory");
 }
 
-__global__ void __launch_bounds__(TS_THREADS, 1) tc_gemm_ts_kernel(TcArgs a, const __grid_constant__ CUtensorMap tmap_c,
-                                                                  const __grid_constant__ CUtensorMap tmap_a) {
+// A launch carries up to TC_MAX_GROUP independent problems of one (N, K) geometry (blockIdx.y = problem): the same layer of
+// several networks -- the eight hypernetworks of the online and target mixers -- runs as ONE launch whose CTAs each walk eight
+// times as many m-tiles, instead of eight launches that each pay the prologue (weight-tile split, pipeline fill) and the tail.
+#define TC_MAX_GROUP 8
+struct TcGroup { TcArgs a[TC_MAX_GROUP]; };
+struct TcMaps { CUtensorMap m[TC_MAX_GROUP]; };
+
+__global__ void __launch_bounds__(TS_THREADS, 1) tc_gemm_ts_kernel(const __grid_constant__ TcGroup grp,
+                                                                  const __grid_constant__ TcMaps maps_c,
+                                                                  const __grid_constant__ TcMaps maps_a) {
+    const TcArgs& a = grp.a[blockIdx.y];
+    const CUtensorMap& tmap_c = maps_c.m[blockIdx.y];
+    const CUtensorMap& tmap_a = maps_a.m[blockIdx.y];
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int BN = a.BN;
@@ -769,30 +780,7 @@ extern "C" int refil_tc_gemm_k_slices(int N, int K) {
     return tc_pick_slices(N, K);
 }
 
-extern "C" int refil_tc_gemm_tn(const float* A, long long lda, const float* relu_y, long long ldy,
-                                const uint8_t* a_row_entity_mask, int a_na, int a_ne, int a_rows_per_copy,
-                                const float* B, long long b_stride_n, long long b_stride_k, int b_k_valid,
-                                const float* bias, int relu, const uint8_t* c_row_entity_mask, int c_na, int c_ne,
-                                int c_rows_per_copy, float* C, long long ldc, int M, int N, int K, cudaStream_t stream) {
-    REFIL_CHECK_ARG(A && B && C, "tc_gemm_tn: null pointer");
-    REFIL_CHECK_ARG(refil_tc_gemm_supported(M, N, K), "tc_gemm_tn: unsupported shape M=%d N=%d K=%d", M, N, K);
-    REFIL_CHECK_ARG((lda % 4) == 0 && (ldc % 4) == 0 && ((uintptr_t)A % 16) == 0 && ((uintptr_t)C % 16) == 0,
-                    "tc_gemm_tn: A / C must be 16-byte aligned with leading dimensions divisible by 4");
-    REFIL_CHECK_ARG(!relu_y || ((ldy % 4) == 0 && ((uintptr_t)relu_y % 16) == 0), "tc_gemm_tn: relu_y alignment");
-    REFIL_CHECK_ARG(b_k_valid >= 0 && b_k_valid <= K, "tc_gemm_tn: b_k_valid=%d outside [0, K=%d]", b_k_valid, K);
-    TcArgs a{};
-    a.kb_valid = b_k_valid > 0 ? b_k_valid : K;
-    a.b_vec = (b_stride_k == 1 && (b_stride_n % 4) == 0 && ((uintptr_t)B % 16) == 0) ? 1 : 0;
-    a.A = A; a.lda = lda; a.relu_y = relu_y; a.ldy = ldy;
-    a.a_rowmask = a_row_entity_mask; a.a_na = a_na > 0 ? a_na : 1; a.a_ne = a_ne; a.a_mper = a_rows_per_copy > 0 ? a_rows_per_copy : 1;
-    a.B = B; a.sbj = b_stride_n; a.sbi = b_stride_k;
-    a.bias = bias; a.relu = relu;
-    a.c_rowmask = c_row_entity_mask; a.c_na = c_na > 0 ? c_na : 1; a.c_ne = c_ne; a.c_mper = c_rows_per_copy > 0 ? c_rows_per_copy : 1;
-    a.M = M; a.N = N; a.K = K;
-    a.k_slices = tc_pick_slices(N, K);
-    a.KS = K / a.k_slices;
-    REFIL_CHECK_ARG(a.k_slices == 1 || (!bias && !relu && !c_row_entity_mask),
-                    "tc_gemm_tn: a sliced reduction (K=%d) cannot carry a non-linear epilogue", K);
+static int tc_mode_ts() {
     // operand path: "ts" (default) keeps the A operand in tensor memory (TMA-fed raw ring + converter warps), "ss" is the
     // all-shared-memory kernel; REFIL_TC_MODE=ss selects the latter for A/B comparisons
     static int mode_ts = -1;
@@ -800,25 +788,69 @@ extern "C" int refil_tc_gemm_tn(const float* A, long long lda, const float* relu
         const char* e = getenv("REFIL_TC_MODE");
         mode_ts = (e && e[0] == 's' && e[1] == 's') ? 0 : 1;
     }
+    return mode_ts;
+}
+
+// one problem of a group: validate, fill TcArgs and the two tensor maps
+static int tc_fill(const RefilGemmDesc& d, int N, int K, int mode_ts, TcArgs& a, CUtensorMap* tmap_c, CUtensorMap* tmap_a) {
+    const int M = d.M;
+    REFIL_CHECK_ARG(d.A && d.B && d.C, "tc_gemm_tn: null pointer");
+    REFIL_CHECK_ARG(refil_tc_gemm_supported(M, N, K), "tc_gemm_tn: unsupported shape M=%d N=%d K=%d", M, N, K);
+    REFIL_CHECK_ARG((d.lda % 4) == 0 && (d.ldc % 4) == 0 && ((uintptr_t)d.A % 16) == 0 && ((uintptr_t)d.C % 16) == 0,
+                    "tc_gemm_tn: A / C must be 16-byte aligned with leading dimensions divisible by 4");
+    REFIL_CHECK_ARG(!d.relu_y || ((d.ldy % 4) == 0 && ((uintptr_t)d.relu_y % 16) == 0), "tc_gemm_tn: relu_y alignment");
+    REFIL_CHECK_ARG(d.b_k_valid >= 0 && d.b_k_valid <= K, "tc_gemm_tn: b_k_valid=%d outside [0, K=%d]", d.b_k_valid, K);
+    a = TcArgs{};
+    a.kb_valid = d.b_k_valid > 0 ? d.b_k_valid : K;
+    a.b_vec = (d.b_stride_k == 1 && (d.b_stride_n % 4) == 0 && ((uintptr_t)d.B % 16) == 0) ? 1 : 0;
+    a.A = d.A; a.lda = d.lda; a.relu_y = d.relu_y; a.ldy = d.ldy;
+    a.a_rowmask = d.a_row_entity_mask; a.a_na = d.a_na > 0 ? d.a_na : 1; a.a_ne = d.a_ne;
+    a.a_mper = d.a_rows_per_copy > 0 ? d.a_rows_per_copy : 1;
+    a.B = d.B; a.sbj = d.b_stride_n; a.sbi = d.b_stride_k;
+    a.bias = d.bias; a.relu = d.relu;
+    a.c_rowmask = d.c_row_entity_mask; a.c_na = d.c_na > 0 ? d.c_na : 1; a.c_ne = d.c_ne;
+    a.c_mper = d.c_rows_per_copy > 0 ? d.c_rows_per_copy : 1;
+    a.M = M; a.N = N; a.K = K;
+    a.k_slices = tc_pick_slices(N, K);
+    a.KS = K / a.k_slices;
+    REFIL_CHECK_ARG(a.k_slices == 1 || (!d.bias && !d.relu && !d.c_row_entity_mask),
+                    "tc_gemm_tn: a sliced reduction (K=%d) cannot carry a non-linear epilogue", K);
     const int BN = tc_pick_bn(N, a.KS, mode_ts ? 128 : 256);      // ts: two accumulators + the operand ring share 512 columns
     a.BN = BN;
     a.n_tiles = N / BN;
     a.m_tiles = refil_cdiv(M, TC_BM);
-    const size_t b_res = (size_t)2 * BN * a.KS * 4, stage_bytes = 2 * (size_t)TC_BM * 128;
+    // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=tf32, both K-major, N>>3, M>>4
+    a.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    if (!tc_make_tmap_c(tmap_c, d.C, d.ldc, M, N) || (mode_ts && !tc_make_tmap_a(tmap_a, d.A, d.lda, M, K))) {
+        refil_set_error("tc_gemm_tn: cuTensorMapEncodeTiled failed (A=%p lda=%lld C=%p ldc=%lld M=%d N=%d K=%d)", (const void*)d.A,
+                        d.lda, (const void*)d.C, d.ldc, M, N, K);
+        return REFIL_ERR_CUDA;
+    }
+    return REFIL_OK;
+}
+
+extern "C" int refil_tc_gemm_tn_group(const RefilGemmDesc* descs, int n_problems, int N, int K, cudaStream_t stream) {
+    REFIL_CHECK_ARG(descs && n_problems >= 1 && n_problems <= TC_MAX_GROUP, "tc_gemm_tn_group: 1..%d problems (got %d)",
+                    TC_MAX_GROUP, n_problems);
+    const int mode_ts = tc_mode_ts();
+    REFIL_CHECK_ARG(mode_ts || n_problems == 1, "tc_gemm_tn_group: grouped launches need the tensor-memory operand path");
+    TcGroup grp{};
+    TcMaps mc{}, ma{};
+    int max_tiles = 1;
+    for (int g = 0; g < n_problems; g++) {
+        int rc = tc_fill(descs[g], N, K, mode_ts, grp.a[g], &mc.m[g], &ma.m[g]);
+        if (rc) return rc;
+        if (grp.a[g].m_tiles > max_tiles) max_tiles = grp.a[g].m_tiles;
+    }
+    TcArgs& a0 = grp.a[0];
+    const int BN = a0.BN;
+    const size_t b_res = (size_t)2 * BN * a0.KS * 4, stage_bytes = 2 * (size_t)TC_BM * 128;
     const size_t stg_bytes = (size_t)TC_EPI_WARPS * TC_STG_BYTES;
     const size_t budget = 227 * 1024 - 1024 /* alignment slack */ - 2048 /* static: barriers, bias */;
     int stages = (int)((budget - b_res - stg_bytes) / stage_bytes);
     if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
     REFIL_CHECK_ARG(stages >= 2, "tc_gemm_tn: shared memory budget (N=%d K=%d)", N, K);
-    a.stages = stages;
-    // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=tf32, both K-major, N>>3, M>>4
-    a.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-    CUtensorMap tmap, tmap_a;
-    if (!tc_make_tmap_c(&tmap, C, ldc, M, N) || (mode_ts && !tc_make_tmap_a(&tmap_a, A, lda, M, K))) {
-        refil_set_error("tc_gemm_tn: cuTensorMapEncodeTiled failed (A=%p lda=%lld C=%p ldc=%lld M=%d N=%d K=%d)", (const void*)A,
-                        lda, (const void*)C, ldc, M, N, K);
-        return REFIL_ERR_CUDA;
-    }
+    for (int g = 0; g < n_problems; g++) grp.a[g].stages = stages;
     const size_t smem = mode_ts ? b_res + (size_t)TS_RAW_STAGES * TC_BM * 128 + stg_bytes + 1024
                                 : b_res + stages * stage_bytes + stg_bytes + 1024;
     static size_t attr_smem[2] = {0, 0};
@@ -831,16 +863,18 @@ extern "C" int refil_tc_gemm_tn(const float* A, long long lda, const float* relu
         }
         attr_smem[mode_ts] = smem;
     }
-    if (a.k_slices > 1) {             // partial tiles are reduce-added into C
-        cudaError_t e = cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)N * 4, (size_t)M, stream);
-        if (e != cudaSuccess) {
-            refil_set_error("tc_gemm_tn: cudaMemset2DAsync: %s", cudaGetErrorString(e));
-            return REFIL_ERR_CUDA;
+    if (a0.k_slices > 1) {            // partial tiles are reduce-added into C
+        for (int g = 0; g < n_problems; g++) {
+            cudaError_t e = cudaMemset2DAsync(descs[g].C, (size_t)descs[g].ldc * 4, 0, (size_t)N * 4, (size_t)descs[g].M, stream);
+            if (e != cudaSuccess) {
+                refil_set_error("tc_gemm_tn: cudaMemset2DAsync: %s", cudaGetErrorString(e));
+                return REFIL_ERR_CUDA;
+            }
         }
     }
     const int sms = refil_num_sms();
-    const int groups = a.n_tiles * a.k_slices;
-    int per_g = sms / groups;                    // CTAs per (n-tile, k-slice)
+    const int groups = a0.n_tiles * a0.k_slices;
+    int per_g = sms / (groups * n_problems);     // CTAs per (problem, n-tile, k-slice): one wave over the whole group
     if (per_g < 1) per_g = 1;
     // every CTA pays a fixed prologue (split of its resident weight tile, pipeline fill): give it at least `min_tiles` m-tiles, so
     // that a small problem (a 16-episode shard) leaves SMs to the independent networks running on the other streams
@@ -850,18 +884,28 @@ extern "C" int refil_tc_gemm_tn(const float* A, long long lda, const float* relu
         min_tiles = e ? atoi(e) : 6;
         if (min_tiles < 1) min_tiles = 1;
     }
-    const int want = refil_cdiv(a.m_tiles, min_tiles);
+    const int want = refil_cdiv(max_tiles, min_tiles);
     if (per_g > want) per_g = want;
-    if (per_g > a.m_tiles) per_g = a.m_tiles;
-    const int grid = per_g * groups;
+    if (per_g > max_tiles) per_g = max_tiles;
+    const dim3 grid(per_g * groups, n_problems);
     if (mode_ts) {
-        tc_gemm_ts_kernel<<<grid, TS_THREADS, smem, stream>>>(a, tmap, tmap_a);
+        tc_gemm_ts_kernel<<<grid, TS_THREADS, smem, stream>>>(grp, mc, ma);
         REFIL_CHECK_LAUNCH("tc_gemm_tn (ts)");
         return REFIL_OK;
     }
-    tc_gemm_tn_kernel<<<grid, TC_THREADS, smem, stream>>>(a, tmap);
+    tc_gemm_tn_kernel<<<grid.x, TC_THREADS, smem, stream>>>(a0, mc.m[0]);
     REFIL_CHECK_LAUNCH("tc_gemm_tn");
     return REFIL_OK;
+}
+
+extern "C" int refil_tc_gemm_tn(const float* A, long long lda, const float* relu_y, long long ldy,
+                                const uint8_t* a_row_entity_mask, int a_na, int a_ne, int a_rows_per_copy,
+                                const float* B, long long b_stride_n, long long b_stride_k, int b_k_valid,
+                                const float* bias, int relu, const uint8_t* c_row_entity_mask, int c_na, int c_ne,
+                                int c_rows_per_copy, float* C, long long ldc, int M, int N, int K, cudaStream_t stream) {
+    RefilGemmDesc d{A, lda, relu_y, ldy, a_row_entity_mask, a_na, a_ne, a_rows_per_copy, B, b_stride_n, b_stride_k, b_k_valid,
+                    bias, relu, c_row_entity_mask, c_na, c_ne, c_rows_per_copy, C, ldc, M};
+    return refil_tc_gemm_tn_group(&d, 1, N, K, stream);
 }
 
 // =====================================================================================================================
@@ -1141,8 +1185,15 @@ struct TcWGeom {
     int raw_stages, y_stages;
 };
 
-__global__ void __launch_bounds__(TW_THREADS, 1) tc_wgrad_ts_kernel(TcWArgs a, TcWGeom g, const __grid_constant__ CUtensorMap tmap_x,
-                                                                   const __grid_constant__ CUtensorMap tmap_r) {
+struct TcWGroup { TcWArgs a[TC_MAX_GROUP]; };
+
+// blockIdx.y = problem of the group (same (P, Q) geometry, own operands and row count)
+__global__ void __launch_bounds__(TW_THREADS, 1) tc_wgrad_ts_kernel(const __grid_constant__ TcWGroup grp, TcWGeom g,
+                                                                   const __grid_constant__ TcMaps maps_x,
+                                                                   const __grid_constant__ TcMaps maps_r) {
+    const TcWArgs& a = grp.a[blockIdx.y];
+    const CUtensorMap& tmap_x = maps_x.m[blockIdx.y];
+    const CUtensorMap& tmap_r = maps_r.m[blockIdx.y];
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int BQ = a.BQ, SY = g.y_stages, RS = g.raw_stages;
@@ -1407,29 +1458,7 @@ extern "C" int refil_tc_wgrad_supported(int M, int P, int Q) {
     return (Q == 32 || Q == 64 || Q == 128) ? 1 : 0;
 }
 
-extern "C" int refil_tc_gemm_wgrad(const float* X, long long ldx, const float* relu_y, long long ldy,
-                                   const uint8_t* x_row_entity_mask, int na, int ne, int rows_per_copy,
-                                   const float* Y, long long ldyy, int y_shift_rows, int y_period, float* dW,
-                                   long long lddw, int q_valid, float* db, int M, int P, int Q, cudaStream_t stream) {
-    REFIL_CHECK_ARG(X && Y && dW, "tc_gemm_wgrad: null pointer");
-    REFIL_CHECK_ARG(refil_tc_wgrad_supported(M, P, Q), "tc_gemm_wgrad: unsupported shape M=%d P=%d Q=%d", M, P, Q);
-    REFIL_CHECK_ARG((ldx % 4) == 0 && (ldyy % 4) == 0 && ((uintptr_t)X % 16) == 0 && ((uintptr_t)Y % 16) == 0 &&
-                    ((uintptr_t)dW % 4) == 0, "tc_gemm_wgrad: alignment");
-    REFIL_CHECK_ARG(q_valid >= 0 && q_valid <= Q && ldx >= (P + 3) / 4 * 4, "tc_gemm_wgrad: q_valid=%d / ldx=%lld", q_valid, ldx);
-    REFIL_CHECK_ARG(!relu_y || ((ldy % 4) == 0 && ((uintptr_t)relu_y % 16) == 0), "tc_gemm_wgrad: relu_y alignment");
-    TcWArgs a{};
-    a.X = X; a.ldx = ldx; a.relu_y = relu_y; a.ldy = ldy;
-    a.x_rowmask = x_row_entity_mask; a.na = na > 0 ? na : 1; a.ne = ne; a.mper = rows_per_copy > 0 ? rows_per_copy : 1;
-    a.Y = Y; a.ldyy = ldyy; a.dW = dW; a.lddw = lddw; a.db = db;
-    a.y_shift = y_shift_rows > 0 ? y_shift_rows : 0; a.y_period = y_period > 0 ? y_period : 1;
-    a.M = M; a.P = P; a.Q = Q;
-    a.q_valid = q_valid > 0 ? q_valid : Q;
-    a.dw_vec = (a.q_valid == Q && (lddw % 4) == 0 && ((uintptr_t)dW % 16) == 0) ? 1 : 0;
-    a.BQ = db ? Q + 32 : Q;              // the bias gradient rides as one extra 32-wide atom whose first column is 1
-    a.p_tiles = refil_cdiv(P, 128);
-    const int chunks_total = refil_cdiv(M, 32);
-    int splits = refil_num_sms() / a.p_tiles;
-    if (splits < 1) splits = 1;
+static int tcw_min_chunks() {
     // every split ends with a [128 x Q] tile of atomics: at least `min_chunks` 32-row chunks of reduction per split
     static int min_chunks = -1;
     if (min_chunks < 0) {
@@ -1437,31 +1466,73 @@ extern "C" int refil_tc_gemm_wgrad(const float* X, long long ldx, const float* r
         min_chunks = e ? atoi(e) : 24;
         if (min_chunks < 1) min_chunks = 1;
     }
-    if (splits > refil_cdiv(chunks_total, min_chunks)) splits = refil_cdiv(chunks_total, min_chunks);
+    return min_chunks;
+}
+
+static int tcw_fill(const RefilWgradDesc& d, int P, int Q, int sm_share, TcWArgs& a) {
+    const int M = d.M;
+    REFIL_CHECK_ARG(d.X && d.Y && d.dW, "tc_gemm_wgrad: null pointer");
+    REFIL_CHECK_ARG(refil_tc_wgrad_supported(M, P, Q), "tc_gemm_wgrad: unsupported shape M=%d P=%d Q=%d", M, P, Q);
+    REFIL_CHECK_ARG((d.ldx % 4) == 0 && (d.ldyy % 4) == 0 && ((uintptr_t)d.X % 16) == 0 && ((uintptr_t)d.Y % 16) == 0 &&
+                    ((uintptr_t)d.dW % 4) == 0, "tc_gemm_wgrad: alignment");
+    REFIL_CHECK_ARG(d.q_valid >= 0 && d.q_valid <= Q && d.ldx >= (P + 3) / 4 * 4, "tc_gemm_wgrad: q_valid=%d / ldx=%lld", d.q_valid,
+                    d.ldx);
+    REFIL_CHECK_ARG(!d.relu_y || ((d.ldy % 4) == 0 && ((uintptr_t)d.relu_y % 16) == 0), "tc_gemm_wgrad: relu_y alignment");
+    a = TcWArgs{};
+    a.X = d.X; a.ldx = d.ldx; a.relu_y = d.relu_y; a.ldy = d.ldy;
+    a.x_rowmask = d.x_row_entity_mask; a.na = d.na > 0 ? d.na : 1; a.ne = d.ne; a.mper = d.rows_per_copy > 0 ? d.rows_per_copy : 1;
+    a.Y = d.Y; a.ldyy = d.ldyy; a.dW = d.dW; a.lddw = d.lddw; a.db = d.db;
+    a.y_shift = d.y_shift_rows > 0 ? d.y_shift_rows : 0; a.y_period = d.y_period > 0 ? d.y_period : 1;
+    a.M = M; a.P = P; a.Q = Q;
+    a.q_valid = d.q_valid > 0 ? d.q_valid : Q;
+    a.dw_vec = (a.q_valid == Q && (d.lddw % 4) == 0 && ((uintptr_t)d.dW % 16) == 0) ? 1 : 0;
+    a.p_tiles = refil_cdiv(P, 128);
+    const int chunks_total = refil_cdiv(M, 32);
+    int splits = sm_share / a.p_tiles;
+    if (splits < 1) splits = 1;
+    if (splits > refil_cdiv(chunks_total, tcw_min_chunks())) splits = refil_cdiv(chunks_total, tcw_min_chunks());
     if (splits > chunks_total) splits = chunks_total;
     a.chunks_per_split = refil_cdiv(chunks_total, splits);
     a.splits = refil_cdiv(chunks_total, a.chunks_per_split);
-    static int mode_ts = -1;
-    if (mode_ts < 0) {
-        const char* e = getenv("REFIL_TC_MODE");
-        mode_ts = (e && e[0] == 's' && e[1] == 's') ? 0 : 1;
+    return REFIL_OK;
+}
+
+extern "C" int refil_tc_gemm_wgrad_group(const RefilWgradDesc* descs, int n_problems, int P, int Q, cudaStream_t stream) {
+    REFIL_CHECK_ARG(descs && n_problems >= 1 && n_problems <= TC_MAX_GROUP, "tc_gemm_wgrad_group: 1..%d problems (got %d)",
+                    TC_MAX_GROUP, n_problems);
+    const int mode_ts = tc_mode_ts();
+    REFIL_CHECK_ARG(mode_ts || n_problems == 1, "tc_gemm_wgrad_group: grouped launches need the tensor-memory operand path");
+    TcWGroup grp{};
+    const bool has_r = descs[0].relu_y != nullptr, has_b = descs[0].db != nullptr;
+    int max_grid = 1;
+    for (int g = 0; g < n_problems; g++) {
+        REFIL_CHECK_ARG((descs[g].relu_y != nullptr) == has_r && (descs[g].db != nullptr) == has_b,
+                        "tc_gemm_wgrad_group: the problems of a group must agree on relu_y / db being present");
+        int rc = tcw_fill(descs[g], P, Q, refil_num_sms() / n_problems, grp.a[g]);
+        if (rc) return rc;
+        grp.a[g].BQ = has_b ? Q + 32 : Q;   // the bias gradient rides as one extra 32-wide atom whose first column is 1
+        if (grp.a[g].p_tiles * grp.a[g].splits > max_grid) max_grid = grp.a[g].p_tiles * grp.a[g].splits;
     }
+    TcWArgs& a = grp.a[0];
     if (mode_ts) {
         // X^T operand in tensor memory (K-major by construction), Y tiles MN-major in shared memory
-        a.idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(a.BQ >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-        TcWGeom g{};
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(a.BQ >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        TcWGeom geo{};
         const size_t raw_bytes = 32 * 128 * 4, y_stage = 2 * (size_t)32 * a.BQ * 4;
-        g.raw_stages = relu_y ? 3 : 4;
-        const size_t raw_total = (size_t)g.raw_stages * raw_bytes * (relu_y ? 2 : 1);
+        geo.raw_stages = has_r ? 3 : 4;
+        const size_t raw_total = (size_t)geo.raw_stages * raw_bytes * (has_r ? 2 : 1);
         int ys = (int)((225 * 1024 - raw_total) / y_stage);
         if (ys > TC_MAX_STAGES) ys = TC_MAX_STAGES;
         REFIL_CHECK_ARG(ys >= 2, "tc_gemm_wgrad: shared memory budget (Q=%d)", Q);
-        g.y_stages = ys;
-        CUtensorMap tmx, tmr;
-        memset(&tmr, 0, sizeof(tmr));
-        if (!tc_make_tmap_rows(&tmx, X, ldx, M, P) || (relu_y && !tc_make_tmap_rows(&tmr, relu_y, ldy, M, P))) {
-            refil_set_error("tc_gemm_wgrad: cuTensorMapEncodeTiled failed (X=%p ldx=%lld M=%d P=%d)", (const void*)X, ldx, M, P);
-            return REFIL_ERR_CUDA;
+        geo.y_stages = ys;
+        TcMaps mx{}, mr{};
+        for (int g = 0; g < n_problems; g++) {
+            grp.a[g].idesc = idesc;
+            const RefilWgradDesc& d = descs[g];
+            if (!tc_make_tmap_rows(&mx.m[g], d.X, d.ldx, d.M, P) || (has_r && !tc_make_tmap_rows(&mr.m[g], d.relu_y, d.ldy, d.M, P))) {
+                refil_set_error("tc_gemm_wgrad: cuTensorMapEncodeTiled failed (X=%p ldx=%lld M=%d P=%d)", (const void*)d.X, d.ldx, d.M, P);
+                return REFIL_ERR_CUDA;
+            }
         }
         const size_t smem = raw_total + (size_t)ys * y_stage + 1024;
         static size_t attr_smem_ts = 0;
@@ -1473,7 +1544,7 @@ extern "C" int refil_tc_gemm_wgrad(const float* X, long long ldx, const float* r
             }
             attr_smem_ts = smem;
         }
-        tc_wgrad_ts_kernel<<<a.p_tiles * a.splits, TW_THREADS, smem, stream>>>(a, g, tmx, tmr);
+        tc_wgrad_ts_kernel<<<dim3(max_grid, n_problems), TW_THREADS, smem, stream>>>(grp, geo, mx, mr);
         REFIL_CHECK_LAUNCH("tc_gemm_wgrad (ts)");
         return REFIL_OK;
     }
@@ -1497,4 +1568,13 @@ extern "C" int refil_tc_gemm_wgrad(const float* X, long long ldx, const float* r
     tc_gemm_wgrad_kernel<<<a.p_tiles * a.splits, TCW_THREADS, smem, stream>>>(a);
     REFIL_CHECK_LAUNCH("tc_gemm_wgrad");
     return REFIL_OK;
+}
+
+extern "C" int refil_tc_gemm_wgrad(const float* X, long long ldx, const float* relu_y, long long ldy,
+                                   const uint8_t* x_row_entity_mask, int na, int ne, int rows_per_copy,
+                                   const float* Y, long long ldyy, int y_shift_rows, int y_period, float* dW,
+                                   long long lddw, int q_valid, float* db, int M, int P, int Q, cudaStream_t stream) {
+    RefilWgradDesc d{X, ldx, relu_y, ldy, x_row_entity_mask, na, ne, rows_per_copy, Y, ldyy, y_shift_rows, y_period, dW, lddw,
+                     q_valid, db, M};
+    return refil_tc_gemm_wgrad_group(&d, 1, P, Q, stream);
 }

@@ -12,7 +12,7 @@ import os
 
 import torch
 from .. import ops, parallel
-from ..modules.nets import Mixer
+from ..modules.nets import Mixer, hypernets_backward_group, hypernets_forward_group
 from ..modules.params import Workspace
 
 N_STATS = 8
@@ -254,9 +254,18 @@ class QLearner:
         with torch.cuda.stream(s_tgt):
             self.target_mac.init_hidden(B)
             q_tgt, _, _, _ = self.target_mac.forward(batch, None, ret_plan=True, inputs=inp)
-        self.target_mixer.hyper_forward(ents, la, em, T, xin=inp.get("xin"), streams=s_thyp)
-        # ---- online hypernetworks (they only need the entities and the partition) -----------------------------------
-        self.mixer.hyper_forward(ents, la, em, T, imagine_masks=mix if self.imagine else None, xin=inp.get("xin"), streams=s_hyp)
+        # ---- hypernetworks of the target and of the online mixer (they only need the entities and the partition) --------
+        grouped = bool(getattr(args, "group_hypernets", True)) and n_h > 0
+        if grouped:
+            # all of them in lock-step on ONE stream: every dense layer of the 2 x n_h networks is a single grouped launch
+            with torch.cuda.stream(s_hyp[0] if two else main):
+                jobs = self.target_mixer.hyper_jobs(em) + self.mixer.hyper_jobs(em, mix if self.imagine else None)
+                outs = hypernets_forward_group(jobs, ents, la, T, inp.get("xin"))
+                self.target_mixer.set_hyper_outputs(outs[:n_h], N, False)
+                self.mixer.set_hyper_outputs(outs[n_h:], N, self.imagine)
+        else:
+            self.target_mixer.hyper_forward(ents, la, em, T, xin=inp.get("xin"), streams=s_thyp)
+            self.mixer.hyper_forward(ents, la, em, T, imagine_masks=mix if self.imagine else None, xin=inp.get("xin"), streams=s_hyp)
         # ---- main: online agent on all T steps, 3 mask copies when imagining (q_learner.py:79-109) -------------------
         self.mac.init_hidden(B)
         q_all, spec, _, _ = self.mac.forward(batch, None, imagine=self.imagine, use_gt_factors=use_gt,
@@ -287,7 +296,12 @@ class QLearner:
             st.wait_stream(main)
         # weight-gradient kernels leave the data-gradient chains: one companion stream per network
         s_w = [self._side_stream(1 + 2 * n_h + i) for i in range(n_h + 1)] if two else None
-        self.mixer.backward_hyper(dhyper, streams=s_hyp, wstreams=s_w[1:] if two else None)
+        if grouped:
+            with torch.cuda.stream(s_hyp[0] if two else main):
+                hypernets_backward_group(list(self.mixer.nets.values()), [dhyper[h] for h in self.mixer.nets],
+                                         wstream=s_w[1] if two else None)
+        else:
+            self.mixer.backward_hyper(dhyper, streams=s_hyp, wstreams=s_w[1:] if two else None)
         Ap = self.mac.agent.dq_width(C * N * na)        # one-hot scatter of d(chosen) into (padded) action columns
         dQ = ops.scatter_dq(dq, actions, ws.get("dQ", (C * N * na, Ap)), C, N * na, Ap, T, na)
         self.mac.agent.backward(dQ, wstream=s_w[0] if two else None)

@@ -296,6 +296,75 @@ class AttnHyperNet:
             torch.cuda.current_stream().wait_stream(wstream)
 
 
+# ---- lock-step execution of several hypernetworks: every dense layer of the group is ONE launch -------------------------------
+def hypernets_forward_group(jobs, ents, la, T, xin):
+    """jobs: list of (AttnHyperNet, MaskSpec) over the SAME entity rows (hypernetworks of the online and of the target mixer).
+    The nets advance layer by layer; the same layer of all nets is one grouped tensor-core launch (ops.linear_fwd_group), the
+    attention of each net its own launch.  Falls back to net-by-net execution when the packed input is absent (small batches run
+    on the FFMA kernels) or a pooling layer replaces the attention.  -> list of outputs [rows_i, me]."""
+    if xin is None or len(jobs) < 2 or any(net.trunk.pool is not None for net, _ in jobs):
+        return [net.forward(ents, la, m, T, xin=xin) for net, m in jobs]
+    N, ne = ents.shape[0], ents.shape[1]
+    trunks = [net.trunk for net, _ in jobs]
+    x1 = [t.ws.get(t.tag + ".x1", (N * ne, t.d)) for t in trunks]
+    ops.linear_fwd_group([(xin, t.s.p[t.pre + "fc1.weight"], t.s.p[t.pre + "fc1.bias"], x, True, None) for t, x in zip(trunks, x1)])
+    qkv = [t.ws.get(t.tag + ".qkv", (N * ne, 3 * t.d)) for t in trunks]
+    ops.linear_fwd_group([(x, t.s.p[t.pre + "attn.in_trans.weight"], None, q, False, None) for t, x, q in zip(trunks, x1, qkv)])
+    att, x2, x3 = [], [], []
+    t0 = trunks[0]
+    for (net, m), t, q in zip(jobs, trunks, qkv):
+        a = t.ws.get(t.tag + ".att", (m.C * N * t.na, t.d))
+        att.append(a)
+        t.row_mask = (m.entity_mask, t.na, N * t.na) if m.entity_mask is not None else None
+        x2.append(t.ws.get(t.tag + ".x2", (m.C * N * t.na, t.d)))
+        x3.append(net.ws.get(net.tag + ".x3", (m.C * N * t.na, net.me)))
+    ops.masked_attn_fwd_group([(q, a, m.copies, m.group_bits, m.entity_mask) for (_, m), q, a in zip(jobs, qkv, att)],
+                              N, T, ne, t0.na, t0.d, t0.H)
+    ops.linear_fwd_group([(a, t.s.p[t.pre + "attn.out_trans.weight"], t.s.p[t.pre + "attn.out_trans.bias"], y, False, t.row_mask)
+                          for t, a, y in zip(trunks, att, x2)])
+    ops.linear_fwd_group([(y, net.s.p[net.pre + "fc2.weight"], net.s.p[net.pre + "fc2.bias"], z, False, net.trunk.row_mask)
+                          for (net, _), y, z in zip(jobs, x2, x3)])
+    for (net, m), t, a, b, c, y in zip(jobs, trunks, x1, qkv, att, x2):
+        t.saved = (ents, la, m, T, False, a, b, c, y, N, ne, xin)
+        net.x2 = y
+    return x3
+
+
+def hypernets_backward_group(nets, douts, wstream=None):
+    """Backward of several hypernetworks (forwarded by hypernets_forward_group on the packed input) in lock-step: the data-gradient
+    chain fc2 -> out_trans -> attention -> in_trans is 3 grouped launches + one attention launch per net; the weight gradients
+    (5 grouped launches) go to the companion stream `wstream`, off the chain."""
+    trunks = [net.trunk for net in nets]
+    if len(nets) < 2 or any(t.saved[11] is None or t.pool is not None for t in trunks):
+        for net, d in zip(nets, douts):
+            net.backward(d, wstream=wstream)
+        return
+    g = [net.s.g for net in nets]
+    p = [net.s.p for net in nets]
+    _on_side(wstream, lambda: ops.linear_bwd_weight_group(
+        [(d, net.x2, gg[net.pre + "fc2.weight"], gg[net.pre + "fc2.bias"], None, net.trunk.row_mask) for net, d, gg in zip(nets, douts, g)]))
+    dx2 = [net.ws.get(net.trunk.scratch + ".dx2h", (d.shape[0], net.he)) for net, d in zip(nets, douts)]
+    ops.linear_bwd_data_group([(d, pp[net.pre + "fc2.weight"], y, None, net.trunk.row_mask) for net, d, y, pp in zip(nets, douts, dx2, p)])
+    sv = [t.saved for t in trunks]          # (ents, la, masks, T, relu_out, x1, qkv, att, x2, N, ne, xin)
+    _on_side(wstream, lambda: ops.linear_bwd_weight_group(
+        [(y, s_[7], gg[t.pre + "attn.out_trans.weight"], gg[t.pre + "attn.out_trans.bias"], None, t.row_mask)
+         for t, y, s_, gg in zip(trunks, dx2, sv, g)]))
+    datt = [t.ws.get(t.scratch + ".datt", tuple(s_[7].shape)) for t, s_ in zip(trunks, sv)]
+    ops.linear_bwd_data_group([(y, pp[t.pre + "attn.out_trans.weight"], a, None, t.row_mask) for t, y, a, pp in zip(trunks, dx2, datt, p)])
+    T, N, ne, t0 = sv[0][3], sv[0][9], sv[0][10], trunks[0]
+    dqkv = [t.ws.get(t.scratch + ".dqkv", (N * ne, 3 * t.d)) for t in trunks]
+    ops.masked_attn_bwd_group([(s_[6], a, q, s_[2].copies, s_[2].group_bits, s_[2].entity_mask) for s_, a, q in zip(sv, datt, dqkv)],
+                              N, T, ne, t0.na, t0.d, t0.H)
+    _on_side(wstream, lambda: ops.linear_bwd_weight_group(
+        [(q, s_[5], gg[t.pre + "attn.in_trans.weight"], None, None, None) for t, q, s_, gg in zip(trunks, dqkv, sv, g)]))
+    dx1 = [t.ws.get(t.scratch + ".dx1", tuple(s_[5].shape)) for t, s_ in zip(trunks, sv)]
+    ops.linear_bwd_data_group([(q, pp[t.pre + "attn.in_trans.weight"], x, None, None) for t, q, x, pp in zip(trunks, dqkv, dx1, p)])
+    ops.linear_bwd_weight_group([(x, s_[11], gg[t.pre + "fc1.weight"], gg[t.pre + "fc1.bias"], s_[5], None)
+                                 for t, x, s_, gg in zip(trunks, dx1, sv, g)])
+    if wstream is not None:
+        torch.cuda.current_stream().wait_stream(wstream)
+
+
 class Mixer:
     """FlexQMixer / LinearFlexQMixer / VDNMixer (modules/mixers/flex_qmix.py:60-172, vdn.py:5-10) over [N] rows."""
 
@@ -371,6 +440,23 @@ class Mixer:
                     outs[h] = net.forward(ents, la, m, T, xin=xin)
         self._hyper = (outs, ents.shape[0], imagine)
         return outs
+
+    def hyper_jobs(self, entity_mask, imagine_masks=None):
+        """(net, MaskSpec) pairs of this mixer's hypernetworks, for hypernets_forward_group."""
+        imagine = imagine_masks is not None
+        jobs = []
+        if self.kind != 2:
+            default = (None, 0, ops.ATTN_DEFAULT)
+            for h, net in self.nets.items():
+                if h == "hyper_w_1." and imagine:
+                    copies, gbits = imagine_masks
+                    jobs.append((net, MaskSpec([default] + list(copies), gbits, entity_mask)))
+                else:
+                    jobs.append((net, MaskSpec([default], None, entity_mask)))
+        return jobs
+
+    def set_hyper_outputs(self, outs_list, n_rows, imagine):
+        self._hyper = (dict(zip(self.nets.keys(), outs_list)), n_rows, imagine)
 
     def mix(self, q, qW, qI, ret_ingroup=False):
         """q [N, na] (+ qW, qI when imagine) combined with the hypernetwork outputs of the last hyper_forward.

@@ -78,7 +78,8 @@ def timing_summary():
     return out
 
 
-def _call(name, *args, shape=None):
+def _call(name, *args, shape=None, as_name=None):
+    """as_name: the timing bucket (a grouped launch is booked under its single-problem entry point, where its work is accounted)."""
     global _launches
     _launches += 1
     if _timing is None:
@@ -88,7 +89,7 @@ def _call(name, *args, shape=None):
     a.record()
     _lib.call(name, *args, _stream())
     b.record()
-    _timing.setdefault(name, []).append((a, b))
+    _timing.setdefault(as_name or name, []).append((a, b))
     if shape is not None:
         _shape_timing.setdefault("%s[%s]" % (name, "x".join(str(int(x)) for x in shape)), []).append((a, b))
 
@@ -126,6 +127,119 @@ def tc_gemm_tn(A, B, sbn, sbk, out, N, K, bias=None, relu=False, relu_y=None, a_
     _call("tc_gemm_tn", _p(A, F32), A.shape[1], _p(relu_y, F32), A.shape[1], aem, ana, ane, amper, _p(B, F32), sbn, sbk,
           int(k_valid), _p(bias, F32), int(relu), cem, cna, cne, cmper, _p(out, F32), out.shape[1], M, N, K, shape=(M, N, K))
     return out
+
+
+# ---- grouped launches: the same layer of several networks in ONE kernel launch (include/refil_b200.h: RefilGemmDesc) ----------
+import ctypes as _ct
+
+
+class _GemmDesc(_ct.Structure):
+    _fields_ = [("A", _ct.c_void_p), ("lda", _ct.c_longlong), ("relu_y", _ct.c_void_p), ("ldy", _ct.c_longlong),
+                ("a_mask", _ct.c_void_p), ("a_na", _ct.c_int), ("a_ne", _ct.c_int), ("a_mper", _ct.c_int),
+                ("B", _ct.c_void_p), ("sbn", _ct.c_longlong), ("sbk", _ct.c_longlong), ("b_k_valid", _ct.c_int),
+                ("bias", _ct.c_void_p), ("relu", _ct.c_int),
+                ("c_mask", _ct.c_void_p), ("c_na", _ct.c_int), ("c_ne", _ct.c_int), ("c_mper", _ct.c_int),
+                ("C", _ct.c_void_p), ("ldc", _ct.c_longlong), ("M", _ct.c_int)]
+
+
+class _WgradDesc(_ct.Structure):
+    _fields_ = [("X", _ct.c_void_p), ("ldx", _ct.c_longlong), ("relu_y", _ct.c_void_p), ("ldy", _ct.c_longlong),
+                ("x_mask", _ct.c_void_p), ("na", _ct.c_int), ("ne", _ct.c_int), ("mper", _ct.c_int),
+                ("Y", _ct.c_void_p), ("ldyy", _ct.c_longlong), ("y_shift", _ct.c_int), ("y_period", _ct.c_int),
+                ("dW", _ct.c_void_p), ("lddw", _ct.c_longlong), ("q_valid", _ct.c_int),
+                ("db", _ct.c_void_p), ("M", _ct.c_int)]
+
+
+MAX_GROUP = 8
+
+
+def _group_ok(rows):
+    return USE_TENSOR_CORES and len(rows) > 1 and min(rows) >= TC_MIN_ROWS
+
+
+def linear_fwd_group(items):
+    """items: list of (A, W, bias, out, relu, row_mask) with one (N, K) geometry -> as few launches as possible (<= 8 problems
+    each); falls back to per-item linear_fwd when the shape is not tensor-core eligible."""
+    A0, W0 = items[0][0], items[0][1]
+    K, N = A0.shape[1], W0.shape[0]
+    same = all(it[0].shape[1] == K and it[1].shape == W0.shape and bool(it[4]) == bool(items[0][4]) for it in items)
+    sliced = _lib.load().refil_tc_gemm_k_slices(N, K) != 1
+    if not (same and _group_ok([it[0].shape[0] for it in items]) and all(_tc_ok(it[0].shape[0], N, K) for it in items)) or \
+            (sliced and any(it[2] is not None or it[4] or it[5] is not None for it in items)):
+        for A, W, bias, out, relu, rm in items:
+            linear_fwd(A, W, bias, out, relu=relu, row_mask=rm)
+        return
+    Kw = W0.shape[1]
+    for lo in range(0, len(items), MAX_GROUP):
+        part = items[lo:lo + MAX_GROUP]
+        arr = (_GemmDesc * len(part))()
+        for d, (A, W, bias, out, relu, rm) in zip(arr, part):
+            cem, cna, cne, cmper = _rm(rm)
+            M = A.shape[0]
+            d.A, d.lda, d.relu_y, d.ldy = _p(A, F32), K, None, K
+            d.a_mask, d.a_na, d.a_ne, d.a_mper = None, 1, 1, 1
+            d.B, d.sbn, d.sbk, d.b_k_valid = _p(W, F32), Kw, 1, (Kw if Kw != K else 0)
+            d.bias, d.relu = _p(bias, F32), int(relu)
+            d.c_mask, d.c_na, d.c_ne, d.c_mper = cem, cna, cne, cmper
+            d.C, d.ldc, d.M = _p(out, F32), out.shape[1], M
+            _account("tc_gemm_tn", 2.0 * M * N * K, 4.0 * (M * K + M * N + N * K))
+        _call("tc_gemm_tn_group", _ct.addressof(arr), len(part), N, K, shape=(len(part), part[0][0].shape[0], N, K),
+              as_name="tc_gemm_tn")
+
+
+def linear_bwd_data_group(items):
+    """items: list of (dC, W, dA, relu_y, row_mask): dA = g(dC) W, grouped like linear_fwd_group."""
+    dC0, W0 = items[0][0], items[0][1]
+    N, K = dC0.shape[1], W0.shape[1]
+    same = all(it[0].shape[1] == N and it[1].shape == W0.shape and (it[3] is None) == (items[0][3] is None) for it in items)
+    if not (same and _group_ok([it[0].shape[0] for it in items]) and all(_tc_ok(it[0].shape[0], K, N) for it in items)):
+        for dC, W, dA, relu_y, rm in items:
+            linear_bwd_data(dC, W, dA, relu_y=relu_y, row_mask=rm)
+        return
+    Nw = W0.shape[0]
+    for lo in range(0, len(items), MAX_GROUP):
+        part = items[lo:lo + MAX_GROUP]
+        arr = (_GemmDesc * len(part))()
+        for d, (dC, W, dA, relu_y, rm) in zip(arr, part):
+            aem, ana, ane, amper = _rm(rm)
+            M = dC.shape[0]
+            d.A, d.lda, d.relu_y, d.ldy = _p(dC, F32), N, _p(relu_y, F32), N
+            d.a_mask, d.a_na, d.a_ne, d.a_mper = aem, ana, ane, amper
+            d.B, d.sbn, d.sbk, d.b_k_valid = _p(W, F32), 1, K, (Nw if Nw != N else 0)     # "B"[j = k, i = n] = W[n * K + k]
+            d.bias, d.relu = None, 0
+            d.c_mask, d.c_na, d.c_ne, d.c_mper = None, 1, 1, 1
+            d.C, d.ldc, d.M = _p(dA, F32), K, M
+            _account("tc_gemm_tn", 2.0 * M * N * K, 4.0 * (M * N * (2 if relu_y is not None else 1) + M * K + N * K))
+        _call("tc_gemm_tn_group", _ct.addressof(arr), len(part), K, N, shape=(len(part), part[0][0].shape[0], K, N),
+              as_name="tc_gemm_tn")
+
+
+def linear_bwd_weight_group(items):
+    """items: list of (dC, A, dW, db, relu_y, row_mask): dW += g(dC)^T A, db += colsum g(dC), grouped."""
+    dC0, A0, dW0 = items[0][0], items[0][1], items[0][2]
+    N, K = dC0.shape[1], A0.shape[1]
+    P, Qv = dW0.shape
+    same = all(it[0].shape[1] == N and it[1].shape[1] == K and it[2].shape == dW0.shape and
+               (it[3] is None) == (items[0][3] is None) and (it[4] is None) == (items[0][4] is None) for it in items)
+    lib = _lib.load()
+    if not (same and _group_ok([it[0].shape[0] for it in items]) and N % 4 == 0 and
+            all(lib.refil_tc_wgrad_supported(it[0].shape[0], P, K) != 0 for it in items)):
+        for dC, A, dW, db, relu_y, rm in items:
+            linear_bwd_weight(dC, A, dW, db, relu_y=relu_y, row_mask=rm)
+        return
+    for lo in range(0, len(items), MAX_GROUP):
+        part = items[lo:lo + MAX_GROUP]
+        arr = (_WgradDesc * len(part))()
+        for d, (dC, A, dW, db, relu_y, rm) in zip(arr, part):
+            em, na, ne, mper = _rm(rm)
+            M = dC.shape[0]
+            d.X, d.ldx, d.relu_y, d.ldy = _p(dC, F32), N, _p(relu_y, F32), N
+            d.x_mask, d.na, d.ne, d.mper = em, na, ne, mper
+            d.Y, d.ldyy, d.y_shift, d.y_period = _p(A, F32), K, 0, 1
+            d.dW, d.lddw, d.q_valid, d.db, d.M = _p(dW, F32), Qv, (Qv if Qv != K else 0), _p(db, F32), M
+            _account("tc_gemm_wgrad", 2.0 * M * N * K, 4.0 * (M * N * (2 if relu_y is not None else 1) + M * K + N * K))
+        _call("tc_gemm_wgrad_group", _ct.addressof(arr), len(part), P, K, shape=(len(part), part[0][0].shape[0], N, K),
+              as_name="tc_gemm_wgrad")
 
 
 def linear_fwd(A, W, bias, out, relu=False, row_mask=None):
@@ -254,6 +368,52 @@ def entity_pool_bwd(E, dout, dE, copies, group_bits, entity_mask, N, T, ne, nq, 
     _call("entity_pool_bwd", _p(E, F32), _p(dout, F32), _p(dE, F32), *_copies(copies), _p(group_bits, U8),
           _p(entity_mask, U8), N, T, ne, nq, d, len(copies), POOL_TYPES[pool_type])
     return dE
+
+
+class _AttnDesc(_ct.Structure):
+    _fields_ = [("qkv", _ct.c_void_p), ("out", _ct.c_void_p), ("dout", _ct.c_void_p), ("dqkv", _ct.c_void_p),
+                ("mask0", _ct.c_void_p), ("mask1", _ct.c_void_p), ("mask2", _ct.c_void_p),
+                ("s0", _ct.c_longlong), ("s1", _ct.c_longlong), ("s2", _ct.c_longlong),
+                ("m0", _ct.c_int), ("m1", _ct.c_int), ("m2", _ct.c_int),
+                ("group_bits", _ct.c_void_p), ("entity_mask", _ct.c_void_p), ("n_copies", _ct.c_int)]
+
+
+def _attn_descs(items, fwd):
+    arr = (_AttnDesc * len(items))()
+    for d, it in zip(arr, items):
+        if fwd:
+            qkv, out, copies, group_bits, entity_mask = it
+            d.out, d.dout, d.dqkv = _p(out, F32), None, None
+        else:
+            qkv, dout, dqkv, copies, group_bits, entity_mask = it
+            d.out, d.dout, d.dqkv = None, _p(dout, F32), _p(dqkv, F32)
+        c = _copies(copies)
+        d.qkv = _p(qkv, F32)
+        d.mask0, d.mask1, d.mask2, d.s0, d.s1, d.s2, d.m0, d.m1, d.m2 = c
+        d.group_bits, d.entity_mask, d.n_copies = _p(group_bits, U8), _p(entity_mask, U8), len(copies)
+    return arr
+
+
+def masked_attn_fwd_group(items, N, T, ne, nq, d, H):
+    """items: list of (qkv, out, copies, group_bits, entity_mask) of one geometry -> <= 8 problems per launch."""
+    for lo in range(0, len(items), MAX_GROUP):
+        part = items[lo:lo + MAX_GROUP]
+        for it in part:
+            C = len(it[2])
+            _account("masked_attn_fwd", 4.0 * nq * ne * d * N * C, (4.0 * d * (2 * ne + 2 * nq) + nq * ne) * N * C)
+        arr = _attn_descs(part, True)
+        _call("masked_attn_fwd_group", _ct.addressof(arr), len(part), N, T, ne, nq, d, H, as_name="masked_attn_fwd")
+
+
+def masked_attn_bwd_group(items, N, T, ne, nq, d, H):
+    """items: list of (qkv, dout, dqkv, copies, group_bits, entity_mask)."""
+    for lo in range(0, len(items), MAX_GROUP):
+        part = items[lo:lo + MAX_GROUP]
+        for it in part:
+            C = len(it[3])
+            _account("masked_attn_bwd", 10.0 * nq * ne * d * N * C, (4.0 * d * (2 * ne + 2 * nq) * 2 + nq * ne) * N * C)
+        arr = _attn_descs(part, False)
+        _call("masked_attn_bwd_group", _ct.addressof(arr), len(part), N, T, ne, nq, d, H, as_name="masked_attn_bwd")
 
 
 # ---------------------------------------------------------------------------------------------------- GRU

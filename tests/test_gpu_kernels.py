@@ -422,3 +422,62 @@ def test_full_size_attention_copies_are_independent():
         acc += dq1
     assert torch.isfinite(out3).all()
     assert (acc - dq3).abs().max().item() <= 1e-4 * dq3.abs().max().item()
+
+
+def test_grouped_dense_launches_match_single_launches():
+    """Grouped tensor-core launches (one kernel, blockIdx.y = problem; include/refil_b200.h RefilGemmDesc / RefilWgradDesc): the
+    same layer of several networks with different operands and ROW COUNTS, against fp64 references -- forward with bias / relu /
+    row mask, backward-data (W^T by strides, k-sliced reduction for K = 3d), weight + bias gradients with a fused relu' mask,
+    and the in-place zero-padded operands (fc1: 53-column weight against a 64-column packed input)."""
+    from refil_b200 import ops
+    g = torch.Generator().manual_seed(77)
+    l0 = ops.launch_count()
+    Ms = [640, 1000, 384, 2048, 300]
+    # forward: N = 128, K = 64 with a 53-column weight (zero-padded reduction), relu
+    K, Kw, N = 64, 53, 128
+    As = [torch.randn(M, K, generator=g) for M in Ms]
+    for A in As:
+        A[:, Kw:] = 0
+    Ws = [torch.randn(N, Kw, generator=g) * 0.2 for _ in Ms]
+    bs = [torch.randn(N, generator=g) for _ in Ms]
+    outs = [torch.empty(M, N, device=DEV) for M in Ms]
+    ops.linear_fwd_group([(A.to(DEV), W.to(DEV), b.to(DEV), o, True, None) for A, W, b, o in zip(As, Ws, bs, outs)])
+    assert ops.launch_count() - l0 == 1
+    for A, W, b, o in zip(As, Ws, bs, outs):
+        ref = torch.relu(A[:, :Kw].double() @ W.double().t() + b.double()).float()
+        _close(o, ref, atol=5e-6 * float((A.abs() @ torch.nn.functional.pad(W, (0, K - Kw)).abs().t()).max()), what="group fwd")
+    # weight gradients into the 53-column weight, relu' fused
+    dCs = [torch.randn(M, N, generator=g) for M in Ms]
+    dWs = [torch.zeros(N, Kw, device=DEV) for _ in Ms]
+    dbs = [torch.zeros(N, device=DEV) for _ in Ms]
+    l1 = ops.launch_count()
+    ops.linear_bwd_weight_group([(dC.to(DEV), A.to(DEV), dW, db, o, None) for dC, A, dW, db, o in zip(dCs, As, dWs, dbs, outs)])
+    assert ops.launch_count() - l1 == 1
+    for dC, A, dW, db, o in zip(dCs, As, dWs, dbs, outs):
+        gm = dC.double() * (o.cpu().double() > 0)
+        _close(dW, (gm.t() @ A[:, :Kw].double()).float(), rtol=2e-4, atol=5e-6 * float((dC.abs().t() @ A.abs()).max()), what="group dW")
+        _close(db, gm.sum(0).float(), rtol=2e-4, atol=2e-4, what="group db")
+    # backward-data with a k-sliced reduction (N = 384 -> K = 128, the in_trans shape): dA = dC W
+    N2, K2 = 384, 128
+    dC2 = [torch.randn(M, N2, generator=g) for M in Ms]
+    W2 = [torch.randn(N2, K2, generator=g) * 0.1 for _ in Ms]
+    dA2 = [torch.empty(M, K2, device=DEV) for M in Ms]
+    l2 = ops.launch_count()
+    ops.linear_bwd_data_group([(dC.to(DEV), W.to(DEV), dA, None, None) for dC, W, dA in zip(dC2, W2, dA2)])
+    assert ops.launch_count() - l2 == 1
+    for dC, W, dA in zip(dC2, W2, dA2):
+        _close(dA, (dC.double() @ W.double()).float(), atol=5e-6 * float((dC.abs() @ W.abs()).max()), what="group dA")
+    # row masks on the output side, 9 problems -> two launches (8 + 1)
+    na, ne, Nn, C = 3, 5, 96, 1
+    em = (torch.rand(Nn, ne, generator=g) < 0.3).to(torch.uint8)
+    X = [torch.randn(C * Nn * na, 128, generator=g) for _ in range(9)]
+    W3 = [torch.randn(32, 128, generator=g) * 0.3 for _ in range(9)]
+    b3 = [torch.randn(32, generator=g) for _ in range(9)]
+    o3 = [torch.empty(C * Nn * na, 32, device=DEV) for _ in range(9)]
+    l3 = ops.launch_count()
+    rm = (em.to(DEV), na, Nn * na)
+    ops.linear_fwd_group([(x.to(DEV), w.to(DEV), b.to(DEV), o, False, rm) for x, w, b, o in zip(X, W3, b3, o3)])
+    assert ops.launch_count() - l3 == 2
+    for x, w, b, o in zip(X, W3, b3, o3):
+        ref = (x @ w.t() + b).view(C, Nn, na, 32).masked_fill(em[:, :na].bool().view(1, Nn, na, 1), 0.0).view(-1, 32)
+        _close(o, ref, atol=1e-4, what="group rowmask")
