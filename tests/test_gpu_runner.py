@@ -166,7 +166,9 @@ def test_graph_rollout_training_mode_explores_and_counts_steps():
     acts, hs = [], []
     for rep in range(4):
         t0 = runner.t_env
+        eps_expected = mac.action_selector.schedule.eval(t0)
         batch = runner.run(test_mode=False)
+        assert abs(mac.action_selector.epsilon - eps_expected) < 1e-12          # the run's epsilon = schedule at its first step
         h = {k: v.cpu() for k, v in batch.data.transition_data.items()}
         lengths = h["filled"].sum(1)[:, 0] - 1
         assert runner.t_env - t0 == int(lengths.sum())
@@ -189,7 +191,8 @@ def test_graph_rollout_training_mode_explores_and_counts_steps():
                 assert np.float32(r) == h["reward"][i, ts, 0].item()
                 ts += 1
             assert int(h["filled"][i].sum()) == ts + 1
-    assert 0.9 < mac.action_selector.epsilon <= 1.0
+    assert 0.05 < mac.action_selector.epsilon < 1.0 and runner._graph_state["graph"] is not None
+    assert abs(float(runner._graph_state["eps"].item()) - mac.action_selector.epsilon) < 1e-6   # the device scalar the graph reads
     assert not torch.equal(acts[1], acts[2]) and not torch.equal(acts[2], acts[3])      # fresh exploration noise per replay
 
 
