@@ -58,7 +58,7 @@ struct AttnArgs {
 #define ATT_MAX_GROUP 8
 // a launch carries up to ATT_MAX_GROUP independent problems of one geometry (the attention of several networks over the same
 // (b, t) units): blockIdx.y selects the problem
-struct AttnGroup { AttnArgs a[ATT_MAX_GROUP]; };
+struct AttnGroup { AttnArgs a[ATT_MAX_GROUP]; int cta_begin[ATT_MAX_GROUP + 1]; };
 struct AttnMaps { CUtensorMap m[ATT_MAX_GROUP]; };
 
 __device__ __forceinline__ uint32_t att_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -201,10 +201,18 @@ __device__ __forceinline__ void att_meta_resolve(const AttnArgs& a, long long n,
 }
 
 // head dim <= 16 (d = 64 configs: small units, latency-bound): registers capped so that two CTAs share an SM
-template <int HD, int H>
+template <int HD, int H, bool GROUPED>
 __global__ void __launch_bounds__(32 * ATT_MAX_WARPS, (HD <= 16) ? 2 : 1) attn_fwd_kernel(const __grid_constant__ AttnGroup grp, int NEB, int tile_floats, int warp_floats, const __grid_constant__ AttnMaps maps, int use_tmap) {
-    const AttnArgs& a = grp.a[blockIdx.y];                 // blockIdx.y = problem of a grouped launch (one network each)
-    const CUtensorMap& tmap = maps.m[blockIdx.y];
+    // grouped launch: the CTAs are dealt out to the problems in proportion to their work (grp.cta_begin); a single-problem launch
+    // reads its arguments at fixed parameter offsets
+    int prob = 0, cta = (int)blockIdx.x, ncta = (int)gridDim.x;
+    if (GROUPED) {
+        while (prob + 1 < ATT_MAX_GROUP && (int)blockIdx.x >= grp.cta_begin[prob + 1]) prob++;
+        cta = (int)blockIdx.x - grp.cta_begin[prob];
+        ncta = grp.cta_begin[prob + 1] - grp.cta_begin[prob];
+    }
+    const AttnArgs& a = grp.a[prob];
+    const CUtensorMap& tmap = maps.m[prob];
     extern __shared__ __align__(128) float smem_raw_[];
     // 128-byte aligned base, derived by pointer arithmetic on the __shared__ symbol so that every access below is
     // provably shared memory (LDS / STS, not generic LD / ST)
@@ -241,7 +249,7 @@ __global__ void __launch_bounds__(32 * ATT_MAX_WARPS, (HD <= 16) ? 2 : 1) attn_f
 #pragma unroll
     for (int kc = 0; kc < NCH; kc++) rot[kc] = h * HD + 4 * ((kc + h) & (NCH - 1));
     const float inv_scale = 1.f / sqrtf((float)HD);
-    const long long gw = (long long)blockIdx.x * wpc + warp, GW = (long long)gridDim.x * wpc;
+    const long long gw = (long long)cta * wpc + warp, GW = (long long)ncta * wpc;
     uint32_t parity = 0;
     // the Q row and the mask bytes of the NEXT unit are requested before the current one is computed
     auto load_q = [&](long long n, int i, float4 (&dst)[NCH]) {
@@ -359,10 +367,18 @@ __global__ void __launch_bounds__(32 * ATT_MAX_WARPS, (HD <= 16) ? 2 : 1) attn_f
 //            / sqrt(hd); dQ_i accumulates in registers over the copies; w and dlogit go to the warp's smem scratch;
 //   phase 2, lane = (entity j, head h): dK_j = sum_{c,i} dlogit_ij Q_i, dV_j = sum_{c,i} w_ij dO_i (Q / dO rows come
 //            back through L1), written over the K|V tile, which is then streamed out as the K|V columns of dQKV.
-template <int HD, int H>
+template <int HD, int H, bool GROUPED>
 __global__ void __launch_bounds__(32 * ATT_MAX_WARPS, (HD <= 16) ? 2 : 1) attn_bwd_kernel(const __grid_constant__ AttnGroup grp, int NEB, int tile_floats, int warp_floats, const __grid_constant__ AttnMaps maps, int use_tmap) {
-    const AttnArgs& a = grp.a[blockIdx.y];                 // blockIdx.y = problem of a grouped launch (one network each)
-    const CUtensorMap& tmap = maps.m[blockIdx.y];
+    // grouped launch: the CTAs are dealt out to the problems in proportion to their work (grp.cta_begin); a single-problem launch
+    // reads its arguments at fixed parameter offsets
+    int prob = 0, cta = (int)blockIdx.x, ncta = (int)gridDim.x;
+    if (GROUPED) {
+        while (prob + 1 < ATT_MAX_GROUP && (int)blockIdx.x >= grp.cta_begin[prob + 1]) prob++;
+        cta = (int)blockIdx.x - grp.cta_begin[prob];
+        ncta = grp.cta_begin[prob + 1] - grp.cta_begin[prob];
+    }
+    const AttnArgs& a = grp.a[prob];
+    const CUtensorMap& tmap = maps.m[prob];
     extern __shared__ __align__(128) float smem_raw_[];
     // 128-byte aligned base, derived by pointer arithmetic on the __shared__ symbol so that every access below is
     // provably shared memory (LDS / STS, not generic LD / ST)
@@ -388,7 +404,7 @@ __global__ void __launch_bounds__(32 * ATT_MAX_WARPS, (HD <= 16) ? 2 : 1) attn_b
     }
     __syncwarp();
     const float inv_scale = 1.f / sqrtf((float)HD);
-    const long long gw = (long long)blockIdx.x * wpc + warp, GW = (long long)gridDim.x * wpc;
+    const long long gw = (long long)cta * wpc + warp, GW = (long long)ncta * wpc;
     uint32_t parity = 0;
     // the Q row and the mask bytes of the NEXT unit are requested before the current one is computed
     auto load_q = [&](long long n, int i, float4 (&dst)[NCH]) {
@@ -789,26 +805,27 @@ static int attn_launch(K kernel, const AttnGroup& a, int n_problems, size_t smem
             return REFIL_ERR_CUDA;
         }
     }
-    kernel<<<dim3(grid, n_problems), 32 * warps, smem, stream>>>(a, extra...);
+    (void)n_problems;
+    kernel<<<grid, 32 * warps, smem, stream>>>(a, extra...);
     REFIL_CHECK_LAUNCH(name);
     return REFIL_OK;
 }
 
 // dispatch on (head dim, heads): both are template parameters so that every tile offset is an immediate
-#define ATT_DISPATCH(KERNEL, name, hd, heads, ...)                                                            \
+#define ATT_DISPATCH(KERNEL, G, name, hd, heads, ...)                                                           \
     switch ((hd) * 100 + (heads)) {                                                                           \
-        case 801: return attn_launch(KERNEL<8, 1>, __VA_ARGS__);                                              \
-        case 802: return attn_launch(KERNEL<8, 2>, __VA_ARGS__);                                              \
-        case 804: return attn_launch(KERNEL<8, 4>, __VA_ARGS__);                                              \
-        case 808: return attn_launch(KERNEL<8, 8>, __VA_ARGS__);                                              \
-        case 1601: return attn_launch(KERNEL<16, 1>, __VA_ARGS__);                                            \
-        case 1602: return attn_launch(KERNEL<16, 2>, __VA_ARGS__);                                            \
-        case 1604: return attn_launch(KERNEL<16, 4>, __VA_ARGS__);                                            \
-        case 1608: return attn_launch(KERNEL<16, 8>, __VA_ARGS__);                                            \
-        case 3201: return attn_launch(KERNEL<32, 1>, __VA_ARGS__);                                            \
-        case 3202: return attn_launch(KERNEL<32, 2>, __VA_ARGS__);                                            \
-        case 3204: return attn_launch(KERNEL<32, 4>, __VA_ARGS__);                                            \
-        case 3208: return attn_launch(KERNEL<32, 8>, __VA_ARGS__);                                            \
+        case 801: return attn_launch(KERNEL<8, 1, G>, __VA_ARGS__);                                              \
+        case 802: return attn_launch(KERNEL<8, 2, G>, __VA_ARGS__);                                              \
+        case 804: return attn_launch(KERNEL<8, 4, G>, __VA_ARGS__);                                              \
+        case 808: return attn_launch(KERNEL<8, 8, G>, __VA_ARGS__);                                              \
+        case 1601: return attn_launch(KERNEL<16, 1, G>, __VA_ARGS__);                                            \
+        case 1602: return attn_launch(KERNEL<16, 2, G>, __VA_ARGS__);                                            \
+        case 1604: return attn_launch(KERNEL<16, 4, G>, __VA_ARGS__);                                            \
+        case 1608: return attn_launch(KERNEL<16, 8, G>, __VA_ARGS__);                                            \
+        case 3201: return attn_launch(KERNEL<32, 1, G>, __VA_ARGS__);                                            \
+        case 3202: return attn_launch(KERNEL<32, 2, G>, __VA_ARGS__);                                            \
+        case 3204: return attn_launch(KERNEL<32, 4, G>, __VA_ARGS__);                                            \
+        case 3208: return attn_launch(KERNEL<32, 8, G>, __VA_ARGS__);                                            \
         default:                                                                                              \
             refil_set_error("%s: (head dim %d, heads %d) not instantiated (heads in {1,2,4,8})", name, hd, heads); \
             return REFIL_ERR_UNSUPPORTED;                                                                     \
@@ -913,14 +930,31 @@ static int attn_group_launch(bool fwd, const RefilAttnDesc* descs, int n_problem
     int rc = attn_geometry(name, N, warp_floats, &warps, &grid, &smem, hd <= 16 ? 2 : 1);
     if (rc) return rc;
     if (fwd) smem += (size_t)warps * 8;                       // two mbarriers per warp (K tile, V tile)
-    if (n_problems > 1) {                                     // the group shares one wave of CTAs
-        const int share = refil_cdiv(refil_num_sms() * (hd <= 16 ? 2 : 1), n_problems);
-        if (grid > share) grid = share;
+    if (n_problems > 1) {
+        // the group shares one wave of CTAs, dealt out in proportion to the mask copies (= work) of each problem
+        const int total = refil_num_sms() * ((hd <= 16 && (smem + 1024) * 2 <= 227 * 1024) ? 2 : 1);
+        int sum_c = 0;
+        for (int g = 0; g < n_problems; g++) sum_c += descs[g].n_copies;
+        int begin = 0;
+        for (int g = 0; g < n_problems; g++) {
+            grp.cta_begin[g] = begin;
+            int share = (int)((long long)total * descs[g].n_copies / sum_c);
+            const int need = refil_cdiv(N, warps);
+            if (share < 1) share = 1;
+            if (share > need) share = need;
+            begin += share;
+        }
+        for (int g = n_problems; g <= ATT_MAX_GROUP; g++) grp.cta_begin[g] = begin;
+        grid = begin;
+        if (fwd) {
+            ATT_DISPATCH(attn_fwd_kernel, true, "masked_attn_fwd", hd, n_heads, grp, n_problems, smem, grid, warps, stream, "masked_attn_fwd", neb, tile_floats, warp_floats, maps, use_tmap)
+        }
+        ATT_DISPATCH(attn_bwd_kernel, true, "masked_attn_bwd", hd, n_heads, grp, n_problems, smem, grid, warps, stream, "masked_attn_bwd", neb, tile_floats, warp_floats, maps, use_tmap)
     }
     if (fwd) {
-        ATT_DISPATCH(attn_fwd_kernel, "masked_attn_fwd", hd, n_heads, grp, n_problems, smem, grid, warps, stream, "masked_attn_fwd", neb, tile_floats, warp_floats, maps, use_tmap)
+        ATT_DISPATCH(attn_fwd_kernel, false, "masked_attn_fwd", hd, n_heads, grp, n_problems, smem, grid, warps, stream, "masked_attn_fwd", neb, tile_floats, warp_floats, maps, use_tmap)
     }
-    ATT_DISPATCH(attn_bwd_kernel, "masked_attn_bwd", hd, n_heads, grp, n_problems, smem, grid, warps, stream, "masked_attn_bwd", neb, tile_floats, warp_floats, maps, use_tmap)
+    ATT_DISPATCH(attn_bwd_kernel, false, "masked_attn_bwd", hd, n_heads, grp, n_problems, smem, grid, warps, stream, "masked_attn_bwd", neb, tile_floats, warp_floats, maps, use_tmap)
 }
 
 extern "C" int refil_masked_attn_fwd_group(const RefilAttnDesc* descs, int n_problems, int N, int T, int n_entities,

@@ -500,15 +500,25 @@ __device__ __forceinline__ void tc_tmem_st16(uint32_t taddr, const uint32_t (&r)
 // several networks -- the eight hypernetworks of the online and target mixers -- runs as ONE launch whose CTAs each walk eight
 // times as many m-tiles, instead of eight launches that each pay the prologue (weight-tile split, pipeline fill) and the tail.
 #define TC_MAX_GROUP 8
-struct TcGroup { TcArgs a[TC_MAX_GROUP]; };
+struct TcGroup { TcArgs a[TC_MAX_GROUP]; int cta_begin[TC_MAX_GROUP + 1]; };   // grouped: CTAs [cta_begin[p], cta_begin[p+1]) -> problem p
 struct TcMaps { CUtensorMap m[TC_MAX_GROUP]; };
 
+// GROUPED = false: the single-problem instantiation reads its arguments at fixed parameter offsets (uniform registers, as before
+// grouping existed); measured: indexing the parameter block with blockIdx.y costs the single launches 3-17 %.
+template <bool GROUPED>
 __global__ void __launch_bounds__(TS_THREADS, 1) tc_gemm_ts_kernel(const __grid_constant__ TcGroup grp,
                                                                   const __grid_constant__ TcMaps maps_c,
                                                                   const __grid_constant__ TcMaps maps_a) {
-    const TcArgs& a = grp.a[blockIdx.y];
-    const CUtensorMap& tmap_c = maps_c.m[blockIdx.y];
-    const CUtensorMap& tmap_a = maps_a.m[blockIdx.y];
+    // grouped launch: the CTAs are dealt out to the problems in proportion to their m-tiles
+    int prob = 0, bid = (int)blockIdx.x, nbid = (int)gridDim.x;
+    if (GROUPED) {
+        while (prob + 1 < TC_MAX_GROUP && (int)blockIdx.x >= grp.cta_begin[prob + 1]) prob++;
+        bid = (int)blockIdx.x - grp.cta_begin[prob];
+        nbid = grp.cta_begin[prob + 1] - grp.cta_begin[prob];
+    }
+    const TcArgs& a = grp.a[prob];
+    const CUtensorMap& tmap_c = maps_c.m[prob];
+    const CUtensorMap& tmap_a = maps_a.m[prob];
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int BN = a.BN;
@@ -525,9 +535,9 @@ __global__ void __launch_bounds__(TS_THREADS, 1) tc_gemm_ts_kernel(const __grid_
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform role index
     const int lane = threadIdx.x & 31;
     const int groups = a.n_tiles * a.k_slices;
-    const int gid = blockIdx.x % groups;
+    const int gid = bid % groups;
     const int nt = gid % a.n_tiles, k_off = (gid / a.n_tiles) * a.KS;
-    const int mt0 = blockIdx.x / groups, mt_step = gridDim.x / groups;
+    const int mt0 = bid / groups, mt_step = nbid / groups;
     const int my_tiles = mt0 < a.m_tiles ? (a.m_tiles - mt0 + mt_step - 1) / mt_step : 0;
     const int total = my_tiles * KC;
     // The TMA lane initialises the barriers and puts the first raw A chunks in flight at once: they do not depend on the weight
@@ -855,8 +865,10 @@ extern "C" int refil_tc_gemm_tn_group(const RefilGemmDesc* descs, int n_problems
                                 : b_res + stages * stage_bytes + stg_bytes + 1024;
     static size_t attr_smem[2] = {0, 0};
     if (smem > attr_smem[mode_ts]) {
-        cudaError_t e = mode_ts ? cudaFuncSetAttribute(tc_gemm_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+        cudaError_t e = mode_ts ? cudaFuncSetAttribute(tc_gemm_ts_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
                                 : cudaFuncSetAttribute(tc_gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess && mode_ts)
+            e = cudaFuncSetAttribute(tc_gemm_ts_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) {
             refil_set_error("tc_gemm_tn: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
             return REFIL_ERR_CUDA;
@@ -874,8 +886,6 @@ extern "C" int refil_tc_gemm_tn_group(const RefilGemmDesc* descs, int n_problems
     }
     const int sms = refil_num_sms();
     const int groups = a0.n_tiles * a0.k_slices;
-    int per_g = sms / (groups * n_problems);     // CTAs per (problem, n-tile, k-slice): one wave over the whole group
-    if (per_g < 1) per_g = 1;
     // every CTA pays a fixed prologue (split of its resident weight tile, pipeline fill): give it at least `min_tiles` m-tiles, so
     // that a small problem (a 16-episode shard) leaves SMs to the independent networks running on the other streams
     static int min_tiles = -1;
@@ -884,12 +894,25 @@ extern "C" int refil_tc_gemm_tn_group(const RefilGemmDesc* descs, int n_problems
         min_tiles = e ? atoi(e) : 6;
         if (min_tiles < 1) min_tiles = 1;
     }
-    const int want = refil_cdiv(max_tiles, min_tiles);
-    if (per_g > want) per_g = want;
-    if (per_g > max_tiles) per_g = max_tiles;
-    const dim3 grid(per_g * groups, n_problems);
+    long long sum_tiles = 0;
+    for (int g = 0; g < n_problems; g++) sum_tiles += grp.a[g].m_tiles;
+    int begin = 0;
+    for (int g = 0; g < n_problems; g++) {
+        // CTAs per (n-tile, k-slice) of this problem: its share of one wave, in proportion to its m-tiles
+        const int mt = grp.a[g].m_tiles;
+        int per_g = (int)((long long)sms * mt / (sum_tiles * groups));
+        if (per_g < 1) per_g = 1;
+        const int want = refil_cdiv(mt, min_tiles);
+        if (per_g > want) per_g = want;
+        if (per_g > mt) per_g = mt;
+        grp.cta_begin[g] = begin;
+        begin += per_g * groups;
+    }
+    for (int g = n_problems; g <= TC_MAX_GROUP; g++) grp.cta_begin[g] = begin;
+    const dim3 grid(begin, 1);
     if (mode_ts) {
-        tc_gemm_ts_kernel<<<grid, TS_THREADS, smem, stream>>>(grp, mc, ma);
+        if (n_problems == 1) tc_gemm_ts_kernel<false><<<grid, TS_THREADS, smem, stream>>>(grp, mc, ma);
+        else tc_gemm_ts_kernel<true><<<grid, TS_THREADS, smem, stream>>>(grp, mc, ma);
         REFIL_CHECK_LAUNCH("tc_gemm_tn (ts)");
         return REFIL_OK;
     }
@@ -1188,12 +1211,14 @@ struct TcWGeom {
 struct TcWGroup { TcWArgs a[TC_MAX_GROUP]; };
 
 // blockIdx.y = problem of the group (same (P, Q) geometry, own operands and row count)
+template <bool GROUPED>
 __global__ void __launch_bounds__(TW_THREADS, 1) tc_wgrad_ts_kernel(const __grid_constant__ TcWGroup grp, TcWGeom g,
                                                                    const __grid_constant__ TcMaps maps_x,
                                                                    const __grid_constant__ TcMaps maps_r) {
-    const TcWArgs& a = grp.a[blockIdx.y];
-    const CUtensorMap& tmap_x = maps_x.m[blockIdx.y];
-    const CUtensorMap& tmap_r = maps_r.m[blockIdx.y];
+    const int prob = GROUPED ? (int)blockIdx.y : 0;
+    const TcWArgs& a = grp.a[prob];
+    const CUtensorMap& tmap_x = maps_x.m[prob];
+    const CUtensorMap& tmap_r = maps_r.m[prob];
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int BQ = a.BQ, SY = g.y_stages, RS = g.raw_stages;
@@ -1505,10 +1530,12 @@ extern "C" int refil_tc_gemm_wgrad_group(const RefilWgradDesc* descs, int n_prob
     TcWGroup grp{};
     const bool has_r = descs[0].relu_y != nullptr, has_b = descs[0].db != nullptr;
     int max_grid = 1;
+    long long sum_rows = 0;
+    for (int g = 0; g < n_problems; g++) sum_rows += descs[g].M > 0 ? descs[g].M : 1;
     for (int g = 0; g < n_problems; g++) {
         REFIL_CHECK_ARG((descs[g].relu_y != nullptr) == has_r && (descs[g].db != nullptr) == has_b,
                         "tc_gemm_wgrad_group: the problems of a group must agree on relu_y / db being present");
-        int rc = tcw_fill(descs[g], P, Q, refil_num_sms() / n_problems, grp.a[g]);
+        int rc = tcw_fill(descs[g], P, Q, (int)((long long)refil_num_sms() * descs[g].M / sum_rows), grp.a[g]);
         if (rc) return rc;
         grp.a[g].BQ = has_b ? Q + 32 : Q;   // the bias gradient rides as one extra 32-wide atom whose first column is 1
         if (grp.a[g].p_tiles * grp.a[g].splits > max_grid) max_grid = grp.a[g].p_tiles * grp.a[g].splits;
@@ -1537,14 +1564,16 @@ extern "C" int refil_tc_gemm_wgrad_group(const RefilWgradDesc* descs, int n_prob
         const size_t smem = raw_total + (size_t)ys * y_stage + 1024;
         static size_t attr_smem_ts = 0;
         if (smem > attr_smem_ts) {
-            cudaError_t e = cudaFuncSetAttribute(tc_wgrad_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaError_t e = cudaFuncSetAttribute(tc_wgrad_ts_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_wgrad_ts_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) {
                 refil_set_error("tc_gemm_wgrad: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
                 return REFIL_ERR_CUDA;
             }
             attr_smem_ts = smem;
         }
-        tc_wgrad_ts_kernel<<<dim3(max_grid, n_problems), TW_THREADS, smem, stream>>>(grp, geo, mx, mr);
+        if (n_problems == 1) tc_wgrad_ts_kernel<false><<<dim3(max_grid, 1), TW_THREADS, smem, stream>>>(grp, geo, mx, mr);
+        else tc_wgrad_ts_kernel<true><<<dim3(max_grid, n_problems), TW_THREADS, smem, stream>>>(grp, geo, mx, mr);
         REFIL_CHECK_LAUNCH("tc_gemm_wgrad (ts)");
         return REFIL_OK;
     }

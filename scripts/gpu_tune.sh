@@ -1,7 +1,9 @@
 #!/bin/bash
-# A/B of the submission knobs on one GPU: grouped hypernetworks on/off, m-tiles per CTA, chunks per weight-gradient split.
-# usage: bash scripts/gpu_tune.sh <tag>
+# A/B of the submission knobs on one GPU: grouped hypernetworks on/off, m-tiles per CTA, GRU scan variant.
+# usage: bash scripts/gpu_tune.sh <tag> "<batches>" "<labels>"
 TAG=${1:-tune}
+BATCHES=${2:-"16 64 128"}
+LABELS=${3:-"group nogroup gru_mma"}
 run() {  # label, B, env..., extra args
   local label=$1 B=$2; shift 2
   local out=gpurun_out/${TAG}_${label}_b${B}.json
@@ -15,13 +17,14 @@ except Exception as e:
     print("$label B=$B failed", e)
 PY
 }
-for B in 16 128; do
-  EXTRA="" run group $B A=1
-  EXTRA="--no-group" run nogroup $B A=1
-  EXTRA="" run tiles2 $B REFIL_TC_MIN_TILES=2
-  EXTRA="" run tiles3 $B REFIL_TC_MIN_TILES=3
-  EXTRA="" run tiles12 $B REFIL_TC_MIN_TILES=12
-  EXTRA="" run chunks8 $B REFIL_TC_MIN_CHUNKS=8
-  EXTRA="" run chunks64 $B REFIL_TC_MIN_CHUNKS=64
-  EXTRA="" run gru_mma $B REFIL_GRU_MODE=mma
+for B in $BATCHES; do
+  for L in $LABELS; do
+    case $L in
+      group) EXTRA="" run group $B A=1;;
+      nogroup) EXTRA="--no-group" run nogroup $B A=1;;
+      gru_mma) EXTRA="" run gru_mma $B REFIL_GRU_MODE=mma;;
+      tiles*) EXTRA="" run $L $B REFIL_TC_MIN_TILES=${L#tiles};;
+      chunks*) EXTRA="" run $L $B REFIL_TC_MIN_CHUNKS=${L#chunks};;
+    esac
+  done
 done
