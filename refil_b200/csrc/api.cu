@@ -1,5 +1,6 @@
 // Error reporting and device queries for the C-ABI (include/refil_b200.h).
 #include <stdarg.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 static thread_local char g_err[512] = "";
@@ -26,3 +27,12 @@ int refil_num_sms() {
 }
 
 extern "C" int refil_device_sm_count() { return refil_num_sms(); }
+
+bool refil_pdl_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("REFIL_PDL");
+        on = (e && e[0] == '0') ? 0 : 1;
+    }
+    return on == 1;
+}

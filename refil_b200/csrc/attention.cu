@@ -235,6 +235,8 @@ __global__ void __launch_bounds__(32 * ATT_MAX_WARPS, (HD <= 16) ? 2 : 1) attn_f
     }
     for (int f = ne * d + lane; f < NEB * d; f += 32) { kt[f] = 0.f; vt[f] = 0.f; }   // padding rows stay zero
     __syncwarp();
+    pdl_launch_dependents();
+    pdl_wait();                                          // QKV is the previous kernel's output
     auto load_k = [&](long long n) {
         if (use_tmap) att_tma_load_tile(kt, &tmap, d, ne, n, bark, lane, d);
         else att_tma_load_rows(kt, a.qkv + ((size_t)n * ne) * 3 * d + d, 3 * d, ne, d, d, bark, lane);
@@ -403,6 +405,8 @@ __global__ void __launch_bounds__(32 * ATT_MAX_WARPS, (HD <= 16) ? 2 : 1) attn_b
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
+    pdl_launch_dependents();
+    pdl_wait();                                          // dOUT (and QKV) come from earlier kernels of the step
     const float inv_scale = 1.f / sqrtf((float)HD);
     const long long gw = (long long)cta * wpc + warp, GW = (long long)ncta * wpc;
     uint32_t parity = 0;
@@ -806,7 +810,11 @@ static int attn_launch(K kernel, const AttnGroup& a, int n_problems, size_t smem
         }
     }
     (void)n_problems;
-    kernel<<<grid, 32 * warps, smem, stream>>>(a, extra...);
+    cudaError_t le = refil_launch(kernel, dim3(grid), dim3(32 * warps), smem, stream, true, a, extra...);
+    if (le != cudaSuccess) {
+        refil_set_error("%s: launch failed: %s", name, cudaGetErrorString(le));
+        return REFIL_ERR_CUDA;
+    }
     REFIL_CHECK_LAUNCH(name);
     return REFIL_OK;
 }

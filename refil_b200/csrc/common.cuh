@@ -45,3 +45,32 @@ __device__ __forceinline__ double warp_sum_d(double v) {
 
 // number of SMs on the current device (cached); B200 = 148
 int refil_num_sms();
+
+// ---- programmatic dependent launch (PDL) -----------------------------------------------------------------------------------
+// The step is a chain of short dependent kernels; with the launch attribute below kernel N+1 may be scheduled while kernel N is
+// still running (on SMs N does not use, or as N's CTAs retire), run its prologue -- barrier init, TMEM allocation, the split of
+// its resident weight tile, register-resident recurrent weights -- and only then block in pdl_wait() until N has completed and
+// its writes are visible.  Rules kept by every kernel launched through refil_launch(..., pdl = true):
+//   * nothing written by an earlier kernel of the step is read, and nothing is written to global memory, before pdl_wait();
+//   * every thread executes pdl_wait() (so a kernel never completes before its predecessor: ordering stays transitive).
+// REFIL_PDL=0 in the environment turns the attribute off (plain stream order).
+bool refil_pdl_enabled();
+
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <class... KArgs, class... Args>
+static inline cudaError_t refil_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, bool pdl,
+                                       Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (pdl && refil_pdl_enabled()) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}

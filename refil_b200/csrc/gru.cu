@@ -704,6 +704,8 @@ __global__ void __launch_bounds__(R * 4, 1) gru_scan_fwd_v3_kernel(const float* 
             w[g][kk] = v.x; w[g][kk + 1] = v.y; w[g][kk + 2] = v.z; w[g][kk + 3] = v.w;
         }
     const float br = __ldg(bhh + j), bz = __ldg(bhh + R + j), bn = __ldg(bhh + 2 * R + j);
+    pdl_launch_dependents();
+    pdl_wait();                        // the 96 weight registers above were loaded beside the previous kernel's tail
     // my (sequence, feature j) pairs: block b = sgp * NB + nb holds local sequences [b SB, b SB + SB); mine are kh + 2 p
     long long row0[NB][PP];
     bool valid[NB][PP];
@@ -810,6 +812,8 @@ __global__ void __launch_bounds__(R * 4, 1) gru_scan_bwd_v3_kernel(const float* 
     float w[GH];                                               // Whh[gj][j] for my half of the 3R gate rows
 #pragma unroll
     for (int i = 0; i < GH; i++) w[i] = __ldg(Whh + (size_t)(GH * kh + i) * R + j);
+    pdl_launch_dependents();
+    pdl_wait();
     long long row0[NB][PP];
     bool valid[NB][PP];
     int sidx[NB][PP];
@@ -917,8 +921,10 @@ static void gru_launch_v3(bool fwd, const float* a0, const float* a1, const floa
     const int grid = refil_cdiv(n_seq, S);
 #define GRU_V3(SBV, NBV)                                                                                                 \
     {                                                                                                                    \
-        if (fwd) gru_scan_fwd_v3_kernel<R, SBV, NBV><<<grid, R * 4, 0, stream>>>(a0, a1, a2, a3, o0, o1, n_seq, T, na);   \
-        else gru_scan_bwd_v3_kernel<R, SBV, NBV><<<grid, R * 4, 0, stream>>>(a0, a1, a2, a3, a4, o0, o1, n_seq, T, na);   \
+        if (fwd) refil_launch(gru_scan_fwd_v3_kernel<R, SBV, NBV>, dim3(grid), dim3(R * 4), 0, stream, true, a0, a1, a2, a3, o0, o1,  \
+                              n_seq, T, na);                                                                              \
+        else refil_launch(gru_scan_bwd_v3_kernel<R, SBV, NBV>, dim3(grid), dim3(R * 4), 0, stream, true, a0, a1, a2, a3, a4, o0, o1, \
+                          n_seq, T, na);                                                                                  \
     }
     if (S == 4) GRU_V3(2, 1) else if (S == 8) GRU_V3(4, 1) else if (S == 16) GRU_V3(4, 2) else GRU_V3(4, 3)
 #undef GRU_V3

@@ -540,6 +540,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) tc_gemm_ts_kernel(const __grid_
     const int mt0 = bid / groups, mt_step = nbid / groups;
     const int my_tiles = mt0 < a.m_tiles ? (a.m_tiles - mt0 + mt_step - 1) / mt_step : 0;
     const int total = my_tiles * KC;
+    pdl_launch_dependents();       // the next kernel of the stream may be scheduled: its prologue overlaps this kernel's tail
     // The TMA lane initialises the barriers and puts the first raw A chunks in flight at once: they do not depend on the weight
     // tile, so their latency overlaps the prologue below instead of following it
     auto tma_chunk = [&](int st, int mt, int kc) {
@@ -557,6 +558,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) tc_gemm_ts_kernel(const __grid_
         for (int s = 0; s < TS_A_STAGES; s++) { mbar_init(&a_full[s], 32 * TS_CONV_WARPS); mbar_init(&a_empty[s], 1); }
         for (int b = 0; b < 2; b++) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 32 * TC_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        pdl_wait();                                            // the A operand is the previous kernel's output
         int kc = 0, mt = mt0;
         for (int cc = 0; cc < pre; cc++) {
             tma_chunk(cc, mt, kc);
@@ -576,6 +578,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) tc_gemm_ts_kernel(const __grid_
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    pdl_wait();                    // weights / bias above are never written inside a step; everything below may depend on it
     const uint32_t tmem_base = tmem_base_s;
 
     if (warp < TC_EPI_WARPS) {
@@ -911,8 +914,14 @@ extern "C" int refil_tc_gemm_tn_group(const RefilGemmDesc* descs, int n_problems
     for (int g = n_problems; g <= TC_MAX_GROUP; g++) grp.cta_begin[g] = begin;
     const dim3 grid(begin, 1);
     if (mode_ts) {
-        if (n_problems == 1) tc_gemm_ts_kernel<false><<<grid, TS_THREADS, smem, stream>>>(grp, mc, ma);
-        else tc_gemm_ts_kernel<true><<<grid, TS_THREADS, smem, stream>>>(grp, mc, ma);
+        // a k-sliced problem is preceded by the memset of C (not a kernel): plain stream order there
+        const bool pdl = a0.k_slices == 1;
+        cudaError_t le = n_problems == 1 ? refil_launch(tc_gemm_ts_kernel<false>, grid, dim3(TS_THREADS), smem, stream, pdl, grp, mc, ma)
+                                         : refil_launch(tc_gemm_ts_kernel<true>, grid, dim3(TS_THREADS), smem, stream, pdl, grp, mc, ma);
+        if (le != cudaSuccess) {
+            refil_set_error("tc_gemm_tn (ts): launch failed: %s", cudaGetErrorString(le));
+            return REFIL_ERR_CUDA;
+        }
         REFIL_CHECK_LAUNCH("tc_gemm_tn (ts)");
         return REFIL_OK;
     }
@@ -1237,6 +1246,7 @@ __global__ void __launch_bounds__(TW_THREADS, 1) tc_wgrad_ts_kernel(const __grid
     const int chunks_total = (a.M + 31) / 32;
     const int c_begin = split * a.chunks_per_split, c_end = min(chunks_total, c_begin + a.chunks_per_split);
     const int n_chunks = max(0, c_end - c_begin);
+    pdl_launch_dependents();
 
     // the TMA lane initialises the barriers and requests the first raw chunks before the rest of the prologue
     auto tma_chunk = [&](int st, int ch) {
@@ -1263,6 +1273,7 @@ __global__ void __launch_bounds__(TW_THREADS, 1) tc_wgrad_ts_kernel(const __grid
         for (int s = 0; s < TC_MAX_STAGES; s++) { mbar_init(&y_full[s], 128); mbar_init(&y_empty[s], 1); }
         mbar_init(&acc_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        pdl_wait();                                            // X (and relu_y) come from the previous kernels
         for (int ch = 0; ch < pre; ch++) tma_chunk(ch, ch);
     }
     if (warp == TW_MMA_WARP) {
@@ -1284,6 +1295,7 @@ __global__ void __launch_bounds__(TW_THREADS, 1) tc_wgrad_ts_kernel(const __grid
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    pdl_wait();
     const uint32_t tmem_base = tmem_base_s;
 
     if (warp < 4) {
@@ -1572,8 +1584,13 @@ extern "C" int refil_tc_gemm_wgrad_group(const RefilWgradDesc* descs, int n_prob
             }
             attr_smem_ts = smem;
         }
-        if (n_problems == 1) tc_wgrad_ts_kernel<false><<<dim3(max_grid, 1), TW_THREADS, smem, stream>>>(grp, geo, mx, mr);
-        else tc_wgrad_ts_kernel<true><<<dim3(max_grid, n_problems), TW_THREADS, smem, stream>>>(grp, geo, mx, mr);
+        cudaError_t le = n_problems == 1
+            ? refil_launch(tc_wgrad_ts_kernel<false>, dim3(max_grid, 1), dim3(TW_THREADS), smem, stream, true, grp, geo, mx, mr)
+            : refil_launch(tc_wgrad_ts_kernel<true>, dim3(max_grid, n_problems), dim3(TW_THREADS), smem, stream, true, grp, geo, mx, mr);
+        if (le != cudaSuccess) {
+            refil_set_error("tc_gemm_wgrad (ts): launch failed: %s", cudaGetErrorString(le));
+            return REFIL_ERR_CUDA;
+        }
         REFIL_CHECK_LAUNCH("tc_gemm_wgrad (ts)");
         return REFIL_OK;
     }
