@@ -32,7 +32,7 @@ bool refil_pdl_enabled() {
     static int on = -1;
     if (on < 0) {
         const char* e = getenv("REFIL_PDL");
-        on = (e && e[0] == '0') ? 0 : 1;
+        on = (e && e[0] == '1') ? 1 : 0;      // measured (profiles/r2_tuning.md): off by default
     }
     return on == 1;
 }

@@ -25,17 +25,35 @@
 #define GM_MAX_GROUPS 8
 #define GM_THREADS 128
 
+// Words of the generator a step may consume are PREFETCHED: the twist of word i reads the old words i, i + 1 and i + 397, none of
+// which an earlier draw of the same step can have rewritten (that would need a look-back of 227 words), so the thread issues
+// all those loads at once -- 2 W + 1 independent requests instead of a chain of dependent round trips (each draw used to wait
+// ~0.5 us on L2; 17 draws per 8-agent step) -- parks them in its shared-memory lane and then runs the sequential draw logic out
+// of shared memory.  Draws beyond the window (long rejection runs) fall back to the global path.
+#define MT_WIN 32
+
 struct MtRef {
     uint32_t* key;  // points at column e of mt_key
     int E;
     int pos;
+    const uint32_t* win_old;   // [MT_WIN + 1] old words pos0 .. pos0 + MT_WIN, stride GM_THREADS (null: no window)
+    const uint32_t* win_m;     // [MT_WIN] old words pos0 + 397 ...
+    int used, nwin;            // draws taken from the window so far / words it holds
 };
 
 __device__ __forceinline__ uint32_t mt_next(MtRef& s) {
     int i = s.pos;
     int i1 = (i + 1 == MT_N) ? 0 : i + 1;
     int im = (i + MT_M >= MT_N) ? i + MT_M - MT_N : i + MT_M;
-    uint32_t ki = s.key[(size_t)i * s.E], k1 = s.key[(size_t)i1 * s.E], km = s.key[(size_t)im * s.E];
+    uint32_t ki, k1, km;
+    if (s.used < s.nwin) {
+        ki = s.win_old[s.used * GM_THREADS];
+        k1 = s.win_old[(s.used + 1) * GM_THREADS];
+        km = s.win_m[s.used * GM_THREADS];
+        s.used++;
+    } else {
+        ki = s.key[(size_t)i * s.E]; k1 = s.key[(size_t)i1 * s.E]; km = s.key[(size_t)im * s.E];
+    }
     uint32_t y = (ki & 0x80000000u) | (k1 & 0x7fffffffu);
     y = km ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
     s.key[(size_t)i * s.E] = y;
@@ -58,6 +76,29 @@ __device__ __forceinline__ uint32_t mt_bounded(MtRef& s, uint32_t mx) {
     mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
     do { v = mt_next(s) & mask; } while (v > mx);
     return v;
+}
+
+// fill the calling thread's window lane (sm_old / sm_m point at its own column of [..][GM_THREADS] shared arrays) with the first
+// `n` <= MT_WIN words it may draw from position pos
+__device__ __forceinline__ void mt_prefetch(const uint32_t* key, int E, int pos, int n, uint32_t* sm_old, uint32_t* sm_m) {
+#pragma unroll 1
+    for (int k0 = 0; k0 < n; k0 += 8) {
+        uint32_t o[8], m[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            int i = pos + k0 + k;
+            if (i >= MT_N) i -= MT_N;
+            int im = i + MT_M;
+            if (im >= MT_N) im -= MT_N;
+            o[k] = key[(size_t)i * E];
+            m[k] = key[(size_t)im * E];
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) { sm_old[(k0 + k) * GM_THREADS] = o[k]; sm_m[(k0 + k) * GM_THREADS] = m[k]; }
+    }
+    int i = pos + n;
+    if (i >= MT_N) i -= MT_N;
+    sm_old[n * GM_THREADS] = key[(size_t)i * E];
 }
 
 // numpy _legacy_seeding(int): init_genrand.  pos=0 in the incremental scheme == numpy's pos=624.
@@ -178,7 +219,7 @@ __global__ void __launch_bounds__(GM_THREADS) gm_reset_kernel(GmParams p, GmBuff
     const int n_env = min(GM_THREADS, p.E - e0);
     s_write[le] = 0;
     if (e < p.E) {
-        MtRef rng{b.mt_key + e, p.E, b.mt_pos[e]};
+        MtRef rng{b.mt_key + e, p.E, b.mt_pos[e], nullptr, nullptr, 0, 0};
         int perm[GM_MAX_AGENTS];
         int parts[GM_MAX_GROUPS + 1];
         for (int i = 0; i < p.na; i++) perm[i] = i;
@@ -224,6 +265,7 @@ __global__ void __launch_bounds__(GM_THREADS) gm_step_kernel(GmParams p, GmBuffe
     __shared__ uint32_t s_grp[GM_THREADS * GM_MAX_GROUPS];
     __shared__ uint8_t s_write[GM_THREADS];
     __shared__ int s_count;
+    __shared__ uint32_t s_old[(MT_WIN + 1) * GM_THREADS], s_m[MT_WIN * GM_THREADS];
     const int e0 = blockIdx.x * GM_THREADS, le = threadIdx.x, e = e0 + le;
     const int n_env = min(GM_THREADS, p.E - e0);
     if (le == 0) s_count = 0;
@@ -232,7 +274,11 @@ __global__ void __launch_bounds__(GM_THREADS) gm_step_kernel(GmParams p, GmBuffe
     if (e < p.E) {
         int flags = b.est[2 * (size_t)p.E + e];
         if (flags & 1) {
-            MtRef rng{b.mt_key + e, p.E, b.mt_pos[e]};
+            const int pos0 = b.mt_pos[e];
+            // window: 2 words per agent + headroom for the rand_trans re-draws; the rest of the state loads overlap it
+            const int nwin = min(MT_WIN, ((2 * p.na + (p.rand_trans > 0.0 ? p.na / 2 + 4 : 0)) + 7) & ~7);
+            mt_prefetch(b.mt_key + e, p.E, pos0, nwin, s_old + le, s_m + le);
+            MtRef rng{b.mt_key + e, p.E, pos0, s_old + le, s_m + le, 0, nwin};
             int loc[GM_MAX_AGENTS];
             uint32_t grp[GM_MAX_GROUPS];
             const size_t row = (size_t)(p.env_offset + e) * p.T + ts;

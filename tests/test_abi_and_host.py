@@ -192,10 +192,11 @@ def test_sass_histogram_has_blackwell_native_instructions():
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     h = mod.histogram()
-    ts, wg = h["tc_gemm_ts_kernel"], h["tc_wgrad_ts_kernel"]
+    ts, wg = h["tc_gemm_ts_kernel<0>"], h["tc_wgrad_ts_kernel<0>"]     # single-problem / grouped instantiations
+    assert h["tc_gemm_ts_kernel<1>"]["UTCHMMA"] >= 12 and h["tc_wgrad_ts_kernel<1>"]["UTCHMMA"] >= 12
     for k in (ts, wg):
         assert k["UTCHMMA"] >= 12 and k["LDTM"] >= 1 and k["STTM"] >= 2 and k["UTMALDG"] >= 1 and k["UTCBAR"] >= 2, dict(k)
     assert ts["UTMASTG"] >= 1 and ts["UTMAREDG"] >= 1                      # TMA tensor store / reduce-add epilogue
-    att = [c for n, c in h.items() if n.startswith("attn_fwd_kernel<32, 4>") or n.startswith("attn_bwd_kernel<32, 4>")]
+    att = [c for n, c in h.items() if n.startswith("attn_fwd_kernel<32, 4, 0>") or n.startswith("attn_bwd_kernel<32, 4, 0>")]
     assert len(att) == 2 and all(c["UTMALDG"] >= 1 and c["FFMA"] > 100 for c in att)
     assert not any(c["HMMA"] for n, c in h.items() if n.startswith("tc_"))   # no legacy mma.sync on the dense path
