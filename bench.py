@@ -616,15 +616,30 @@ def bench_env(dev, world, rank, a, hbm, src):
 
     for _ in range(3):
         rollout()
+    torch.cuda.synchronize()
+    # the 51 launches of a rollout are replayed as ONE CUDA graph: enqueueing them from Python costs ~70 us each (ctypes call with
+    # 27 arguments), several times the kernel itself -- the eager figure measured the host, not the kernel
+    graph = None
+    if not a.no_graph:
+        try:
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                rollout()
+        except Exception:
+            graph = None
+            torch.cuda.synchronize()
+    run = graph.replay if graph is not None else rollout
+    for _ in range(2):
+        run()
     env.step_counter.zero_()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 5
+    reps = 20
     e0.record()
     for _ in range(reps):
-        rollout()
+        run()
     e1.record()
     torch.cuda.synchronize()
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -638,7 +653,8 @@ def bench_env(dev, world, rank, a, hbm, src):
     return {"metric": "GroupMatching env-steps/sec", "value": rate, "unit": "env-steps/s", "n_envs": E * world,
             "n_agents": na, "ms_per_rollout": float(ms.item()) / reps, "env_steps_per_rollout": float(steps.item()) / reps,
             "config": "group_matching 8 agents, 6 states, 2 groups, rand_trans 0.1, limit 50; random action tape; "
-                      "reset + 50 step launches per rollout, rollout tensors written in place",
+                      "reset + 50 step launches per rollout (%s), rollout tensors written in place"
+                      % ("one CUDA graph replay per rollout" if graph is not None else "eager launches"),
             "roofline": {"kernel": "gm_step_kernel (K0)", "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s",
                          "frac": ach / hbm, "traffic": None, "bytes_per_env_step": bytes_per_step, "peak_source": src}}
 
