@@ -14,6 +14,10 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1400 --
 timeout 900 ncu --set full --clock-control none --import-source on \
   -k regex:'tc_gemm_ts_kernel|tc_wgrad_ts_kernel|attn_fwd_kernel|attn_bwd_kernel|gru_scan' -s 560 -c 40 \
   -o gpurun_out/${TAG}_prof -f python bench.py --steps 1 --warmup 1 --no-cpu --no-graph --no-extra > gpurun_out/${TAG}_ncu_full.log 2>&1
+# the report itself is ~2.5 MB per kernel with sources (gpurun_out/ is capped at 64 MiB): keep the raw metrics page as CSV, and
+# the report only when small
+ncu -i gpurun_out/${TAG}_prof.ncu-rep --page raw --csv > gpurun_out/${TAG}_ncu_full_raw.csv 2>/dev/null
+if [ $(stat -c %s gpurun_out/${TAG}_prof.ncu-rep) -gt 30000000 ]; then rm -f gpurun_out/${TAG}_prof.ncu-rep; fi
 # DRAM traffic of every dense forward / backward-data launch
 timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none \
   -k regex:'tc_gemm_ts_kernel' -c 600 --csv --log-file gpurun_out/${TAG}_traffic.csv \
