@@ -78,6 +78,18 @@ int refil_select_actions(const float* q, long long q_stride_b, const int32_t* av
                          long long* actions_out, long long out_stride_b, int B, int n_agents, int n_actions,
                          cudaStream_t stream);
 
+/* ---- fused acting step of the feed-forward entity-attention agent: EntityAttentionFFAgent.forward
+ *      (modules/agents/entity_ff_agent.py:30-57) on the inputs of EntityMAC._build_inputs (controllers/entity_controller.py:11-30),
+ *      read in place from the EpisodeBatch tensors at timestep t ([E, T, ...] layouts).  q [E, na, A].  actions: null, or the
+ *      [E, T, na, 1] tensor whose step t-1 is appended as a one-hot (entity_last_action).  mask_rows = ne (obs_mask) or na (gt_mask
+ *      with gt_obs_mask).  Supported: embed 64, 4 heads, <= 8 entities, <= 32 input features, <= 16 actions. */
+int refil_ff_agent_act_supported(int n_entities, int n_agents, int input_dim, int embed_dim, int n_heads, int n_actions);
+int refil_ff_agent_act(const float* entities, int entity_dim, const long long* actions, int n_actions_onehot,
+                       const uint8_t* obs_mask, int mask_rows, const uint8_t* entity_mask, const float* fc1_w,
+                       const float* fc1_b, const float* in_trans_w, const float* out_trans_w, const float* out_trans_b,
+                       const float* fc2_w, const float* fc2_b, float* q, int n_envs, int T, int t, int n_entities,
+                       int n_agents, int n_actions, cudaStream_t stream);
+
 /* ---- dense layers (nn.Linear of modules/layers/attention.py:21-22, agents/entity_rnn_agent.py:12,23-25,
  *      mixers/flex_qmix.py:29,39).  C = [rowmask][relu](A W^T + b); row r of a [C, N, na] stack is zeroed when
  *      row_entity_mask[n, a] != 0 (attention.py:66-67, entity_rnn_agent.py:60, flex_qmix.py:50). */

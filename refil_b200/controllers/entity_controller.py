@@ -61,6 +61,24 @@ class EntityMAC(BasicMAC):
             inp["xin"] = ops.pack_inputs(inp["entities"], la, args.n_actions, xin)
         return inp
 
+    def _fused_acting_ok(self, batch):
+        """args.fused_acting (default on): FF agent with the Group Matching widths (d = 64, 4 heads, <= 8 entities, <= 32 input
+        features) on contiguous device tensors -> the fused acting kernel; anything else takes the layer-by-layer path."""
+        a = self.agent
+        if a.rnn or a.pool is not None or not getattr(self.args, "fused_acting", True):
+            return False
+        ok = getattr(self, "_fused_ok", None)
+        if ok is None:
+            ok = self._fused_ok = ops.ff_agent_act_supported(int(self.args.n_entities), self.n_agents, a.ein, a.d, a.H, a.A)
+        if not ok:
+            return False
+        keys = ["entities", "obs_mask", "entity_mask"] + (["gt_mask"] if getattr(self.args, "gt_obs_mask", False) else []) + \
+               (["actions"] if a.one_hot_la else [])
+        try:
+            return all(batch[k].is_cuda and batch[k].is_contiguous() for k in keys)
+        except (KeyError, ValueError):
+            return False
+
     def draw_groups(self, bs, ne, device):
         """Random 2-partition of the entities, one Bernoulli parameter per episode
         (entity_rnn_agent.py:94-96 / entity_ff_agent.py:87,96)."""
@@ -118,6 +136,15 @@ class EntityMAC(BasicMAC):
         """t=int: one acting step -> (bs, na, A), hidden state carried.  t=None: whole sequence -> (bs, T, na, A), or with
         imagine=True ((3 bs, T, na, A), (Wmask, Imask)) exactly as basic_controller.py:28-67."""
         int_t = isinstance(t, int)
+        if int_t and not imagine and inputs is None and not ret_plan and self._fused_acting_ok(ep_batch):
+            # acting step of the small FF agent: ONE fused kernel reading the rollout tensors in place (csrc/ffact.cu)
+            a = self.agent
+            ents = ep_batch["entities"]
+            gt_obs = bool(getattr(self.args, "gt_obs_mask", False))
+            q = a.ws.get(a.tag + ".q_act", (ents.shape[0], self.n_agents, a.A))
+            ops.ff_agent_act(ents, ep_batch["actions"] if a.one_hot_la else None, a.A,
+                             ep_batch["gt_mask"] if gt_obs else ep_batch["obs_mask"], ep_batch["entity_mask"], a.store.p, q, t)
+            return q
         T_all = ep_batch["avail_actions"].shape[1]
         sl = slice(t, t + 1) if int_t else (slice(0, T_all) if t is None else t)
         inp = inputs if inputs is not None else self._build_inputs(ep_batch, sl)

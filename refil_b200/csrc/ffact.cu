@@ -1,0 +1,240 @@
+// Fused acting step of the feed-forward entity-attention agent.
+//
+// One launch computes, for timestep t of the rollout tensors and every environment, the utilities
+//   q = fc2( relu( rowmask( out_trans( MHA( in_trans( relu( fc1(entities) ) ), obs_mask ) ) ) ) )         [E, na, A]
+// i.e. EntityAttentionFFAgent.forward (/root/reference/src/modules/agents/entity_ff_agent.py:30-57) on the inputs of
+// EntityMAC._build_inputs (controllers/entity_controller.py:11-30), read IN PLACE from the EpisodeBatch tensors (row stride T: no
+// time-slice copies, no packed input).  The generic acting path runs the same five layers as ~12 launches (three tensor-core GEMMs of
+// < 2 us of work each, the attention kernel, a head GEMM and half a dozen slice copies): with the small Group Matching networks
+// (d = 64, <= 8 entities of <= 32 features) a rollout timestep was bound by their fixed costs.  Here all weights (80 KB) sit in one
+// CTA's shared memory (105 KB: two CTAs per SM) and two environments advance per iteration through the five stages on the fp32 pipe:
+//   stage GEMMs: thread = (output column j, row group g), inner loop over k with W^T[k][j] (conflict-free) and the stage input stored
+//   TRANSPOSED [k][row] so that the 8 rows of a group arrive as two broadcast 128-bit loads; every stage writes its output transposed
+//   for the next one;
+//   attention: thread = (env, agent i, head h, half of the head dim): 8 partial products + one shuffle per logit, softmax in
+//   registers (a fully masked row gives zeros, attention.py:58-60), 8 output features per thread.
+// fp32 FFMA throughout (no TF32): utilities agree with the reference to ~1e-6; the greedy index is compared bit-exactly in the tests.
+#include "common.cuh"
+
+#define FA_D 64
+#define FA_H 4
+#define FA_HD 16
+#define FA_EPI 2                 // environments per iteration
+#define FA_NE_MAX 8
+#define FA_R (FA_EPI * FA_NE_MAX)   // rows of a stage tile (16)
+#define FA_THREADS 128
+#define FA_EIN_MAX 32
+#define FA_A_MAX 16
+
+struct FfActArgs {
+    const float* entities; int ed;            // [E, T, ne, ed]
+    const long long* actions; int n_actions;  // [E, T, na, 1] or null: last-action one-hot appended to agent rows (entity_last_action)
+    const uint8_t* obs_mask; int mask_rows;   // [E, T, mask_rows, ne]; rows = ne (obs_mask) or na (gt_mask with gt_obs_mask)
+    const uint8_t* entity_mask;               // [E, T, ne]
+    const float *w1, *b1, *win, *wout, *bout, *w2, *b2;
+    float* q;                                 // [E, na, A]
+    int E, T, t, ne, na, ein, A;
+};
+
+__global__ void __launch_bounds__(FA_THREADS) ff_agent_act_kernel(FfActArgs a) {
+    extern __shared__ __align__(16) float sm[];
+    const int ein = a.ein, ne = a.ne, na = a.na, A = a.A;
+    float* w1t = sm;                                  // [ein][64]
+    float* wint = w1t + FA_EIN_MAX * FA_D;            // [64][192]
+    float* woutt = wint + FA_D * 3 * FA_D;            // [64][64]
+    float* w2s = woutt + FA_D * FA_D;                 // [A][64]
+    float* bias = w2s + FA_A_MAX * FA_D;              // b1[64] | bout[64] | b2[16]
+    float* xin = bias + 2 * FA_D + FA_A_MAX;          // [ein][R]   stage-1 input, transposed
+    float* x1t = xin + FA_EIN_MAX * FA_R;             // [64][R]
+    float* qkv = x1t + FA_D * FA_R;                   // [R][192]
+    float* attt = qkv + FA_R * 3 * FA_D;              // [64][R]    attention output, transposed (rows = env * NE_MAX + agent)
+    float* x2t = attt + FA_D * FA_R;                  // [64][R]
+    __shared__ uint8_t s_obs[FA_EPI][FA_NE_MAX][FA_NE_MAX], s_em[FA_EPI][FA_NE_MAX];
+    const int tid = threadIdx.x;
+    for (int f = tid; f < ein * FA_D; f += FA_THREADS) { const int j = f / ein, k = f - j * ein; w1t[k * FA_D + j] = __ldg(a.w1 + f); }
+    for (int f = tid; f < 3 * FA_D * FA_D; f += FA_THREADS) { const int c = f / FA_D, k = f - c * FA_D; wint[k * 3 * FA_D + c] = __ldg(a.win + f); }
+    for (int f = tid; f < FA_D * FA_D; f += FA_THREADS) { const int j = f / FA_D, k = f - j * FA_D; woutt[k * FA_D + j] = __ldg(a.wout + f); }
+    for (int f = tid; f < A * FA_D; f += FA_THREADS) w2s[f] = __ldg(a.w2 + f);
+    if (tid < FA_D) { bias[tid] = __ldg(a.b1 + tid); bias[FA_D + tid] = __ldg(a.bout + tid); }
+    if (tid < A) bias[2 * FA_D + tid] = __ldg(a.b2 + tid);
+    const int j = tid & 63, g = tid >> 6;              // GEMM stages: output column j, row group g (rows 8 g .. 8 g + 7)
+    const float inv_scale = 0.25f;                     // 1 / sqrt(head dim 16)
+    __syncthreads();
+    for (int e0 = blockIdx.x * FA_EPI; e0 < a.E; e0 += gridDim.x * FA_EPI) {
+        // ---- stage 0: inputs of FA_EPI environments, transposed; masks ------------------------------------------------------
+        for (int f = tid; f < FA_R * ein; f += FA_THREADS) {
+            const int r = f / ein, k = f - r * ein, ev = r / FA_NE_MAX, en = r - ev * FA_NE_MAX, e = e0 + ev;
+            float v = 0.f;
+            if (e < a.E && en < ne) {
+                const size_t row = (size_t)e * a.T + a.t;
+                if (k < a.ed) v = __ldg(a.entities + (row * ne + en) * a.ed + k);
+                else if (a.actions && a.t > 0 && en < na)      // one-hot of the previous action (entity_controller.py:14-27)
+                    v = (__ldg(a.actions + ((row - 1) * na + en)) == (long long)(k - a.ed)) ? 1.f : 0.f;
+            }
+            xin[k * FA_R + r] = v;
+        }
+        for (int f = tid; f < FA_EPI * FA_NE_MAX * FA_NE_MAX; f += FA_THREADS) {
+            const int ev = f / (FA_NE_MAX * FA_NE_MAX), i = (f / FA_NE_MAX) % FA_NE_MAX, jj = f % FA_NE_MAX, e = e0 + ev;
+            uint8_t m = 1;
+            if (e < a.E && i < na && jj < ne) m = a.obs_mask[(((size_t)e * a.T + a.t) * a.mask_rows + i) * ne + jj];
+            s_obs[ev][i][jj] = m;
+        }
+        if (tid < FA_EPI * FA_NE_MAX) {
+            const int ev = tid / FA_NE_MAX, en = tid - ev * FA_NE_MAX, e = e0 + ev;
+            s_em[ev][en] = (e < a.E && en < ne) ? a.entity_mask[((size_t)e * a.T + a.t) * ne + en] : 1;
+        }
+        __syncthreads();
+        // ---- stage 1: x1 = relu(fc1(x))  [R, 64] -----------------------------------------------------------------------------
+        {
+            float acc[8];
+#pragma unroll
+            for (int r = 0; r < 8; r++) acc[r] = bias[j];
+            for (int k = 0; k < ein; k++) {
+                const float w = w1t[k * FA_D + j];
+                const float4 x0 = *reinterpret_cast<const float4*>(xin + k * FA_R + 8 * g);
+                const float4 x1 = *reinterpret_cast<const float4*>(xin + k * FA_R + 8 * g + 4);
+                acc[0] = fmaf(x0.x, w, acc[0]); acc[1] = fmaf(x0.y, w, acc[1]); acc[2] = fmaf(x0.z, w, acc[2]); acc[3] = fmaf(x0.w, w, acc[3]);
+                acc[4] = fmaf(x1.x, w, acc[4]); acc[5] = fmaf(x1.y, w, acc[5]); acc[6] = fmaf(x1.z, w, acc[6]); acc[7] = fmaf(x1.w, w, acc[7]);
+            }
+            float* o = x1t + j * FA_R + 8 * g;
+            *reinterpret_cast<float4*>(o) = make_float4(fmaxf(acc[0], 0.f), fmaxf(acc[1], 0.f), fmaxf(acc[2], 0.f), fmaxf(acc[3], 0.f));
+            *reinterpret_cast<float4*>(o + 4) = make_float4(fmaxf(acc[4], 0.f), fmaxf(acc[5], 0.f), fmaxf(acc[6], 0.f), fmaxf(acc[7], 0.f));
+        }
+        __syncthreads();
+        // ---- stage 2: QKV = in_trans(x1)  [R, 192], no bias -------------------------------------------------------------------
+        {
+            float acc[3][8];
+#pragma unroll
+            for (int c = 0; c < 3; c++)
+#pragma unroll
+                for (int r = 0; r < 8; r++) acc[c][r] = 0.f;
+#pragma unroll 4
+            for (int k = 0; k < FA_D; k++) {
+                const float w0 = wint[k * 3 * FA_D + j], w1 = wint[k * 3 * FA_D + FA_D + j], w2 = wint[k * 3 * FA_D + 2 * FA_D + j];
+                const float4 x0 = *reinterpret_cast<const float4*>(x1t + k * FA_R + 8 * g);
+                const float4 x1 = *reinterpret_cast<const float4*>(x1t + k * FA_R + 8 * g + 4);
+                const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+                for (int r = 0; r < 8; r++) {
+                    acc[0][r] = fmaf(xv[r], w0, acc[0][r]);
+                    acc[1][r] = fmaf(xv[r], w1, acc[1][r]);
+                    acc[2][r] = fmaf(xv[r], w2, acc[2][r]);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+                float* o = qkv + (8 * g + r) * 3 * FA_D + j;
+                o[0] = acc[0][r]; o[FA_D] = acc[1][r]; o[2 * FA_D] = acc[2][r];
+            }
+        }
+        __syncthreads();
+        // ---- stage 3: masked multi-head attention; thread = (env, agent, head, half) ------------------------------------------
+        {
+            const int half = tid & 1, h = (tid >> 1) & 3, i = (tid >> 3) & 7, ev = tid >> 6;
+            const int col = h * FA_HD + half * 8;
+            const float* qr = qkv + (ev * FA_NE_MAX + i) * 3 * FA_D + col;
+            float qv[8];
+#pragma unroll
+            for (int c = 0; c < 8; c++) qv[c] = qr[c];
+            float lg[FA_NE_MAX], mx = -INFINITY;
+#pragma unroll
+            for (int jj = 0; jj < FA_NE_MAX; jj++) {
+                const float* kr = qkv + (ev * FA_NE_MAX + jj) * 3 * FA_D + FA_D + col;
+                float s = 0.f;
+#pragma unroll
+                for (int c = 0; c < 8; c++) s = fmaf(qv[c], kr[c], s);
+                s += __shfl_xor_sync(0xffffffffu, s, 1);
+                lg[jj] = s * inv_scale;
+                if (!s_obs[ev][i][jj]) mx = fmaxf(mx, lg[jj]);
+            }
+            float ssum = 0.f, o[8];
+#pragma unroll
+            for (int c = 0; c < 8; c++) o[c] = 0.f;
+#pragma unroll
+            for (int jj = 0; jj < FA_NE_MAX; jj++) {
+                const float ew = s_obs[ev][i][jj] ? 0.f : expf(lg[jj] - mx);
+                ssum += ew;
+                const float* vr = qkv + (ev * FA_NE_MAX + jj) * 3 * FA_D + 2 * FA_D + col;
+#pragma unroll
+                for (int c = 0; c < 8; c++) o[c] = fmaf(ew, vr[c], o[c]);
+            }
+            const float rn = ssum > 0.f ? 1.f / ssum : 0.f;        // all-masked row -> zeros (attention.py:58-60)
+#pragma unroll
+            for (int c = 0; c < 8; c++) attt[(col + c) * FA_R + ev * FA_NE_MAX + i] = o[c] * rn;
+        }
+        __syncthreads();
+        // ---- stage 4: x2 = relu(rowmask(out_trans(att)))  [R, 64] (rows of inactive agents zero, entity_ff_agent.py:44-46) -------
+        {
+            float acc[8];
+#pragma unroll
+            for (int r = 0; r < 8; r++) acc[r] = bias[FA_D + j];
+#pragma unroll 4
+            for (int k = 0; k < FA_D; k++) {
+                const float w = woutt[k * FA_D + j];
+                const float4 x0 = *reinterpret_cast<const float4*>(attt + k * FA_R + 8 * g);
+                const float4 x1 = *reinterpret_cast<const float4*>(attt + k * FA_R + 8 * g + 4);
+                acc[0] = fmaf(x0.x, w, acc[0]); acc[1] = fmaf(x0.y, w, acc[1]); acc[2] = fmaf(x0.z, w, acc[2]); acc[3] = fmaf(x0.w, w, acc[3]);
+                acc[4] = fmaf(x1.x, w, acc[4]); acc[5] = fmaf(x1.y, w, acc[5]); acc[6] = fmaf(x1.z, w, acc[6]); acc[7] = fmaf(x1.w, w, acc[7]);
+            }
+            float v[8];
+#pragma unroll
+            for (int r = 0; r < 8; r++) v[r] = s_em[g][r] ? 0.f : fmaxf(acc[r], 0.f);     // row group g == environment g (8 rows each)
+            float* o = x2t + j * FA_R + 8 * g;
+            *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+        }
+        __syncthreads();
+        // ---- stage 5: q = rowmask(fc2(x2))  [na, A] per environment -----------------------------------------------------------
+        for (int f = tid; f < FA_EPI * na * A; f += FA_THREADS) {
+            const int ev = f / (na * A), i = (f / A) % na, ac = f % A, e = e0 + ev;
+            if (e >= a.E) continue;
+            float s = bias[2 * FA_D + ac];
+            const float* w = w2s + ac * FA_D;
+            const int r = ev * FA_NE_MAX + i;
+#pragma unroll 8
+            for (int k = 0; k < FA_D; k++) s = fmaf(x2t[k * FA_R + r], w[k], s);
+            a.q[((size_t)e * na + i) * A + ac] = s_em[ev][i] ? 0.f : s;
+        }
+        __syncthreads();
+    }
+}
+
+extern "C" int refil_ff_agent_act_supported(int n_entities, int n_agents, int input_dim, int embed_dim, int n_heads,
+                                            int n_actions) {
+    return (embed_dim == FA_D && n_heads == FA_H && n_entities >= 1 && n_entities <= FA_NE_MAX && n_agents >= 1 &&
+            n_agents <= n_entities && input_dim >= 1 && input_dim <= FA_EIN_MAX && n_actions >= 1 && n_actions <= FA_A_MAX) ? 1 : 0;
+}
+
+extern "C" int refil_ff_agent_act(const float* entities, int entity_dim, const long long* actions, int n_actions_onehot,
+                                  const uint8_t* obs_mask, int mask_rows, const uint8_t* entity_mask, const float* fc1_w,
+                                  const float* fc1_b, const float* in_trans_w, const float* out_trans_w,
+                                  const float* out_trans_b, const float* fc2_w, const float* fc2_b, float* q, int n_envs,
+                                  int T, int t, int n_entities, int n_agents, int n_actions, cudaStream_t stream) {
+    const int ein = entity_dim + (actions ? n_actions_onehot : 0);
+    REFIL_CHECK_ARG(entities && obs_mask && entity_mask && fc1_w && fc1_b && in_trans_w && out_trans_w && out_trans_b && fc2_w &&
+                    fc2_b && q, "ff_agent_act: null pointer");
+    REFIL_CHECK_ARG(refil_ff_agent_act_supported(n_entities, n_agents, ein, FA_D, FA_H, n_actions),
+                    "ff_agent_act: unsupported shape (ne=%d na=%d ein=%d A=%d; d=64, 4 heads, <= 8 entities)", n_entities, n_agents, ein,
+                    n_actions);
+    REFIL_CHECK_ARG(n_envs > 0 && T > 0 && t >= 0 && t < T && (mask_rows == n_entities || mask_rows == n_agents),
+                    "ff_agent_act: bad n_envs=%d T=%d t=%d mask_rows=%d", n_envs, T, t, mask_rows);
+    FfActArgs a{entities, entity_dim, actions, n_actions_onehot, obs_mask, mask_rows, entity_mask, fc1_w, fc1_b, in_trans_w,
+                out_trans_w, out_trans_b, fc2_w, fc2_b, q, n_envs, T, t, n_entities, n_agents, ein, n_actions};
+    const size_t smem = sizeof(float) * (FA_EIN_MAX * FA_D + FA_D * 3 * FA_D + FA_D * FA_D + FA_A_MAX * FA_D + 2 * FA_D + FA_A_MAX +
+                                         FA_EIN_MAX * FA_R + FA_D * FA_R + FA_R * 3 * FA_D + 2 * FA_D * FA_R);
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(ff_agent_act_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) {
+            refil_set_error("ff_agent_act: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
+            return REFIL_ERR_CUDA;
+        }
+        attr = true;
+    }
+    int grid = refil_cdiv(n_envs, FA_EPI);
+    const int cap = 2 * refil_num_sms();              // two CTAs (2 x 110 KB) per SM
+    if (grid > cap) grid = cap;
+    ff_agent_act_kernel<<<grid, FA_THREADS, smem, stream>>>(a);
+    REFIL_CHECK_LAUNCH("ff_agent_act");
+    return REFIL_OK;
+}

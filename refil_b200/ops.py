@@ -481,6 +481,21 @@ def clip_rmsprop_step(params, grads, square_avg, n_params, mask_sum, sumsq, grad
 
 
 # ---------------------------------------------------------------------------------------------------- acting / env
+def ff_agent_act_supported(ne, na, ein, d, H, A):
+    return _lib.load().refil_ff_agent_act_supported(ne, na, ein, d, H, A) != 0
+
+
+def ff_agent_act(entities, actions, n_actions, obs_mask, entity_mask, params, q, t):
+    """Fused acting forward of the FF entity-attention agent on timestep t of the EpisodeBatch tensors (read in place).
+    params: dict with fc1 / attn.in_trans / attn.out_trans / fc2 weights.  q [E, na, A] is written."""
+    E, T, ne, ed = entities.shape
+    na, A = q.shape[1], q.shape[2]
+    _call("ff_agent_act", _p(entities, F32), ed, _p(actions, I64), n_actions, _p(obs_mask, U8), obs_mask.shape[2],
+          _p(entity_mask, U8), _p(params["fc1.weight"], F32), _p(params["fc1.bias"], F32), _p(params["attn.in_trans.weight"], F32),
+          _p(params["attn.out_trans.weight"], F32), _p(params["attn.out_trans.bias"], F32), _p(params["fc2.weight"], F32),
+          _p(params["fc2.bias"], F32), _p(q, F32), E, T, int(t), ne, na, A)
+    return q
+
 def select_actions(q, avail, u_pick, u_act, est_flags, epsilon, actions_out, B, na, A, eps_dev=None):
     """q [B, na, A] contiguous; avail / actions_out may be time slices of EpisodeBatch tensors (row stride taken from them)."""
     if avail.stride(-1) != 1 or avail.stride(-2) != A or actions_out.stride(-1) != 1:
