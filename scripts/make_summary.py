@@ -34,6 +34,7 @@ def short(name):
 
 def launches_table(path):
     rows = [r for r in csv.reader(open(path)) if len(r) > 10 and r[0].isdigit()]
+    rows = [r for r in rows if not short(r[4]).startswith("gm_")]     # the env leg of bench.py is not part of the learner step
     agg, tot = collections.OrderedDict(), 0.0
     for r in rows:
         k, ns = short(r[4]), float(r[-1])
@@ -153,7 +154,8 @@ def main(tag):
     if os.path.exists(lp):
         tbl, n = launches_table(lp)
         shutil.copy(lp, os.path.join(PROF, tag + "_ncu_launches.csv"))
-        lines.append("\n## ncu launch list (%s_ncu_launches.csv, %d launches), aggregated by kernel\n\n%s" % (tag, n, tbl))
+        lines.append("\n## ncu launch list (%s_ncu_launches.csv, %d launches of the learner steps; the env leg's gm_* kernels left out), "
+                     "aggregated by kernel\n\n%s" % (tag, n, tbl))
     tp = os.path.join(OUT, tag + "_traffic.csv")
     if os.path.exists(tp) and d.get("roofline"):
         per_step = int(d["roofline"]["launches_per_step"])
