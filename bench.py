@@ -318,6 +318,9 @@ def bench_learner(w, B, a, dev, rank, world, do_e2e=True, do_breakdown=False, st
     args.device = dev
     args.cuda_graph = not a.no_graph
     args.group_hypernets = False if a.no_group else (True if a.group else "auto")
+    if a.crit_tiles >= 0:
+        args.critical_min_tiles = a.crit_tiles
+    args.critical_priority = not a.no_prio
     gm = w == "gm"
     scheme, groups, preprocess = entity_scheme(na, ne, ed, A, gt_mask=gm)
     syn = synthetic_replay(B, T, na, ne, ed, A, seed=1000 + rank, gt_mask=gm, pad=ne > na)
@@ -729,6 +732,8 @@ if __name__ == "__main__":
     ap.add_argument("--batch", type=int, default=0, help="episodes per GPU (default: the workload's)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-extra", action="store_true", help="skip the other-workload and rollout legs")
+    ap.add_argument("--crit-tiles", type=int, default=-1, help="m-tiles per CTA on the agent chain (QLearner args.critical_min_tiles; 0 = default)")
+    ap.add_argument("--no-prio", action="store_true", help="agent chain on the default-priority stream")
     ap.add_argument("--group", action="store_true", help="force the lock-step grouped hypernetwork launches (default: auto by size)")
     ap.add_argument("--no-group", action="store_true", help="run the hypernetworks net by net on their own streams instead of "
                     "in lock-step with grouped launches (QLearner args.group_hypernets)")

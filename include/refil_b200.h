@@ -125,6 +125,9 @@ int refil_last_action_index(const long long* actions, int32_t* la, int B, int T,
  *      selects the all-shared-memory predecessor for A/B comparisons.
  *      refil_tc_gemm_k_slices() > 1: the reduction is too long for a resident weight tile and is cut into k-slices whose
  *      partial tiles are reduce-added into a zeroed C -- only for a linear epilogue (no bias / relu / output row mask). */
+/* launch-shape hint for the dense kernel: m-tiles every CTA should at least get (0 = default / REFIL_TC_MIN_TILES); returns the
+ * previous override.  Small on a latency-critical chain (more CTAs, shorter kernel), large beside it (fewer SMs taken). */
+int refil_tc_set_min_tiles(int min_tiles);
 int refil_tc_gemm_supported(int M, int N, int K);
 int refil_tc_gemm_k_slices(int N, int K);
 int refil_tc_gemm_tn(const float* A, long long lda, const float* relu_y, long long ldy,

@@ -793,6 +793,24 @@ extern "C" int refil_tc_gemm_k_slices(int N, int K) {
     return tc_pick_slices(N, K);
 }
 
+// m-tiles a CTA of the dense kernel should at least get (REFIL_TC_MIN_TILES, default 6; refil_tc_set_min_tiles overrides it for the
+// launches that follow: the learner asks for short kernels on its critical chain and long-lived CTAs on the side chains)
+static int g_min_tiles_override = 0;
+static int tc_min_tiles() {
+    static int env_tiles = -1;
+    if (env_tiles < 0) {
+        const char* e = getenv("REFIL_TC_MIN_TILES");
+        env_tiles = e ? atoi(e) : 6;
+        if (env_tiles < 1) env_tiles = 1;
+    }
+    return g_min_tiles_override > 0 ? g_min_tiles_override : env_tiles;
+}
+extern "C" int refil_tc_set_min_tiles(int min_tiles) {
+    const int prev = g_min_tiles_override;
+    g_min_tiles_override = min_tiles > 0 ? min_tiles : 0;
+    return prev;
+}
+
 static int tc_mode_ts() {
     // operand path: "ts" (default) keeps the A operand in tensor memory (TMA-fed raw ring + converter warps), "ss" is the
     // all-shared-memory kernel; REFIL_TC_MODE=ss selects the latter for A/B comparisons
@@ -891,12 +909,7 @@ extern "C" int refil_tc_gemm_tn_group(const RefilGemmDesc* descs, int n_problems
     const int groups = a0.n_tiles * a0.k_slices;
     // every CTA pays a fixed prologue (split of its resident weight tile, pipeline fill): give it at least `min_tiles` m-tiles, so
     // that a small problem (a 16-episode shard) leaves SMs to the independent networks running on the other streams
-    static int min_tiles = -1;
-    if (min_tiles < 0) {
-        const char* e = getenv("REFIL_TC_MIN_TILES");
-        min_tiles = e ? atoi(e) : 6;
-        if (min_tiles < 1) min_tiles = 1;
-    }
+    const int min_tiles = tc_min_tiles();
     long long sum_tiles = 0;
     for (int g = 0; g < n_problems; g++) sum_tiles += grp.a[g].m_tiles;
     int begin = 0;

@@ -99,6 +99,12 @@ class QLearner:
             self._side = [torch.cuda.Stream(device=self.device) for _ in range(self.N_SIDE)]
         return self._side[i]
 
+    def _crit_stream(self):
+        """High-priority stream for the agent chain (the step's critical path): when SMs free up, its CTAs are placed first."""
+        if getattr(self, "_crit", None) is None:
+            self._crit = torch.cuda.Stream(device=self.device, priority=-1)
+        return self._crit
+
     def cuda(self):
         self.mac.cuda()
         self.target_mac.cuda()
@@ -272,12 +278,20 @@ class QLearner:
             self.target_mixer.hyper_forward(ents, la, em, T, xin=inp.get("xin"), streams=s_thyp)
             self.mixer.hyper_forward(ents, la, em, T, imagine_masks=mix if self.imagine else None, xin=inp.get("xin"), streams=s_hyp)
         # ---- main: online agent on all T steps, 3 mask copies when imagining (q_learner.py:79-109) -------------------
-        self.mac.init_hidden(B)
-        q_all, spec, _, _ = self.mac.forward(batch, None, imagine=self.imagine, use_gt_factors=use_gt,
-                                             use_rand_gt_factors=use_rgt, group_bits=group_bits, train=True,
-                                             ret_plan=True, inputs=inp)
-        C = spec.C
-        chosen = ops.gather_chosen(q_all, actions, ws.get("chosen", (3, N, na)), C, N * na, A)
+        # the agent chain is the step's critical path: short kernels (few m-tiles per CTA) on a high-priority stream
+        crit_tiles = int(getattr(args, "critical_min_tiles", 2)) if two else 0
+        crit = self._crit_stream() if (two and getattr(args, "critical_priority", True)) else None
+        if crit is not None:
+            crit.wait_stream(main)
+        with torch.cuda.stream(crit if crit is not None else main), ops.min_tiles(crit_tiles):
+            self.mac.init_hidden(B)
+            q_all, spec, _, _ = self.mac.forward(batch, None, imagine=self.imagine, use_gt_factors=use_gt,
+                                                 use_rand_gt_factors=use_rgt, group_bits=group_bits, train=True,
+                                                 ret_plan=True, inputs=inp)
+            C = spec.C
+            chosen = ops.gather_chosen(q_all, actions, ws.get("chosen", (3, N, na)), C, N * na, A)
+        if crit is not None:
+            main.wait_stream(crit)
         for st in (s_hyp or []):
             main.wait_stream(st)
         qtot, qtot_im = self.mixer.mix(chosen[0], chosen[1] if self.imagine else None,
@@ -309,7 +323,12 @@ class QLearner:
             self.mixer.backward_hyper(dhyper, streams=s_hyp, wstreams=s_w[1:] if two else None)
         Ap = self.mac.agent.dq_width(C * N * na)        # one-hot scatter of d(chosen) into (padded) action columns
         dQ = ops.scatter_dq(dq, actions, ws.get("dQ", (C * N * na, Ap)), C, N * na, Ap, T, na)
-        self.mac.agent.backward(dQ, wstream=s_w[0] if two else None)
+        if crit is not None:
+            crit.wait_stream(main)
+        with torch.cuda.stream(crit if crit is not None else main), ops.min_tiles(crit_tiles):
+            self.mac.agent.backward(dQ, wstream=s_w[0] if two else None)
+        if crit is not None:
+            main.wait_stream(crit)
         for st in (s_hyp or []):
             main.wait_stream(st)
         # one all-reduce of [grads | stats], then normalise + clip + RMSprop (q_learner.py:177-178)

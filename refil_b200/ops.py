@@ -114,6 +114,21 @@ def _tc_ok(M, N, K):
     return USE_TENSOR_CORES and M >= TC_MIN_ROWS and _lib.load().refil_tc_gemm_supported(M, N, K) != 0
 
 
+class min_tiles:
+    """with ops.min_tiles(n): dense launches inside give every CTA at least n m-tiles (see refil_tc_set_min_tiles)."""
+
+    def __init__(self, n):
+        self.n = int(n or 0)
+
+    def __enter__(self):
+        self.prev = _lib.load().refil_tc_set_min_tiles(self.n) if self.n else None
+
+    def __exit__(self, *exc):
+        if self.n:
+            _lib.load().refil_tc_set_min_tiles(self.prev)
+        return False
+
+
 def tc_head_ok(rows, n_out, width):
     """Can the backward of an [n_out <= 32, width] output head run on the tensor cores with its gradient padded to 32 columns?"""
     return _tc_ok(rows, width, 32) and _lib.load().refil_tc_wgrad_supported(rows, n_out, width) != 0
