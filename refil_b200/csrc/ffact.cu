@@ -6,8 +6,8 @@
 // EntityMAC._build_inputs (controllers/entity_controller.py:11-30), read IN PLACE from the EpisodeBatch tensors (row stride T: no
 // time-slice copies, no packed input).  The generic acting path runs the same five layers as ~12 launches (three tensor-core GEMMs of
 // < 2 us of work each, the attention kernel, a head GEMM and half a dozen slice copies): with the small Group Matching networks
-// (d = 64, <= 8 entities of <= 32 features) a rollout timestep was bound by their fixed costs.  Here all weights (80 KB) sit in one
-// CTA's shared memory (105 KB: two CTAs per SM) and two environments advance per iteration through the five stages on the fp32 pipe:
+// (d = 64, <= 8 entities of <= 32 features) a rollout timestep was bound by their fixed costs.  Here the weights sit in one CTA's
+// shared memory and registers (54 KB + 96 registers per thread: three CTAs per SM) and two environments advance per iteration through the five stages on the fp32 pipe:
 //   stage GEMMs: thread = (output column j, row group g), inner loop over k with W^T[k][j] (conflict-free) and the stage input stored
 //   TRANSPOSED [k][row] so that the 8 rows of a group arrive as two broadcast 128-bit loads; every stage writes its output transposed
 //   for the next one;
@@ -36,28 +36,41 @@ struct FfActArgs {
     int E, T, t, ne, na, ein, A;
 };
 
-__global__ void __launch_bounds__(FA_THREADS) ff_agent_act_kernel(FfActArgs a) {
+// shared-memory strides: +1 float per transposed weight row, so that the transposing prologue stores (k fastest across a warp)
+// spread over the banks instead of hitting one
+#define FA_LD1 (FA_D + 1)
+
+__global__ void __launch_bounds__(FA_THREADS, 3) ff_agent_act_kernel(FfActArgs a) {
     extern __shared__ __align__(16) float sm[];
     const int ein = a.ein, ne = a.ne, na = a.na, A = a.A;
-    float* w1t = sm;                                  // [ein][64]
-    float* wint = w1t + FA_EIN_MAX * FA_D;            // [64][192]
-    float* woutt = wint + FA_D * 3 * FA_D;            // [64][64]
-    float* w2s = woutt + FA_D * FA_D;                 // [A][64]
+    float* w1t = sm;                                  // [ein][65]
+    float* woutt = w1t + FA_EIN_MAX * FA_LD1;         // [64][65]
+    float* w2s = woutt + FA_D * FA_LD1;               // [A][64]
     float* bias = w2s + FA_A_MAX * FA_D;              // b1[64] | bout[64] | b2[16]
-    float* xin = bias + 2 * FA_D + FA_A_MAX;          // [ein][R]   stage-1 input, transposed
+    float* xin = bias + 2 * FA_D + FA_A_MAX;          // [ein][R]   stage-1 input, transposed; later the stage-2 partial sums
     float* x1t = xin + FA_EIN_MAX * FA_R;             // [64][R]
     float* qkv = x1t + FA_D * FA_R;                   // [R][192]
     float* attt = qkv + FA_R * 3 * FA_D;              // [64][R]    attention output, transposed (rows = env * NE_MAX + agent)
     float* x2t = attt + FA_D * FA_R;                  // [64][R]
     __shared__ uint8_t s_obs[FA_EPI][FA_NE_MAX][FA_NE_MAX], s_em[FA_EPI][FA_NE_MAX];
     const int tid = threadIdx.x;
-    for (int f = tid; f < ein * FA_D; f += FA_THREADS) { const int j = f / ein, k = f - j * ein; w1t[k * FA_D + j] = __ldg(a.w1 + f); }
-    for (int f = tid; f < 3 * FA_D * FA_D; f += FA_THREADS) { const int c = f / FA_D, k = f - c * FA_D; wint[k * 3 * FA_D + c] = __ldg(a.win + f); }
-    for (int f = tid; f < FA_D * FA_D; f += FA_THREADS) { const int j = f / FA_D, k = f - j * FA_D; woutt[k * FA_D + j] = __ldg(a.wout + f); }
+    const int j = tid & 63, g = tid >> 6;              // GEMM stages: output column j, row group / reduction half g
+    for (int f = tid; f < ein * FA_D; f += FA_THREADS) { const int jj = f / ein, k = f - jj * ein; w1t[k * FA_LD1 + jj] = __ldg(a.w1 + f); }
+    for (int f = tid; f < FA_D * FA_D; f += FA_THREADS) { const int jj = f / FA_D, k = f - jj * FA_D; woutt[k * FA_LD1 + jj] = __ldg(a.wout + f); }
     for (int f = tid; f < A * FA_D; f += FA_THREADS) w2s[f] = __ldg(a.w2 + f);
     if (tid < FA_D) { bias[tid] = __ldg(a.b1 + tid); bias[FA_D + tid] = __ldg(a.bout + tid); }
     if (tid < A) bias[2 * FA_D + tid] = __ldg(a.b2 + tid);
-    const int j = tid & 63, g = tid >> 6;              // GEMM stages: output column j, row group g (rows 8 g .. 8 g + 7)
+    // in_trans (192 x 64 = 12288 weights = 96 per thread) lives in REGISTERS: thread (j, g) holds rows j, j + 64, j + 128 of W_in for
+    // the reduction half k in [32 g, 32 g + 32) -- 48 KB less shared memory (three CTAs per SM instead of two) and 48 FMAs per 4
+    // broadcast loads in the heaviest stage
+    float win[3][32];
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+#pragma unroll
+        for (int k = 0; k < 32; k += 4) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(a.win + (size_t)(c * FA_D + j) * FA_D + 32 * g + k));
+            win[c][k] = v.x; win[c][k + 1] = v.y; win[c][k + 2] = v.z; win[c][k + 3] = v.w;
+        }
     const float inv_scale = 0.25f;                     // 1 / sqrt(head dim 16)
     __syncthreads();
     for (int e0 = blockIdx.x * FA_EPI; e0 < a.E; e0 += gridDim.x * FA_EPI) {
@@ -84,13 +97,13 @@ __global__ void __launch_bounds__(FA_THREADS) ff_agent_act_kernel(FfActArgs a) {
             s_em[ev][en] = (e < a.E && en < ne) ? a.entity_mask[((size_t)e * a.T + a.t) * ne + en] : 1;
         }
         __syncthreads();
-        // ---- stage 1: x1 = relu(fc1(x))  [R, 64] -----------------------------------------------------------------------------
+        // ---- stage 1: x1 = relu(fc1(x))  [R, 64]; thread = (column j, rows 8 g .. 8 g + 7) -----------------------------------
         {
             float acc[8];
 #pragma unroll
             for (int r = 0; r < 8; r++) acc[r] = bias[j];
             for (int k = 0; k < ein; k++) {
-                const float w = w1t[k * FA_D + j];
+                const float w = w1t[k * FA_LD1 + j];
                 const float4 x0 = *reinterpret_cast<const float4*>(xin + k * FA_R + 8 * g);
                 const float4 x1 = *reinterpret_cast<const float4*>(xin + k * FA_R + 8 * g + 4);
                 acc[0] = fmaf(x0.x, w, acc[0]); acc[1] = fmaf(x0.y, w, acc[1]); acc[2] = fmaf(x0.z, w, acc[2]); acc[3] = fmaf(x0.w, w, acc[3]);
@@ -101,30 +114,44 @@ __global__ void __launch_bounds__(FA_THREADS) ff_agent_act_kernel(FfActArgs a) {
             *reinterpret_cast<float4*>(o + 4) = make_float4(fmaxf(acc[4], 0.f), fmaxf(acc[5], 0.f), fmaxf(acc[6], 0.f), fmaxf(acc[7], 0.f));
         }
         __syncthreads();
-        // ---- stage 2: QKV = in_trans(x1)  [R, 192], no bias -------------------------------------------------------------------
+        // ---- stage 2: QKV = in_trans(x1)  [R, 192], no bias; thread = (columns j, j + 64, j + 128; reduction half g), all 16 rows ----
         {
-            float acc[3][8];
+            float acc[3][FA_R];
 #pragma unroll
             for (int c = 0; c < 3; c++)
 #pragma unroll
-                for (int r = 0; r < 8; r++) acc[c][r] = 0.f;
-#pragma unroll 4
-            for (int k = 0; k < FA_D; k++) {
-                const float w0 = wint[k * 3 * FA_D + j], w1 = wint[k * 3 * FA_D + FA_D + j], w2 = wint[k * 3 * FA_D + 2 * FA_D + j];
-                const float4 x0 = *reinterpret_cast<const float4*>(x1t + k * FA_R + 8 * g);
-                const float4 x1 = *reinterpret_cast<const float4*>(x1t + k * FA_R + 8 * g + 4);
-                const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+                for (int r = 0; r < FA_R; r++) acc[c][r] = 0.f;
 #pragma unroll
-                for (int r = 0; r < 8; r++) {
-                    acc[0][r] = fmaf(xv[r], w0, acc[0][r]);
-                    acc[1][r] = fmaf(xv[r], w1, acc[1][r]);
-                    acc[2][r] = fmaf(xv[r], w2, acc[2][r]);
+            for (int k = 0; k < 32; k++) {
+                const float* xr = x1t + (32 * g + k) * FA_R;
+                float xv[FA_R];
+#pragma unroll
+                for (int r4 = 0; r4 < FA_R; r4 += 4) {
+                    const float4 v = *reinterpret_cast<const float4*>(xr + r4);
+                    xv[r4] = v.x; xv[r4 + 1] = v.y; xv[r4 + 2] = v.z; xv[r4 + 3] = v.w;
+                }
+#pragma unroll
+                for (int r = 0; r < FA_R; r++) {
+                    acc[0][r] = fmaf(xv[r], win[0][k], acc[0][r]);
+                    acc[1][r] = fmaf(xv[r], win[1][k], acc[1][r]);
+                    acc[2][r] = fmaf(xv[r], win[2][k], acc[2][r]);
                 }
             }
+            // the two reduction halves meet in shared memory: half 1 parks its partial sums (xin is dead by now), half 0 adds them
+            if (g == 1) {
 #pragma unroll
-            for (int r = 0; r < 8; r++) {
-                float* o = qkv + (8 * g + r) * 3 * FA_D + j;
-                o[0] = acc[0][r]; o[FA_D] = acc[1][r]; o[2 * FA_D] = acc[2][r];
+                for (int r = 0; r < FA_R; r++) {
+                    float* o = qkv + r * 3 * FA_D + j;
+                    o[0] = acc[0][r]; o[FA_D] = acc[1][r]; o[2 * FA_D] = acc[2][r];
+                }
+            }
+            __syncthreads();
+            if (g == 0) {
+#pragma unroll
+                for (int r = 0; r < FA_R; r++) {
+                    float* o = qkv + r * 3 * FA_D + j;
+                    o[0] += acc[0][r]; o[FA_D] += acc[1][r]; o[2 * FA_D] += acc[2][r];
+                }
             }
         }
         __syncthreads();
@@ -170,7 +197,7 @@ __global__ void __launch_bounds__(FA_THREADS) ff_agent_act_kernel(FfActArgs a) {
             for (int r = 0; r < 8; r++) acc[r] = bias[FA_D + j];
 #pragma unroll 4
             for (int k = 0; k < FA_D; k++) {
-                const float w = woutt[k * FA_D + j];
+                const float w = woutt[k * FA_LD1 + j];
                 const float4 x0 = *reinterpret_cast<const float4*>(attt + k * FA_R + 8 * g);
                 const float4 x1 = *reinterpret_cast<const float4*>(attt + k * FA_R + 8 * g + 4);
                 acc[0] = fmaf(x0.x, w, acc[0]); acc[1] = fmaf(x0.y, w, acc[1]); acc[2] = fmaf(x0.z, w, acc[2]); acc[3] = fmaf(x0.w, w, acc[3]);
@@ -220,7 +247,7 @@ extern "C" int refil_ff_agent_act(const float* entities, int entity_dim, const l
                     "ff_agent_act: bad n_envs=%d T=%d t=%d mask_rows=%d", n_envs, T, t, mask_rows);
     FfActArgs a{entities, entity_dim, actions, n_actions_onehot, obs_mask, mask_rows, entity_mask, fc1_w, fc1_b, in_trans_w,
                 out_trans_w, out_trans_b, fc2_w, fc2_b, q, n_envs, T, t, n_entities, n_agents, ein, n_actions};
-    const size_t smem = sizeof(float) * (FA_EIN_MAX * FA_D + FA_D * 3 * FA_D + FA_D * FA_D + FA_A_MAX * FA_D + 2 * FA_D + FA_A_MAX +
+    const size_t smem = sizeof(float) * (FA_EIN_MAX * FA_LD1 + FA_D * FA_LD1 + FA_A_MAX * FA_D + 2 * FA_D + FA_A_MAX +
                                          FA_EIN_MAX * FA_R + FA_D * FA_R + FA_R * 3 * FA_D + 2 * FA_D * FA_R);
     static bool attr = false;
     if (!attr) {
@@ -232,7 +259,7 @@ extern "C" int refil_ff_agent_act(const float* entities, int entity_dim, const l
         attr = true;
     }
     int grid = refil_cdiv(n_envs, FA_EPI);
-    const int cap = 2 * refil_num_sms();              // two CTAs (2 x 110 KB) per SM
+    const int cap = 3 * refil_num_sms();              // three CTAs per SM (54 KB of shared memory, <= 170 registers per thread)
     if (grid > cap) grid = cap;
     ff_agent_act_kernel<<<grid, FA_THREADS, smem, stream>>>(a);
     REFIL_CHECK_LAUNCH("ff_agent_act");

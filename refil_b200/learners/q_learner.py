@@ -279,7 +279,10 @@ class QLearner:
             self.mixer.hyper_forward(ents, la, em, T, imagine_masks=mix if self.imagine else None, xin=inp.get("xin"), streams=s_hyp)
         # ---- main: online agent on all T steps, 3 mask copies when imagining (q_learner.py:79-109) -------------------
         # the agent chain is the step's critical path: short kernels (few m-tiles per CTA) on a high-priority stream
-        crit_tiles = int(getattr(args, "critical_min_tiles", 2)) if two else 0
+        # (measured, profiles/r2_tuning.md: priority 1.107 -> 1.089 ms at 16 episodes, 4 m-tiles per CTA on the chain -> 1.080; at
+        # 128 episodes everything within noise, so the tile hint is only given to small shards)
+        small = N * inp["ne"] <= self.GROUP_MAX_ENTITY_ROWS
+        crit_tiles = int(getattr(args, "critical_min_tiles", 4 if small else 0)) if two else 0
         crit = self._crit_stream() if (two and getattr(args, "critical_priority", True)) else None
         if crit is not None:
             crit.wait_stream(main)
