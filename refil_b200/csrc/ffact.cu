@@ -7,7 +7,7 @@
 // time-slice copies, no packed input).  The generic acting path runs the same five layers as ~12 launches (three tensor-core GEMMs of
 // < 2 us of work each, the attention kernel, a head GEMM and half a dozen slice copies): with the small Group Matching networks
 // (d = 64, <= 8 entities of <= 32 features) a rollout timestep was bound by their fixed costs.  Here the weights sit in one CTA's
-// shared memory and registers (54 KB + 96 registers per thread: three CTAs per SM) and two environments advance per iteration through the five stages on the fp32 pipe:
+// shared memory and registers (54 KB + 96 registers per thread: three CTAs per SM) and 16 entity rows (two 8-slot or four 4-slot environments) advance per iteration through the five stages on the fp32 pipe:
 //   stage GEMMs: thread = (output column j, row group g), inner loop over k with W^T[k][j] (conflict-free) and the stage input stored
 //   TRANSPOSED [k][row] so that the 8 rows of a group arrive as two broadcast 128-bit loads; every stage writes its output transposed
 //   for the next one;
@@ -19,9 +19,8 @@
 #define FA_D 64
 #define FA_H 4
 #define FA_HD 16
-#define FA_EPI 2                 // environments per iteration
 #define FA_NE_MAX 8
-#define FA_R (FA_EPI * FA_NE_MAX)   // rows of a stage tile (16)
+#define FA_R 16                  // rows of a stage tile: 16 / NE environments advance per iteration (NE = entity slots per env: 4 or 8)
 #define FA_THREADS 128
 #define FA_EIN_MAX 32
 #define FA_A_MAX 16
@@ -40,7 +39,9 @@ struct FfActArgs {
 // spread over the banks instead of hitting one
 #define FA_LD1 (FA_D + 1)
 
+template <int NE>
 __global__ void __launch_bounds__(FA_THREADS, 3) ff_agent_act_kernel(FfActArgs a) {
+    constexpr int EPI = FA_R / NE;
     extern __shared__ __align__(16) float sm[];
     const int ein = a.ein, ne = a.ne, na = a.na, A = a.A;
     float* w1t = sm;                                  // [ein][65]
@@ -52,7 +53,7 @@ __global__ void __launch_bounds__(FA_THREADS, 3) ff_agent_act_kernel(FfActArgs a
     float* qkv = x1t + FA_D * FA_R;                   // [R][192]
     float* attt = qkv + FA_R * 3 * FA_D;              // [64][R]    attention output, transposed (rows = env * NE_MAX + agent)
     float* x2t = attt + FA_D * FA_R;                  // [64][R]
-    __shared__ uint8_t s_obs[FA_EPI][FA_NE_MAX][FA_NE_MAX], s_em[FA_EPI][FA_NE_MAX];
+    __shared__ uint8_t s_obs[FA_R][NE], s_em[FA_R];     // rows = env * NE + entity slot
     const int tid = threadIdx.x;
     const int j = tid & 63, g = tid >> 6;              // GEMM stages: output column j, row group / reduction half g
     for (int f = tid; f < ein * FA_D; f += FA_THREADS) { const int jj = f / ein, k = f - jj * ein; w1t[k * FA_LD1 + jj] = __ldg(a.w1 + f); }
@@ -73,10 +74,10 @@ __global__ void __launch_bounds__(FA_THREADS, 3) ff_agent_act_kernel(FfActArgs a
         }
     const float inv_scale = 0.25f;                     // 1 / sqrt(head dim 16)
     __syncthreads();
-    for (int e0 = blockIdx.x * FA_EPI; e0 < a.E; e0 += gridDim.x * FA_EPI) {
+    for (int e0 = blockIdx.x * EPI; e0 < a.E; e0 += gridDim.x * EPI) {
         // ---- stage 0: inputs of FA_EPI environments, transposed; masks ------------------------------------------------------
         for (int f = tid; f < FA_R * ein; f += FA_THREADS) {
-            const int r = f / ein, k = f - r * ein, ev = r / FA_NE_MAX, en = r - ev * FA_NE_MAX, e = e0 + ev;
+            const int r = f / ein, k = f - r * ein, ev = r / NE, en = r - ev * NE, e = e0 + ev;
             float v = 0.f;
             if (e < a.E && en < ne) {
                 const size_t row = (size_t)e * a.T + a.t;
@@ -86,15 +87,15 @@ __global__ void __launch_bounds__(FA_THREADS, 3) ff_agent_act_kernel(FfActArgs a
             }
             xin[k * FA_R + r] = v;
         }
-        for (int f = tid; f < FA_EPI * FA_NE_MAX * FA_NE_MAX; f += FA_THREADS) {
-            const int ev = f / (FA_NE_MAX * FA_NE_MAX), i = (f / FA_NE_MAX) % FA_NE_MAX, jj = f % FA_NE_MAX, e = e0 + ev;
+        for (int f = tid; f < FA_R * NE; f += FA_THREADS) {
+            const int r = f / NE, jj = f - r * NE, ev = r / NE, i = r - ev * NE, e = e0 + ev;
             uint8_t m = 1;
             if (e < a.E && i < na && jj < ne) m = a.obs_mask[(((size_t)e * a.T + a.t) * a.mask_rows + i) * ne + jj];
-            s_obs[ev][i][jj] = m;
+            s_obs[r][jj] = m;
         }
-        if (tid < FA_EPI * FA_NE_MAX) {
-            const int ev = tid / FA_NE_MAX, en = tid - ev * FA_NE_MAX, e = e0 + ev;
-            s_em[ev][en] = (e < a.E && en < ne) ? a.entity_mask[((size_t)e * a.T + a.t) * ne + en] : 1;
+        if (tid < FA_R) {
+            const int ev = tid / NE, en = tid - ev * NE, e = e0 + ev;
+            s_em[tid] = (e < a.E && en < ne) ? a.entity_mask[((size_t)e * a.T + a.t) * ne + en] : 1;
         }
         __syncthreads();
         // ---- stage 1: x1 = relu(fc1(x))  [R, 64]; thread = (column j, rows 8 g .. 8 g + 7) -----------------------------------
@@ -155,39 +156,39 @@ __global__ void __launch_bounds__(FA_THREADS, 3) ff_agent_act_kernel(FfActArgs a
             }
         }
         __syncthreads();
-        // ---- stage 3: masked multi-head attention; thread = (env, agent, head, half) ------------------------------------------
+        // ---- stage 3: masked multi-head attention; thread = (row = (env, agent slot), head h, half of the head dim) ----------------
         {
-            const int half = tid & 1, h = (tid >> 1) & 3, i = (tid >> 3) & 7, ev = tid >> 6;
+            const int half = tid & 1, h = (tid >> 1) & 3, r = tid >> 3, ev = r / NE;
             const int col = h * FA_HD + half * 8;
-            const float* qr = qkv + (ev * FA_NE_MAX + i) * 3 * FA_D + col;
+            const float* qr = qkv + r * 3 * FA_D + col;
             float qv[8];
 #pragma unroll
             for (int c = 0; c < 8; c++) qv[c] = qr[c];
-            float lg[FA_NE_MAX], mx = -INFINITY;
+            float lg[NE], mx = -INFINITY;
 #pragma unroll
-            for (int jj = 0; jj < FA_NE_MAX; jj++) {
-                const float* kr = qkv + (ev * FA_NE_MAX + jj) * 3 * FA_D + FA_D + col;
-                float s = 0.f;
+            for (int jj = 0; jj < NE; jj++) {
+                const float* kr = qkv + (ev * NE + jj) * 3 * FA_D + FA_D + col;
+                float sdot = 0.f;
 #pragma unroll
-                for (int c = 0; c < 8; c++) s = fmaf(qv[c], kr[c], s);
-                s += __shfl_xor_sync(0xffffffffu, s, 1);
-                lg[jj] = s * inv_scale;
-                if (!s_obs[ev][i][jj]) mx = fmaxf(mx, lg[jj]);
+                for (int c = 0; c < 8; c++) sdot = fmaf(qv[c], kr[c], sdot);
+                sdot += __shfl_xor_sync(0xffffffffu, sdot, 1);
+                lg[jj] = sdot * inv_scale;
+                if (!s_obs[r][jj]) mx = fmaxf(mx, lg[jj]);
             }
             float ssum = 0.f, o[8];
 #pragma unroll
             for (int c = 0; c < 8; c++) o[c] = 0.f;
 #pragma unroll
-            for (int jj = 0; jj < FA_NE_MAX; jj++) {
-                const float ew = s_obs[ev][i][jj] ? 0.f : expf(lg[jj] - mx);
+            for (int jj = 0; jj < NE; jj++) {
+                const float ew = s_obs[r][jj] ? 0.f : expf(lg[jj] - mx);
                 ssum += ew;
-                const float* vr = qkv + (ev * FA_NE_MAX + jj) * 3 * FA_D + 2 * FA_D + col;
+                const float* vr = qkv + (ev * NE + jj) * 3 * FA_D + 2 * FA_D + col;
 #pragma unroll
                 for (int c = 0; c < 8; c++) o[c] = fmaf(ew, vr[c], o[c]);
             }
             const float rn = ssum > 0.f ? 1.f / ssum : 0.f;        // all-masked row -> zeros (attention.py:58-60)
 #pragma unroll
-            for (int c = 0; c < 8; c++) attt[(col + c) * FA_R + ev * FA_NE_MAX + i] = o[c] * rn;
+            for (int c = 0; c < 8; c++) attt[(col + c) * FA_R + r] = o[c] * rn;
         }
         __syncthreads();
         // ---- stage 4: x2 = relu(rowmask(out_trans(att)))  [R, 64] (rows of inactive agents zero, entity_ff_agent.py:44-46) -------
@@ -205,22 +206,22 @@ __global__ void __launch_bounds__(FA_THREADS, 3) ff_agent_act_kernel(FfActArgs a
             }
             float v[8];
 #pragma unroll
-            for (int r = 0; r < 8; r++) v[r] = s_em[g][r] ? 0.f : fmaxf(acc[r], 0.f);     // row group g == environment g (8 rows each)
+            for (int r = 0; r < 8; r++) v[r] = s_em[8 * g + r] ? 0.f : fmaxf(acc[r], 0.f);
             float* o = x2t + j * FA_R + 8 * g;
             *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
             *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
         }
         __syncthreads();
         // ---- stage 5: q = rowmask(fc2(x2))  [na, A] per environment -----------------------------------------------------------
-        for (int f = tid; f < FA_EPI * na * A; f += FA_THREADS) {
+        for (int f = tid; f < EPI * na * A; f += FA_THREADS) {
             const int ev = f / (na * A), i = (f / A) % na, ac = f % A, e = e0 + ev;
             if (e >= a.E) continue;
-            float s = bias[2 * FA_D + ac];
+            float sq = bias[2 * FA_D + ac];
             const float* w = w2s + ac * FA_D;
-            const int r = ev * FA_NE_MAX + i;
+            const int r = ev * NE + i;
 #pragma unroll 8
-            for (int k = 0; k < FA_D; k++) s = fmaf(x2t[k * FA_R + r], w[k], s);
-            a.q[((size_t)e * na + i) * A + ac] = s_em[ev][i] ? 0.f : s;
+            for (int k = 0; k < FA_D; k++) sq = fmaf(x2t[k * FA_R + r], w[k], sq);
+            a.q[((size_t)e * na + i) * A + ac] = s_em[r] ? 0.f : sq;
         }
         __syncthreads();
     }
@@ -251,17 +252,20 @@ extern "C" int refil_ff_agent_act(const float* entities, int entity_dim, const l
                                          FA_EIN_MAX * FA_R + FA_D * FA_R + FA_R * 3 * FA_D + 2 * FA_D * FA_R);
     static bool attr = false;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(ff_agent_act_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(ff_agent_act_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(ff_agent_act_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) {
             refil_set_error("ff_agent_act: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
             return REFIL_ERR_CUDA;
         }
         attr = true;
     }
-    int grid = refil_cdiv(n_envs, FA_EPI);
+    const int NE = n_entities <= 4 ? 4 : 8;           // entity slots per environment in the 16-row stage tile
+    int grid = refil_cdiv(n_envs, FA_R / NE);
     const int cap = 3 * refil_num_sms();              // three CTAs per SM (54 KB of shared memory, <= 170 registers per thread)
     if (grid > cap) grid = cap;
-    ff_agent_act_kernel<<<grid, FA_THREADS, smem, stream>>>(a);
+    if (NE == 4) ff_agent_act_kernel<4><<<grid, FA_THREADS, smem, stream>>>(a);
+    else ff_agent_act_kernel<8><<<grid, FA_THREADS, smem, stream>>>(a);
     REFIL_CHECK_LAUNCH("ff_agent_act");
     return REFIL_OK;
 }
