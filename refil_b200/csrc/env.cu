@@ -23,7 +23,8 @@
 #define MT_M 397
 #define GM_MAX_AGENTS 32
 #define GM_MAX_GROUPS 8
-#define GM_THREADS 128
+#define GM_THREADS 128   // threads of a CTA: all of them write observation rows (phase 2)
+#define GM_ENVS 32       // environments of a CTA: one warp runs their sequential logic (phase 1), four warps share the row writes
 
 // Words of the generator a step may consume are PREFETCHED: the twist of word i reads the old words i, i + 1 and i + 397, none of
 // which an earlier draw of the same step can have rewritten (that would need a look-back of 227 words), so the thread issues
@@ -36,7 +37,7 @@ struct MtRef {
     uint32_t* key;  // points at column e of mt_key
     int E;
     int pos;
-    const uint32_t* win_old;   // [MT_WIN + 1] old words pos0 .. pos0 + MT_WIN, stride GM_THREADS (null: no window)
+    const uint32_t* win_old;   // [MT_WIN + 1] old words pos0 .. pos0 + MT_WIN, stride GM_ENVS (null: no window)
     const uint32_t* win_m;     // [MT_WIN] old words pos0 + 397 ...
     int used, nwin;            // draws taken from the window so far / words it holds
 };
@@ -47,9 +48,9 @@ __device__ __forceinline__ uint32_t mt_next(MtRef& s) {
     int im = (i + MT_M >= MT_N) ? i + MT_M - MT_N : i + MT_M;
     uint32_t ki, k1, km;
     if (s.used < s.nwin) {
-        ki = s.win_old[s.used * GM_THREADS];
-        k1 = s.win_old[(s.used + 1) * GM_THREADS];
-        km = s.win_m[s.used * GM_THREADS];
+        ki = s.win_old[s.used * GM_ENVS];
+        k1 = s.win_old[(s.used + 1) * GM_ENVS];
+        km = s.win_m[s.used * GM_ENVS];
         s.used++;
     } else {
         ki = s.key[(size_t)i * s.E]; k1 = s.key[(size_t)i1 * s.E]; km = s.key[(size_t)im * s.E];
@@ -78,7 +79,7 @@ __device__ __forceinline__ uint32_t mt_bounded(MtRef& s, uint32_t mx) {
     return v;
 }
 
-// fill the calling thread's window lane (sm_old / sm_m point at its own column of [..][GM_THREADS] shared arrays) with the first
+// fill the calling thread's window lane (sm_old / sm_m point at its own column of [..][GM_ENVS] shared arrays) with the first
 // `n` <= MT_WIN words it may draw from position pos
 __device__ __forceinline__ void mt_prefetch(const uint32_t* key, int E, int pos, int n, uint32_t* sm_old, uint32_t* sm_m) {
 #pragma unroll 1
@@ -94,11 +95,11 @@ __device__ __forceinline__ void mt_prefetch(const uint32_t* key, int E, int pos,
             m[k] = key[(size_t)im * E];
         }
 #pragma unroll
-        for (int k = 0; k < 8; k++) { sm_old[(k0 + k) * GM_THREADS] = o[k]; sm_m[(k0 + k) * GM_THREADS] = m[k]; }
+        for (int k = 0; k < 8; k++) { sm_old[(k0 + k) * GM_ENVS] = o[k]; sm_m[(k0 + k) * GM_ENVS] = m[k]; }
     }
     int i = pos + n;
     if (i >= MT_N) i -= MT_N;
-    sm_old[n * GM_THREADS] = key[(size_t)i * E];
+    sm_old[n * GM_ENVS] = key[(size_t)i * E];
 }
 
 // numpy _legacy_seeding(int): init_genrand.  pos=0 in the incremental scheme == numpy's pos=624.
@@ -220,13 +221,13 @@ __device__ void gm_write_obs(const GmParams& p, const GmBuffers& b, int ts, int 
 }
 
 __global__ void __launch_bounds__(GM_THREADS) gm_reset_kernel(GmParams p, GmBuffers b) {
-    __shared__ uint8_t s_loc[GM_THREADS * GM_MAX_AGENTS];
-    __shared__ uint32_t s_grp[GM_THREADS * GM_MAX_GROUPS];
-    __shared__ uint8_t s_write[GM_THREADS];
-    const int e0 = blockIdx.x * GM_THREADS, le = threadIdx.x, e = e0 + le;
-    const int n_env = min(GM_THREADS, p.E - e0);
-    s_write[le] = 0;
-    if (e < p.E) {
+    __shared__ uint8_t s_loc[GM_ENVS * GM_MAX_AGENTS];
+    __shared__ uint32_t s_grp[GM_ENVS * GM_MAX_GROUPS];
+    __shared__ uint8_t s_write[GM_ENVS];
+    const int e0 = blockIdx.x * GM_ENVS, le = threadIdx.x, e = e0 + le;
+    const int n_env = min(GM_ENVS, p.E - e0);
+    if (le < GM_ENVS) s_write[le] = 0;
+    if (le < GM_ENVS && e < p.E) {
         MtRef rng{b.mt_key + e, p.E, b.mt_pos[e], nullptr, nullptr, 0, 0};
         int perm[GM_MAX_AGENTS];
         int parts[GM_MAX_GROUPS + 1];
@@ -269,17 +270,17 @@ __global__ void __launch_bounds__(GM_THREADS) gm_reset_kernel(GmParams p, GmBuff
 }
 
 __global__ void __launch_bounds__(GM_THREADS) gm_step_kernel(GmParams p, GmBuffers b, int ts) {
-    __shared__ uint8_t s_loc[GM_THREADS * GM_MAX_AGENTS];
-    __shared__ uint32_t s_grp[GM_THREADS * GM_MAX_GROUPS];
-    __shared__ uint8_t s_write[GM_THREADS];
+    __shared__ uint8_t s_loc[GM_ENVS * GM_MAX_AGENTS];
+    __shared__ uint32_t s_grp[GM_ENVS * GM_MAX_GROUPS];
+    __shared__ uint8_t s_write[GM_ENVS];
     __shared__ int s_count;
-    __shared__ uint32_t s_old[(MT_WIN + 1) * GM_THREADS], s_m[MT_WIN * GM_THREADS];
-    const int e0 = blockIdx.x * GM_THREADS, le = threadIdx.x, e = e0 + le;
-    const int n_env = min(GM_THREADS, p.E - e0);
+    __shared__ uint32_t s_old[(MT_WIN + 1) * GM_ENVS], s_m[MT_WIN * GM_ENVS];
+    const int e0 = blockIdx.x * GM_ENVS, le = threadIdx.x, e = e0 + le;
+    const int n_env = min(GM_ENVS, p.E - e0);
     if (le == 0) s_count = 0;
-    s_write[le] = 0;
+    if (le < GM_ENVS) s_write[le] = 0;
     __syncthreads();
-    if (e < p.E) {
+    if (le < GM_ENVS && e < p.E) {
         int flags = b.est[2 * (size_t)p.E + e];
         if (flags & 1) {
             const int pos0 = b.mt_pos[e];
@@ -366,7 +367,7 @@ extern "C" int refil_gm_env_reset(uint32_t* mt_key, int32_t* mt_pos, int32_t* lo
                0.0, fixed_scen, env_offset};
     GmBuffers b{mt_key, mt_pos, loc, grp, est, ep_ret, entities, obs_mask, entity_mask, gt_mask, avail_actions,
                 nullptr, nullptr, filled, nullptr, nullptr};
-    gm_reset_kernel<<<refil_cdiv(n_envs, GM_THREADS), GM_THREADS, 0, stream>>>(p, b);
+    gm_reset_kernel<<<refil_cdiv(n_envs, GM_ENVS), GM_THREADS, 0, stream>>>(p, b);
     REFIL_CHECK_LAUNCH("gm_env_reset");
     return REFIL_OK;
 }
@@ -386,7 +387,7 @@ extern "C" int refil_gm_env_step(uint32_t* mt_key, int32_t* mt_pos, int32_t* loc
                rand_trans, 0, env_offset};
     GmBuffers b{mt_key, mt_pos, loc, grp, est, ep_ret, entities, obs_mask, entity_mask, gt_mask, avail_actions,
                 reward, terminated, filled, actions, step_counter};
-    gm_step_kernel<<<refil_cdiv(n_envs, GM_THREADS), GM_THREADS, 0, stream>>>(p, b, ts);
+    gm_step_kernel<<<refil_cdiv(n_envs, GM_ENVS), GM_THREADS, 0, stream>>>(p, b, ts);
     REFIL_CHECK_LAUNCH("gm_env_step");
     return REFIL_OK;
 }
