@@ -18,7 +18,8 @@ class EpsilonGreedyActionSelector:
                                               decay="linear")
         self.epsilon = self.schedule.eval(0)
 
-    def select_action(self, agent_inputs, avail_actions, t_env, test_mode=False, est_flags=None, out=None, eps_dev=None):
+    def select_action(self, agent_inputs, avail_actions, t_env, test_mode=False, est_flags=None, out=None, eps_dev=None,
+                      uniforms=None):
         """agent_inputs [bs, na, A] f32, avail_actions [bs, na, A] int32 -> actions [bs, na] int64.
         avail_actions / out may be time slices of the EpisodeBatch tensors (no copies).  eps_dev: optional device scalar holding
         epsilon (the graph-captured rollout sets it per run: schedule value, or 0 in test mode) -- then t_env is not consulted."""
@@ -33,7 +34,7 @@ class EpsilonGreedyActionSelector:
         if eps_dev is None:
             self.epsilon = 0.0 if test_mode else self.schedule.eval(t_env)
         if eps_dev is not None or self.epsilon > 0.0:
-            u = torch.rand(2, bs, na, device=q.device)
+            u = uniforms if uniforms is not None else torch.rand(2, bs, na, device=q.device)
             u_pick, u_act = u[0], u[1]
         ops.select_actions(q, avail, u_pick, u_act, est_flags, 0.0 if eps_dev is not None else self.epsilon, out, bs, na, A,
                            eps_dev=eps_dev)
