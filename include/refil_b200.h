@@ -88,7 +88,12 @@ int refil_ff_agent_act(const float* entities, int entity_dim, const long long* a
                        const uint8_t* obs_mask, int mask_rows, const uint8_t* entity_mask, const float* fc1_w,
                        const float* fc1_b, const float* in_trans_w, const float* out_trans_w, const float* out_trans_b,
                        const float* fc2_w, const float* fc2_b, float* q, int n_envs, int T, int t, int n_entities,
-                       int n_agents, int n_actions, cudaStream_t stream);
+                       int n_agents, int n_actions,
+                       const int32_t* avail /* optional fused epsilon-greedy selection (action_selectors.py:45-63): the
+                       [E, T, na, A] availability tensor, read at t; null = utilities only */,
+                       const float* u_pick, const float* u_act, const int32_t* est_flags, float epsilon,
+                       const float* epsilon_dev, long long* actions_out /* [E, T, na, 1], written at t */,
+                       cudaStream_t stream);
 
 /* ---- dense layers (nn.Linear of modules/layers/attention.py:21-22, agents/entity_rnn_agent.py:12,23-25,
  *      mixers/flex_qmix.py:29,39).  C = [rowmask][relu](A W^T + b); row r of a [C, N, na] stack is zeroed when

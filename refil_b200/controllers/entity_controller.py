@@ -79,6 +79,26 @@ class EntityMAC(BasicMAC):
         except (KeyError, ValueError):
             return False
 
+    def act_and_select(self, batch, t, t_env, test_mode=False, est_flags=None, eps_dev=None, uniforms=None):
+        """Acting step t in ONE launch: fused FF-agent forward + epsilon-greedy selection written to batch["actions"][:, t]
+        (callers check _fused_acting_ok first).  Same rules as select_actions + EpsilonGreedyActionSelector.select_action."""
+        a, sel = self.agent, self.action_selector
+        ents = batch["entities"]
+        if eps_dev is None:
+            sel.epsilon = 0.0 if test_mode else sel.schedule.eval(t_env)
+        eps = 0.0 if eps_dev is not None else sel.epsilon
+        explore = eps_dev is not None or eps > 0.0
+        if explore and uniforms is None:
+            uniforms = torch.rand(2, ents.shape[0], self.n_agents, device=ents.device)
+        gt_obs = bool(getattr(self.args, "gt_obs_mask", False))
+        q = a.ws.get(a.tag + ".q_act", (ents.shape[0], self.n_agents, a.A))
+        ops.ff_agent_act(ents, batch["actions"] if a.one_hot_la else None, a.A, batch["gt_mask"] if gt_obs else batch["obs_mask"],
+                         batch["entity_mask"], a.store.p, q, t,
+                         select=dict(avail=batch["avail_actions"], actions_out=batch["actions"], est_flags=est_flags, epsilon=eps,
+                                     eps_dev=eps_dev, u_pick=uniforms[0] if explore else None,
+                                     u_act=uniforms[1] if explore else None))
+        return q
+
     def draw_groups(self, bs, ne, device):
         """Random 2-partition of the entities, one Bernoulli parameter per episode
         (entity_rnn_agent.py:94-96 / entity_ff_agent.py:87,96)."""

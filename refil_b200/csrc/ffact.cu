@@ -33,6 +33,12 @@ struct FfActArgs {
     const float *w1, *b1, *win, *wout, *bout, *w2, *b2;
     float* q;                                 // [E, na, A]
     int E, T, t, ne, na, ein, A;
+    // optional fused epsilon-greedy selection (components/action_selectors.py:45-63; same rules as select_actions_kernel)
+    const int32_t* avail;                     // [E, T, na, A] or null: no selection
+    const float *u_pick, *u_act;              // [E, na] uniforms (null: greedy)
+    const int32_t* est_flags;                 // [E] env flags (bit 1: still in the runner's live list) or null
+    float eps_host; const float* eps_dev;     // epsilon: host value, overridden by the device scalar when given
+    long long* actions_out;                   // the rollout's actions tensor [E, T, na, 1]: written at timestep t
 };
 
 // shared-memory strides: +1 float per transposed weight row, so that the transposing prologue stores (k fastest across a warp)
@@ -54,6 +60,7 @@ __global__ void __launch_bounds__(FA_THREADS, 3) ff_agent_act_kernel(FfActArgs a
     float* attt = qkv + FA_R * 3 * FA_D;              // [64][R]    attention output, transposed (rows = env * NE_MAX + agent)
     float* x2t = attt + FA_D * FA_R;                  // [64][R]
     __shared__ uint8_t s_obs[FA_R][NE], s_em[FA_R];     // rows = env * NE + entity slot
+    __shared__ float s_q[FA_R][FA_A_MAX];               // utilities of the iteration's agents, for the fused selection
     const int tid = threadIdx.x;
     const int j = tid & 63, g = tid >> 6;              // GEMM stages: output column j, row group / reduction half g
     for (int f = tid; f < ein * FA_D; f += FA_THREADS) { const int jj = f / ein, k = f - jj * ein; w1t[k * FA_LD1 + jj] = __ldg(a.w1 + f); }
@@ -221,8 +228,38 @@ __global__ void __launch_bounds__(FA_THREADS, 3) ff_agent_act_kernel(FfActArgs a
             const int r = ev * NE + i;
 #pragma unroll 8
             for (int k = 0; k < FA_D; k++) sq = fmaf(x2t[k * FA_R + r], w[k], sq);
-            a.q[((size_t)e * na + i) * A + ac] = s_em[r] ? 0.f : sq;
+            sq = s_em[r] ? 0.f : sq;
+            a.q[((size_t)e * na + i) * A + ac] = sq;
+            s_q[r][ac] = sq;
         }
+        __syncthreads();
+        // ---- stage 6 (optional): epsilon-greedy selection, one thread per (env, agent) ---------------------------------------
+        if (a.avail && tid < EPI * na) {
+            const int ev = tid / na, i = tid - ev * na, e = e0 + ev, r = ev * NE + i;
+            if (e < a.E && !(a.est_flags && !(a.est_flags[e] & 2))) {
+                const int32_t* av = a.avail + (((size_t)e * a.T + a.t) * na + i) * A;
+                int best = 0, n_avail = 0;
+                float bv = -INFINITY;
+                bool have = false;
+                for (int k = 0; k < A; k++) {               // unavailable -> -inf, FIRST maximum wins
+                    const bool ok = av[k] != 0;
+                    n_avail += ok;
+                    const float v = ok ? s_q[r][k] : -INFINITY;
+                    if (!have || v > bv) { best = k; bv = v; have = true; }
+                }
+                int pick = best;
+                const float eps = a.eps_dev ? __ldg(a.eps_dev) : a.eps_host;
+                const size_t idx = (size_t)e * na + i;
+                if (a.u_pick && eps > 0.f && a.u_pick[idx] < eps && n_avail > 0) {
+                    const int target = min((int)(a.u_act[idx] * (float)n_avail), n_avail - 1);
+                    int seen = 0;
+                    for (int k = 0; k < A; k++)
+                        if (av[k] != 0) { if (seen == target) { pick = k; break; } seen++; }
+                }
+                a.actions_out[((size_t)e * a.T + a.t) * na + i] = pick;
+            }
+        }
+        // (the next iteration's stage 0 does not touch s_q / s_em before its own barrier; s_em is rewritten after it)
         __syncthreads();
     }
 }
@@ -237,7 +274,9 @@ extern "C" int refil_ff_agent_act(const float* entities, int entity_dim, const l
                                   const uint8_t* obs_mask, int mask_rows, const uint8_t* entity_mask, const float* fc1_w,
                                   const float* fc1_b, const float* in_trans_w, const float* out_trans_w,
                                   const float* out_trans_b, const float* fc2_w, const float* fc2_b, float* q, int n_envs,
-                                  int T, int t, int n_entities, int n_agents, int n_actions, cudaStream_t stream) {
+                                  int T, int t, int n_entities, int n_agents, int n_actions, const int32_t* avail,
+                                  const float* u_pick, const float* u_act, const int32_t* est_flags, float epsilon,
+                                  const float* epsilon_dev, long long* actions_out, cudaStream_t stream) {
     const int ein = entity_dim + (actions ? n_actions_onehot : 0);
     REFIL_CHECK_ARG(entities && obs_mask && entity_mask && fc1_w && fc1_b && in_trans_w && out_trans_w && out_trans_b && fc2_w &&
                     fc2_b && q, "ff_agent_act: null pointer");
@@ -246,8 +285,11 @@ extern "C" int refil_ff_agent_act(const float* entities, int entity_dim, const l
                     n_actions);
     REFIL_CHECK_ARG(n_envs > 0 && T > 0 && t >= 0 && t < T && (mask_rows == n_entities || mask_rows == n_agents),
                     "ff_agent_act: bad n_envs=%d T=%d t=%d mask_rows=%d", n_envs, T, t, mask_rows);
+    REFIL_CHECK_ARG(!avail || actions_out, "ff_agent_act: selection (avail given) needs actions_out");
+    REFIL_CHECK_ARG(!avail || ((epsilon <= 0.f && !epsilon_dev) || (u_pick && u_act)), "ff_agent_act: epsilon > 0 needs u_pick and u_act");
     FfActArgs a{entities, entity_dim, actions, n_actions_onehot, obs_mask, mask_rows, entity_mask, fc1_w, fc1_b, in_trans_w,
-                out_trans_w, out_trans_b, fc2_w, fc2_b, q, n_envs, T, t, n_entities, n_agents, ein, n_actions};
+                out_trans_w, out_trans_b, fc2_w, fc2_b, q, n_envs, T, t, n_entities, n_agents, ein, n_actions,
+                avail, u_pick, u_act, est_flags, epsilon, epsilon_dev, actions_out};
     const size_t smem = sizeof(float) * (FA_EIN_MAX * FA_LD1 + FA_D * FA_LD1 + FA_A_MAX * FA_D + 2 * FA_D + FA_A_MAX +
                                          FA_EIN_MAX * FA_R + FA_D * FA_R + FA_R * 3 * FA_D + 2 * FA_D * FA_R);
     static bool attr = false;

@@ -500,16 +500,22 @@ def ff_agent_act_supported(ne, na, ein, d, H, A):
     return _lib.load().refil_ff_agent_act_supported(ne, na, ein, d, H, A) != 0
 
 
-def ff_agent_act(entities, actions, n_actions, obs_mask, entity_mask, params, q, t):
+def ff_agent_act(entities, actions, n_actions, obs_mask, entity_mask, params, q, t, select=None):
     """Fused acting forward of the FF entity-attention agent on timestep t of the EpisodeBatch tensors (read in place).
-    params: dict with fc1 / attn.in_trans / attn.out_trans / fc2 weights.  q [E, na, A] is written."""
+    params: dict with fc1 / attn.in_trans / attn.out_trans / fc2 weights.  q [E, na, A] is written.
+    select: optional dict(avail [E,T,na,A] i32, actions_out [E,T,na,1] i64, u_pick, u_act, est_flags, epsilon, eps_dev) -> the
+    epsilon-greedy choice is made in the same launch and written to actions_out[:, t]."""
     E, T, ne, ed = entities.shape
     na, A = q.shape[1], q.shape[2]
+    sel = select or {}
     _call("ff_agent_act", _p(entities, F32), ed, _p(actions, I64), n_actions, _p(obs_mask, U8), obs_mask.shape[2],
           _p(entity_mask, U8), _p(params["fc1.weight"], F32), _p(params["fc1.bias"], F32), _p(params["attn.in_trans.weight"], F32),
           _p(params["attn.out_trans.weight"], F32), _p(params["attn.out_trans.bias"], F32), _p(params["fc2.weight"], F32),
-          _p(params["fc2.bias"], F32), _p(q, F32), E, T, int(t), ne, na, A)
+          _p(params["fc2.bias"], F32), _p(q, F32), E, T, int(t), ne, na, A, _p(sel.get("avail"), I32), _p(sel.get("u_pick"), F32),
+          _p(sel.get("u_act"), F32), _p(sel.get("est_flags"), I32), float(sel.get("epsilon", 0.0)), _p(sel.get("eps_dev"), F32),
+          _p(sel.get("actions_out"), I64))
     return q
+
 
 def select_actions(q, avail, u_pick, u_act, est_flags, epsilon, actions_out, B, na, A, eps_dev=None):
     """q [B, na, A] contiguous; avail / actions_out may be time slices of EpisodeBatch tensors (row stride taken from them)."""

@@ -77,11 +77,16 @@ class ParallelRunner:
         # the exploration uniforms of the whole rollout in ONE draw (one launch instead of one per timestep)
         explore = eps_dev is not None or (not test_mode and self.mac.action_selector.schedule.eval(self.t_env) > 0.0)
         u_all = torch.rand(self.episode_limit, 2, self.batch_size, self.args.n_agents, device=self.args.device) if explore else None
+        fused = (hasattr(self.mac, "act_and_select") and self.mac._fused_acting_ok(batch) and avail.is_contiguous()
+                 and avail.dtype == torch.int32 and acts.is_contiguous())
         for t in range(self.episode_limit):
-            q = self.mac.forward(batch, t, test_mode=test_mode)
-            self.mac.action_selector.select_action(q, avail[:, t], self.t_env, test_mode=test_mode, est_flags=env.flags,
-                                                   out=acts[:, t, :, 0], eps_dev=eps_dev,
-                                                   uniforms=u_all[t] if u_all is not None else None)
+            u_t = u_all[t] if u_all is not None else None
+            if fused:       # small FF agent: forward + selection are one launch (csrc/ffact.cu)
+                self.mac.act_and_select(batch, t, self.t_env, test_mode=test_mode, est_flags=env.flags, eps_dev=eps_dev, uniforms=u_t)
+            else:
+                q = self.mac.forward(batch, t, test_mode=test_mode)
+                self.mac.action_selector.select_action(q, avail[:, t], self.t_env, test_mode=test_mode, est_flags=env.flags,
+                                                       out=acts[:, t, :, 0], eps_dev=eps_dev, uniforms=u_t)
             env.step(batch, t, write_gt=self.write_gt_every_step)   # reward / terminated at t, observations + filled at t + 1
             self.t = t + 1
             if early_exit and (t & 7) == 7 and not bool(env.alive().any()):
