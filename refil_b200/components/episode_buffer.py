@@ -18,13 +18,14 @@ def _as_shape(v):
 
 
 class EpisodeBatch:
-    def __init__(self, scheme, groups, batch_size, max_seq_length, data=None, preprocess=None, device="cpu"):
+    def __init__(self, scheme, groups, batch_size, max_seq_length, data=None, preprocess=None, device="cpu", zero_init=True):
         self.scheme = dict(scheme)
         self.groups = groups
         self.batch_size = batch_size
         self.max_seq_length = max_seq_length
         self.preprocess = {} if preprocess is None else preprocess
         self.device = device
+        self._alloc = torch.zeros if zero_init else torch.empty       # zero_init=False: the caller overwrites every tensor at once
         if data is not None:
             self.data = data
         else:
@@ -60,9 +61,9 @@ class EpisodeBatch:
                 shape = (groups[group],) + shape
             dtype = info.get("dtype", torch.float32)
             if info.get("episode_const", False):
-                self.data.episode_data[key] = torch.zeros((batch_size,) + shape, dtype=dtype, device=self.device)
+                self.data.episode_data[key] = self._alloc((batch_size,) + shape, dtype=dtype, device=self.device)
             else:
-                self.data.transition_data[key] = torch.zeros((batch_size, max_seq_length) + shape, dtype=dtype,
+                self.data.transition_data[key] = self._alloc((batch_size, max_seq_length) + shape, dtype=dtype,
                                                              device=self.device)
 
     def to(self, device):

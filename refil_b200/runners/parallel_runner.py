@@ -133,7 +133,7 @@ class ParallelRunner:
         st["graph"].replay()
         from .. import ops
         ops.add_launches(st["launches"])
-        self.batch = self.new_batch()
+        self.batch = self.new_batch(zero_init=False)       # every tensor is overwritten by the copy below
         for k, v in st["static"].data.transition_data.items():
             self.batch.data.transition_data[k].copy_(v)
         self.t = self.episode_limit

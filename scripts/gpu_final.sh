@@ -22,4 +22,11 @@ if [ $(stat -c %s gpurun_out/${TAG}_prof.ncu-rep) -gt 30000000 ]; then rm -f gpu
 timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none \
   -k regex:'tc_gemm_ts_kernel' -c 600 --csv --log-file gpurun_out/${TAG}_traffic.csv \
   python bench.py --steps 1 --warmup 1 --no-cpu --no-graph --no-extra > gpurun_out/${TAG}_traffic.log 2>&1
+# rollouts: launch lists of 6 timesteps of BASELINE config 2 (fused FF acting kernel) and config 4 (RNN agent, tensor-core path)
+LIMIT=6 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
+  --log-file gpurun_out/${TAG}_rollout_cfg2_launches.csv python scripts/prof_rollout.py refil_group_matching 4096 4 4 > /dev/null 2>&1
+LIMIT=6 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
+  --log-file gpurun_out/${TAG}_rollout_cfg4_launches.csv python scripts/prof_rollout.py refil 4096 8 24 > /dev/null 2>&1
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${TAG}_smoke.log 2>&1
+tail -1 gpurun_out/${TAG}_smoke.log
 ls -la gpurun_out/ | grep ${TAG}
