@@ -32,6 +32,7 @@
 // access is an LDS.128 with an immediate offset.
 #include <cuda.h>   // CUtensorMap (the encode function is fetched through cudaGetDriverEntryPoint, libcuda is not linked)
 
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -617,6 +618,245 @@ __global__ void __launch_bounds__(32 * ATT_MAX_WARPS, (HD <= 16) ? 2 : 1) attn_b
     }
 }
 
+// =====================================================================================================================
+// Backward, specialised for the benchmark's geometry (4 heads of 32, <= 8 query rows): TWO agents per lane.
+// ncu on attn_bwd_kernel<32, 4> (profiles/r2n_ncu_full.md): DRAM 35 %, l1/smem 61 %, 8.9 % warps -- it is bound by the shared-memory
+// pipe.  With lane = (agent, head) the eight agent-lanes of a head read the same 16 bytes of a K / V row: a 128-bit load delivers
+// 64 distinct bytes per wavefront and every row chunk is fetched once per agent pass.  Here lane = (agent pair ip, head h, half dh
+// of the head dim): the eight lanes of a quarter-warp read eight DISTINCT 16-byte chunks (all 32 banks, chunk order rotated by the
+// head) and every chunk feeds two agents -- half the 128-bit loads of phase 1, each at full width.  The halves of a dot product meet
+// with one shuffle; per-row scalars (max, sum, t) are computed by the lane that owns the row (dh = 0: agent ip, dh = 1: agent ip + 4).
+// Phase 2 (dK / dV accumulation over the scratch) and the scratch layout are those of the generic kernel.
+// =====================================================================================================================
+template <bool GROUPED>
+__global__ void __launch_bounds__(32 * ATT_MAX_WARPS, 1) attn_bwd_h4_kernel(const __grid_constant__ AttnGroup grp, int NEB, int tile_floats, int warp_floats, const __grid_constant__ AttnMaps maps, int use_tmap) {
+    int prob = 0, cta = (int)blockIdx.x, ncta = (int)gridDim.x;
+    if (GROUPED) {
+        while (prob + 1 < ATT_MAX_GROUP && (int)blockIdx.x >= grp.cta_begin[prob + 1]) prob++;
+        cta = (int)blockIdx.x - grp.cta_begin[prob];
+        ncta = grp.cta_begin[prob + 1] - grp.cta_begin[prob];
+    }
+    const AttnArgs& a = grp.a[prob];
+    const CUtensorMap& tmap = maps.m[prob];
+    extern __shared__ __align__(128) float smem_raw_[];
+    float* smem = smem_raw_ + (((128u - (att_smem_u32(smem_raw_) & 127u)) & 127u) >> 2);
+    constexpr int HD = 32, H = 4, d = HD * H, ldk = 2 * d, nqp = 8;
+    const int ne = a.ne, nq = a.nq;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
+    const int dh = lane & 1, h = (lane >> 1) & 3, ip = lane >> 3;          // half of the head dim, head, agent pair (ip, ip + 4)
+    const int i0 = ip, i1 = ip + 4, io = dh ? i1 : i0;                      // io: the row whose scalars this lane owns
+    int rot[4];                                                             // float offset of my kc-th chunk inside a row
+#pragma unroll
+    for (int kc = 0; kc < 4; kc++) rot[kc] = h * HD + dh * 16 + 4 * ((kc + h) & 3);
+    float* kv = smem + (size_t)warp * warp_floats;                       // [NEB][ldk]
+    const int sstr = H * nqp;                                            // scratch stride between entities j
+    float* sw = kv + tile_floats;                                        // [C][NEB][H][nqp]  softmax weights
+    float* sdl = sw + a.C * NEB * sstr;                                  // [C][NEB][H][nqp]  dw, then dlogits
+    float* lgs = sdl + a.C * NEB * sstr + lane;                          // [NEB][32]         logits of my own row
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + (size_t)wpc * warp_floats) + warp;
+    if (lane == 0) {
+        att_mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    pdl_launch_dependents();
+    pdl_wait();
+    const float inv_scale = 1.f / sqrtf((float)HD);
+    const long long gw = (long long)cta * wpc + warp, GW = (long long)ncta * wpc;
+    uint32_t parity = 0;
+    auto load_row = [&](const float* base, float (&dst)[16]) {             // my 16 floats of a [d]-wide row, rotated chunk order
+#pragma unroll
+        for (int kc = 0; kc < 4; kc++) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(base + rot[kc]));
+            dst[4 * kc] = v.x; dst[4 * kc + 1] = v.y; dst[4 * kc + 2] = v.z; dst[4 * kc + 3] = v.w;
+        }
+    };
+    for (long long n = gw; n < a.N; n += GW) {
+        for (int f = ne * ldk + lane; f < NEB * ldk; f += 32) kv[f] = 0.f;   // padding rows (the tile is reused for dK|dV)
+        if (use_tmap) att_tma_load_tile(kv, &tmap, d, ne, n, bar, lane, 2 * d);
+        else att_tma_load_rows(kv, a.qkv + ((size_t)n * ne) * 3 * d + d, 3 * d, ne, 2 * d, ldk, bar, lane);
+        AttMeta mc;
+        att_meta_load(a, n, lane, 0, mc);
+        const bool act0 = i0 < nq, act1 = i1 < nq, acto = io < nq;
+        float q0[16], q1[16];
+        load_row(a.qkv + ((size_t)n * ne + (act0 ? i0 : 0)) * 3 * d, q0);
+        load_row(a.qkv + ((size_t)n * ne + (act1 ? i1 : 0)) * 3 * d, q1);
+        if (!act0) {
+#pragma unroll
+            for (int k = 0; k < 16; k++) q0[k] = 0.f;
+        }
+        if (!act1) {
+#pragma unroll
+            for (int k = 0; k < 16; k++) q1[k] = 0.f;
+        }
+        // dQ of the non-query rows is zero
+        {
+            const int d4 = d >> 2;
+            for (int f = lane; f < (ne - nq) * d4; f += 32) {
+                const int r = nq + f / d4, c4 = f % d4;
+                *reinterpret_cast<float4*>(a.dqkv + ((size_t)n * ne + r) * 3 * d + 4 * c4) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        uint32_t mb[ATT_MAX_COPIES];                                       // mask words of MY OWN row io
+        att_meta_resolve(a, n, lane, 0, 8, io, mc, mb);
+        att_mbar_wait(bar, parity);
+        parity ^= 1;
+        // ---- logits of both agents (shared by the copies); the owner keeps its row in lgs -----------------------------------
+        float mx[ATT_MAX_COPIES] = {-INFINITY, -INFINITY, -INFINITY};
+#pragma unroll 2
+        for (int j = 0; j < NEB; j++) {
+            float p0 = 0.f, p1 = 0.f;
+#pragma unroll
+            for (int kc = 0; kc < 4; kc++) {
+                const float4 k4 = *reinterpret_cast<const float4*>(kv + j * ldk + rot[kc]);
+                p0 = fmaf(q0[4 * kc], k4.x, p0); p0 = fmaf(q0[4 * kc + 1], k4.y, p0); p0 = fmaf(q0[4 * kc + 2], k4.z, p0); p0 = fmaf(q0[4 * kc + 3], k4.w, p0);
+                p1 = fmaf(q1[4 * kc], k4.x, p1); p1 = fmaf(q1[4 * kc + 1], k4.y, p1); p1 = fmaf(q1[4 * kc + 2], k4.z, p1); p1 = fmaf(q1[4 * kc + 3], k4.w, p1);
+            }
+            p0 += __shfl_xor_sync(0xffffffffu, p0, 1);
+            p1 += __shfl_xor_sync(0xffffffffu, p1, 1);
+            const float lg = (dh ? p1 : p0) * inv_scale;
+            lgs[j * 32] = lg;
+#pragma unroll
+            for (int c = 0; c < ATT_MAX_COPIES; c++)
+                if (!((mb[c] >> j) & 1u)) mx[c] = fmaxf(mx[c], lg);
+        }
+        float dq0[16], dq1[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) { dq0[k] = 0.f; dq1[k] = 0.f; }
+#pragma unroll
+        for (int c = 0; c < ATT_MAX_COPIES; c++) {
+            if (c < a.C) {
+                const uint32_t bits = mb[c];
+                const float m = mx[c];
+                float g0[16], g1[16];                                  // dO rows of both agents for this copy (my half dims)
+                load_row(a.dout + (((size_t)c * a.N + n) * nq + (act0 ? i0 : 0)) * d, g0);
+                load_row(a.dout + (((size_t)c * a.N + n) * nq + (act1 ? i1 : 0)) * d, g1);
+                if (!act0) {
+#pragma unroll
+                    for (int k = 0; k < 16; k++) g0[k] = 0.f;
+                }
+                if (!act1) {
+#pragma unroll
+                    for (int k = 0; k < 16; k++) g1[k] = 0.f;
+                }
+                float* swr = sw + ((size_t)c * NEB * H + h) * nqp + io;   // [j * sstr]: my own row's column of the scratch
+                float* sdr = sdl + ((size_t)c * NEB * H + h) * nqp + io;
+                float ssum = 0.f;
+#pragma unroll 4
+                for (int j = 0; j < NEB; j++) {
+                    const float e = ((bits >> j) & 1u) ? 0.f : __expf(lgs[j * 32] - m);
+                    ssum += e;
+                    swr[j * sstr] = e;
+                }
+                const float r = ssum > 0.f ? 1.f / ssum : 0.f;
+                float t = 0.f;
+#pragma unroll 2
+                for (int j = 0; j < NEB; j++) {
+                    float p0 = 0.f, p1 = 0.f;
+#pragma unroll
+                    for (int kc = 0; kc < 4; kc++) {
+                        const float4 v4 = *reinterpret_cast<const float4*>(kv + j * ldk + d + rot[kc]);
+                        p0 = fmaf(g0[4 * kc], v4.x, p0); p0 = fmaf(g0[4 * kc + 1], v4.y, p0); p0 = fmaf(g0[4 * kc + 2], v4.z, p0); p0 = fmaf(g0[4 * kc + 3], v4.w, p0);
+                        p1 = fmaf(g1[4 * kc], v4.x, p1); p1 = fmaf(g1[4 * kc + 1], v4.y, p1); p1 = fmaf(g1[4 * kc + 2], v4.z, p1); p1 = fmaf(g1[4 * kc + 3], v4.w, p1);
+                    }
+                    p0 += __shfl_xor_sync(0xffffffffu, p0, 1);
+                    p1 += __shfl_xor_sync(0xffffffffu, p1, 1);
+                    const float dw = dh ? p1 : p0;                     // <dO_io, V_j> of my own row
+                    const float w = swr[j * sstr] * r;
+                    swr[j * sstr] = w;
+                    sdr[j * sstr] = dw;
+                    t = fmaf(w, dw, t);
+                }
+#pragma unroll 2
+                for (int j = 0; j < NEB; j++) {
+                    const float dl = swr[j * sstr] * (sdr[j * sstr] - t) * inv_scale;     // dlogit of my own row
+                    sdr[j * sstr] = dl;
+                    const float dlo = __shfl_xor_sync(0xffffffffu, dl, 1);                 // ... and of my partner's row
+                    const float dl0 = dh ? dlo : dl, dl1 = dh ? dl : dlo;
+#pragma unroll
+                    for (int kc = 0; kc < 4; kc++) {
+                        const float4 k4 = *reinterpret_cast<const float4*>(kv + j * ldk + rot[kc]);
+                        dq0[4 * kc] = fmaf(dl0, k4.x, dq0[4 * kc]); dq0[4 * kc + 1] = fmaf(dl0, k4.y, dq0[4 * kc + 1]);
+                        dq0[4 * kc + 2] = fmaf(dl0, k4.z, dq0[4 * kc + 2]); dq0[4 * kc + 3] = fmaf(dl0, k4.w, dq0[4 * kc + 3]);
+                        dq1[4 * kc] = fmaf(dl1, k4.x, dq1[4 * kc]); dq1[4 * kc + 1] = fmaf(dl1, k4.y, dq1[4 * kc + 1]);
+                        dq1[4 * kc + 2] = fmaf(dl1, k4.z, dq1[4 * kc + 2]); dq1[4 * kc + 3] = fmaf(dl1, k4.w, dq1[4 * kc + 3]);
+                    }
+                }
+            }
+        }
+        if (act0) {
+            float* dst = a.dqkv + ((size_t)n * ne + i0) * 3 * d;
+#pragma unroll
+            for (int kc = 0; kc < 4; kc++)
+                *reinterpret_cast<float4*>(dst + rot[kc]) = make_float4(dq0[4 * kc], dq0[4 * kc + 1], dq0[4 * kc + 2], dq0[4 * kc + 3]);
+        }
+        if (act1) {
+            float* dst = a.dqkv + ((size_t)n * ne + i1) * 3 * d;
+#pragma unroll
+            for (int kc = 0; kc < 4; kc++)
+                *reinterpret_cast<float4*>(dst + rot[kc]) = make_float4(dq1[4 * kc], dq1[4 * kc + 1], dq1[4 * kc + 2], dq1[4 * kc + 3]);
+        }
+        (void)acto;
+        __syncwarp();          // scratch complete; nobody reads K / V any more
+        // ---- phase 2 (as in the generic kernel): lane = 4 features (head h2, chunk kc2) of every entity row ------------------
+        {
+            constexpr int NCH = HD / 4;
+            const int h2 = lane / NCH, kc2 = lane - h2 * NCH;
+            bool first = true;
+            for (int c = 0; c < a.C; c++) {
+                float4 qs[8], gs[8];
+#pragma unroll
+                for (int ii = 0; ii < 8; ii++) {
+                    const bool ok = ii < nq;
+                    qs[ii] = ok ? __ldg(reinterpret_cast<const float4*>(a.qkv + ((size_t)n * ne + ii) * 3 * d) + lane)
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
+                    gs[ii] = ok ? __ldg(reinterpret_cast<const float4*>(a.dout + (((size_t)c * a.N + n) * nq + ii) * d) + lane)
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                const float* swb = sw + ((size_t)c * NEB * H + h2) * nqp;
+                const float* sdb = sdl + ((size_t)c * NEB * H + h2) * nqp;
+#pragma unroll 2
+                for (int j = 0; j < NEB; j++) {
+                    float4 dk = make_float4(0.f, 0.f, 0.f, 0.f), dv = make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float4 dla = *reinterpret_cast<const float4*>(sdb + j * sstr), dlb = *reinterpret_cast<const float4*>(sdb + j * sstr + 4);
+                    const float4 wa = *reinterpret_cast<const float4*>(swb + j * sstr), wb = *reinterpret_cast<const float4*>(swb + j * sstr + 4);
+                    const float dlv[8] = {dla.x, dla.y, dla.z, dla.w, dlb.x, dlb.y, dlb.z, dlb.w};
+                    const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+                    for (int ii = 0; ii < 8; ii++) {
+                        dk.x = fmaf(dlv[ii], qs[ii].x, dk.x); dk.y = fmaf(dlv[ii], qs[ii].y, dk.y);
+                        dk.z = fmaf(dlv[ii], qs[ii].z, dk.z); dk.w = fmaf(dlv[ii], qs[ii].w, dk.w);
+                        dv.x = fmaf(wv[ii], gs[ii].x, dv.x); dv.y = fmaf(wv[ii], gs[ii].y, dv.y);
+                        dv.z = fmaf(wv[ii], gs[ii].z, dv.z); dv.w = fmaf(wv[ii], gs[ii].w, dv.w);
+                    }
+                    float4* kd = reinterpret_cast<float4*>(kv + j * ldk + h2 * HD + 4 * kc2);
+                    float4* vd = reinterpret_cast<float4*>(kv + j * ldk + d + h2 * HD + 4 * kc2);
+                    if (!first) {
+                        const float4 k0 = *kd, v0 = *vd;
+                        dk.x += k0.x; dk.y += k0.y; dk.z += k0.z; dk.w += k0.w;
+                        dv.x += v0.x; dv.y += v0.y; dv.z += v0.z; dv.w += v0.w;
+                    }
+                    *kd = dk;
+                    *vd = dv;
+                }
+                first = false;
+            }
+        }
+        __syncwarp();
+        // stream the dK | dV tile out as columns d..3d of dQKV (coalesced 128-bit stores)
+        {
+            const int d2 = (2 * d) >> 2;
+            float* dst = a.dqkv + ((size_t)n * ne) * 3 * d + d;
+            for (int f = lane; f < ne * d2; f += 32) {
+                const int rr = f / d2, c4 = f - rr * d2;
+                const float4 v = *reinterpret_cast<const float4*>(kv + rr * ldk + 4 * c4);
+                *reinterpret_cast<float4*>(dst + (size_t)rr * 3 * d + 4 * c4) = v;
+            }
+        }
+        __syncwarp();
+    }
+}
+
 static int attn_fill(AttnArgs& a, const float* qkv, const uint8_t* m0, const uint8_t* m1, const uint8_t* m2,
                      long long s0, long long s1, long long s2, int mode0, int mode1, int mode2,
                      const uint8_t* group_bits, const uint8_t* entity_mask, int N, int T, int ne, int nq, int d, int H,
@@ -933,6 +1173,13 @@ static int attn_group_launch(bool fwd, const RefilAttnDesc* descs, int n_problem
         const int ipp = 32 / n_heads, nqp = (n_queries + ipp - 1) / ipp * ipp;
         warp_floats = (tile_floats + 2 * max_c * neb * n_heads * nqp + neb * 32 + 31) / 32 * 32;
     }
+    // backward at the benchmark's geometry: the two-agents-per-lane kernel (REFIL_ATTN_BWD=generic selects the generic one)
+    static int bwd_generic = -1;
+    if (bwd_generic < 0) {
+        const char* e = getenv("REFIL_ATTN_BWD");
+        bwd_generic = (e && e[0] == 'g') ? 1 : 0;
+    }
+    const bool bwd_h4 = !fwd && !bwd_generic && hd == 32 && n_heads == 4 && n_queries <= 8;
     int warps, grid;
     size_t smem;
     int rc = attn_geometry(name, N, warp_floats, &warps, &grid, &smem, hd <= 16 ? 2 : 1);
@@ -957,11 +1204,13 @@ static int attn_group_launch(bool fwd, const RefilAttnDesc* descs, int n_problem
         if (fwd) {
             ATT_DISPATCH(attn_fwd_kernel, true, "masked_attn_fwd", hd, n_heads, grp, n_problems, smem, grid, warps, stream, "masked_attn_fwd", neb, tile_floats, warp_floats, maps, use_tmap)
         }
+        if (bwd_h4) return attn_launch(attn_bwd_h4_kernel<true>, grp, n_problems, smem, grid, warps, stream, "masked_attn_bwd", neb, tile_floats, warp_floats, maps, use_tmap);
         ATT_DISPATCH(attn_bwd_kernel, true, "masked_attn_bwd", hd, n_heads, grp, n_problems, smem, grid, warps, stream, "masked_attn_bwd", neb, tile_floats, warp_floats, maps, use_tmap)
     }
     if (fwd) {
         ATT_DISPATCH(attn_fwd_kernel, false, "masked_attn_fwd", hd, n_heads, grp, n_problems, smem, grid, warps, stream, "masked_attn_fwd", neb, tile_floats, warp_floats, maps, use_tmap)
     }
+    if (bwd_h4) return attn_launch(attn_bwd_h4_kernel<false>, grp, n_problems, smem, grid, warps, stream, "masked_attn_bwd", neb, tile_floats, warp_floats, maps, use_tmap);
     ATT_DISPATCH(attn_bwd_kernel, false, "masked_attn_bwd", hd, n_heads, grp, n_problems, smem, grid, warps, stream, "masked_attn_bwd", neb, tile_floats, warp_floats, maps, use_tmap)
 }
 
