@@ -628,6 +628,38 @@ __global__ void __launch_bounds__(32 * ATT_MAX_WARPS, (HD <= 16) ? 2 : 1) attn_b
 // with one shuffle; per-row scalars (max, sum, t) are computed by the lane that owns the row (dh = 0: agent ip, dh = 1: agent ip + 4).
 // Phase 2 (dK / dV accumulation over the scratch) and the scratch layout are those of the generic kernel.
 // =====================================================================================================================
+// dV_j = sum_c sum_i w^c_ij dO^c_i for the NC mask copies at once: the lane keeps its 4-feature slice of the dO rows of all copies
+// in registers, so the V half of the tile is written exactly once (no read-modify-write per copy)
+template <int NC>
+__device__ __forceinline__ void att_h4_dv_pass(const AttnArgs& a, long long n, int lane, int nq, int NEB, float* kv, const float* sw) {
+    constexpr int HD = 32, H = 4, d = HD * H, ldk = 2 * d, nqp = 8, sstr = H * nqp;
+    const int h2 = lane >> 3;
+    float4 gs[NC][8];
+#pragma unroll
+    for (int c = 0; c < NC; c++)
+#pragma unroll
+        for (int ii = 0; ii < 8; ii++)
+            gs[c][ii] = ii < nq ? __ldg(reinterpret_cast<const float4*>(a.dout + (((size_t)c * a.N + n) * nq + ii) * d) + lane)
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* swb = sw + h2 * nqp;
+#pragma unroll 2
+    for (int j = 0; j < NEB; j++) {
+        float4 dv = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int c = 0; c < NC; c++) {
+            const float4 wa = *reinterpret_cast<const float4*>(swb + ((size_t)c * NEB + j) * sstr);
+            const float4 wb = *reinterpret_cast<const float4*>(swb + ((size_t)c * NEB + j) * sstr + 4);
+            const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+            for (int ii = 0; ii < 8; ii++) {
+                dv.x = fmaf(wv[ii], gs[c][ii].x, dv.x); dv.y = fmaf(wv[ii], gs[c][ii].y, dv.y);
+                dv.z = fmaf(wv[ii], gs[c][ii].z, dv.z); dv.w = fmaf(wv[ii], gs[c][ii].w, dv.w);
+            }
+        }
+        *reinterpret_cast<float4*>(kv + j * ldk + d + 4 * lane) = dv;
+    }
+}
+
 template <bool GROUPED>
 __global__ void __launch_bounds__(32 * ATT_MAX_WARPS, 1) attn_bwd_h4_kernel(const __grid_constant__ AttnGroup grp, int NEB, int tile_floats, int warp_floats, const __grid_constant__ AttnMaps maps, int use_tmap) {
     int prob = 0, cta = (int)blockIdx.x, ncta = (int)gridDim.x;
@@ -649,10 +681,11 @@ __global__ void __launch_bounds__(32 * ATT_MAX_WARPS, 1) attn_bwd_h4_kernel(cons
 #pragma unroll
     for (int kc = 0; kc < 4; kc++) rot[kc] = h * HD + dh * 16 + 4 * ((kc + h) & 3);
     float* kv = smem + (size_t)warp * warp_floats;                       // [NEB][ldk]
-    const int sstr = H * nqp;                                            // scratch stride between entities j
-    float* sw = kv + tile_floats;                                        // [C][NEB][H][nqp]  softmax weights
-    float* sdl = sw + a.C * NEB * sstr;                                  // [C][NEB][H][nqp]  dw, then dlogits
-    float* lgs = sdl + a.C * NEB * sstr + lane;                          // [NEB][32]         logits of my own row
+    constexpr int sstr = H * nqp;                                        // scratch stride between entities j (= 32)
+    float* sw = kv + tile_floats;                                        // [C][NEB][H][nqp]  softmax weights of every copy
+    float* sdw = sw + a.C * NEB * sstr;                                  // [NEB][H][nqp]     dw of the copy in flight
+    float* sdl = a.C > 1 ? sdw + NEB * sstr : sdw;                       // [NEB][H][nqp]     dlogits SUMMED over the copies
+    float* lgs = sdl + NEB * sstr + lane;                                // [NEB][32]         logits of my own row
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + (size_t)wpc * warp_floats) + warp;
     if (lane == 0) {
         att_mbar_init(bar, 1);
@@ -664,12 +697,27 @@ __global__ void __launch_bounds__(32 * ATT_MAX_WARPS, 1) attn_bwd_h4_kernel(cons
     const float inv_scale = 1.f / sqrtf((float)HD);
     const long long gw = (long long)cta * wpc + warp, GW = (long long)ncta * wpc;
     uint32_t parity = 0;
-    auto load_row = [&](const float* base, float (&dst)[16]) {             // my 16 floats of a [d]-wide row, rotated chunk order
+    auto load_row = [&](const float* base, bool ok, float (&dst)[16]) {    // my 16 floats of a [d]-wide row, rotated chunk order
 #pragma unroll
         for (int kc = 0; kc < 4; kc++) {
-            const float4 v = __ldg(reinterpret_cast<const float4*>(base + rot[kc]));
+            const float4 v = ok ? __ldg(reinterpret_cast<const float4*>(base + rot[kc])) : make_float4(0.f, 0.f, 0.f, 0.f);
             dst[4 * kc] = v.x; dst[4 * kc + 1] = v.y; dst[4 * kc + 2] = v.z; dst[4 * kc + 3] = v.w;
         }
+    };
+    // two agents' dot products of their 16-float register rows with my 16 floats of the smem row at `row`; two accumulators
+    // per agent keep the dependent FMA chains at 8
+    auto dot2 = [&](const float* row, const float (&x0)[16], const float (&x1)[16], float& r0, float& r1) {
+        float p0a = 0.f, p0b = 0.f, p1a = 0.f, p1b = 0.f;
+#pragma unroll
+        for (int kc = 0; kc < 4; kc++) {
+            const float4 k4 = *reinterpret_cast<const float4*>(row + rot[kc]);
+            p0a = fmaf(x0[4 * kc], k4.x, p0a); p0b = fmaf(x0[4 * kc + 1], k4.y, p0b);
+            p0a = fmaf(x0[4 * kc + 2], k4.z, p0a); p0b = fmaf(x0[4 * kc + 3], k4.w, p0b);
+            p1a = fmaf(x1[4 * kc], k4.x, p1a); p1b = fmaf(x1[4 * kc + 1], k4.y, p1b);
+            p1a = fmaf(x1[4 * kc + 2], k4.z, p1a); p1b = fmaf(x1[4 * kc + 3], k4.w, p1b);
+        }
+        r0 = p0a + p0b;
+        r1 = p1a + p1b;
     };
     for (long long n = gw; n < a.N; n += GW) {
         for (int f = ne * ldk + lane; f < NEB * ldk; f += 32) kv[f] = 0.f;   // padding rows (the tile is reused for dK|dV)
@@ -677,18 +725,10 @@ __global__ void __launch_bounds__(32 * ATT_MAX_WARPS, 1) attn_bwd_h4_kernel(cons
         else att_tma_load_rows(kv, a.qkv + ((size_t)n * ne) * 3 * d + d, 3 * d, ne, 2 * d, ldk, bar, lane);
         AttMeta mc;
         att_meta_load(a, n, lane, 0, mc);
-        const bool act0 = i0 < nq, act1 = i1 < nq, acto = io < nq;
+        const bool act0 = i0 < nq, act1 = i1 < nq;
         float q0[16], q1[16];
-        load_row(a.qkv + ((size_t)n * ne + (act0 ? i0 : 0)) * 3 * d, q0);
-        load_row(a.qkv + ((size_t)n * ne + (act1 ? i1 : 0)) * 3 * d, q1);
-        if (!act0) {
-#pragma unroll
-            for (int k = 0; k < 16; k++) q0[k] = 0.f;
-        }
-        if (!act1) {
-#pragma unroll
-            for (int k = 0; k < 16; k++) q1[k] = 0.f;
-        }
+        load_row(a.qkv + ((size_t)n * ne + (act0 ? i0 : 0)) * 3 * d, act0, q0);
+        load_row(a.qkv + ((size_t)n * ne + (act1 ? i1 : 0)) * 3 * d, act1, q1);
         // dQ of the non-query rows is zero
         {
             const int d4 = d >> 2;
@@ -703,15 +743,10 @@ __global__ void __launch_bounds__(32 * ATT_MAX_WARPS, 1) attn_bwd_h4_kernel(cons
         parity ^= 1;
         // ---- logits of both agents (shared by the copies); the owner keeps its row in lgs -----------------------------------
         float mx[ATT_MAX_COPIES] = {-INFINITY, -INFINITY, -INFINITY};
-#pragma unroll 2
+#pragma unroll 4
         for (int j = 0; j < NEB; j++) {
-            float p0 = 0.f, p1 = 0.f;
-#pragma unroll
-            for (int kc = 0; kc < 4; kc++) {
-                const float4 k4 = *reinterpret_cast<const float4*>(kv + j * ldk + rot[kc]);
-                p0 = fmaf(q0[4 * kc], k4.x, p0); p0 = fmaf(q0[4 * kc + 1], k4.y, p0); p0 = fmaf(q0[4 * kc + 2], k4.z, p0); p0 = fmaf(q0[4 * kc + 3], k4.w, p0);
-                p1 = fmaf(q1[4 * kc], k4.x, p1); p1 = fmaf(q1[4 * kc + 1], k4.y, p1); p1 = fmaf(q1[4 * kc + 2], k4.z, p1); p1 = fmaf(q1[4 * kc + 3], k4.w, p1);
-            }
+            float p0, p1;
+            dot2(kv + j * ldk, q0, q1, p0, p1);
             p0 += __shfl_xor_sync(0xffffffffu, p0, 1);
             p1 += __shfl_xor_sync(0xffffffffu, p1, 1);
             const float lg = (dh ? p1 : p0) * inv_scale;
@@ -720,27 +755,17 @@ __global__ void __launch_bounds__(32 * ATT_MAX_WARPS, 1) attn_bwd_h4_kernel(cons
             for (int c = 0; c < ATT_MAX_COPIES; c++)
                 if (!((mb[c] >> j) & 1u)) mx[c] = fmaxf(mx[c], lg);
         }
-        float dq0[16], dq1[16];
-#pragma unroll
-        for (int k = 0; k < 16; k++) { dq0[k] = 0.f; dq1[k] = 0.f; }
+        float* sdr = sdw + h * nqp + io;                                 // [j * sstr]: my own row's column of the scratch
+        float* slr = sdl + h * nqp + io;
 #pragma unroll
         for (int c = 0; c < ATT_MAX_COPIES; c++) {
             if (c < a.C) {
                 const uint32_t bits = mb[c];
                 const float m = mx[c];
                 float g0[16], g1[16];                                  // dO rows of both agents for this copy (my half dims)
-                load_row(a.dout + (((size_t)c * a.N + n) * nq + (act0 ? i0 : 0)) * d, g0);
-                load_row(a.dout + (((size_t)c * a.N + n) * nq + (act1 ? i1 : 0)) * d, g1);
-                if (!act0) {
-#pragma unroll
-                    for (int k = 0; k < 16; k++) g0[k] = 0.f;
-                }
-                if (!act1) {
-#pragma unroll
-                    for (int k = 0; k < 16; k++) g1[k] = 0.f;
-                }
-                float* swr = sw + ((size_t)c * NEB * H + h) * nqp + io;   // [j * sstr]: my own row's column of the scratch
-                float* sdr = sdl + ((size_t)c * NEB * H + h) * nqp + io;
+                load_row(a.dout + (((size_t)c * a.N + n) * nq + (act0 ? i0 : 0)) * d, act0, g0);
+                load_row(a.dout + (((size_t)c * a.N + n) * nq + (act1 ? i1 : 0)) * d, act1, g1);
+                float* swr = sw + ((size_t)c * NEB * H + h) * nqp + io;
                 float ssum = 0.f;
 #pragma unroll 4
                 for (int j = 0; j < NEB; j++) {
@@ -750,15 +775,10 @@ __global__ void __launch_bounds__(32 * ATT_MAX_WARPS, 1) attn_bwd_h4_kernel(cons
                 }
                 const float r = ssum > 0.f ? 1.f / ssum : 0.f;
                 float t = 0.f;
-#pragma unroll 2
+#pragma unroll 4
                 for (int j = 0; j < NEB; j++) {
-                    float p0 = 0.f, p1 = 0.f;
-#pragma unroll
-                    for (int kc = 0; kc < 4; kc++) {
-                        const float4 v4 = *reinterpret_cast<const float4*>(kv + j * ldk + d + rot[kc]);
-                        p0 = fmaf(g0[4 * kc], v4.x, p0); p0 = fmaf(g0[4 * kc + 1], v4.y, p0); p0 = fmaf(g0[4 * kc + 2], v4.z, p0); p0 = fmaf(g0[4 * kc + 3], v4.w, p0);
-                        p1 = fmaf(g1[4 * kc], v4.x, p1); p1 = fmaf(g1[4 * kc + 1], v4.y, p1); p1 = fmaf(g1[4 * kc + 2], v4.z, p1); p1 = fmaf(g1[4 * kc + 3], v4.w, p1);
-                    }
+                    float p0, p1;
+                    dot2(kv + j * ldk + d, g0, g1, p0, p1);
                     p0 += __shfl_xor_sync(0xffffffffu, p0, 1);
                     p1 += __shfl_xor_sync(0xffffffffu, p1, 1);
                     const float dw = dh ? p1 : p0;                     // <dO_io, V_j> of my own row
@@ -767,21 +787,29 @@ __global__ void __launch_bounds__(32 * ATT_MAX_WARPS, 1) attn_bwd_h4_kernel(cons
                     sdr[j * sstr] = dw;
                     t = fmaf(w, dw, t);
                 }
-#pragma unroll 2
+                // dlogits are summed over the copies: dQ and dK are linear in them, so ONE pass each serves all copies
+#pragma unroll 4
                 for (int j = 0; j < NEB; j++) {
-                    const float dl = swr[j * sstr] * (sdr[j * sstr] - t) * inv_scale;     // dlogit of my own row
-                    sdr[j * sstr] = dl;
-                    const float dlo = __shfl_xor_sync(0xffffffffu, dl, 1);                 // ... and of my partner's row
-                    const float dl0 = dh ? dlo : dl, dl1 = dh ? dl : dlo;
-#pragma unroll
-                    for (int kc = 0; kc < 4; kc++) {
-                        const float4 k4 = *reinterpret_cast<const float4*>(kv + j * ldk + rot[kc]);
-                        dq0[4 * kc] = fmaf(dl0, k4.x, dq0[4 * kc]); dq0[4 * kc + 1] = fmaf(dl0, k4.y, dq0[4 * kc + 1]);
-                        dq0[4 * kc + 2] = fmaf(dl0, k4.z, dq0[4 * kc + 2]); dq0[4 * kc + 3] = fmaf(dl0, k4.w, dq0[4 * kc + 3]);
-                        dq1[4 * kc] = fmaf(dl1, k4.x, dq1[4 * kc]); dq1[4 * kc + 1] = fmaf(dl1, k4.y, dq1[4 * kc + 1]);
-                        dq1[4 * kc + 2] = fmaf(dl1, k4.z, dq1[4 * kc + 2]); dq1[4 * kc + 3] = fmaf(dl1, k4.w, dq1[4 * kc + 3]);
-                    }
+                    const float dl = swr[j * sstr] * (sdr[j * sstr] - t) * inv_scale;
+                    slr[j * sstr] = c == 0 ? dl : slr[j * sstr] + dl;
                 }
+            }
+        }
+        float dq0[16], dq1[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) { dq0[k] = 0.f; dq1[k] = 0.f; }
+#pragma unroll 4
+        for (int j = 0; j < NEB; j++) {
+            const float dl = slr[j * sstr];                                       // summed dlogit of my own row
+            const float dlo = __shfl_xor_sync(0xffffffffu, dl, 1);                 // ... and of my partner's row
+            const float dl0 = dh ? dlo : dl, dl1 = dh ? dl : dlo;
+#pragma unroll
+            for (int kc = 0; kc < 4; kc++) {
+                const float4 k4 = *reinterpret_cast<const float4*>(kv + j * ldk + rot[kc]);
+                dq0[4 * kc] = fmaf(dl0, k4.x, dq0[4 * kc]); dq0[4 * kc + 1] = fmaf(dl0, k4.y, dq0[4 * kc + 1]);
+                dq0[4 * kc + 2] = fmaf(dl0, k4.z, dq0[4 * kc + 2]); dq0[4 * kc + 3] = fmaf(dl0, k4.w, dq0[4 * kc + 3]);
+                dq1[4 * kc] = fmaf(dl1, k4.x, dq1[4 * kc]); dq1[4 * kc + 1] = fmaf(dl1, k4.y, dq1[4 * kc + 1]);
+                dq1[4 * kc + 2] = fmaf(dl1, k4.z, dq1[4 * kc + 2]); dq1[4 * kc + 3] = fmaf(dl1, k4.w, dq1[4 * kc + 3]);
             }
         }
         if (act0) {
@@ -796,51 +824,31 @@ __global__ void __launch_bounds__(32 * ATT_MAX_WARPS, 1) attn_bwd_h4_kernel(cons
             for (int kc = 0; kc < 4; kc++)
                 *reinterpret_cast<float4*>(dst + rot[kc]) = make_float4(dq1[4 * kc], dq1[4 * kc + 1], dq1[4 * kc + 2], dq1[4 * kc + 3]);
         }
-        (void)acto;
         __syncwarp();          // scratch complete; nobody reads K / V any more
-        // ---- phase 2 (as in the generic kernel): lane = 4 features (head h2, chunk kc2) of every entity row ------------------
+        // ---- phase 2: lane = features 4*lane .. 4*lane+3 (head lane / 8) of every entity row; the tile becomes dK | dV ----------
         {
-            constexpr int NCH = HD / 4;
-            const int h2 = lane / NCH, kc2 = lane - h2 * NCH;
-            bool first = true;
-            for (int c = 0; c < a.C; c++) {
-                float4 qs[8], gs[8];
+            const int h2 = lane >> 3;
+            float4 qs[8];
+#pragma unroll
+            for (int ii = 0; ii < 8; ii++)
+                qs[ii] = ii < nq ? __ldg(reinterpret_cast<const float4*>(a.qkv + ((size_t)n * ne + ii) * 3 * d) + lane)
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float* sdb = sdl + h2 * nqp;
+#pragma unroll 2
+            for (int j = 0; j < NEB; j++) {                              // dK_j = sum_i (sum_c dlogit^c_ij) Q_i
+                float4 dk = make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4 dla = *reinterpret_cast<const float4*>(sdb + j * sstr), dlb = *reinterpret_cast<const float4*>(sdb + j * sstr + 4);
+                const float dlv[8] = {dla.x, dla.y, dla.z, dla.w, dlb.x, dlb.y, dlb.z, dlb.w};
 #pragma unroll
                 for (int ii = 0; ii < 8; ii++) {
-                    const bool ok = ii < nq;
-                    qs[ii] = ok ? __ldg(reinterpret_cast<const float4*>(a.qkv + ((size_t)n * ne + ii) * 3 * d) + lane)
-                                : make_float4(0.f, 0.f, 0.f, 0.f);
-                    gs[ii] = ok ? __ldg(reinterpret_cast<const float4*>(a.dout + (((size_t)c * a.N + n) * nq + ii) * d) + lane)
-                                : make_float4(0.f, 0.f, 0.f, 0.f);
+                    dk.x = fmaf(dlv[ii], qs[ii].x, dk.x); dk.y = fmaf(dlv[ii], qs[ii].y, dk.y);
+                    dk.z = fmaf(dlv[ii], qs[ii].z, dk.z); dk.w = fmaf(dlv[ii], qs[ii].w, dk.w);
                 }
-                const float* swb = sw + ((size_t)c * NEB * H + h2) * nqp;
-                const float* sdb = sdl + ((size_t)c * NEB * H + h2) * nqp;
-#pragma unroll 2
-                for (int j = 0; j < NEB; j++) {
-                    float4 dk = make_float4(0.f, 0.f, 0.f, 0.f), dv = make_float4(0.f, 0.f, 0.f, 0.f);
-                    const float4 dla = *reinterpret_cast<const float4*>(sdb + j * sstr), dlb = *reinterpret_cast<const float4*>(sdb + j * sstr + 4);
-                    const float4 wa = *reinterpret_cast<const float4*>(swb + j * sstr), wb = *reinterpret_cast<const float4*>(swb + j * sstr + 4);
-                    const float dlv[8] = {dla.x, dla.y, dla.z, dla.w, dlb.x, dlb.y, dlb.z, dlb.w};
-                    const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
-#pragma unroll
-                    for (int ii = 0; ii < 8; ii++) {
-                        dk.x = fmaf(dlv[ii], qs[ii].x, dk.x); dk.y = fmaf(dlv[ii], qs[ii].y, dk.y);
-                        dk.z = fmaf(dlv[ii], qs[ii].z, dk.z); dk.w = fmaf(dlv[ii], qs[ii].w, dk.w);
-                        dv.x = fmaf(wv[ii], gs[ii].x, dv.x); dv.y = fmaf(wv[ii], gs[ii].y, dv.y);
-                        dv.z = fmaf(wv[ii], gs[ii].z, dv.z); dv.w = fmaf(wv[ii], gs[ii].w, dv.w);
-                    }
-                    float4* kd = reinterpret_cast<float4*>(kv + j * ldk + h2 * HD + 4 * kc2);
-                    float4* vd = reinterpret_cast<float4*>(kv + j * ldk + d + h2 * HD + 4 * kc2);
-                    if (!first) {
-                        const float4 k0 = *kd, v0 = *vd;
-                        dk.x += k0.x; dk.y += k0.y; dk.z += k0.z; dk.w += k0.w;
-                        dv.x += v0.x; dv.y += v0.y; dv.z += v0.z; dv.w += v0.w;
-                    }
-                    *kd = dk;
-                    *vd = dv;
-                }
-                first = false;
+                *reinterpret_cast<float4*>(kv + j * ldk + 4 * lane) = dk;
             }
+            if (a.C == 1) att_h4_dv_pass<1>(a, n, lane, nq, NEB, kv, sw);
+            else if (a.C == 2) att_h4_dv_pass<2>(a, n, lane, nq, NEB, kv, sw);
+            else att_h4_dv_pass<3>(a, n, lane, nq, NEB, kv, sw);
         }
         __syncwarp();
         // stream the dK | dV tile out as columns d..3d of dQKV (coalesced 128-bit stores)
@@ -1166,13 +1174,6 @@ static int attn_group_launch(bool fwd, const RefilAttnDesc* descs, int n_problem
     }
     const int hd = embed_dim / n_heads, neb = (n_entities + 7) / 8 * 8;
     const int tile_floats = neb * 2 * embed_dim;              // K tile | V tile, [neb][d] each
-    int warp_floats;
-    if (fwd) {
-        warp_floats = tile_floats + neb * 32;                 // multiples of 32 floats: every warp tile is 128-byte aligned
-    } else {
-        const int ipp = 32 / n_heads, nqp = (n_queries + ipp - 1) / ipp * ipp;
-        warp_floats = (tile_floats + 2 * max_c * neb * n_heads * nqp + neb * 32 + 31) / 32 * 32;
-    }
     // backward at the benchmark's geometry: the two-agents-per-lane kernel (REFIL_ATTN_BWD=generic selects the generic one)
     static int bwd_generic = -1;
     if (bwd_generic < 0) {
@@ -1180,6 +1181,15 @@ static int attn_group_launch(bool fwd, const RefilAttnDesc* descs, int n_problem
         bwd_generic = (e && e[0] == 'g') ? 1 : 0;
     }
     const bool bwd_h4 = !fwd && !bwd_generic && hd == 32 && n_heads == 4 && n_queries <= 8;
+    int warp_floats;
+    if (fwd) {
+        warp_floats = tile_floats + neb * 32;                 // multiples of 32 floats: every warp tile is 128-byte aligned
+    } else {
+        const int ipp = 32 / n_heads, nqp = (n_queries + ipp - 1) / ipp * ipp;
+        // generic kernel: w and dw/dlogit scratch per copy; h4 kernel: w per copy, one dw, one copy-summed dlogit (aliased for C = 1)
+        const int scratch = bwd_h4 ? (max_c + (max_c > 1 ? 2 : 1)) : 2 * max_c;
+        warp_floats = (tile_floats + scratch * neb * n_heads * nqp + neb * 32 + 31) / 32 * 32;
+    }
     int warps, grid;
     size_t smem;
     int rc = attn_geometry(name, N, warp_floats, &warps, &grid, &smem, hd <= 16 ? 2 : 1);
