@@ -33,6 +33,7 @@
 #include <cuda.h>   // CUtensorMap (the encode function is fetched through cudaGetDriverEntryPoint, libcuda is not linked)
 
 #include <stdlib.h>
+#include <type_traits>
 #include <string.h>
 
 #include "common.cuh"
@@ -628,8 +629,9 @@ __global__ void __launch_bounds__(32 * ATT_MAX_WARPS, (HD <= 16) ? 2 : 1) attn_b
 // with one shuffle; per-row scalars (max, sum, t) are computed by the lane that owns the row (dh = 0: agent ip, dh = 1: agent ip + 4).
 // The mask copies share work that is linear in the dlogits: dQ_i = sum_j (sum_c dl^c_ij) K_j and dK_j = sum_i (sum_c dl^c_ij) Q_i, so the
 // dlogits are summed over the copies in the scratch and dQ / dK take ONE pass for all copies (the generic kernel: one per copy); dV
-// takes its dO rows of all copies in registers and writes the tile once.  C = 3: 9 instead of 13 contraction passes per unit, 15 KB
-// instead of 18 KB of scratch (5 warps per SM instead of 4).
+// and dw = <dO, V> take the dO rows of all copies in registers and sweep V / write the tile once.  sum_c dl^c_j = (sum_c w^c_j dw^c_j -
+// sum_c w^c_j t_c) / scale needs no per-copy dw scratch, and the logits live in the column that later holds the summed dlogits: C = 3
+// costs 9 instead of 13 contraction passes per unit and 12 KB instead of 21 KB of scratch (6 warps per SM instead of 4).
 // =====================================================================================================================
 // dV_j = sum_c sum_i w^c_ij dO^c_i for the NC mask copies at once: the lane keeps its 4-feature slice of the dO rows of all copies
 // in registers, so the V half of the tile is written exactly once (no read-modify-write per copy)
@@ -686,9 +688,8 @@ __global__ void __launch_bounds__(32 * ATT_MAX_WARPS, 1) attn_bwd_h4_kernel(cons
     float* kv = smem + (size_t)warp * warp_floats;                       // [NEB][ldk]
     constexpr int sstr = H * nqp;                                        // scratch stride between entities j (= 32)
     float* sw = kv + tile_floats;                                        // [C][NEB][H][nqp]  softmax weights of every copy
-    float* sdw = sw + a.C * NEB * sstr;                                  // [NEB][H][nqp]     dw of the copy in flight
-    float* sdl = a.C > 1 ? sdw + NEB * sstr : sdw;                       // [NEB][H][nqp]     dlogits SUMMED over the copies
-    float* lgs = sdl + NEB * sstr + lane;                                // [NEB][32]         logits of my own row
+    float* sdl = sw + a.C * NEB * sstr;                                  // [NEB][H][nqp]     logits, then sum_c w dw, then the dlogits
+                                                                         //                   SUMMED over the copies
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + (size_t)wpc * warp_floats) + warp;
     if (lane == 0) {
         att_mbar_init(bar, 1);
@@ -744,7 +745,8 @@ __global__ void __launch_bounds__(32 * ATT_MAX_WARPS, 1) attn_bwd_h4_kernel(cons
         att_meta_resolve(a, n, lane, 0, 8, io, mc, mb);
         att_mbar_wait(bar, parity);
         parity ^= 1;
-        // ---- logits of both agents (shared by the copies); the owner keeps its row in lgs -----------------------------------
+        // ---- logits of both agents (shared by the copies); the owner keeps its row in the scratch column it owns ----------
+        float* slr = sdl + h * nqp + io;                                 // [j * sstr]: my own row's column of the scratch
         float mx[ATT_MAX_COPIES] = {-INFINITY, -INFINITY, -INFINITY};
 #pragma unroll 4
         for (int j = 0; j < NEB; j++) {
@@ -753,57 +755,92 @@ __global__ void __launch_bounds__(32 * ATT_MAX_WARPS, 1) attn_bwd_h4_kernel(cons
             p0 += __shfl_xor_sync(0xffffffffu, p0, 1);
             p1 += __shfl_xor_sync(0xffffffffu, p1, 1);
             const float lg = (dh ? p1 : p0) * inv_scale;
-            lgs[j * 32] = lg;
+            slr[j * sstr] = lg;
 #pragma unroll
             for (int c = 0; c < ATT_MAX_COPIES; c++)
                 if (!((mb[c] >> j) & 1u)) mx[c] = fmaxf(mx[c], lg);
         }
-        float* sdr = sdw + h * nqp + io;                                 // [j * sstr]: my own row's column of the scratch
-        float* slr = sdl + h * nqp + io;
+        // ---- softmax numerators of every copy (the logits die here: their column becomes the sum_c w dw accumulator) ------------
+        float rs[ATT_MAX_COPIES] = {0.f, 0.f, 0.f};
 #pragma unroll
         for (int c = 0; c < ATT_MAX_COPIES; c++) {
             if (c < a.C) {
                 const uint32_t bits = mb[c];
                 const float m = mx[c];
-                float g0[16], g1[16];                                  // dO rows of both agents for this copy (my half dims)
-                load_row(a.dout + (((size_t)c * a.N + n) * nq + (act0 ? i0 : 0)) * d, act0, g0);
-                load_row(a.dout + (((size_t)c * a.N + n) * nq + (act1 ? i1 : 0)) * d, act1, g1);
                 float* swr = sw + ((size_t)c * NEB * H + h) * nqp + io;
                 float ssum = 0.f;
 #pragma unroll 4
                 for (int j = 0; j < NEB; j++) {
-                    const float e = ((bits >> j) & 1u) ? 0.f : __expf(lgs[j * 32] - m);
+                    const float e = ((bits >> j) & 1u) ? 0.f : __expf(slr[j * sstr] - m);
                     ssum += e;
                     swr[j * sstr] = e;
                 }
-                const float r = ssum > 0.f ? 1.f / ssum : 0.f;
-                float t = 0.f;
-#pragma unroll 4
-                for (int j = 0; j < NEB; j++) {
-                    float p0, p1;
-                    dot2(kv + j * ldk + d, g0, g1, p0, p1);
-                    p0 += __shfl_xor_sync(0xffffffffu, p0, 1);
-                    p1 += __shfl_xor_sync(0xffffffffu, p1, 1);
-                    const float dw = dh ? p1 : p0;                     // <dO_io, V_j> of my own row
-                    const float w = swr[j * sstr] * r;
-                    swr[j * sstr] = w;
-                    sdr[j * sstr] = dw;
-                    t = fmaf(w, dw, t);
-                }
-                // dlogits are summed over the copies: dQ and dK are linear in them, so ONE pass each serves all copies
-#pragma unroll 4
-                for (int j = 0; j < NEB; j++) {
-                    const float dl = swr[j * sstr] * (sdr[j * sstr] - t) * inv_scale;
-                    slr[j * sstr] = c == 0 ? dl : slr[j * sstr] + dl;
-                }
+                rs[c] = ssum > 0.f ? 1.f / ssum : 0.f;
             }
         }
+        // ---- ONE pass over V for all copies: dw^c_ij = <dO^c_i, V_j>, t_c = sum_j w^c_j dw^c_j, A_j = sum_c w^c_j dw^c_j -------------
+        // (dlogit^c_j = w^c_j (dw^c_j - t_c) / scale, so sum_c dlogit^c_j = (A_j - sum_c w^c_j t_c) / scale: no per-copy dw scratch)
+        float ts[ATT_MAX_COPIES] = {0.f, 0.f, 0.f};
+        auto v_pass = [&](auto nc_tag) {
+            constexpr int NC = decltype(nc_tag)::value;
+            float g[NC][2][16];                                        // dO rows of both agents for every copy (my half dims)
+#pragma unroll
+            for (int c = 0; c < NC; c++) {
+                load_row(a.dout + (((size_t)c * a.N + n) * nq + (act0 ? i0 : 0)) * d, act0, g[c][0]);
+                load_row(a.dout + (((size_t)c * a.N + n) * nq + (act1 ? i1 : 0)) * d, act1, g[c][1]);
+            }
+            float* swo = sw + h * nqp + io;
+#pragma unroll 2
+            for (int j = 0; j < NEB; j++) {
+                float p[NC][2];
+#pragma unroll
+                for (int c = 0; c < NC; c++) { p[c][0] = 0.f; p[c][1] = 0.f; }
+                float pb[NC][2];
+#pragma unroll
+                for (int c = 0; c < NC; c++) { pb[c][0] = 0.f; pb[c][1] = 0.f; }
+#pragma unroll
+                for (int kc = 0; kc < 4; kc++) {
+                    const float4 v4 = *reinterpret_cast<const float4*>(kv + j * ldk + d + rot[kc]);
+#pragma unroll
+                    for (int c = 0; c < NC; c++)
+#pragma unroll
+                        for (int ag = 0; ag < 2; ag++) {
+                            p[c][ag] = fmaf(g[c][ag][4 * kc], v4.x, p[c][ag]); pb[c][ag] = fmaf(g[c][ag][4 * kc + 1], v4.y, pb[c][ag]);
+                            p[c][ag] = fmaf(g[c][ag][4 * kc + 2], v4.z, p[c][ag]); pb[c][ag] = fmaf(g[c][ag][4 * kc + 3], v4.w, pb[c][ag]);
+                        }
+                }
+                float acc = 0.f;
+#pragma unroll
+                for (int c = 0; c < NC; c++) {
+                    float d0 = p[c][0] + pb[c][0], d1 = p[c][1] + pb[c][1];
+                    d0 += __shfl_xor_sync(0xffffffffu, d0, 1);
+                    d1 += __shfl_xor_sync(0xffffffffu, d1, 1);
+                    const float dw = dh ? d1 : d0;                     // <dO^c_io, V_j> of my own row
+                    const float w = swo[((size_t)c * NEB + j) * sstr] * rs[c];
+                    swo[((size_t)c * NEB + j) * sstr] = w;
+                    const float wd = w * dw;
+                    ts[c] += wd;
+                    acc += wd;
+                }
+                slr[j * sstr] = acc;
+            }
+        };
+        if (a.C == 1) v_pass(std::integral_constant<int, 1>{});
+        else if (a.C == 2) v_pass(std::integral_constant<int, 2>{});
+        else v_pass(std::integral_constant<int, 3>{});
+        // ---- dQ: one pass over K with the copy-summed dlogits (kept in the scratch for the dK pass) -----------------------------
         float dq0[16], dq1[16];
 #pragma unroll
         for (int k = 0; k < 16; k++) { dq0[k] = 0.f; dq1[k] = 0.f; }
+        const float* swo = sw + h * nqp + io;
 #pragma unroll 4
         for (int j = 0; j < NEB; j++) {
-            const float dl = slr[j * sstr];                                       // summed dlogit of my own row
+            float wt = 0.f;
+#pragma unroll
+            for (int c = 0; c < ATT_MAX_COPIES; c++)
+                if (c < a.C) wt = fmaf(swo[((size_t)c * NEB + j) * sstr], ts[c], wt);
+            const float dl = (slr[j * sstr] - wt) * inv_scale;                     // summed dlogit of my own row
+            slr[j * sstr] = dl;
             const float dlo = __shfl_xor_sync(0xffffffffu, dl, 1);                 // ... and of my partner's row
             const float dl0 = dh ? dlo : dl, dl1 = dh ? dl : dlo;
 #pragma unroll
@@ -1189,9 +1226,8 @@ static int attn_group_launch(bool fwd, const RefilAttnDesc* descs, int n_problem
         warp_floats = tile_floats + neb * 32;                 // multiples of 32 floats: every warp tile is 128-byte aligned
     } else {
         const int ipp = 32 / n_heads, nqp = (n_queries + ipp - 1) / ipp * ipp;
-        // generic kernel: w and dw/dlogit scratch per copy; h4 kernel: w per copy, one dw, one copy-summed dlogit (aliased for C = 1)
-        const int scratch = bwd_h4 ? (max_c + (max_c > 1 ? 2 : 1)) : 2 * max_c;
-        warp_floats = (tile_floats + scratch * neb * n_heads * nqp + neb * 32 + 31) / 32 * 32;
+        if (bwd_h4) warp_floats = tile_floats + (max_c + 1) * neb * 32;      // w per copy + ONE logit / dlogit column set
+        else warp_floats = (tile_floats + 2 * max_c * neb * n_heads * nqp + neb * 32 + 31) / 32 * 32;
     }
     int warps, grid;
     size_t smem;
