@@ -25,7 +25,7 @@ for B in $BATCHES; do
       gru_mma) EXTRA="" run gru_mma $B REFIL_GRU_MODE=mma;;
       crit*) EXTRA="--crit-tiles ${L#crit}" run $L $B A=1;;
       noprio*) EXTRA="--no-prio --crit-tiles ${L#noprio}" run $L $B A=1;;
-      attn_generic) EXTRA="" run attn_generic $B REFIL_ATTN_BWD=generic;;
+      attn_generic) EXTRA="" run attn_generic $B REFIL_ATTN=generic;;
       pdl0) EXTRA="" run pdl0 $B REFIL_PDL=0;;
       pdl0_nogroup) EXTRA="--no-group" run pdl0_nogroup $B REFIL_PDL=0;;
       tiles*) EXTRA="" run $L $B REFIL_TC_MIN_TILES=${L#tiles};;
