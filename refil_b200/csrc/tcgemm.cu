@@ -743,13 +743,13 @@ static int tc_make_tmap_a(CUtensorMap* tm, const float* A, long long lda, int M,
 
 // CUtensorMap of a row-major [M][P] fp32 matrix with a (128 columns, 32 rows) box, no swizzle: one raw reduction chunk of
 // the weight-gradient kernel; columns >= P and rows >= M are zero-filled
-static int tc_make_tmap_rows(CUtensorMap* tm, const float* X, long long ldx, int M, int P) {
+static int tc_make_tmap_rows(CUtensorMap* tm, const float* X, long long ldx, int M, int P, int box_cols = 128) {
     memset(tm, 0, sizeof(*tm));
     tc_encode_fn enc = tc_encoder();
     if (!enc) return 0;
     const cuuint64_t dims[2] = {(cuuint64_t)P, (cuuint64_t)M};
     const cuuint64_t strides[1] = {(cuuint64_t)ldx * 4};
-    const cuuint32_t box[2] = {128, 32};
+    const cuuint32_t box[2] = {(cuuint32_t)box_cols, 32};
     const cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)X, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -974,6 +974,7 @@ struct TcWArgs {
     float* db;
     int M, P, Q, BQ, p_tiles, splits, stages, chunks_per_split;
     int q_valid, dw_vec;                 // columns >= q_valid of dW do not exist (zero-padded Y); dw_vec: 16-byte atomics allowed
+    int y_tma;                           // TS kernel: raw Y chunks arrive by TMA (y_shift == 0), else the producers load them
     uint32_t idesc;
 };
 
@@ -1227,7 +1228,7 @@ __global__ void __launch_bounds__(TCW_THREADS, 1) tc_gemm_wgrad_kernel(TcWArgs a
 #define TW_X_COL0 256
 
 struct TcWGeom {
-    int raw_stages, y_stages;
+    int raw_stages, y_stages, y_raw_stages;
 };
 
 struct TcWGroup { TcWArgs a[TC_MAX_GROUP]; };
@@ -1236,21 +1237,26 @@ struct TcWGroup { TcWArgs a[TC_MAX_GROUP]; };
 template <bool GROUPED>
 __global__ void __launch_bounds__(TW_THREADS, 1) tc_wgrad_ts_kernel(const __grid_constant__ TcWGroup grp, TcWGeom g,
                                                                    const __grid_constant__ TcMaps maps_x,
-                                                                   const __grid_constant__ TcMaps maps_r) {
+                                                                   const __grid_constant__ TcMaps maps_r,
+                                                                   const __grid_constant__ TcMaps maps_y) {
     const int prob = GROUPED ? (int)blockIdx.y : 0;
     const TcWArgs& a = grp.a[prob];
     const CUtensorMap& tmap_x = maps_x.m[prob];
     const CUtensorMap& tmap_r = maps_r.m[prob];
+    const CUtensorMap& tmap_y = maps_y.m[prob];
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    const int BQ = a.BQ, SY = g.y_stages, RS = g.raw_stages;
+    const int BQ = a.BQ, SY = g.y_stages, RS = g.raw_stages, RY = g.y_raw_stages;
     const int ya = BQ / 32;                                   // MN atoms of the Y tile
     const bool has_r = a.relu_y != nullptr;
     const uint32_t raw_bytes = 32 * 128 * 4, y_bytes = 32 * (uint32_t)BQ * 4, y_stage_bytes = 2 * y_bytes;
     uint8_t* smem_x = smem;                                               // [RS][32][128] raw X chunks
     uint8_t* smem_rl = smem_x + (size_t)RS * raw_bytes;                   // [RS][32][128] raw relu_y chunks (if fused)
     uint8_t* smem_y = smem_rl + (has_r ? (size_t)RS * raw_bytes : 0);     // [SY][Y_hi | Y_lo]
+    const uint32_t yraw_bytes = 32 * (uint32_t)a.Q * 4;
+    uint8_t* smem_yr = smem_y + (size_t)SY * y_stage_bytes;               // [RY][32][Q] raw Y chunks (TMA path)
     __shared__ uint64_t xr_full[TW_X_STAGES], xr_empty[TW_X_STAGES], xa_full[TW_X_STAGES], xa_empty[TW_X_STAGES];
+    __shared__ uint64_t yr_full[TW_X_STAGES], yr_empty[TW_X_STAGES];
     __shared__ uint64_t y_full[TC_MAX_STAGES], y_empty[TC_MAX_STAGES], acc_bar;
     __shared__ uint32_t tmem_base_s;
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform role index
@@ -1277,17 +1283,30 @@ __global__ void __launch_bounds__(TW_THREADS, 1) tc_wgrad_ts_kernel(const __grid
                   "r"(smem_u32(&xr_full[st]))
                 : "memory");
     };
+    auto tma_ychunk = [&](int st, int ch) {
+        const int m0 = (c_begin + ch) * 32;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&yr_full[st])), "r"(yraw_bytes) : "memory");
+        asm volatile(
+            "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+            ::"r"(smem_u32(smem_yr + (size_t)st * yraw_bytes)), "l"(&tmap_y), "r"(0), "r"(m0), "r"(smem_u32(&yr_full[st]))
+            : "memory");
+    };
     const int pre = min(n_chunks, RS);
+    const int pre_y = a.y_tma ? min(n_chunks, RY) : 0;
     if (threadIdx.x == TW_TMA_WARP * 32) {
         for (int s = 0; s < TW_X_STAGES; s++) {
             mbar_init(&xr_full[s], 1); mbar_init(&xr_empty[s], 128);
             mbar_init(&xa_full[s], 128); mbar_init(&xa_empty[s], 1);
+            mbar_init(&yr_full[s], 1); mbar_init(&yr_empty[s], 128);
         }
         for (int s = 0; s < TC_MAX_STAGES; s++) { mbar_init(&y_full[s], 128); mbar_init(&y_empty[s], 1); }
         mbar_init(&acc_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         pdl_wait();                                            // X (and relu_y) come from the previous kernels
-        for (int ch = 0; ch < pre; ch++) tma_chunk(ch, ch);
+        for (int ch = 0; ch < max(pre, pre_y); ch++) {
+            if (ch < pre) tma_chunk(ch, ch);
+            if (ch < pre_y) tma_ychunk(ch, ch);
+        }
     }
     if (warp == TW_MMA_WARP) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512u));
@@ -1424,6 +1443,7 @@ __global__ void __launch_bounds__(TW_THREADS, 1) tc_wgrad_ts_kernel(const __grid
         }
     } else if (warp == TW_TMA_WARP) {
         // ===================== TMA producer: raw X (and relu_y) chunks =====================
+        // lane 0 streams the X (and relu_y) chunks, lane 1 the raw Y chunks: two independent rings
         if (lane == 0) {
             int st = pre % RS;
             uint32_t ph = (uint32_t)(pre / RS) & 1u;
@@ -1431,6 +1451,14 @@ __global__ void __launch_bounds__(TW_THREADS, 1) tc_wgrad_ts_kernel(const __grid
                 mbar_wait(&xr_empty[st], ph ^ 1);
                 tma_chunk(st, ch);
                 if (++st == RS) { st = 0; ph ^= 1; }
+            }
+        } else if (lane == 1 && a.y_tma) {
+            int st = pre_y % RY;
+            uint32_t ph = (uint32_t)(pre_y / RY) & 1u;
+            for (int ch = pre_y; ch < n_chunks; ch++) {
+                mbar_wait(&yr_empty[st], ph ^ 1);
+                tma_ychunk(st, ch);
+                if (++st == RY) { st = 0; ph ^= 1; }
             }
         }
         __syncwarp();
@@ -1477,8 +1505,23 @@ __global__ void __launch_bounds__(TW_THREADS, 1) tc_wgrad_ts_kernel(const __grid
             fence_async_smem();
             mbar_arrive(&y_full[stage]);
         };
+        if (a.y_tma) {
+            // raw chunk from the TMA ring (rows beyond M arrive as zeros): my 16-byte pieces, conflict-free LDS.128
+            const float* yr0 = reinterpret_cast<const float*>(smem_yr) + (size_t)ry0 * a.Q + cy * 4;
+            for (int ch = grp; ch < n_chunks; ch += 2) {
+                const int st = ch % RY;
+                mbar_wait(&yr_full[st], (uint32_t)(ch / RY) & 1u);
+                const float* src = yr0 + (size_t)st * (yraw_bytes >> 2);
+                float4 vy[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++)
+                    vy[i] = i < ny ? *reinterpret_cast<const float4*>(src + (size_t)ry_step * i * a.Q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                mbar_arrive(&yr_empty[st]);
+                store_y(ch, vy);
+            }
+        }
         float4 va[8], vb[8];
-        int ch = grp;
+        int ch = a.y_tma ? n_chunks : grp;
         if (ch < n_chunks) {
             load_y(ch, va);
             for (;;) {
@@ -1573,20 +1616,35 @@ extern "C" int refil_tc_gemm_wgrad_group(const RefilWgradDesc* descs, int n_prob
         const size_t raw_bytes = 32 * 128 * 4, y_stage = 2 * (size_t)32 * a.BQ * 4;
         geo.raw_stages = has_r ? 3 : 4;
         const size_t raw_total = (size_t)geo.raw_stages * raw_bytes * (has_r ? 2 : 1);
-        int ys = (int)((225 * 1024 - raw_total) / y_stage);
+        // Y: raw chunks by TMA into their own ring (the producers only split hi / lo out of shared memory) unless a problem reads
+        // shifted rows (GRU h_{t-1}); REFIL_TCW_Y=ldg keeps the register-staged global loads (A/B runs)
+        static int y_ldg = -1;
+        if (y_ldg < 0) {
+            const char* e = getenv("REFIL_TCW_Y");
+            y_ldg = (e && e[0] == 'l') ? 1 : 0;
+        }
+        int y_tma = y_ldg ? 0 : 1;
+        for (int g = 0; g < n_problems; g++)
+            if (grp.a[g].y_shift != 0) y_tma = 0;
+        const size_t yraw_bytes = (size_t)32 * Q * 4;
+        geo.y_raw_stages = y_tma ? (has_r ? 3 : 4) : 0;
+        int ys = (int)((225 * 1024 - raw_total - geo.y_raw_stages * yraw_bytes) / y_stage);
         if (ys > TC_MAX_STAGES) ys = TC_MAX_STAGES;
+        if (y_tma && ys > 3) ys = 3;                  // the raw ring holds the latency; the split tiles only double-buffer the MMA
         REFIL_CHECK_ARG(ys >= 2, "tc_gemm_wgrad: shared memory budget (Q=%d)", Q);
         geo.y_stages = ys;
-        TcMaps mx{}, mr{};
+        TcMaps mx{}, mr{}, my{};
         for (int g = 0; g < n_problems; g++) {
             grp.a[g].idesc = idesc;
+            grp.a[g].y_tma = y_tma;
             const RefilWgradDesc& d = descs[g];
-            if (!tc_make_tmap_rows(&mx.m[g], d.X, d.ldx, d.M, P) || (has_r && !tc_make_tmap_rows(&mr.m[g], d.relu_y, d.ldy, d.M, P))) {
+            if (!tc_make_tmap_rows(&mx.m[g], d.X, d.ldx, d.M, P) || (has_r && !tc_make_tmap_rows(&mr.m[g], d.relu_y, d.ldy, d.M, P)) ||
+                (y_tma && !tc_make_tmap_rows(&my.m[g], d.Y, d.ldyy, d.M, Q, Q))) {
                 refil_set_error("tc_gemm_wgrad: cuTensorMapEncodeTiled failed (X=%p ldx=%lld M=%d P=%d)", (const void*)d.X, d.ldx, d.M, P);
                 return REFIL_ERR_CUDA;
             }
         }
-        const size_t smem = raw_total + (size_t)ys * y_stage + 1024;
+        const size_t smem = raw_total + geo.y_raw_stages * yraw_bytes + (size_t)ys * y_stage + 1024;
         static size_t attr_smem_ts = 0;
         if (smem > attr_smem_ts) {
             cudaError_t e = cudaFuncSetAttribute(tc_wgrad_ts_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1598,8 +1656,8 @@ extern "C" int refil_tc_gemm_wgrad_group(const RefilWgradDesc* descs, int n_prob
             attr_smem_ts = smem;
         }
         cudaError_t le = n_problems == 1
-            ? refil_launch(tc_wgrad_ts_kernel<false>, dim3(max_grid, 1), dim3(TW_THREADS), smem, stream, true, grp, geo, mx, mr)
-            : refil_launch(tc_wgrad_ts_kernel<true>, dim3(max_grid, n_problems), dim3(TW_THREADS), smem, stream, true, grp, geo, mx, mr);
+            ? refil_launch(tc_wgrad_ts_kernel<false>, dim3(max_grid, 1), dim3(TW_THREADS), smem, stream, true, grp, geo, mx, mr, my)
+            : refil_launch(tc_wgrad_ts_kernel<true>, dim3(max_grid, n_problems), dim3(TW_THREADS), smem, stream, true, grp, geo, mx, mr, my);
         if (le != cudaSuccess) {
             refil_set_error("tc_gemm_wgrad (ts): launch failed: %s", cudaGetErrorString(le));
             return REFIL_ERR_CUDA;

@@ -26,6 +26,7 @@ for B in $BATCHES; do
       crit*) EXTRA="--crit-tiles ${L#crit}" run $L $B A=1;;
       noprio*) EXTRA="--no-prio --crit-tiles ${L#noprio}" run $L $B A=1;;
       attn_generic) EXTRA="" run attn_generic $B REFIL_ATTN=generic;;
+      y_ldg) EXTRA="" run y_ldg $B REFIL_TCW_Y=ldg;;
       pdl0) EXTRA="" run pdl0 $B REFIL_PDL=0;;
       pdl0_nogroup) EXTRA="--no-group" run pdl0_nogroup $B REFIL_PDL=0;;
       tiles*) EXTRA="" run $L $B REFIL_TC_MIN_TILES=${L#tiles};;
