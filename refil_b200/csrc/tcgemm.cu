@@ -1443,22 +1443,22 @@ __global__ void __launch_bounds__(TW_THREADS, 1) tc_wgrad_ts_kernel(const __grid
         }
     } else if (warp == TW_TMA_WARP) {
         // ===================== TMA producer: raw X (and relu_y) chunks =====================
-        // lane 0 streams the X (and relu_y) chunks, lane 1 the raw Y chunks: two independent rings
+        // one lane streams the X (and relu_y) chunks and the raw Y chunks: two rings, issued in chunk order (a slot of either ring
+        // frees once the MMAs of an EARLIER chunk have retired, and every earlier chunk of both rings has been requested by then)
         if (lane == 0) {
-            int st = pre % RS;
-            uint32_t ph = (uint32_t)(pre / RS) & 1u;
-            for (int ch = pre; ch < n_chunks; ch++) {
-                mbar_wait(&xr_empty[st], ph ^ 1);
-                tma_chunk(st, ch);
-                if (++st == RS) { st = 0; ph ^= 1; }
-            }
-        } else if (lane == 1 && a.y_tma) {
-            int st = pre_y % RY;
-            uint32_t ph = (uint32_t)(pre_y / RY) & 1u;
-            for (int ch = pre_y; ch < n_chunks; ch++) {
-                mbar_wait(&yr_empty[st], ph ^ 1);
-                tma_ychunk(st, ch);
-                if (++st == RY) { st = 0; ph ^= 1; }
+            int sx = pre % RS, sy = a.y_tma ? pre_y % RY : 0;
+            uint32_t phx = (uint32_t)(pre / RS) & 1u, phy = a.y_tma ? (uint32_t)(pre_y / RY) & 1u : 0u;
+            for (int ch = min(pre, a.y_tma ? pre_y : pre); ch < n_chunks; ch++) {
+                if (ch >= pre) {
+                    mbar_wait(&xr_empty[sx], phx ^ 1);
+                    tma_chunk(sx, ch);
+                    if (++sx == RS) { sx = 0; phx ^= 1; }
+                }
+                if (a.y_tma && ch >= pre_y) {
+                    mbar_wait(&yr_empty[sy], phy ^ 1);
+                    tma_ychunk(sy, ch);
+                    if (++sy == RY) { sy = 0; phy ^= 1; }
+                }
             }
         }
         __syncwarp();
@@ -1627,7 +1627,11 @@ extern "C" int refil_tc_gemm_wgrad_group(const RefilWgradDesc* descs, int n_prob
         for (int g = 0; g < n_problems; g++)
             if (grp.a[g].y_shift != 0) y_tma = 0;
         const size_t yraw_bytes = (size_t)32 * Q * 4;
-        geo.y_raw_stages = y_tma ? (has_r ? 3 : 4) : 0;
+        // The raw ring depth must be EVEN: the two producer groups take alternate chunks, so with an even ring every slot always
+        // belongs to the same group and that group's previous visit orders the slot's phases.  With an odd ring a group could ask
+        // for chunk c + 3 of a slot while chunk c (the other group's) is still in flight -- TMA completions are not ordered -- and the
+        // one-bit parity wait would pass a phase early (seen as a launch failure at 39 chunks per CTA with all SMs loaded).
+        geo.y_raw_stages = y_tma ? ((225 * 1024 - raw_total - 4 * yraw_bytes) >= 2 * y_stage ? 4 : 2) : 0;
         int ys = (int)((225 * 1024 - raw_total - geo.y_raw_stages * yraw_bytes) / y_stage);
         if (ys > TC_MAX_STAGES) ys = TC_MAX_STAGES;
         if (y_tma && ys > 3) ys = 3;                  // the raw ring holds the latency; the split tiles only double-buffer the MMA
