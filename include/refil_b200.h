@@ -155,8 +155,18 @@ typedef struct RefilGemmDesc {
     const uint8_t* c_row_entity_mask; int c_na, c_ne, c_rows_per_copy;
     float* C; long long ldc;
     int M;
+    int row_group, row_group_stride;   /* > 0: row m of A and of C is physical row (m / row_group) * row_group_stride + m % row_group */
+    int accumulate;                    /* C += A B^T instead of C = (linear epilogue only) */
 } RefilGemmDesc;
 int refil_tc_gemm_tn_group(const RefilGemmDesc* descs, int n_problems, int N, int K, cudaStream_t stream);
+
+/* The same product on ROW GROUPS: only the first group_rows of every group_stride rows of A are read and only those rows of C are
+ * written -- the agent rows of an [N, n_entities, d] entity tensor.  The attention layer of the reference computes queries for all
+ * entities and keeps the agents' (modules/layers/attention.py:46-48, `query = query[:n_queries]` right after in_trans): here the Q
+ * third of in_trans runs on the agent rows alone.  accumulate: C += (the matching piece of the backward). */
+int refil_tc_gemm_tn_rows(const float* A, long long lda, const float* B, long long b_stride_n, long long b_stride_k,
+                          float* C, long long ldc, int n_groups, int group_rows, int group_stride, int accumulate,
+                          int N, int K, cudaStream_t stream);
 
 /* weight gradient on the tensor cores: dW[P,Q] += g(X)[M,P]^T Y[M,Q]; db[P] += colsum g(X) (db may be null).
  * y_shift_rows > 0: Y row m is read from row m - y_shift_rows and is zero where (m / y_shift_rows) % y_period == 0

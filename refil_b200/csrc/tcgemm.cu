@@ -60,6 +60,8 @@ struct TcArgs {
     int M, N, K;                             // K = whole reduction length
     int KS, k_slices;                        // reduction length of one k-slice (multiple of 32), K / KS
     int BN, n_tiles, m_tiles, stages;
+    int row_group;                           // > 0: row m of A and C is physical row (m / row_group) * stride + m % row_group (rank-3 tensor maps)
+    int accumulate;                          // C += A B^T (reduce-add stores, no clearing of C)
     uint32_t idesc;
 };
 
@@ -150,6 +152,15 @@ __device__ __forceinline__ void tc_tma_store(const CUtensorMap* tmap, int col, i
 __device__ __forceinline__ void tc_tma_reduce_add(const CUtensorMap* tmap, int col, int row, uint32_t saddr) {
     asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2}], [%3];"
                  ::"l"(tmap), "r"(col), "r"(row), "r"(saddr) : "memory");
+}
+// the same for a row-grouped C (rank-3 map: column, row inside the group, group)
+__device__ __forceinline__ void tc_tma_store3(const CUtensorMap* tmap, int col, int grp, uint32_t saddr) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];"
+                 ::"l"(tmap), "r"(col), "r"(0), "r"(grp), "r"(saddr) : "memory");
+}
+__device__ __forceinline__ void tc_tma_reduce_add3(const CUtensorMap* tmap, int col, int grp, uint32_t saddr) {
+    asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2, %3}], [%4];"
+                 ::"l"(tmap), "r"(col), "r"(0), "r"(grp), "r"(saddr) : "memory");
 }
 __device__ __forceinline__ void tc_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tc_bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
@@ -298,7 +309,11 @@ __device__ __forceinline__ void tc_epilogue(const TcArgs& a, const CUtensorMap* 
                 fence_async_smem();                        // staging writes -> visible to the TMA (async proxy)
                 __syncwarp();
                 if (lane == 0 && row0 < a.M) {
-                    if (a.k_slices > 1) tc_tma_reduce_add(tmap_c, nt * BN + c0, row0, stg_addr);
+                    const bool add = a.k_slices > 1 || a.accumulate;
+                    if (a.row_group > 0) {
+                        if (add) tc_tma_reduce_add3(tmap_c, nt * BN + c0, row0 / a.row_group, stg_addr);
+                        else tc_tma_store3(tmap_c, nt * BN + c0, row0 / a.row_group, stg_addr);
+                    } else if (add) tc_tma_reduce_add(tmap_c, nt * BN + c0, row0, stg_addr);
                     else tc_tma_store(tmap_c, nt * BN + c0, row0, stg_addr);
                     tc_bulk_commit();
                 }
@@ -546,11 +561,18 @@ __global__ void __launch_bounds__(TS_THREADS, 1) tc_gemm_ts_kernel(const __grid_
     auto tma_chunk = [&](int st, int mt, int kc) {
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&raw_full[st])), "r"(raw_bytes)
                      : "memory");
-        asm volatile(
-            "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-            ::"r"(smem_u32(smem_r + (size_t)st * raw_bytes)), "l"(&tmap_a), "r"(k_off + kc * TC_BK), "r"(mt * TC_BM),
-              "r"(smem_u32(&raw_full[st]))
-            : "memory");
+        if (a.row_group > 0)          // row-grouped A: (column, row inside the group, group) -- the box lands as the same 128 x 32 chunk
+            asm volatile(
+                "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                ::"r"(smem_u32(smem_r + (size_t)st * raw_bytes)), "l"(&tmap_a), "r"(k_off + kc * TC_BK), "r"(0),
+                  "r"(mt * TC_BM / a.row_group), "r"(smem_u32(&raw_full[st]))
+                : "memory");
+        else
+            asm volatile(
+                "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                ::"r"(smem_u32(smem_r + (size_t)st * raw_bytes)), "l"(&tmap_a), "r"(k_off + kc * TC_BK), "r"(mt * TC_BM),
+                  "r"(smem_u32(&raw_full[st]))
+                : "memory");
     };
     const int pre = min(total, TS_RAW_STAGES);                 // chunks requested before the prologue
     if (threadIdx.x == TS_TMA_WARP * 32) {
@@ -741,6 +763,23 @@ static int tc_make_tmap_a(CUtensorMap* tm, const float* A, long long lda, int M,
     return r == CUDA_SUCCESS ? 1 : 0;
 }
 
+// Row-grouped operands: logical row m = g * R + i (i < R) lives at physical row g * S + i (the first R of every S rows: the agent
+// rows of an [N, ne, d] entity tensor).  Rank-3 maps (column, i, g) whose boxes (32, R, 128 / R) resp. (32, R, 32 / R) land in
+// shared memory exactly like the rank-2 boxes (32 columns x 128 resp. 32 rows, 128B swizzle), so the kernel only changes coordinates.
+static int tc_make_tmap_grouped(CUtensorMap* tm, const float* P, long long ld, int G, int cols, int R, int S, int box_rows, bool load) {
+    memset(tm, 0, sizeof(*tm));
+    tc_encode_fn enc = tc_encoder();
+    if (!enc) return 0;
+    const cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)R, (cuuint64_t)G};
+    const cuuint64_t strides[2] = {(cuuint64_t)ld * 4, (cuuint64_t)S * ld * 4};
+    const cuuint32_t box[3] = {32, (cuuint32_t)R, (cuuint32_t)(box_rows / R)};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)P, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, load ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 1 : 0;
+}
+
 // CUtensorMap of a row-major [M][P] fp32 matrix with a (128 columns, 32 rows) box, no swizzle: one raw reduction chunk of
 // the weight-gradient kernel; columns >= P and rows >= M are zero-filled
 static int tc_make_tmap_rows(CUtensorMap* tm, const float* X, long long ldx, int M, int P, int box_cols = 128) {
@@ -852,6 +891,22 @@ static int tc_fill(const RefilGemmDesc& d, int N, int K, int mode_ts, TcArgs& a,
     a.m_tiles = refil_cdiv(M, TC_BM);
     // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=tf32, both K-major, N>>3, M>>4
     a.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    a.accumulate = d.accumulate ? 1 : 0;
+    REFIL_CHECK_ARG(!a.accumulate || (!d.bias && !d.relu && !d.c_row_entity_mask), "tc_gemm_tn: accumulate cannot carry a non-linear epilogue");
+    if (d.row_group > 0) {
+        const int R = d.row_group;
+        REFIL_CHECK_ARG(mode_ts && (32 % R) == 0 && d.row_group_stride >= R && (M % R) == 0,
+                        "tc_gemm_tn: row groups of %d rows (stride %d, M=%d) need the tensor-memory path, R | 32 and R | M", R,
+                        d.row_group_stride, M);
+        REFIL_CHECK_ARG(!d.relu_y && !d.a_row_entity_mask && !d.c_row_entity_mask, "tc_gemm_tn: row groups cannot carry row functors");
+        a.row_group = R;
+        if (!tc_make_tmap_grouped(tmap_c, d.C, d.ldc, M / R, N, R, d.row_group_stride, 32, false) ||
+            !tc_make_tmap_grouped(tmap_a, d.A, d.lda, M / R, K, R, d.row_group_stride, TC_BM, true)) {
+            refil_set_error("tc_gemm_tn: cuTensorMapEncodeTiled failed for row groups (R=%d S=%d M=%d N=%d K=%d)", R, d.row_group_stride, M, N, K);
+            return REFIL_ERR_CUDA;
+        }
+        return REFIL_OK;
+    }
     if (!tc_make_tmap_c(tmap_c, d.C, d.ldc, M, N) || (mode_ts && !tc_make_tmap_a(tmap_a, d.A, d.lda, M, K))) {
         refil_set_error("tc_gemm_tn: cuTensorMapEncodeTiled failed (A=%p lda=%lld C=%p ldc=%lld M=%d N=%d K=%d)", (const void*)d.A,
                         d.lda, (const void*)d.C, d.ldc, M, N, K);
@@ -898,6 +953,8 @@ extern "C" int refil_tc_gemm_tn_group(const RefilGemmDesc* descs, int n_problems
     }
     if (a0.k_slices > 1) {            // partial tiles are reduce-added into C
         for (int g = 0; g < n_problems; g++) {
+            if (grp.a[g].accumulate) continue;
+            REFIL_CHECK_ARG(grp.a[g].row_group == 0, "tc_gemm_tn: a sliced reduction into row groups must accumulate");
             cudaError_t e = cudaMemset2DAsync(descs[g].C, (size_t)descs[g].ldc * 4, 0, (size_t)N * 4, (size_t)descs[g].M, stream);
             if (e != cudaSuccess) {
                 refil_set_error("tc_gemm_tn: cudaMemset2DAsync: %s", cudaGetErrorString(e));
@@ -949,7 +1006,16 @@ extern "C" int refil_tc_gemm_tn(const float* A, long long lda, const float* relu
                                 const float* bias, int relu, const uint8_t* c_row_entity_mask, int c_na, int c_ne,
                                 int c_rows_per_copy, float* C, long long ldc, int M, int N, int K, cudaStream_t stream) {
     RefilGemmDesc d{A, lda, relu_y, ldy, a_row_entity_mask, a_na, a_ne, a_rows_per_copy, B, b_stride_n, b_stride_k, b_k_valid,
-                    bias, relu, c_row_entity_mask, c_na, c_ne, c_rows_per_copy, C, ldc, M};
+                    bias, relu, c_row_entity_mask, c_na, c_ne, c_rows_per_copy, C, ldc, M, 0, 0, 0};
+    return refil_tc_gemm_tn_group(&d, 1, N, K, stream);
+}
+
+extern "C" int refil_tc_gemm_tn_rows(const float* A, long long lda, const float* B, long long b_stride_n, long long b_stride_k,
+                                     float* C, long long ldc, int n_groups, int group_rows, int group_stride, int accumulate,
+                                     int N, int K, cudaStream_t stream) {
+    RefilGemmDesc d{};
+    d.A = A; d.lda = lda; d.B = B; d.b_stride_n = b_stride_n; d.b_stride_k = b_stride_k; d.C = C; d.ldc = ldc;
+    d.M = n_groups * group_rows; d.row_group = group_rows; d.row_group_stride = group_stride; d.accumulate = accumulate;
     return refil_tc_gemm_tn_group(&d, 1, N, K, stream);
 }
 

@@ -89,7 +89,10 @@ class AttnTrunk:
         att = ws.get(tag + ".att", (C * N * na, d))
         if self.pool is None:
             qkv = ws.get(tag + ".qkv", (N * ne, 3 * d))
-            ops.linear_fwd(x1, p[pre + "attn.in_trans.weight"], None, qkv)
+            if ops.qkv_split_ok(N, ne, na, d):    # queries for the agent rows only (the reference slices them after in_trans)
+                ops.in_trans_fwd_split(x1, p[pre + "attn.in_trans.weight"], qkv, N, ne, na)
+            else:
+                ops.linear_fwd(x1, p[pre + "attn.in_trans.weight"], None, qkv)
             ops.masked_attn_fwd(qkv, att, masks.copies, masks.group_bits, masks.entity_mask, N, T, ne, na, d, self.H)
         else:                               # pooling ablation: qkv holds E = in_trans(x1) [N*ne, d]
             qkv = ws.get(tag + ".qkv", (N * ne, d))

@@ -94,6 +94,19 @@ def _call(name, *args, shape=None, as_name=None):
         _shape_timing.setdefault("%s[%s]" % (name, "x".join(str(int(x)) for x in shape)), []).append((a, b))
 
 
+def _pv(t, dtype=None):
+    """device pointer of a 2-D CUDA tensor with contiguous rows -- a matrix or a column slice of a wider one (row stride = stride(0))"""
+    if t.is_contiguous():
+        return _p(t, dtype)
+    if not t.is_cuda:
+        raise _lib.RefilError("refil_b200 kernels need CUDA tensors (got a %s tensor); there is no CPU fallback" % t.device)
+    if t.dim() != 2 or t.stride(1) != 1:
+        raise _lib.RefilError("tensor of shape %s / strides %s is not a row-strided matrix" % (tuple(t.shape), tuple(t.stride())))
+    if dtype is not None and t.dtype != dtype:
+        raise _lib.RefilError("expected dtype %s, got %s" % (dtype, t.dtype))
+    return t.data_ptr()
+
+
 F32, U8, I32, I64, F64 = torch.float32, torch.uint8, torch.int32, torch.int64, torch.float64
 
 
@@ -139,9 +152,50 @@ def tc_gemm_tn(A, B, sbn, sbk, out, N, K, bias=None, relu=False, relu_y=None, a_
     aem, ana, ane, amper = _rm(a_row_mask)
     cem, cna, cne, cmper = _rm(c_row_mask)
     _account("tc_gemm_tn", 2.0 * M * N * K, 4.0 * (M * K * (2 if relu_y is not None else 1) + M * N + N * K))
-    _call("tc_gemm_tn", _p(A, F32), A.shape[1], _p(relu_y, F32), A.shape[1], aem, ana, ane, amper, _p(B, F32), sbn, sbk,
-          int(k_valid), _p(bias, F32), int(relu), cem, cna, cne, cmper, _p(out, F32), out.shape[1], M, N, K, shape=(M, N, K))
+    _call("tc_gemm_tn", _pv(A, F32), A.stride(0), _p(relu_y, F32), A.shape[1], aem, ana, ane, amper, _pv(B, F32), sbn, sbk,
+          int(k_valid), _p(bias, F32), int(relu), cem, cna, cne, cmper, _pv(out, F32), out.stride(0), M, N, K, shape=(M, N, K))
     return out
+
+
+QKV_SPLIT_MIN_ROWS = 65536   # entity rows from which in_trans is split into K|V (all rows) and Q (agent rows only)
+
+
+def qkv_split_ok(n_units, ne, na, d):
+    """Split in_trans into a K|V product over all entity rows and a Q product over the agent rows alone?  The reference computes
+    queries for every entity and keeps the agents' (modules/layers/attention.py:46-48); the other 2/3 of the Q third are never read.
+    REFIL_QKV_SPLIT=0 / 1 forces the choice (A/B runs)."""
+    import os
+    env = os.environ.get("REFIL_QKV_SPLIT")
+    if env == "0" or not USE_TENSOR_CORES or na >= ne or 32 % na != 0 or os.environ.get("REFIL_TC_MODE") == "ss":
+        return False
+    if not (_tc_ok(n_units * ne, 2 * d, d) and _tc_ok(n_units * na, d, d) and _lib.load().refil_tc_gemm_k_slices(d, 2 * d) >= 1):
+        return False
+    return env == "1" or n_units * ne >= QKV_SPLIT_MIN_ROWS
+
+
+def tc_gemm_tn_rows(A, W, out, n_groups, group_rows, group_stride, accumulate=False, transpose_w=False):
+    """Row-grouped product on the first `group_rows` of every `group_stride` rows of A and out (refil_tc_gemm_tn_rows):
+    out (+)= A W^T, or A W with transpose_w (backward-data).  A / out may be column slices of wider matrices."""
+    if transpose_w:
+        K, N = W.shape
+        sbn, sbk = 1, W.stride(0)
+    else:
+        N, K = W.shape
+        sbn, sbk = W.stride(0), 1
+    M = n_groups * group_rows
+    _account("tc_gemm_tn", 2.0 * M * N * K, 4.0 * (M * K + M * N * (2 if accumulate else 1) + N * K))
+    _call("tc_gemm_tn_rows", _pv(A, F32), A.stride(0), _pv(W, F32), sbn, sbk, _pv(out, F32), out.stride(0), n_groups, group_rows,
+          group_stride, int(accumulate), N, K, shape=(M, N, K), as_name="tc_gemm_tn")
+    return out
+
+
+def in_trans_fwd_split(x1, W, qkv, n_units, ne, na):
+    """qkv[:, d:] = x1 W[d:]^T for every entity row, qkv[agent rows, :d] = x1[agent rows] W[:d]^T; the Q columns of the other rows
+    are left unwritten (nothing reads them: the attention kernels take queries from the agent rows only)."""
+    d = x1.shape[1]
+    tc_gemm_tn(x1, W[d:], W.stride(0), 1, qkv[:, d:], 2 * d, d)
+    tc_gemm_tn_rows(x1, W[:d], qkv, n_units, na, ne)
+    return qkv
 
 
 # ---- grouped launches: the same layer of several networks in ONE kernel launch (include/refil_b200.h: RefilGemmDesc) ----------
@@ -154,7 +208,8 @@ class _GemmDesc(_ct.Structure):
                 ("B", _ct.c_void_p), ("sbn", _ct.c_longlong), ("sbk", _ct.c_longlong), ("b_k_valid", _ct.c_int),
                 ("bias", _ct.c_void_p), ("relu", _ct.c_int),
                 ("c_mask", _ct.c_void_p), ("c_na", _ct.c_int), ("c_ne", _ct.c_int), ("c_mper", _ct.c_int),
-                ("C", _ct.c_void_p), ("ldc", _ct.c_longlong), ("M", _ct.c_int)]
+                ("C", _ct.c_void_p), ("ldc", _ct.c_longlong), ("M", _ct.c_int),
+                ("row_group", _ct.c_int), ("row_group_stride", _ct.c_int), ("accumulate", _ct.c_int)]
 
 
 class _WgradDesc(_ct.Structure):

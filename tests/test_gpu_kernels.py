@@ -481,3 +481,64 @@ def test_grouped_dense_launches_match_single_launches():
     for x, w, b, o in zip(X, W3, b3, o3):
         ref = (x @ w.t() + b).view(C, Nn, na, 32).masked_fill(em[:, :na].bool().view(1, Nn, na, 1), 0.0).view(-1, 32)
         _close(o, ref, atol=1e-4, what="group rowmask")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("units,ne,na", [(200, 24, 8), (61, 16, 4)])
+def test_row_grouped_dense_product_touches_only_the_agent_rows(units, ne, na):
+    """refil_tc_gemm_tn_rows: C[g*ne + i] (+)= A[g*ne + i] W^T for i < na only -- the Q third of in_trans on the agent rows
+    (attention.py:46-48).  The other rows of C keep their (NaN) contents; accumulate adds into C."""
+    from refil_b200 import ops
+    d = 128
+    g = torch.Generator().manual_seed(units)
+    A = torch.randn(units * ne, d, generator=g)
+    W = torch.randn(d, d, generator=g) * 0.2
+    C = torch.full((units * ne, 3 * d), float("nan"), device=DEV)
+    ops.tc_gemm_tn_rows(A.to(DEV), W.to(DEV), C, units, na, ne)
+    torch.cuda.synchronize()
+    ref = (A.double() @ W.double().t()).view(units, ne, d)
+    got = C.cpu().view(units, ne, 3 * d)
+    scale = (A.abs().double() @ W.abs().double().t()).max().item()
+    assert (got[:, :na, :d].double() - ref[:, :na]).abs().max().item() <= 4e-6 * scale
+    assert torch.isnan(got[:, na:]).all() and torch.isnan(got[:, :na, d:]).all()
+    # accumulate, transposed weight (the backward-data form) into a column slice
+    D = torch.ones(units * ne, d, device=DEV)
+    G = torch.randn(units * ne, 3 * d, generator=g)
+    ops.tc_gemm_tn_rows(G.to(DEV)[:, :d], W.to(DEV), D, units, na, ne, accumulate=True, transpose_w=True)
+    torch.cuda.synchronize()
+    refd = (G[:, :d].double() @ W.double()).view(units, ne, d)
+    gd = D.cpu().view(units, ne, d)
+    scale = (G[:, :d].abs().double() @ W.abs().double()).max().item()
+    assert (gd[:, :na].double() - 1.0 - refd[:, :na]).abs().max().item() <= 4e-6 * scale
+    assert (gd[:, na:] == 1.0).all()
+
+
+@pytest.mark.gpu
+def test_split_in_trans_feeds_the_attention_kernels_like_the_full_product():
+    """K|V for all rows + Q for the agent rows (Q of the other rows left as NaN) gives the same attention output and the same
+    backward as the full in_trans product."""
+    from refil_b200 import ops
+    units, ne, na, d, H, T = 96, 24, 8, 128, 4, 8
+    g = torch.Generator().manual_seed(7)
+    x1 = torch.randn(units * ne, d, generator=g).to(DEV)
+    W = (torch.randn(3 * d, d, generator=g) * 0.2).to(DEV)
+    full = torch.empty(units * ne, 3 * d, device=DEV)
+    ops.linear_fwd(x1, W, None, full)
+    split = torch.full((units * ne, 3 * d), float("nan"), device=DEV)
+    ops.in_trans_fwd_split(x1, W, split, units, ne, na)
+    em = (torch.rand(units, ne, generator=g) < 0.2).to(torch.uint8).to(DEV)
+    om = (torch.rand(units, ne, ne, generator=g) < 0.3).to(torch.uint8).to(DEV)
+    copies = [(om, ne * ne, 0)]
+    outs, grads = [], []
+    dout = torch.randn(1, units, na, d, generator=g).to(DEV)
+    for qkv in (full, split):
+        out = torch.empty(1 * units * na, d, device=DEV)
+        ops.masked_attn_fwd(qkv, out, copies, None, em, units, T, ne, na, d, H)
+        dqkv = torch.empty(units * ne, 3 * d, device=DEV)
+        ops.masked_attn_bwd(qkv, dout.view(-1, d), dqkv, copies, None, em, units, T, ne, na, d, H)
+        outs.append(out)
+        grads.append(dqkv)
+    torch.cuda.synchronize()
+    assert torch.isfinite(outs[1]).all() and torch.isfinite(grads[1]).all()
+    assert (outs[0] - outs[1]).abs().max().item() <= 1e-5 * outs[0].abs().max().item()
+    assert (grads[0] - grads[1]).abs().max().item() <= 1e-5 * grads[0].abs().max().item()

@@ -77,13 +77,17 @@ def test_train_step_matches_reference(name):
         assert float((learner.mixer.store.p[k].cpu() - p).abs().max()) <= 1e-4, k
 
 
-@pytest.mark.parametrize("alg", ["refil", "qmix_atten", "refil_gm", "refil_pool_mean", "refil_pool_max", "refil_cfg5"])
-def test_train_step_matches_oracle_mid_size(alg):
+@pytest.mark.parametrize("alg", ["refil", "qmix_atten", "refil_gm", "refil_pool_mean", "refil_pool_max", "refil_cfg5", "refil_qsplit"])
+def test_train_step_matches_oracle_mid_size(alg, monkeypatch):
     """Same seeded inputs through the CUDA path and the CPU oracle at a size the oracle finishes in seconds.  `refil_cfg5` is
     BASELINE config 5's shape (sc2 3-8csz: 16 entities, T = 120) on 2 episodes; `refil_pool_*` the EntityPoolingLayer ablation at
-    the real layer widths."""
+    the real layer widths; `refil_qsplit` forces the split in_trans (queries for the agent rows only, forward and backward) that
+    large shards take by default."""
     from oracle import learner_oracle as lo
     gen = torch.Generator().manual_seed(123)
+    if alg == "refil_qsplit":
+        monkeypatch.setenv("REFIL_QKV_SPLIT", "1")
+        alg = "refil"
     pool = alg.split("_pool_")[1] if "_pool_" in alg else None
     if alg == "refil_cfg5":
         B, T, na, ne, ed, A = 2, 120, 8, 16, 39, 14
