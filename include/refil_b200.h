@@ -157,6 +157,8 @@ typedef struct RefilGemmDesc {
     int M;
     int row_group, row_group_stride;   /* > 0: row m of A and of C is physical row (m / row_group) * row_group_stride + m % row_group */
     int accumulate;                    /* C += A B^T instead of C = (linear epilogue only) */
+    int n_cols;                        /* > 0: this problem has n_cols output columns instead of the group's N (same reduction length):
+                                          in_trans as ONE launch of K|V for all entity rows (2d columns) + Q for the agent rows (d) */
 } RefilGemmDesc;
 int refil_tc_gemm_tn_group(const RefilGemmDesc* descs, int n_problems, int N, int K, cudaStream_t stream);
 

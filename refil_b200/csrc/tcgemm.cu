@@ -862,8 +862,9 @@ static int tc_mode_ts() {
 }
 
 // one problem of a group: validate, fill TcArgs and the two tensor maps
-static int tc_fill(const RefilGemmDesc& d, int N, int K, int mode_ts, TcArgs& a, CUtensorMap* tmap_c, CUtensorMap* tmap_a) {
+static int tc_fill(const RefilGemmDesc& d, int N_group, int K, int mode_ts, TcArgs& a, CUtensorMap* tmap_c, CUtensorMap* tmap_a) {
     const int M = d.M;
+    const int N = d.n_cols > 0 ? d.n_cols : N_group;      // a problem may be narrower / wider than the group's N (same n-tile width)
     REFIL_CHECK_ARG(d.A && d.B && d.C, "tc_gemm_tn: null pointer");
     REFIL_CHECK_ARG(refil_tc_gemm_supported(M, N, K), "tc_gemm_tn: unsupported shape M=%d N=%d K=%d", M, N, K);
     REFIL_CHECK_ARG((d.lda % 4) == 0 && (d.ldc % 4) == 0 && ((uintptr_t)d.A % 16) == 0 && ((uintptr_t)d.C % 16) == 0,
@@ -930,6 +931,9 @@ extern "C" int refil_tc_gemm_tn_group(const RefilGemmDesc* descs, int n_problems
     }
     TcArgs& a0 = grp.a[0];
     const int BN = a0.BN;
+    for (int g = 1; g < n_problems; g++)
+        REFIL_CHECK_ARG(grp.a[g].BN == BN && grp.a[g].KS == a0.KS && grp.a[g].k_slices == a0.k_slices,
+                        "tc_gemm_tn_group: the problems of a group must share the n-tile width and the k-slicing");
     const size_t b_res = (size_t)2 * BN * a0.KS * 4, stage_bytes = 2 * (size_t)TC_BM * 128;
     const size_t stg_bytes = (size_t)TC_EPI_WARPS * TC_STG_BYTES;
     const size_t budget = 227 * 1024 - 1024 /* alignment slack */ - 2048 /* static: barriers, bias */;
@@ -955,7 +959,7 @@ extern "C" int refil_tc_gemm_tn_group(const RefilGemmDesc* descs, int n_problems
         for (int g = 0; g < n_problems; g++) {
             if (grp.a[g].accumulate) continue;
             REFIL_CHECK_ARG(grp.a[g].row_group == 0, "tc_gemm_tn: a sliced reduction into row groups must accumulate");
-            cudaError_t e = cudaMemset2DAsync(descs[g].C, (size_t)descs[g].ldc * 4, 0, (size_t)N * 4, (size_t)descs[g].M, stream);
+            cudaError_t e = cudaMemset2DAsync(descs[g].C, (size_t)descs[g].ldc * 4, 0, (size_t)grp.a[g].N * 4, (size_t)descs[g].M, stream);
             if (e != cudaSuccess) {
                 refil_set_error("tc_gemm_tn: cudaMemset2DAsync: %s", cudaGetErrorString(e));
                 return REFIL_ERR_CUDA;
@@ -963,17 +967,16 @@ extern "C" int refil_tc_gemm_tn_group(const RefilGemmDesc* descs, int n_problems
         }
     }
     const int sms = refil_num_sms();
-    const int groups = a0.n_tiles * a0.k_slices;
     // every CTA pays a fixed prologue (split of its resident weight tile, pipeline fill): give it at least `min_tiles` m-tiles, so
     // that a small problem (a 16-episode shard) leaves SMs to the independent networks running on the other streams
     const int min_tiles = tc_min_tiles();
-    long long sum_tiles = 0;
-    for (int g = 0; g < n_problems; g++) sum_tiles += grp.a[g].m_tiles;
+    long long sum_units = 0;                                  // (m-tile, n-tile, k-slice) units of the whole launch
+    for (int g = 0; g < n_problems; g++) sum_units += (long long)grp.a[g].m_tiles * grp.a[g].n_tiles * grp.a[g].k_slices;
     int begin = 0;
     for (int g = 0; g < n_problems; g++) {
         // CTAs per (n-tile, k-slice) of this problem: its share of one wave, in proportion to its m-tiles
-        const int mt = grp.a[g].m_tiles;
-        int per_g = (int)((long long)sms * mt / (sum_tiles * groups));
+        const int mt = grp.a[g].m_tiles, groups = grp.a[g].n_tiles * grp.a[g].k_slices;
+        int per_g = (int)((long long)sms * mt / sum_units);
         if (per_g < 1) per_g = 1;
         const int want = refil_cdiv(mt, min_tiles);
         if (per_g > want) per_g = want;
@@ -1006,7 +1009,7 @@ extern "C" int refil_tc_gemm_tn(const float* A, long long lda, const float* relu
                                 const float* bias, int relu, const uint8_t* c_row_entity_mask, int c_na, int c_ne,
                                 int c_rows_per_copy, float* C, long long ldc, int M, int N, int K, cudaStream_t stream) {
     RefilGemmDesc d{A, lda, relu_y, ldy, a_row_entity_mask, a_na, a_ne, a_rows_per_copy, B, b_stride_n, b_stride_k, b_k_valid,
-                    bias, relu, c_row_entity_mask, c_na, c_ne, c_rows_per_copy, C, ldc, M, 0, 0, 0};
+                    bias, relu, c_row_entity_mask, c_na, c_ne, c_rows_per_copy, C, ldc, M, 0, 0, 0, 0};
     return refil_tc_gemm_tn_group(&d, 1, N, K, stream);
 }
 
