@@ -209,3 +209,388 @@ def in_trans_fwd_split(x1, W, qkv, n_units, ne, na):
     _account("tc_gemm_tn", 2.0 * (M * 2 * d + n_units * na * d) * d, 4.0 * (M * d + M * 2 * d + n_units * na * d + 3 * d * d))
     _call("tc_gemm_tn_group", _ct.addressof(arr), 2, 2 * d, d, shape=(2, M, 2 * d, d), as_name="tc_gemm_tn")
     return qkv
+
+
+# ---- grouped launches: the same layer of several networks in ONE kernel launch (include/refil_b200.h: RefilGemmDesc) ----------
+import ctypes as _ct
+
+
+class _GemmDesc(_ct.Structure):
+    _fields_ = [("A", _ct.c_void_p), ("lda", _ct.c_longlong), ("relu_y", _ct.c_void_p), ("ldy", _ct.c_longlong),
+                ("a_mask", _ct.c_void_p), ("a_na", _ct.c_int), ("a_ne", _ct.c_int), ("a_mper", _ct.c_int),
+                ("B", _ct.c_void_p), ("sbn", _ct.c_longlong), ("sbk", _ct.c_longlong), ("b_k_valid", _ct.c_int),
+                ("bias", _ct.c_void_p), ("relu", _ct.c_int),
+                ("c_mask", _ct.c_void_p), ("c_na", _ct.c_int), ("c_ne", _ct.c_int), ("c_mper", _ct.c_int),
+                ("C", _ct.c_void_p), ("ldc", _ct.c_longlong), ("M", _ct.c_int),
+                ("row_group", _ct.c_int), ("row_group_stride", _ct.c_int), ("accumulate", _ct.c_int)]
+
+
+class _WgradDesc(_ct.Structure):
+    _fields_ = [("X", _ct.c_void_p), ("ldx", _ct.c_longlong), ("relu_y", _ct.c_void_p), ("ldy", _ct.c_longlong),
+                ("x_mask", _ct.c_void_p), ("na", _ct.c_int), ("ne", _ct.c_int), ("mper", _ct.c_int),
+                ("Y", _ct.c_void_p), ("ldyy", _ct.c_longlong), ("y_shift", _ct.c_int), ("y_period", _ct.c_int),
+                ("dW", _ct.c_void_p), ("lddw", _ct.c_longlong), ("q_valid", _ct.c_int),
+                ("db", _ct.c_void_p), ("M", _ct.c_int)]
+
+
+MAX_GROUP = 8
+
+
+def _group_ok(rows):
+    return USE_TENSOR_CORES and len(rows) > 1 and min(rows) >= TC_MIN_ROWS
+
+
+def linear_fwd_group(items):
+    """items: list of (A, W, bias, out, relu, row_mask) with one (N, K) geometry -> as few launches as possible (<= 8 problems
+    each); falls back to per-item linear_fwd when the shape is not tensor-core eligible."""
+    A0, W0 = items[0][0], items[0][1]
+    K, N = A0.shape[1], W0.shape[0]
+    same = all(it[0].shape[1] == K and it[1].shape == W0.shape and bool(it[4]) == bool(items[0][4]) for it in items)
+    sliced = _lib.load().refil_tc_gemm_k_slices(N, K) != 1
+    if not (same and _group_ok([it[0].shape[0] for it in items]) and all(_tc_ok(it[0].shape[0], N, K) for it in items)) or \
+            (sliced and any(it[2] is not None or it[4] or it[5] is not None for it in items)):
+        for A, W, bias, out, relu, rm in items:
+            linear_fwd(A, W, bias, out, relu=relu, row_mask=rm)
+        return
+    Kw = W0.shape[1]
+    for lo in range(0, len(items), MAX_GROUP):
+        part = items[lo:lo + MAX_GROUP]
+        arr = (_GemmDesc * len(part))()
+        for d, (A, W, bias, out, relu, rm) in zip(arr, part):
+            cem, cna, cne, cmper = _rm(rm)
+            M = A.shape[0]
+            d.A, d.lda, d.relu_y, d.ldy = _p(A, F32), K, None, K
+            d.a_mask, d.a_na, d.a_ne, d.a_mper = None, 1, 1, 1
+            d.B, d.sbn, d.sbk, d.b_k_valid = _p(W, F32), Kw, 1, (Kw if Kw != K else 0)
+            d.bias, d.relu = _p(bias, F32), int(relu)
+            d.c_mask, d.c_na, d.c_ne, d.c_mper = cem, cna, cne, cmper
+            d.C, d.ldc, d.M = _p(out, F32), out.shape[1], M
+            _account("tc_gemm_tn", 2.0 * M * N * K, 4.0 * (M * K + M * N + N * K))
+        _call("tc_gemm_tn_group", _ct.addressof(arr), len(part), N, K, shape=(len(part), part[0][0].shape[0], N, K),
+              as_name="tc_gemm_tn")
+
+
+def linear_bwd_data_group(items):
+    """items: list of (dC, W, dA, relu_y, row_mask): dA = g(dC) W, grouped like linear_fwd_group."""
+    dC0, W0 = items[0][0], items[0][1]
+    N, K = dC0.shape[1], W0.shape[1]
+    same = all(it[0].shape[1] == N and it[1].shape == W0.shape and (it[3] is None) == (items[0][3] is None) for it in items)
+    if not (same and _group_ok([it[0].shape[0] for it in items]) and all(_tc_ok(it[0].shape[0], K, N) for it in items)):
+        for dC, W, dA, relu_y, rm in items:
+            linear_bwd_data(dC, W, dA, relu_y=relu_y, row_mask=rm)
+        return
+    Nw = W0.shape[0]
+    for lo in range(0, len(items), MAX_GROUP):
+        part = items[lo:lo + MAX_GROUP]
+        arr = (_GemmDesc * len(part))()
+        for d, (dC, W, dA, relu_y, rm) in zip(arr, part):
+            aem, ana, ane, amper = _rm(rm)
+            M = dC.shape[0]
+            d.A, d.lda, d.relu_y, d.ldy = _p(dC, F32), N, _p(relu_y, F32), N
+            d.a_mask, d.a_na, d.a_ne, d.a_mper = aem, ana, ane, amper
+            d.B, d.sbn, d.sbk, d.b_k_valid = _p(W, F32), 1, K, (Nw if Nw != N else 0)     # "B"[j = k, i = n] = W[n * K + k]
+            d.bias, d.relu = None, 0
+            d.c_mask, d.c_na, d.c_ne, d.c_mper = None, 1, 1, 1
+            d.C, d.ldc, d.M = _p(dA, F32), K, M
+            _account("tc_gemm_tn", 2.0 * M * N * K, 4.0 * (M * N * (2 if relu_y is not None else 1) + M * K + N * K))
+        _call("tc_gemm_tn_group", _ct.addressof(arr), len(part), K, N, shape=(len(part), part[0][0].shape[0], K, N),
+              as_name="tc_gemm_tn")
+
+
+def linear_bwd_weight_group(items):
+    """items: list of (dC, A, dW, db, relu_y, row_mask): dW += g(dC)^T A, db += colsum g(dC), grouped."""
+    dC0, A0, dW0 = items[0][0], items[0][1], items[0][2]
+    N, K = dC0.shape[1], A0.shape[1]
+    P, Qv = dW0.shape
+    same = all(it[0].shape[1] == N and it[1].shape[1] == K and it[2].shape == dW0.shape and
+               (it[3] is None) == (items[0][3] is None) and (it[4] is None) == (items[0][4] is None) for it in items)
+    lib = _lib.load()
+    if not (same and _group_ok([it[0].shape[0] for it in items]) and N % 4 == 0 and
+            all(lib.refil_tc_wgrad_supported(it[0].shape[0], P, K) != 0 for it in items)):
+        for dC, A, dW, db, relu_y, rm in items:
+            linear_bwd_weight(dC, A, dW, db, relu_y=relu_y, row_mask=rm)
+        return
+    for lo in range(0, len(items), MAX_GROUP):
+        part = items[lo:lo + MAX_GROUP]
+        arr = (_WgradDesc * len(part))()
+        for d, (dC, A, dW, db, relu_y, rm) in zip(arr, part):
+            em, na, ne, mper = _rm(rm)
+            M = dC.shape[0]
+            d.X, d.ldx, d.relu_y, d.ldy = _p(dC, F32), N, _p(relu_y, F32), N
+            d.x_mask, d.na, d.ne, d.mper = em, na, ne, mper
+            d.Y, d.ldyy, d.y_shift, d.y_period = _p(A, F32), K, 0, 1
+            d.dW, d.lddw, d.q_valid, d.db, d.M = _p(dW, F32), Qv, (Qv if Qv != K else 0), _p(db, F32), M
+            _account("tc_gemm_wgrad", 2.0 * M * N * K, 4.0 * (M * N * (2 if relu_y is not None else 1) + M * K + N * K))
+        _call("tc_gemm_wgrad_group", _ct.addressof(arr), len(part), P, K, shape=(len(part), part[0][0].shape[0], N, K),
+              as_name="tc_gemm_wgrad")
+
+
+def linear_fwd(A, W, bias, out, relu=False, row_mask=None):
+    """out = [rowmask][relu](A W^T + bias).  A may be wider than W (zero-padded input columns, e.g. the packed fc1 input of 64
+    columns against the 53-column weight): the weight is read in place with the tail of the reduction taken as zero."""
+    M, K = A.shape
+    N, Kw = W.shape
+    if _tc_ok(M, N, K) and (_lib.load().refil_tc_gemm_k_slices(N, K) == 1 or (bias is None and not relu and row_mask is None)):
+        return tc_gemm_tn(A, W, Kw, 1, out, N, K, bias=bias, relu=relu, c_row_mask=row_mask, k_valid=Kw if Kw != K else 0)
+    if Kw != K:
+        raise _lib.RefilError("linear_fwd: input has %d columns, weight %d (only the tensor-core path takes a padded input)" % (K, Kw))
+    em, na, ne, mper = _rm(row_mask)
+    _call("linear_fwd", _p(A, F32), K, _p(W, F32), W.shape[1], _p(bias, F32), _p(out, F32), N, M, N, K, int(relu),
+          em, na, ne, mper)
+    return out
+
+
+def embed_fwd(entities, last_action, n_actions, W, bias, out, relu=True):
+    M = entities.numel() // entities.shape[-1]
+    ed = entities.shape[-1]
+    _call("embed_fwd", _p(entities, F32), ed, _p(last_action, I32), n_actions, _p(W, F32), _p(bias, F32), _p(out, F32),
+          M, W.shape[0], int(relu))
+    return out
+
+
+def linear_bwd_data(dC, W, dA, relu_y=None, row_mask=None):
+    """dA = g(dC) W.  dC may be wider than W has rows (zero-padded output columns, e.g. the 14-action head in 32 columns)."""
+    M, N = dC.shape
+    Nw, K = W.shape
+    if _tc_ok(M, K, N):      # dA[M,K] = g(dC)[M,N] W[N,K]: "B"[j=k, i=n] = W[n*K + k]
+        return tc_gemm_tn(dC, W, 1, K, dA, K, N, relu_y=relu_y, a_row_mask=row_mask, k_valid=Nw if Nw != N else 0)
+    if Nw != N:
+        raise _lib.RefilError("linear_bwd_data: gradient has %d columns, weight %d rows" % (N, Nw))
+    em, na, ne, mper = _rm(row_mask)
+    _call("linear_bwd_data", _p(dC, F32), N, _p(relu_y, F32), N, em, na, ne, mper, _p(W, F32), K, _p(dA, F32), K, M, N, K)
+    return dA
+
+
+def linear_bwd_weight(dC, A, dW, db, relu_y=None, row_mask=None):
+    """dW[P, Q] += g(dC)^T A, db += colsum g(dC).  dW may be narrower than A (zero-padded input columns: fc1) and have fewer
+    rows than dC has columns (zero-padded output columns: the action head); it is accumulated in place."""
+    M, N = dC.shape
+    K = A.shape[1]
+    P, Qv = dW.shape
+    em, na, ne, mper = _rm(row_mask)
+    if USE_TENSOR_CORES and M >= TC_MIN_ROWS and N % 4 == 0 and _lib.load().refil_tc_wgrad_supported(M, P, K) != 0:
+        _account("tc_gemm_wgrad", 2.0 * M * N * K, 4.0 * (M * N * (2 if relu_y is not None else 1) + M * K + N * K))
+        _call("tc_gemm_wgrad", _p(dC, F32), N, _p(relu_y, F32), N, em, na, ne, mper, _p(A, F32), K, 0, 1, _p(dW, F32), Qv,
+              Qv if Qv != K else 0, _p(db, F32), M, P, K, shape=(M, N, K))
+        return
+    if (P, Qv) != (N, K):
+        raise _lib.RefilError("linear_bwd_weight: padded operands need the tensor-core path")
+    _call("linear_bwd_weight", _p(dC, F32), N, _p(relu_y, F32), N, em, na, ne, mper, _p(A, F32), K, _p(dW, F32), K,
+          _p(db, F32), M, N, K)
+
+
+def embed_bwd_weight(dC, relu_y, entities, last_action, n_actions, dW, db):
+    M, N = dC.shape
+    _call("embed_bwd_weight", _p(dC, F32), N, _p(relu_y, F32), N, _p(entities, F32), entities.shape[-1],
+          _p(last_action, I32), n_actions, _p(dW, F32), _p(db, F32), M, N)
+
+
+def gru_bwd_weight_hh(dGH, HS, n_agents, T, dWhh, dbhh):
+    M, r = HS.shape
+    if USE_TENSOR_CORES and M >= TC_MIN_ROWS and _lib.load().refil_tc_wgrad_supported(M, 3 * r, r) != 0:
+        _call("tc_gemm_wgrad", _p(dGH, F32), 3 * r, None, 3 * r, None, 1, 1, 1, _p(HS, F32), r, n_agents, T,
+              _p(dWhh, F32), r, 0, _p(dbhh, F32), M, 3 * r, r)
+        return
+    _call("gru_bwd_weight_hh", _p(dGH, F32), _p(HS, F32), n_agents, T, _p(dWhh, F32), _p(dbhh, F32), M, r)
+
+
+def pack_inputs(entities, last_action, n_actions, out):
+    rows = entities.numel() // entities.shape[-1]
+    _call("pack_inputs", _p(entities, F32), entities.shape[-1], _p(last_action, I32), n_actions, _p(out, F32), rows,
+          out.shape[-1])
+    return out
+
+
+def last_action_index(actions, out, n_entities):
+    B, T, na = actions.shape[0], actions.shape[1], actions.shape[2]
+    _call("last_action_index", _p(actions, I64), _p(out, I32), B, T, na, n_entities)
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------- attention
+def _copies(copies):
+    m = [None, None, None]
+    s = [0, 0, 0]
+    mode = [0, 0, 0]
+    for i, (mask, stride, md) in enumerate(copies):
+        m[i] = _p(mask, U8)
+        s[i] = int(stride)
+        mode[i] = int(md)
+    return m + s + mode
+
+
+def masked_attn_fwd(qkv, out, copies, group_bits, entity_mask, N, T, ne, nq, d, H):
+    # SURVEY.md section 8d: algorithmic bytes per (b, t, copy) unit = 4d(2ne + 2nq) + nq*ne, flops = 4*nq*ne*d
+    _account("masked_attn_fwd", 4.0 * nq * ne * d * N * len(copies), (4.0 * d * (2 * ne + 2 * nq) + nq * ne) * N * len(copies))
+    _call("masked_attn_fwd", _p(qkv, F32), _p(out, F32), *_copies(copies), _p(group_bits, U8), _p(entity_mask, U8),
+          N, T, ne, nq, d, H, len(copies))
+    return out
+
+
+def masked_attn_bwd(qkv, dout, dqkv, copies, group_bits, entity_mask, N, T, ne, nq, d, H):
+    _account("masked_attn_bwd", 10.0 * nq * ne * d * N * len(copies),
+             (4.0 * d * (2 * ne + 2 * nq) * 2 + nq * ne) * N * len(copies))
+    _call("masked_attn_bwd", _p(qkv, F32), _p(dout, F32), _p(dqkv, F32), *_copies(copies), _p(group_bits, U8),
+          _p(entity_mask, U8), N, T, ne, nq, d, H, len(copies))
+    return dqkv
+
+
+POOL_TYPES = {"mean": 0, "max": 1}
+
+
+def entity_pool_fwd(E, out, copies, group_bits, entity_mask, N, T, ne, nq, d, pool_type):
+    """EntityPoolingLayer between in_trans and out_trans (attention.py:111-124): E [N*ne, d] -> out [C*N*nq, d]."""
+    _account("entity_pool_fwd", 0.0, 4.0 * d * (ne + nq * len(copies)) * N)
+    _call("entity_pool_fwd", _p(E, F32), _p(out, F32), *_copies(copies), _p(group_bits, U8), _p(entity_mask, U8),
+          N, T, ne, nq, d, len(copies), POOL_TYPES[pool_type])
+    return out
+
+
+def entity_pool_bwd(E, dout, dE, copies, group_bits, entity_mask, N, T, ne, nq, d, pool_type):
+    _account("entity_pool_bwd", 0.0, 4.0 * d * (2 * ne + nq * len(copies)) * N)
+    _call("entity_pool_bwd", _p(E, F32), _p(dout, F32), _p(dE, F32), *_copies(copies), _p(group_bits, U8),
+          _p(entity_mask, U8), N, T, ne, nq, d, len(copies), POOL_TYPES[pool_type])
+    return dE
+
+
+class _AttnDesc(_ct.Structure):
+    _fields_ = [("qkv", _ct.c_void_p), ("out", _ct.c_void_p), ("dout", _ct.c_void_p), ("dqkv", _ct.c_void_p),
+                ("mask0", _ct.c_void_p), ("mask1", _ct.c_void_p), ("mask2", _ct.c_void_p),
+                ("s0", _ct.c_longlong), ("s1", _ct.c_longlong), ("s2", _ct.c_longlong),
+                ("m0", _ct.c_int), ("m1", _ct.c_int), ("m2", _ct.c_int),
+                ("group_bits", _ct.c_void_p), ("entity_mask", _ct.c_void_p), ("n_copies", _ct.c_int)]
+
+
+def _attn_descs(items, fwd):
+    arr = (_AttnDesc * len(items))()
+    for d, it in zip(arr, items):
+        if fwd:
+            qkv, out, copies, group_bits, entity_mask = it
+            d.out, d.dout, d.dqkv = _p(out, F32), None, None
+        else:
+            qkv, dout, dqkv, copies, group_bits, entity_mask = it
+            d.out, d.dout, d.dqkv = None, _p(dout, F32), _p(dqkv, F32)
+        c = _copies(copies)
+        d.qkv = _p(qkv, F32)
+        d.mask0, d.mask1, d.mask2, d.s0, d.s1, d.s2, d.m0, d.m1, d.m2 = c
+        d.group_bits, d.entity_mask, d.n_copies = _p(group_bits, U8), _p(entity_mask, U8), len(copies)
+    return arr
+
+
+def masked_attn_fwd_group(items, N, T, ne, nq, d, H):
+    """items: list of (qkv, out, copies, group_bits, entity_mask) of one geometry -> <= 8 problems per launch."""
+    for lo in range(0, len(items), MAX_GROUP):
+        part = items[lo:lo + MAX_GROUP]
+        for it in part:
+            C = len(it[2])
+            _account("masked_attn_fwd", 4.0 * nq * ne * d * N * C, (4.0 * d * (2 * ne + 2 * nq) + nq * ne) * N * C)
+        arr = _attn_descs(part, True)
+        _call("masked_attn_fwd_group", _ct.addressof(arr), len(part), N, T, ne, nq, d, H, as_name="masked_attn_fwd")
+
+
+def masked_attn_bwd_group(items, N, T, ne, nq, d, H):
+    """items: list of (qkv, dout, dqkv, copies, group_bits, entity_mask)."""
+    for lo in range(0, len(items), MAX_GROUP):
+        part = items[lo:lo + MAX_GROUP]
+        for it in part:
+            C = len(it[3])
+            _account("masked_attn_bwd", 10.0 * nq * ne * d * N * C, (4.0 * d * (2 * ne + 2 * nq) * 2 + nq * ne) * N * C)
+        arr = _attn_descs(part, False)
+        _call("masked_attn_bwd_group", _ct.addressof(arr), len(part), N, T, ne, nq, d, H, as_name="masked_attn_bwd")
+
+
+# ---------------------------------------------------------------------------------------------------- GRU
+def gru_scan_fwd(GI, Whh, bhh, h0, HS, gates, n_seq, T, na):
+    r = Whh.shape[1]
+    _call("gru_scan_fwd", _p(GI, F32), _p(Whh, F32), _p(bhh, F32), _p(h0, F32), _p(HS, F32), _p(gates, F32), n_seq, T,
+          na, r)
+    return HS
+
+
+def gru_scan_bwd(dHS, gates, HS, h0, Whh, dGI, dGH, n_seq, T, na):
+    r = Whh.shape[1]
+    _call("gru_scan_bwd", _p(dHS, F32), _p(gates, F32), _p(HS, F32), _p(h0, F32), _p(Whh, F32), _p(dGI, F32),
+          _p(dGH, F32), n_seq, T, na, r)
+
+
+# ---------------------------------------------------------------------------------------------------- mixers / TD
+def mixer_fwd(kind, W1, B1, WF, V, q, qW, qI, qtot, qtot_im, N, na, me, w1_copies, imagine, softmax_w, tanh_nl,
+              ingroup=None):
+    _call("mixer_fwd", kind, _p(W1, F32), _p(B1, F32), _p(WF, F32), _p(V, F32), _p(q, F32), _p(qW, F32), _p(qI, F32),
+          _p(qtot, F32), _p(qtot_im, F32), _p(ingroup, F32), N, na, me, w1_copies, int(imagine), int(softmax_w),
+          int(tanh_nl))
+
+
+def mixer_bwd(kind, W1, B1, WF, V, q, qW, qI, g_plain, g_im, dW1, dB1, dWF, dV, dq, dqW, dqI, N, na, me, w1_copies,
+              imagine, softmax_w, tanh_nl):
+    _call("mixer_bwd", kind, _p(W1, F32), _p(B1, F32), _p(WF, F32), _p(V, F32), _p(q, F32), _p(qW, F32), _p(qI, F32),
+          _p(g_plain, F32), _p(g_im, F32), _p(dW1, F32), _p(dB1, F32), _p(dWF, F32), _p(dV, F32), _p(dq, F32),
+          _p(dqW, F32), _p(dqI, F32), N, na, me, w1_copies, int(imagine), int(softmax_w), int(tanh_nl))
+
+
+def gather_chosen(Q, actions, chosen, copies, rows_per_copy, A):
+    _call("gather_chosen", _p(Q, F32), _p(actions, I64), _p(chosen, F32), copies, rows_per_copy, A)
+    return chosen
+
+
+def scatter_dq(dchosen, actions, dQ, copies, rows_per_copy, A, T, na):
+    _call("scatter_dq", _p(dchosen, F32), _p(actions, I64), _p(dQ, F32), copies, rows_per_copy, A, T, na)
+    return dQ
+
+
+def target_max(q_online, q_target, avail, tgt, cur_max, rows, A, double_q):
+    _call("target_max", _p(q_online, F32), _p(q_target, F32), _p(avail, I32), _p(tgt, F32), _p(cur_max, I64), rows, A,
+          int(double_q))
+    return tgt
+
+
+def td_loss(qtot, qtot_im, tgt_tot, reward, terminated, filled, g_plain, g_im, targets_out, stats, B, T, gamma, lmbda):
+    _call("td_loss", _p(qtot, F32), _p(qtot_im, F32), _p(tgt_tot, F32), _p(reward, F32), _p(terminated, U8),
+          _p(filled, I64), _p(g_plain, F32), _p(g_im, F32), _p(targets_out, F32), _p(stats, F64), B, T, float(gamma),
+          float(lmbda))
+
+
+def grad_sumsq(grads, n_params, out):
+    _call("grad_sumsq", _p(grads, F32), n_params, _p(out, F64))
+
+
+def pack_stats(stats, tail, n):
+    _call("pack_stats", _p(stats, F64), _p(tail, F32), n)
+
+
+def clip_rmsprop_step(params, grads, square_avg, n_params, mask_sum, sumsq, grad_norm_out, clip, lr, alpha, eps, wd):
+    _call("clip_rmsprop_step", _p(params, F32), _p(grads, F32), _p(square_avg, F32), n_params, _p(mask_sum, F32),
+          _p(sumsq, F64), _p(grad_norm_out, F32), float(clip), float(lr), float(alpha), float(eps), float(wd))
+
+
+# ---------------------------------------------------------------------------------------------------- acting / env
+def ff_agent_act_supported(ne, na, ein, d, H, A):
+    return _lib.load().refil_ff_agent_act_supported(ne, na, ein, d, H, A) != 0
+
+
+def ff_agent_act(entities, actions, n_actions, obs_mask, entity_mask, params, q, t, select=None):
+    """Fused acting forward of the FF entity-attention agent on timestep t of the EpisodeBatch tensors (read in place).
+    params: dict with fc1 / attn.in_trans / attn.out_trans / fc2 weights.  q [E, na, A] is written.
+    select: optional dict(avail [E,T,na,A] i32, actions_out [E,T,na,1] i64, u_pick, u_act, est_flags, epsilon, eps_dev) -> the
+    epsilon-greedy choice is made in the same launch and written to actions_out[:, t]."""
+    E, T, ne, ed = entities.shape
+    na, A = q.shape[1], q.shape[2]
+    sel = select or {}
+    _call("ff_agent_act", _p(entities, F32), ed, _p(actions, I64), n_actions, _p(obs_mask, U8), obs_mask.shape[2],
+          _p(entity_mask, U8), _p(params["fc1.weight"], F32), _p(params["fc1.bias"], F32), _p(params["attn.in_trans.weight"], F32),
+          _p(params["attn.out_trans.weight"], F32), _p(params["attn.out_trans.bias"], F32), _p(params["fc2.weight"], F32),
+          _p(params["fc2.bias"], F32), _p(q, F32), E, T, int(t), ne, na, A, _p(sel.get("avail"), I32), _p(sel.get("u_pick"), F32),
+          _p(sel.get("u_act"), F32), _p(sel.get("est_flags"), I32), float(sel.get("epsilon", 0.0)), _p(sel.get("eps_dev"), F32),
+          _p(sel.get("actions_out"), I64))
+    return q
+
+
+def select_actions(q, avail, u_pick, u_act, est_flags, epsilon, actions_out, B, na, A, eps_dev=None):
+    """q [B, na, A] contiguous; avail / actions_out may be time slices of EpisodeBatch tensors (row stride taken from them)."""
+    if avail.stride(-1) != 1 or avail.stride(-2) != A or actions_out.stride(-1) != 1:
+        raise _lib.RefilError("select_actions: avail / actions_out must be contiguous in their last two dimensions")
+    if not (avail.is_cuda and actions_out.is_cuda and avail.dtype == I32 and actions_out.dtype == I64):
+        raise _lib.RefilError("select_actions: avail int32 / actions int64 CUDA tensors expected")
+    _call("select_actions", _p(q, F32), na * A, avail.data_ptr(), avail.stride(0), _p(u_pick, F32), _p(u_act, F32),
+          _p(est_flags, I32), float(epsilon), _p(eps_dev, F32), actions_out.data_ptr(), actions_out.stride(0), B, na, A)
+    return actions_out
