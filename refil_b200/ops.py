@@ -222,7 +222,7 @@ class _GemmDesc(_ct.Structure):
                 ("bias", _ct.c_void_p), ("relu", _ct.c_int),
                 ("c_mask", _ct.c_void_p), ("c_na", _ct.c_int), ("c_ne", _ct.c_int), ("c_mper", _ct.c_int),
                 ("C", _ct.c_void_p), ("ldc", _ct.c_longlong), ("M", _ct.c_int),
-                ("row_group", _ct.c_int), ("row_group_stride", _ct.c_int), ("accumulate", _ct.c_int)]
+                ("row_group", _ct.c_int), ("row_group_stride", _ct.c_int), ("accumulate", _ct.c_int), ("n_cols", _ct.c_int)]
 
 
 class _WgradDesc(_ct.Structure):

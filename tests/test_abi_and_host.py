@@ -200,3 +200,21 @@ def test_sass_histogram_has_blackwell_native_instructions():
     att = [c for n, c in h.items() if n.startswith("attn_fwd_kernel<32, 4, 0>") or n.startswith("attn_bwd_kernel<32, 4, 0>")]
     assert len(att) == 2 and all(c["UTMALDG"] >= 1 and c["FFMA"] > 100 for c in att)
     assert not any(c["HMMA"] for n, c in h.items() if n.startswith("tc_"))   # no legacy mma.sync on the dense path
+
+
+def test_ctypes_descriptor_structs_match_the_header(tmp_path):
+    """ops.py mirrors RefilGemmDesc / RefilWgradDesc / RefilAttnDesc by hand: their sizes and last-field offsets must be the C ones."""
+    import ctypes
+    import subprocess
+    from refil_b200 import ops
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "%s"\n'
+                   'int main(void) { printf("%%zu %%zu %%zu %%zu %%zu %%zu\\n", sizeof(RefilGemmDesc), offsetof(RefilGemmDesc, n_cols), '
+                   'sizeof(RefilWgradDesc), offsetof(RefilWgradDesc, M), sizeof(RefilAttnDesc), offsetof(RefilAttnDesc, n_copies)); '
+                   'return 0; }\n' % os.path.join(ROOT, "include", "refil_b200.h"))
+    exe = tmp_path / "sz"
+    subprocess.run(["gcc", "-o", str(exe), str(src)], check=True)
+    got = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    want = [ctypes.sizeof(ops._GemmDesc), ops._GemmDesc.n_cols.offset, ctypes.sizeof(ops._WgradDesc), ops._WgradDesc.M.offset,
+            ctypes.sizeof(ops._AttnDesc), ops._AttnDesc.n_copies.offset]
+    assert got == want, (got, want)
