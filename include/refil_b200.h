@@ -159,6 +159,7 @@ typedef struct RefilGemmDesc {
     int accumulate;                    /* C += A B^T instead of C = (linear epilogue only) */
     int n_cols;                        /* > 0: this problem has n_cols output columns instead of the group's N (same reduction length):
                                           in_trans as ONE launch of K|V for all entity rows (2d columns) + Q for the agent rows (d) */
+    int k_len;                         /* > 0: this problem reduces over k_len instead of the group's K (a multiple of the same k-slice) */
 } RefilGemmDesc;
 int refil_tc_gemm_tn_group(const RefilGemmDesc* descs, int n_problems, int N, int K, cudaStream_t stream);
 

@@ -862,8 +862,9 @@ static int tc_mode_ts() {
 }
 
 // one problem of a group: validate, fill TcArgs and the two tensor maps
-static int tc_fill(const RefilGemmDesc& d, int N_group, int K, int mode_ts, TcArgs& a, CUtensorMap* tmap_c, CUtensorMap* tmap_a) {
+static int tc_fill(const RefilGemmDesc& d, int N_group, int K_group, int mode_ts, TcArgs& a, CUtensorMap* tmap_c, CUtensorMap* tmap_a) {
     const int M = d.M;
+    const int K = d.k_len > 0 ? d.k_len : K_group;        // ... and reduce over fewer / more k-slices of the same length
     const int N = d.n_cols > 0 ? d.n_cols : N_group;      // a problem may be narrower / wider than the group's N (same n-tile width)
     REFIL_CHECK_ARG(d.A && d.B && d.C, "tc_gemm_tn: null pointer");
     REFIL_CHECK_ARG(refil_tc_gemm_supported(M, N, K), "tc_gemm_tn: unsupported shape M=%d N=%d K=%d", M, N, K);
@@ -932,8 +933,8 @@ extern "C" int refil_tc_gemm_tn_group(const RefilGemmDesc* descs, int n_problems
     TcArgs& a0 = grp.a[0];
     const int BN = a0.BN;
     for (int g = 1; g < n_problems; g++)
-        REFIL_CHECK_ARG(grp.a[g].BN == BN && grp.a[g].KS == a0.KS && grp.a[g].k_slices == a0.k_slices,
-                        "tc_gemm_tn_group: the problems of a group must share the n-tile width and the k-slicing");
+        REFIL_CHECK_ARG(grp.a[g].BN == BN && grp.a[g].KS == a0.KS && grp.a[g].k_slices <= a0.k_slices,
+                        "tc_gemm_tn_group: the problems of a group must share the n-tile width and the k-slice length (most slices first)");
     const size_t b_res = (size_t)2 * BN * a0.KS * 4, stage_bytes = 2 * (size_t)TC_BM * 128;
     const size_t stg_bytes = (size_t)TC_EPI_WARPS * TC_STG_BYTES;
     const size_t budget = 227 * 1024 - 1024 /* alignment slack */ - 2048 /* static: barriers, bias */;
@@ -958,7 +959,8 @@ extern "C" int refil_tc_gemm_tn_group(const RefilGemmDesc* descs, int n_problems
     if (a0.k_slices > 1) {            // partial tiles are reduce-added into C
         for (int g = 0; g < n_problems; g++) {
             if (grp.a[g].accumulate) continue;
-            REFIL_CHECK_ARG(grp.a[g].row_group == 0, "tc_gemm_tn: a sliced reduction into row groups must accumulate");
+            REFIL_CHECK_ARG(grp.a[g].k_slices > 1 && grp.a[g].row_group == 0,
+                            "tc_gemm_tn_group: next to a sliced reduction every other problem must accumulate");
             cudaError_t e = cudaMemset2DAsync(descs[g].C, (size_t)descs[g].ldc * 4, 0, (size_t)grp.a[g].N * 4, (size_t)descs[g].M, stream);
             if (e != cudaSuccess) {
                 refil_set_error("tc_gemm_tn: cudaMemset2DAsync: %s", cudaGetErrorString(e));
@@ -1009,7 +1011,7 @@ extern "C" int refil_tc_gemm_tn(const float* A, long long lda, const float* relu
                                 const float* bias, int relu, const uint8_t* c_row_entity_mask, int c_na, int c_ne,
                                 int c_rows_per_copy, float* C, long long ldc, int M, int N, int K, cudaStream_t stream) {
     RefilGemmDesc d{A, lda, relu_y, ldy, a_row_entity_mask, a_na, a_ne, a_rows_per_copy, B, b_stride_n, b_stride_k, b_k_valid,
-                    bias, relu, c_row_entity_mask, c_na, c_ne, c_rows_per_copy, C, ldc, M, 0, 0, 0, 0};
+                    bias, relu, c_row_entity_mask, c_na, c_ne, c_rows_per_copy, C, ldc, M, 0, 0, 0, 0, 0};
     return refil_tc_gemm_tn_group(&d, 1, N, K, stream);
 }
 

@@ -124,7 +124,10 @@ class AttnTrunk:
             _on_side(wstream, lambda: ops.linear_bwd_weight(dqkv, x1, g[pre + "attn.in_trans.weight"],
                                                             g[pre + "attn.in_trans.bias"]))
         dx1 = ws.get(self.scratch + ".dx1", (N * ne, d))
-        ops.linear_bwd_data(dqkv, p[pre + "attn.in_trans.weight"], dx1)
+        if self.pool is None and ops.qkv_split_ok(N, ne, na, d):
+            ops.in_trans_bwd_data_split(dqkv, p[pre + "attn.in_trans.weight"], dx1, N, ne, na)
+        else:
+            ops.linear_bwd_data(dqkv, p[pre + "attn.in_trans.weight"], dx1)
         if xin is not None:
             ops.linear_bwd_weight(dx1, xin, g[pre + "fc1.weight"], g[pre + "fc1.bias"], relu_y=x1)
         else:

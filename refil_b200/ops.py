@@ -211,6 +211,27 @@ def in_trans_fwd_split(x1, W, qkv, n_units, ne, na):
     return qkv
 
 
+def in_trans_bwd_data_split(dqkv, W, dx1, n_units, ne, na):
+    """dx1 = dqkv[:, d:] W[d:] on every entity row + dqkv[agent rows, :d] W[:d] accumulated into the agent rows, as ONE launch of two
+    problems (the Q columns of dqkv are zero outside the agent rows: the backward of the slice `query[:n_queries]`)."""
+    d = dx1.shape[1]
+    M = n_units * ne
+    arr = (_GemmDesc * 2)()
+    kv, q = arr[0], arr[1]
+    for dsc in (kv, q):
+        dsc.lda, dsc.relu_y, dsc.ldy = dqkv.stride(0), None, dqkv.stride(0)
+        dsc.a_mask, dsc.a_na, dsc.a_ne, dsc.a_mper = None, 1, 1, 1
+        dsc.sbn, dsc.sbk, dsc.b_k_valid, dsc.bias, dsc.relu = 1, W.stride(0), 0, None, 0     # "B"[n = k_in, i] = W[i, n]
+        dsc.c_mask, dsc.c_na, dsc.c_ne, dsc.c_mper = None, 1, 1, 1
+        dsc.C, dsc.ldc = _p(dx1, F32), d
+    kv.A, kv.B, kv.M, kv.k_len = _pv(dqkv[:, d:], F32), _pv(W[d:], F32), M, 2 * d
+    q.A, q.B, q.M, q.k_len = _p(dqkv, F32), _pv(W[:d], F32), n_units * na, d
+    q.row_group, q.row_group_stride, q.accumulate = na, ne, 1
+    _account("tc_gemm_tn", 2.0 * (M * 2 * d + n_units * na * d) * d, 4.0 * (M * 2 * d + n_units * na * d + M * d + 3 * d * d))
+    _call("tc_gemm_tn_group", _ct.addressof(arr), 2, d, 2 * d, shape=(2, M, d, 2 * d), as_name="tc_gemm_tn")
+    return dx1
+
+
 # ---- grouped launches: the same layer of several networks in ONE kernel launch (include/refil_b200.h: RefilGemmDesc) ----------
 import ctypes as _ct
 
@@ -222,7 +243,8 @@ class _GemmDesc(_ct.Structure):
                 ("bias", _ct.c_void_p), ("relu", _ct.c_int),
                 ("c_mask", _ct.c_void_p), ("c_na", _ct.c_int), ("c_ne", _ct.c_int), ("c_mper", _ct.c_int),
                 ("C", _ct.c_void_p), ("ldc", _ct.c_longlong), ("M", _ct.c_int),
-                ("row_group", _ct.c_int), ("row_group_stride", _ct.c_int), ("accumulate", _ct.c_int), ("n_cols", _ct.c_int)]
+                ("row_group", _ct.c_int), ("row_group_stride", _ct.c_int), ("accumulate", _ct.c_int), ("n_cols", _ct.c_int),
+                ("k_len", _ct.c_int)]
 
 
 class _WgradDesc(_ct.Structure):
