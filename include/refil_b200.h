@@ -190,6 +190,8 @@ typedef struct RefilWgradDesc {
     float* dW; long long lddw; int q_valid;
     float* db;
     int M;
+    int p_cols;                        /* > 0: this problem has p_cols columns of X (rows of dW) instead of the group's P */
+    int row_group, row_group_stride;   /* > 0: row m of X and Y is physical row (m / row_group) * row_group_stride + m % row_group */
 } RefilWgradDesc;
 int refil_tc_gemm_wgrad_group(const RefilWgradDesc* descs, int n_problems, int P, int Q, cudaStream_t stream);
 

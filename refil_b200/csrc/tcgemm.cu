@@ -795,6 +795,20 @@ static int tc_make_tmap_rows(CUtensorMap* tm, const float* X, long long ldx, int
     return r == CUDA_SUCCESS ? 1 : 0;
 }
 
+// the same for row groups (first R of every S rows): rank-3 map (column, row inside the group, group), box (box_cols, R, 32 / R)
+static int tc_make_tmap_rows_grouped(CUtensorMap* tm, const float* X, long long ldx, int G, int P, int R, int S, int box_cols) {
+    memset(tm, 0, sizeof(*tm));
+    tc_encode_fn enc = tc_encoder();
+    if (!enc) return 0;
+    const cuuint64_t dims[3] = {(cuuint64_t)P, (cuuint64_t)R, (cuuint64_t)G};
+    const cuuint64_t strides[2] = {(cuuint64_t)ldx * 4, (cuuint64_t)S * ldx * 4};
+    const cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)R, (cuuint32_t)(32 / R)};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)X, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 1 : 0;
+}
+
 // resident split weight tile (2 * BN * KS fp32) must leave room for >= 2 A stages and the staging tiles
 #define TC_B_BUDGET (128 * 1024)
 
@@ -1046,6 +1060,7 @@ struct TcWArgs {
     int M, P, Q, BQ, p_tiles, splits, stages, chunks_per_split;
     int q_valid, dw_vec;                 // columns >= q_valid of dW do not exist (zero-padded Y); dw_vec: 16-byte atomics allowed
     int y_tma;                           // TS kernel: raw Y chunks arrive by TMA (y_shift == 0), else the producers load them
+    int row_group;                       // > 0: row m of X and Y is physical row (m / row_group) * stride + m % row_group (rank-3 maps)
     uint32_t idesc;
 };
 
@@ -1343,6 +1358,14 @@ __global__ void __launch_bounds__(TW_THREADS, 1) tc_wgrad_ts_kernel(const __grid
         const int m0 = (c_begin + ch) * 32;
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&xr_full[st])),
                      "r"(raw_bytes * (has_r ? 2u : 1u)) : "memory");
+        if (a.row_group > 0) {            // row-grouped X (no relu_y): (column, row inside the group, group)
+            asm volatile(
+                "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                ::"r"(smem_u32(smem_x + (size_t)st * raw_bytes)), "l"(&tmap_x), "r"(ptile * 128), "r"(0), "r"(m0 / a.row_group),
+                  "r"(smem_u32(&xr_full[st]))
+                : "memory");
+            return;
+        }
         asm volatile(
             "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
             ::"r"(smem_u32(smem_x + (size_t)st * raw_bytes)), "l"(&tmap_x), "r"(ptile * 128), "r"(m0), "r"(smem_u32(&xr_full[st]))
@@ -1357,10 +1380,17 @@ __global__ void __launch_bounds__(TW_THREADS, 1) tc_wgrad_ts_kernel(const __grid
     auto tma_ychunk = [&](int st, int ch) {
         const int m0 = (c_begin + ch) * 32;
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&yr_full[st])), "r"(yraw_bytes) : "memory");
-        asm volatile(
-            "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-            ::"r"(smem_u32(smem_yr + (size_t)st * yraw_bytes)), "l"(&tmap_y), "r"(0), "r"(m0), "r"(smem_u32(&yr_full[st]))
-            : "memory");
+        if (a.row_group > 0)
+            asm volatile(
+                "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                ::"r"(smem_u32(smem_yr + (size_t)st * yraw_bytes)), "l"(&tmap_y), "r"(0), "r"(0), "r"(m0 / a.row_group),
+                  "r"(smem_u32(&yr_full[st]))
+                : "memory");
+        else
+            asm volatile(
+                "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                ::"r"(smem_u32(smem_yr + (size_t)st * yraw_bytes)), "l"(&tmap_y), "r"(0), "r"(m0), "r"(smem_u32(&yr_full[st]))
+                : "memory");
     };
     const int pre = min(n_chunks, RS);
     const int pre_y = a.y_tma ? min(n_chunks, RY) : 0;
@@ -1633,8 +1663,9 @@ static int tcw_min_chunks() {
     return min_chunks;
 }
 
-static int tcw_fill(const RefilWgradDesc& d, int P, int Q, int sm_share, TcWArgs& a) {
+static int tcw_fill(const RefilWgradDesc& d, int P_group, int Q, int sm_share, TcWArgs& a) {
     const int M = d.M;
+    const int P = d.p_cols > 0 ? d.p_cols : P_group;     // a problem may own fewer / more 128-wide p-tiles than the group's P
     REFIL_CHECK_ARG(d.X && d.Y && d.dW, "tc_gemm_wgrad: null pointer");
     REFIL_CHECK_ARG(refil_tc_wgrad_supported(M, P, Q), "tc_gemm_wgrad: unsupported shape M=%d P=%d Q=%d", M, P, Q);
     REFIL_CHECK_ARG((d.ldx % 4) == 0 && (d.ldyy % 4) == 0 && ((uintptr_t)d.X % 16) == 0 && ((uintptr_t)d.Y % 16) == 0 &&
@@ -1651,6 +1682,12 @@ static int tcw_fill(const RefilWgradDesc& d, int P, int Q, int sm_share, TcWArgs
     a.q_valid = d.q_valid > 0 ? d.q_valid : Q;
     a.dw_vec = (a.q_valid == Q && (d.lddw % 4) == 0 && ((uintptr_t)d.dW % 16) == 0) ? 1 : 0;
     a.p_tiles = refil_cdiv(P, 128);
+    if (d.row_group > 0) {
+        REFIL_CHECK_ARG((32 % d.row_group) == 0 && d.row_group_stride >= d.row_group && (M % d.row_group) == 0 && !d.relu_y &&
+                        !d.x_row_entity_mask && d.y_shift_rows <= 0,
+                        "tc_gemm_wgrad: row groups of %d rows need R | 32, R | M and no relu_y / row mask / shifted Y", d.row_group);
+        a.row_group = d.row_group;
+    }
     const int chunks_total = refil_cdiv(M, 32);
     int splits = sm_share / a.p_tiles;
     if (splits < 1) splits = 1;
@@ -1669,12 +1706,18 @@ extern "C" int refil_tc_gemm_wgrad_group(const RefilWgradDesc* descs, int n_prob
     TcWGroup grp{};
     const bool has_r = descs[0].relu_y != nullptr, has_b = descs[0].db != nullptr;
     int max_grid = 1;
-    long long sum_rows = 0;
-    for (int g = 0; g < n_problems; g++) sum_rows += descs[g].M > 0 ? descs[g].M : 1;
+    // every problem gets its share of one wave of CTAs in proportion to its work (rows x p-tiles); tcw_fill divides the share by the
+    // p-tiles again to get the row splits
+    long long sum_work = 0;
+    auto work = [&](int g) {
+        const int Pg = descs[g].p_cols > 0 ? descs[g].p_cols : P;
+        return (long long)(descs[g].M > 0 ? descs[g].M : 1) * refil_cdiv(Pg, 128);
+    };
+    for (int g = 0; g < n_problems; g++) sum_work += work(g);
     for (int g = 0; g < n_problems; g++) {
         REFIL_CHECK_ARG((descs[g].relu_y != nullptr) == has_r && (descs[g].db != nullptr) == has_b,
                         "tc_gemm_wgrad_group: the problems of a group must agree on relu_y / db being present");
-        int rc = tcw_fill(descs[g], P, Q, (int)((long long)refil_num_sms() * descs[g].M / sum_rows), grp.a[g]);
+        int rc = tcw_fill(descs[g], P, Q, (int)((long long)refil_num_sms() * work(g) / sum_work), grp.a[g]);
         if (rc) return rc;
         grp.a[g].BQ = has_b ? Q + 32 : Q;   // the bias gradient rides as one extra 32-wide atom whose first column is 1
         if (grp.a[g].p_tiles * grp.a[g].splits > max_grid) max_grid = grp.a[g].p_tiles * grp.a[g].splits;
@@ -1697,6 +1740,8 @@ extern "C" int refil_tc_gemm_wgrad_group(const RefilWgradDesc* descs, int n_prob
         int y_tma = y_ldg ? 0 : 1;
         for (int g = 0; g < n_problems; g++)
             if (grp.a[g].y_shift != 0) y_tma = 0;
+        for (int g = 0; g < n_problems; g++)
+            REFIL_CHECK_ARG(grp.a[g].row_group == 0 || y_tma, "tc_gemm_wgrad: row groups need the TMA path of Y");
         const size_t yraw_bytes = (size_t)32 * Q * 4;
         // The raw ring depth must be EVEN: the two producer groups take alternate chunks, so with an even ring every slot always
         // belongs to the same group and that group's previous visit orders the slot's phases.  With an odd ring a group could ask
@@ -1713,8 +1758,13 @@ extern "C" int refil_tc_gemm_wgrad_group(const RefilWgradDesc* descs, int n_prob
             grp.a[g].idesc = idesc;
             grp.a[g].y_tma = y_tma;
             const RefilWgradDesc& d = descs[g];
-            if (!tc_make_tmap_rows(&mx.m[g], d.X, d.ldx, d.M, P) || (has_r && !tc_make_tmap_rows(&mr.m[g], d.relu_y, d.ldy, d.M, P)) ||
-                (y_tma && !tc_make_tmap_rows(&my.m[g], d.Y, d.ldyy, d.M, Q, Q))) {
+            const int Pg = grp.a[g].P, R = grp.a[g].row_group;
+            const bool ok = R > 0 ? (tc_make_tmap_rows_grouped(&mx.m[g], d.X, d.ldx, d.M / R, Pg, R, d.row_group_stride, 128) &&
+                                     tc_make_tmap_rows_grouped(&my.m[g], d.Y, d.ldyy, d.M / R, Q, R, d.row_group_stride, Q))
+                                  : (tc_make_tmap_rows(&mx.m[g], d.X, d.ldx, d.M, Pg) &&
+                                     (!has_r || tc_make_tmap_rows(&mr.m[g], d.relu_y, d.ldy, d.M, Pg)) &&
+                                     (!y_tma || tc_make_tmap_rows(&my.m[g], d.Y, d.ldyy, d.M, Q, Q)));
+            if (!ok) {
                 refil_set_error("tc_gemm_wgrad: cuTensorMapEncodeTiled failed (X=%p ldx=%lld M=%d P=%d)", (const void*)d.X, d.ldx, d.M, P);
                 return REFIL_ERR_CUDA;
             }

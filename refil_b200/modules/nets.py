@@ -117,7 +117,10 @@ class AttnTrunk:
         if self.pool is None:
             dqkv = ws.get(self.scratch + ".dqkv", (N * ne, 3 * d))
             ops.masked_attn_bwd(qkv, datt, dqkv, masks.copies, masks.group_bits, masks.entity_mask, N, T, ne, na, d, self.H)
-            _on_side(wstream, lambda: ops.linear_bwd_weight(dqkv, x1, g[pre + "attn.in_trans.weight"], None))
+            if ops.qkv_split_ok(N, ne, na, d) and ops.tc_wgrad_y_tma():
+                _on_side(wstream, lambda: ops.in_trans_bwd_weight_split(dqkv, x1, g[pre + "attn.in_trans.weight"], N, ne, na))
+            else:
+                _on_side(wstream, lambda: ops.linear_bwd_weight(dqkv, x1, g[pre + "attn.in_trans.weight"], None))
         else:
             dqkv = ws.get(self.scratch + ".dqkv", (N * ne, d))
             ops.entity_pool_bwd(qkv, datt, dqkv, masks.copies, masks.group_bits, masks.entity_mask, N, T, ne, na, d, self.pool)

@@ -232,6 +232,31 @@ def in_trans_bwd_data_split(dqkv, W, dx1, n_units, ne, na):
     return dx1
 
 
+def tc_wgrad_y_tma():
+    """Is the TMA path of the weight-gradient kernel's Y operand on (row-grouped problems need it)?  REFIL_TCW_Y=ldg turns it off."""
+    import os
+    return os.environ.get("REFIL_TCW_Y", "")[:1] != "l" and os.environ.get("REFIL_TC_MODE") != "ss"
+
+
+def in_trans_bwd_weight_split(dqkv, x1, dW, n_units, ne, na):
+    """dW[d:] += dqkv[:, d:]^T x1 over every entity row, dW[:d] += dqkv[agent rows, :d]^T x1[agent rows], as ONE launch of two
+    problems (the Q columns of dqkv are zero outside the agent rows)."""
+    d = x1.shape[1]
+    M = n_units * ne
+    arr = (_WgradDesc * 2)()
+    kv, q = arr[0], arr[1]
+    for dsc in (kv, q):
+        dsc.ldx, dsc.relu_y, dsc.ldy = dqkv.stride(0), None, dqkv.stride(0)
+        dsc.x_mask, dsc.na, dsc.ne, dsc.mper = None, 1, 1, 1
+        dsc.Y, dsc.ldyy, dsc.y_shift, dsc.y_period = _p(x1, F32), d, 0, 1
+        dsc.lddw, dsc.q_valid, dsc.db = d, 0, None
+    kv.X, kv.dW, kv.M, kv.p_cols = _pv(dqkv[:, d:], F32), _pv(dW[d:], F32), M, 2 * d
+    q.X, q.dW, q.M, q.p_cols = _p(dqkv, F32), _pv(dW[:d], F32), n_units * na, d
+    q.row_group, q.row_group_stride = na, ne
+    _account("tc_gemm_wgrad", 2.0 * (M * 2 * d + n_units * na * d) * d, 4.0 * (M * 2 * d + M * d + 2 * n_units * na * d + 3 * d * d))
+    _call("tc_gemm_wgrad_group", _ct.addressof(arr), 2, 2 * d, d, shape=(2, M, 2 * d, d), as_name="tc_gemm_wgrad")
+
+
 # ---- grouped launches: the same layer of several networks in ONE kernel launch (include/refil_b200.h: RefilGemmDesc) ----------
 import ctypes as _ct
 
@@ -252,7 +277,8 @@ class _WgradDesc(_ct.Structure):
                 ("x_mask", _ct.c_void_p), ("na", _ct.c_int), ("ne", _ct.c_int), ("mper", _ct.c_int),
                 ("Y", _ct.c_void_p), ("ldyy", _ct.c_longlong), ("y_shift", _ct.c_int), ("y_period", _ct.c_int),
                 ("dW", _ct.c_void_p), ("lddw", _ct.c_longlong), ("q_valid", _ct.c_int),
-                ("db", _ct.c_void_p), ("M", _ct.c_int)]
+                ("db", _ct.c_void_p), ("M", _ct.c_int),
+                ("p_cols", _ct.c_int), ("row_group", _ct.c_int), ("row_group_stride", _ct.c_int)]
 
 
 MAX_GROUP = 8
