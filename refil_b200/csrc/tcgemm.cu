@@ -1317,15 +1317,19 @@ struct TcWGeom {
     int raw_stages, y_stages, y_raw_stages;
 };
 
-struct TcWGroup { TcWArgs a[TC_MAX_GROUP]; };
+struct TcWGroup { TcWArgs a[TC_MAX_GROUP]; int cta_begin[TC_MAX_GROUP + 1]; };   // grouped: CTAs [cta_begin[p], cta_begin[p+1]) -> problem p
 
-// blockIdx.y = problem of the group (same (P, Q) geometry, own operands and row count)
+// grouped launch: one grid, every problem owns exactly its p_tiles x splits CTAs (own operands, row count and P)
 template <bool GROUPED>
 __global__ void __launch_bounds__(TW_THREADS, 1) tc_wgrad_ts_kernel(const __grid_constant__ TcWGroup grp, TcWGeom g,
                                                                    const __grid_constant__ TcMaps maps_x,
                                                                    const __grid_constant__ TcMaps maps_r,
                                                                    const __grid_constant__ TcMaps maps_y) {
-    const int prob = GROUPED ? (int)blockIdx.y : 0;
+    int prob = 0, bid = (int)blockIdx.x;
+    if (GROUPED) {
+        while (prob + 1 < TC_MAX_GROUP && (int)blockIdx.x >= grp.cta_begin[prob + 1]) prob++;
+        bid = (int)blockIdx.x - grp.cta_begin[prob];
+    }
     const TcWArgs& a = grp.a[prob];
     const CUtensorMap& tmap_x = maps_x.m[prob];
     const CUtensorMap& tmap_r = maps_r.m[prob];
@@ -1347,7 +1351,7 @@ __global__ void __launch_bounds__(TW_THREADS, 1) tc_wgrad_ts_kernel(const __grid
     __shared__ uint32_t tmem_base_s;
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform role index
     const int lane = threadIdx.x & 31;
-    const int ptile = blockIdx.x % a.p_tiles, split = blockIdx.x / a.p_tiles;
+    const int ptile = bid % a.p_tiles, split = bid / a.p_tiles;
     const int chunks_total = (a.M + 31) / 32;
     const int c_begin = split * a.chunks_per_split, c_end = min(chunks_total, c_begin + a.chunks_per_split);
     const int n_chunks = max(0, c_end - c_begin);
@@ -1720,8 +1724,10 @@ extern "C" int refil_tc_gemm_wgrad_group(const RefilWgradDesc* descs, int n_prob
         int rc = tcw_fill(descs[g], P, Q, (int)((long long)refil_num_sms() * work(g) / sum_work), grp.a[g]);
         if (rc) return rc;
         grp.a[g].BQ = has_b ? Q + 32 : Q;   // the bias gradient rides as one extra 32-wide atom whose first column is 1
-        if (grp.a[g].p_tiles * grp.a[g].splits > max_grid) max_grid = grp.a[g].p_tiles * grp.a[g].splits;
+        grp.cta_begin[g] = g == 0 ? 0 : grp.cta_begin[g - 1] + grp.a[g - 1].p_tiles * grp.a[g - 1].splits;
+        max_grid = grp.cta_begin[g] + grp.a[g].p_tiles * grp.a[g].splits;
     }
+    for (int g = n_problems; g <= TC_MAX_GROUP; g++) grp.cta_begin[g] = max_grid;
     TcWArgs& a = grp.a[0];
     if (mode_ts) {
         // X^T operand in tensor memory (K-major by construction), Y tiles MN-major in shared memory
@@ -1782,7 +1788,7 @@ extern "C" int refil_tc_gemm_wgrad_group(const RefilWgradDesc* descs, int n_prob
         }
         cudaError_t le = n_problems == 1
             ? refil_launch(tc_wgrad_ts_kernel<false>, dim3(max_grid, 1), dim3(TW_THREADS), smem, stream, true, grp, geo, mx, mr, my)
-            : refil_launch(tc_wgrad_ts_kernel<true>, dim3(max_grid, n_problems), dim3(TW_THREADS), smem, stream, true, grp, geo, mx, mr, my);
+            : refil_launch(tc_wgrad_ts_kernel<true>, dim3(max_grid, 1), dim3(TW_THREADS), smem, stream, true, grp, geo, mx, mr, my);
         if (le != cudaSuccess) {
             refil_set_error("tc_gemm_wgrad (ts): launch failed: %s", cudaGetErrorString(le));
             return REFIL_ERR_CUDA;
