@@ -12,7 +12,7 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1400 --
   python bench.py --steps 1 --warmup 1 --no-cpu --no-graph --no-extra > gpurun_out/${TAG}_ncu_launches.log 2>&1
 # full-set captures: one launch of each hot kernel from the last steps of the same command
 timeout 900 ncu --set full --clock-control none --import-source on \
-  -k regex:'tc_gemm_ts_kernel|tc_wgrad_ts_kernel|attn_fwd_kernel|attn_bwd_kernel|gru_scan' -s 560 -c 40 \
+  -k regex:'tc_gemm_ts_kernel|tc_wgrad_ts_kernel|attn_fwd|attn_bwd|gru_scan' -s 560 -c 40 \
   -o gpurun_out/${TAG}_prof -f python bench.py --steps 1 --warmup 1 --no-cpu --no-graph --no-extra > gpurun_out/${TAG}_ncu_full.log 2>&1
 # the report itself is ~2.5 MB per kernel with sources (gpurun_out/ is capped at 64 MiB): keep the raw metrics page as CSV, and
 # the report only when small
