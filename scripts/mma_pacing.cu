@@ -27,7 +27,13 @@ __device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a, uint64_t b, uint3
                  ::"r"(d), "r"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
 }
 
-// mode bit 0: TS, bit 1: alternate two accumulators
+__device__ __forceinline__ void mma_ts_f16(uint32_t d, uint32_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+                 ::"r"(d), "r"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
+}
+
+// mode bit 0: TS, bit 1: alternate two accumulators, bit 2: kind::f16 with bf16 operands (K = 16 per instruction; TS only),
+// bit 3: 4 tf32 MMAs followed by 4 bf16 MMAs into the same accumulator (the "tf32 main term + bf16 correction terms" mix; TS only)
 __global__ void __launch_bounds__(128, 1) pacing_kernel(int N, int mode, int iters, long long* out) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -51,14 +57,19 @@ __global__ void __launch_bounds__(128, 1) pacing_kernel(int N, int mode, int ite
     if (threadIdx.x == 0) {
         const uint64_t a_desc = desc_sw128(smem_u32(smem)), b_desc = desc_sw128(smem_u32(smem + 16384));
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-        const bool ts = mode & 1, alt = mode & 2;
+        const bool ts = mode & 1, alt = mode & 2, f16 = mode & 4, mix = mode & 8;
+        const uint32_t idesc16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         const uint32_t a_tmem = tmem + 448;                      // 32 operand columns at the top of tensor memory
         const long long t0 = clock64();
         for (int it = 0; it < iters; it++) {
 #pragma unroll
             for (int ks = 0; ks < 4; ks++) {
                 const uint32_t d = tmem + ((alt && (ks & 1)) ? (uint32_t)N : 0u);
-                if (ts) mma_ts(d, a_tmem + ks * 8, b_desc + ks * 2, idesc, 1);
+                if (mix) {
+                    mma_ts(d, a_tmem + ks * 8, b_desc + ks * 2, idesc, 1);
+                    mma_ts_f16(d, a_tmem + 32 + ks * 8, b_desc + 512 + ks * 2, idesc16, 1);
+                } else if (f16) mma_ts_f16(d, a_tmem + ks * 8, b_desc + ks * 2, idesc16, 1);
+                else if (ts) mma_ts(d, a_tmem + ks * 8, b_desc + ks * 2, idesc, 1);
                 else mma_ss(d, a_desc + ks * 2, b_desc + ks * 2, idesc, 1);
             }
         }
@@ -69,7 +80,7 @@ __global__ void __launch_bounds__(128, 1) pacing_kernel(int N, int mode, int ite
                          : "=r"(done) : "r"(smem_u32(&bar)), "r"(0) : "memory");
         } while (!done);
         const long long t1 = clock64();
-        if (blockIdx.x == 0) out[0] = t1 - t0;
+        if (blockIdx.x == 0) out[0] = (t1 - t0) / (mix ? 2 : 1);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -90,14 +101,16 @@ int main() {
     printf("tcgen05.mma kind::tf32 M=128 K=8, %d MMAs back to back per SM, all %d SMs busy\n", iters * 4, sms);
     printf("%-4s %-5s %-12s %10s %8s\n", "A", "N", "accumulators", "cyc/MMA", "floor");
     for (int n : {64, 128, 256}) {
-        for (int mode = 0; mode < 4; mode++) {
+        for (int mode : {0, 1, 2, 3, 5, 9}) {
             if ((mode & 2) && 2 * n > 448) continue;
+            if ((mode & 8) && n > 128) continue;
             pacing_kernel<<<sms, 128, smem>>>(n, mode, iters, d_out);          // warm-up
             pacing_kernel<<<sms, 128, smem>>>(n, mode, iters, d_out);
             long long cyc = 0;
             cudaError_t e = cudaMemcpy(&cyc, d_out, sizeof(cyc), cudaMemcpyDeviceToHost);
             if (e != cudaSuccess) { printf("error: %s\n", cudaGetErrorString(e)); return 1; }
-            printf("%-4s %-5d %-12s %10.1f %8d\n", (mode & 1) ? "TS" : "SS", n, (mode & 2) ? "2 alternating" : "1", (double)cyc / (iters * 4.0),
+            printf("%-4s %-5d %-12s %10.1f %8d\n", (mode & 1) ? "TS" : "SS", n,
+                   (mode & 8) ? "tf32+bf16 mix" : (mode & 4) ? "bf16 K=16" : (mode & 2) ? "2 alternating" : "1", (double)cyc / (iters * 4.0),
                    128 * n / 256);
         }
     }
