@@ -542,3 +542,48 @@ def test_split_in_trans_feeds_the_attention_kernels_like_the_full_product():
     assert torch.isfinite(outs[1]).all() and torch.isfinite(grads[1]).all()
     assert (outs[0] - outs[1]).abs().max().item() <= 1e-5 * outs[0].abs().max().item()
     assert (grads[0] - grads[1]).abs().max().item() <= 1e-5 * grads[0].abs().max().item()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("P,Q,qv", [(128, 64, 53), (128, 128, 128), (32, 128, 128)])
+def test_full_size_weight_gradient_with_relu_mask_and_bias(P, Q, qv):
+    """fc1 / fc2-shaped weight gradients at the benchmark's row count with the relu' mask and the bias gradient: 39 row chunks per CTA
+    on every SM -- the regime in which an odd-depth raw Y ring let a producer group pass an mbarrier phase early (launch failure at
+    full size only; scripts/repro_wgrad.py).  Checked against float64."""
+    from refil_b200 import ops
+    g = torch.Generator(device=DEV).manual_seed(P + Q)
+    M = NS_ROWS
+    dC = torch.randn(M, P, device=DEV, generator=g)
+    A = torch.randn(M, Q, device=DEV, generator=g)
+    if qv != Q:
+        A[:, qv:] = 0
+    y = torch.randn(M, P, device=DEV, generator=g)
+    dW, db = torch.zeros(P, qv, device=DEV), torch.zeros(P, device=DEV)
+    for _ in range(2):
+        ops.linear_bwd_weight(dC, A, dW, db, relu_y=y)
+    torch.cuda.synchronize()
+    gm = dC.double() * (y > 0).double()
+    ref = 2 * (gm.t() @ A.double())[:, :qv]
+    scale = 2 * (gm.abs().t() @ A.abs().double()).max().item()
+    assert (dW.double() - ref).abs().max().item() <= 4e-6 * scale
+    assert (db.double() - 2 * gm.sum(0)).abs().max().item() <= 4e-6 * 2 * gm.abs().sum(0).max().item()
+
+
+@pytest.mark.gpu
+def test_row_grouped_weight_gradient_matches_float64():
+    """in_trans weight gradient split: the K|V rows of dW from every entity row, the Q rows from the agent rows only (rank-3 tensor maps
+    for X and Y), one launch of two problems."""
+    from refil_b200 import ops
+    units, ne, na, d = 300, 24, 8, 128
+    g = torch.Generator(device=DEV).manual_seed(11)
+    dqkv = torch.randn(units * ne, 3 * d, device=DEV, generator=g)
+    dqkv.view(units, ne, 3 * d)[:, na:, :d] = float("nan")        # never read: the split takes the Q columns of the agent rows only
+    x1 = torch.randn(units * ne, d, device=DEV, generator=g)
+    dW = torch.ones(3 * d, d, device=DEV)
+    ops.in_trans_bwd_weight_split(dqkv, x1, dW, units, ne, na)
+    torch.cuda.synchronize()
+    clean = torch.nan_to_num(dqkv, nan=0.0)
+    ref = clean.double().t() @ x1.double()
+    scale = (clean.abs().double().t() @ x1.abs().double()).max().item()
+    assert torch.isfinite(dW).all()
+    assert (dW.double() - 1.0 - ref).abs().max().item() <= 4e-6 * scale
