@@ -62,8 +62,6 @@ struct TcArgs {
     int BN, n_tiles, m_tiles, stages;
     int row_group;                           // > 0: row m of A and C is physical row (m / row_group) * stride + m % row_group (rank-3 tensor maps)
     int accumulate;                          // C += A B^T (reduce-add stores, no clearing of C)
-    int stg_bufs;                            // staging tiles per epilogue warp (2 where the weight tile leaves room: the next slab is
-                                             // written while the TMA store of the previous one still reads its tile)
     uint32_t idesc;
 };
 
@@ -166,7 +164,6 @@ __device__ __forceinline__ void tc_tma_reduce_add3(const CUtensorMap* tmap, int 
 }
 __device__ __forceinline__ void tc_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tc_bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void tc_bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void tc_bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // the 8 float4 of one A chunk a producer thread owns: 16-byte chunk c of rows r0 + 16 i of m-tile mt, k-chunk kc
@@ -269,12 +266,11 @@ __device__ __forceinline__ void tc_epilogue(const TcArgs& a, const CUtensorMap* 
                                             int mt_step, int my_tiles, uint32_t tmem_base, uint8_t* smem_stg,
                                             const float* epi_bias, uint64_t* tmem_full, uint64_t* tmem_empty) {
     const int BN = a.BN;
-    const bool has_bias = a.bias != nullptr;
     {
         const int quad = warp & 3, half = warp >> 2;
-        const int nbuf = a.stg_bufs > 1 ? 2 : 1;
-        float* stg0 = reinterpret_cast<float*>(smem_stg + (size_t)warp * nbuf * TC_STG_BYTES);
-        int slab = 0;
+        float* stg = reinterpret_cast<float*>(smem_stg + (size_t)warp * TC_STG_BYTES);
+        const uint32_t stg_addr = smem_u32(stg);
+        float* my_stg = stg + lane * 32;
         const int sw = lane & 7;
         for (int it = 0; it < my_tiles; it++) {
             const int mt = mt0 + it * mt_step;
@@ -295,29 +291,17 @@ __device__ __forceinline__ void tc_epilogue(const TcArgs& a, const CUtensorMap* 
                       "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
                       "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                     : "r"(taddr + (uint32_t)c0));
-                // the slab's bias values are fetched while the tcgen05.ld is in flight (ncu r4a: a third of the epilogue warps' samples
-                // sat on the LDS -> FADD dependency when the loads followed the wait); layers without a bias skip them
-                float4 b4[8];
-#pragma unroll
-                for (int q = 0; q < 8; q++)
-                    b4[q] = has_bias ? *reinterpret_cast<const float4*>(epi_bias + c0 + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
-                float* stg = stg0 + (slab & (nbuf - 1)) * (TC_STG_BYTES / 4);
-                const uint32_t stg_addr = smem_u32(stg);
-                float* my_stg = stg + lane * 32;
-                slab++;
-                if (lane == 0) {                           // the store that last used this staging tile has read it
-                    if (nbuf > 1) tc_bulk_wait_read1();
-                    else tc_bulk_wait_read();
-                }
+                if (lane == 0) tc_bulk_wait_read();        // the previous store of this warp has read the staging tile
                 __syncwarp();
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
                 for (int q = 0; q < 8; q++) {
+                    const float4 b4 = *reinterpret_cast<const float4*>(epi_bias + c0 + 4 * q);
                     float4 v;
-                    v.x = __uint_as_float(r[4 * q + 0]) + b4[q].x;
-                    v.y = __uint_as_float(r[4 * q + 1]) + b4[q].y;
-                    v.z = __uint_as_float(r[4 * q + 2]) + b4[q].z;
-                    v.w = __uint_as_float(r[4 * q + 3]) + b4[q].w;
+                    v.x = __uint_as_float(r[4 * q + 0]) + b4.x;
+                    v.y = __uint_as_float(r[4 * q + 1]) + b4.y;
+                    v.z = __uint_as_float(r[4 * q + 2]) + b4.z;
+                    v.w = __uint_as_float(r[4 * q + 3]) + b4.w;
                     if (a.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
                     if (masked) v = make_float4(0.f, 0.f, 0.f, 0.f);
                     *reinterpret_cast<float4*>(my_stg + ((q ^ sw) << 2)) = v;
@@ -966,12 +950,7 @@ extern "C" int refil_tc_gemm_tn_group(const RefilGemmDesc* descs, int n_problems
         REFIL_CHECK_ARG(grp.a[g].BN == BN && grp.a[g].KS == a0.KS && grp.a[g].k_slices <= a0.k_slices,
                         "tc_gemm_tn_group: the problems of a group must share the n-tile width and the k-slice length (most slices first)");
     const size_t b_res = (size_t)2 * BN * a0.KS * 4, stage_bytes = 2 * (size_t)TC_BM * 128;
-    // two staging tiles per epilogue warp where the resident weight tile leaves room (tensor-memory path, K <= 64 or narrow N)
-    const size_t b_res0 = (size_t)2 * grp.a[0].BN * grp.a[0].KS * 4;
-    const int stg_bufs = (mode_ts && b_res0 + (size_t)TS_RAW_STAGES * TC_BM * 128 + 2 * (size_t)TC_EPI_WARPS * TC_STG_BYTES + 1024 <=
-                          227 * 1024 - 1024 - 2048) ? 2 : 1;
-    for (int g = 0; g < n_problems; g++) grp.a[g].stg_bufs = stg_bufs;
-    const size_t stg_bytes = (size_t)TC_EPI_WARPS * TC_STG_BYTES * stg_bufs;
+    const size_t stg_bytes = (size_t)TC_EPI_WARPS * TC_STG_BYTES;
     const size_t budget = 227 * 1024 - 1024 /* alignment slack */ - 2048 /* static: barriers, bias */;
     int stages = (int)((budget - b_res - stg_bytes) / stage_bytes);
     if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
