@@ -218,3 +218,23 @@ def test_ctypes_descriptor_structs_match_the_header(tmp_path):
     want = [ctypes.sizeof(ops._GemmDesc), ops._GemmDesc.n_cols.offset, ctypes.sizeof(ops._WgradDesc), ops._WgradDesc.M.offset,
             ctypes.sizeof(ops._AttnDesc), ops._AttnDesc.n_copies.offset]
     assert got == want, (got, want)
+
+
+def test_qkv_split_policy(monkeypatch):
+    """Host-side choice of the split in_trans (queries for the agent rows only): large shards by default, never when every entity is
+    an agent or the agent count does not divide 32, REFIL_QKV_SPLIT forces it either way."""
+    from refil_b200 import ops
+    monkeypatch.delenv("REFIL_QKV_SPLIT", raising=False)
+    monkeypatch.delenv("REFIL_TC_MODE", raising=False)
+    assert ops.qkv_split_ok(128 * 60, 24, 8, 128)              # the benchmark shard: 184 320 entity rows
+    assert not ops.qkv_split_ok(16 * 60, 24, 8, 128)           # a 16-episode shard stays on the full product
+    assert not ops.qkv_split_ok(4096 * 51, 4, 4, 64)           # Group Matching: every entity is an agent
+    assert not ops.qkv_split_ok(128 * 60, 24, 5, 128)          # 5 agents: row groups must divide 32
+    monkeypatch.setenv("REFIL_QKV_SPLIT", "1")
+    assert ops.qkv_split_ok(60, 24, 8, 128)                    # forced on where the tensor-core path applies (480 agent rows)
+    assert not ops.qkv_split_ok(4, 24, 8, 128)                 # ... but never below the tensor-core row threshold
+    monkeypatch.setenv("REFIL_QKV_SPLIT", "0")
+    assert not ops.qkv_split_ok(128 * 60, 24, 8, 128)
+    monkeypatch.setenv("REFIL_QKV_SPLIT", "1")
+    monkeypatch.setenv("REFIL_TC_MODE", "ss")
+    assert not ops.qkv_split_ok(128 * 60, 24, 8, 128)          # the all-shared-memory kernel has no row groups
