@@ -77,7 +77,10 @@ def test_linear_row_mask_and_embed():
 
 
 @pytest.mark.parametrize("ne,na,d,H", [(5, 3, 32, 2), (4, 4, 32, 4), (24, 8, 128, 4), (32, 32, 64, 4), (1, 1, 32, 2),
-                                      (12, 12, 32, 2), (6, 4, 64, 8), (4, 2, 32, 1), (17, 9, 64, 4)])
+                                      (12, 12, 32, 2), (6, 4, 64, 8), (4, 2, 32, 1), (17, 9, 64, 4),
+                                      # 4 heads of 32 with <= 8 query rows: the two-agents-per-lane kernels (attn_*_h4_kernel) with fewer
+                                      # than 8 agents, an odd agent count, a single agent, entity counts off the 8-row padding
+                                      (16, 5, 128, 4), (9, 8, 128, 4), (8, 3, 128, 4), (24, 1, 128, 4), (31, 6, 128, 4)])
 def test_masked_attention_fwd_bwd(ne, na, d, H):
     from oracle import learner_oracle as lo
     from refil_b200 import ops
